@@ -1,0 +1,217 @@
+"""ctypes binding of the C ABI declared in include/biogo_align.h.
+
+The product library is ``biogo_b200/lib/libbiogoalign.so`` (built in-tree by
+``__graft_entry__.build()``).  Loading fails loudly when it is missing and every call
+fails loudly when no B200 is usable -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+BA_SW, BA_NW, BA_FITTED = 0, 1, 2
+
+BA_OK = 0
+BA_ERR_ARG, BA_ERR_CUDA, BA_ERR_MATRIX_SIZE, BA_ERR_RANGE, BA_ERR_NOMEM, BA_ERR_NO_SCORING = -1, -2, -3, -4, -5, -6
+BA_PAIR_OK, BA_PAIR_ILLEGAL_REF, BA_PAIR_ILLEGAL_QRY, BA_PAIR_PANIC, BA_PAIR_NO_PATH = 0, 1, 2, 3, 4
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "lib", "libbiogoalign.so")
+
+# every symbol include/biogo_align.h declares
+ABI_SYMBOLS = (
+    "ba_create", "ba_destroy", "ba_last_error", "ba_set_scoring", "ba_align_batch",
+    "ba_align_batch_device", "ba_free_result", "ba_alloc_host", "ba_free_host",
+    "ba_set_option", "ba_abi_version", "ba_build_info",
+)
+
+
+class BaResult(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("status", C.POINTER(C.c_int32)),
+        ("err_pos", C.POINTER(C.c_int64)),
+        ("seg_start", C.POINTER(C.c_int64)),
+        ("seg_count", C.POINTER(C.c_int32)),
+        ("segs", C.POINTER(C.c_int32)),
+        ("n_segs", C.c_int64),
+        ("ms_h2d", C.c_float),
+        ("ms_kernels", C.c_float),
+        ("ms_d2h", C.c_float),
+        ("cells", C.c_int64),
+        ("gpu_launches", C.c_int64),
+    ]
+
+
+class AlignError(RuntimeError):
+    """A ba_* call failed (CUDA error, range error ...)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libbiogoalign: status {code}: {msg}")
+        self.code = code
+
+
+def _bind(lib):
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.ba_create.argtypes = [i32, C.POINTER(vp)]
+    lib.ba_create.restype = i32
+    lib.ba_destroy.argtypes = [vp]
+    lib.ba_destroy.restype = None
+    lib.ba_last_error.argtypes = [vp]
+    lib.ba_last_error.restype = C.c_char_p
+    lib.ba_set_scoring.argtypes = [vp, i32, i32, vp, i32, i32, i64, vp]
+    lib.ba_set_scoring.restype = i32
+    lib.ba_align_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, C.POINTER(BaResult)]
+    lib.ba_align_batch.restype = i32
+    lib.ba_align_batch_device.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp, C.POINTER(BaResult)]
+    lib.ba_align_batch_device.restype = i32
+    lib.ba_free_result.argtypes = [vp, C.POINTER(BaResult)]
+    lib.ba_free_result.restype = None
+    lib.ba_alloc_host.argtypes = [C.c_size_t]
+    lib.ba_alloc_host.restype = vp
+    lib.ba_free_host.argtypes = [vp]
+    lib.ba_free_host.restype = None
+    lib.ba_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.ba_set_option.restype = i32
+    lib.ba_abi_version.argtypes = []
+    lib.ba_abi_version.restype = i32
+    lib.ba_build_info.argtypes = []
+    lib.ba_build_info.restype = C.c_char_p
+    return lib
+
+
+_libs: dict = {}
+
+
+def load(path: str | None = None):
+    """dlopen the C-ABI library (default: the in-tree CUDA build)."""
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(biogo_b200 has no CPU fallback)"
+            )
+        _libs[path] = _bind(C.CDLL(path))
+    return _libs[path]
+
+
+class BatchResult:
+    """numpy views of a ba_result, copied out so the pinned buffers can be recycled."""
+
+    __slots__ = ("n", "status", "err_pos", "seg_start", "seg_count", "segs", "ms_h2d", "ms_kernels",
+                 "ms_d2h", "cells", "gpu_launches")
+
+    def pairs(self, p: int):
+        s, c = int(self.seg_start[p]), int(self.seg_count[p])
+        return self.segs[s : s + c]
+
+
+def _as_array(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class Context:
+    """A ba_ctx: one per (host thread, device)."""
+
+    def __init__(self, device: int = 0, lib_path: str | None = None):
+        self.lib = load(lib_path)
+        h = C.c_void_p()
+        rc = self.lib.ba_create(device, C.byref(h))
+        self._h = h
+        if rc != BA_OK:
+            msg = self.lib.ba_last_error(h).decode() if h else "ba_create failed"
+            if h:
+                self.lib.ba_destroy(h)
+                self._h = None
+            raise AlignError(rc, msg)
+        self.device = device
+        self._scoring_key = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != BA_OK:
+            raise AlignError(rc, self.lib.ba_last_error(self._h).decode())
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.ba_set_option(self._h, key.encode(), int(value)))
+
+    def set_scoring(self, kind: int, affine: bool, la, let: int, alpha_len: int, gap_open: int, index):
+        la = np.ascontiguousarray(la, dtype=np.int64).reshape(-1)
+        index = np.ascontiguousarray(index, dtype=np.int32)
+        key = (kind, bool(affine), la.tobytes(), let, alpha_len, int(gap_open), index.tobytes())
+        if key == self._scoring_key:
+            return
+        rc = self.lib.ba_set_scoring(self._h, kind, int(bool(affine)), la.ctypes.data, let, alpha_len,
+                                     int(gap_open), index.ctypes.data)
+        self._scoring_key = None
+        self._check(rc)
+        self._scoring_key = key
+
+    def _collect(self, res: BaResult) -> BatchResult:
+        out = BatchResult()
+        n = int(res.n)
+        out.n = n
+        out.status = _as_array(res.status, n, np.int32)
+        out.err_pos = _as_array(res.err_pos, n, np.int64)
+        out.seg_start = _as_array(res.seg_start, n, np.int64)
+        out.seg_count = _as_array(res.seg_count, n, np.int32)
+        ns = int(res.n_segs)
+        out.segs = _as_array(res.segs, 5 * ns, np.int32).reshape(ns, 5)
+        out.ms_h2d, out.ms_kernels, out.ms_d2h = float(res.ms_h2d), float(res.ms_kernels), float(res.ms_d2h)
+        out.cells, out.gpu_launches = int(res.cells), int(res.gpu_launches)
+        self.lib.ba_free_result(self._h, C.byref(res))
+        return out
+
+    def align_packed(self, letters, stride: int, ref_off, ref_len, qry_off, qry_len, collect: bool = True):
+        """ba_align_batch on packed host buffers (numpy arrays or pinned ctypes memory)."""
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+        qry_off = np.ascontiguousarray(qry_off, dtype=np.int64)
+        ref_len = np.ascontiguousarray(ref_len, dtype=np.int32)
+        qry_len = np.ascontiguousarray(qry_len, dtype=np.int32)
+        n = len(ref_off)
+        res = BaResult()
+        rc = self.lib.ba_align_batch(self._h, letters.ctypes.data, stride, ref_off.ctypes.data,
+                                     ref_len.ctypes.data, qry_off.ctypes.data, qry_len.ctypes.data, n,
+                                     C.byref(res))
+        self._check(rc)
+        if collect:
+            return self._collect(res)
+        stats = (float(res.ms_h2d), float(res.ms_kernels), float(res.ms_d2h), int(res.cells),
+                 int(res.gpu_launches), int(res.n_segs))
+        self.lib.ba_free_result(self._h, C.byref(res))
+        return stats
+
+    def align_device(self, d_letters: int, letters_bytes: int, stride: int, d_ref_off: int, d_ref_len: int,
+                     d_qry_off: int, d_qry_len: int, h_ref_len, h_qry_len, stream: int = 0,
+                     collect: bool = True):
+        """ba_align_batch_device: inputs already resident in HBM (raw device pointers)."""
+        h_ref_len = np.ascontiguousarray(h_ref_len, dtype=np.int32)
+        h_qry_len = np.ascontiguousarray(h_qry_len, dtype=np.int32)
+        n = len(h_ref_len)
+        res = BaResult()
+        rc = self.lib.ba_align_batch_device(self._h, d_letters, letters_bytes, stride, d_ref_off, d_ref_len,
+                                            d_qry_off, d_qry_len, h_ref_len.ctypes.data,
+                                            h_qry_len.ctypes.data, n, stream or None, C.byref(res))
+        self._check(rc)
+        if collect:
+            return self._collect(res)
+        stats = (float(res.ms_h2d), float(res.ms_kernels), float(res.ms_d2h), int(res.cells),
+                 int(res.gpu_launches), int(res.n_segs))
+        self.lib.ba_free_result(self._h, C.byref(res))
+        return stats

@@ -1,0 +1,698 @@
+// ba_api.cu -- C ABI of libbiogoalign.so (see include/biogo_align.h) and the host-side
+// batch scheduler: scoring upload, length-bucketed work lists, wave sizing against the
+// traceback-code arena, kernel launches and result gathering.  Plain CUDA runtime; no
+// torch types, no CPU fallback.
+#include "../../include/biogo_align.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ba_common.cuh"
+#ifndef BA_EMULATE
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
+#endif
+#include "ba_fill32.cuh"
+#include "ba_walk.cuh"
+#include "ba_plan.h"
+
+// One spelling for kernel launches so the same scheduler source also drives the CPU
+// emulator of the no-GPU test tier (tests/emu).
+#ifdef BA_EMULATE
+#define BA_LAUNCH(kernel, grid, block, stream, ...) emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#else
+#define BA_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct PinnedBlock {
+    void *p;
+    size_t cap;
+    bool used;
+};
+
+struct ToInt64 {
+    __host__ __device__ int64_t operator()(int32_t v) const { return (int64_t)v; }
+};
+
+typedef void (*FillFn)(FillParams);
+typedef void (*WalkFn)(WalkParams);
+
+template <int KIND, bool AFFINE>
+FillFn fill_for_cols(int cols)
+{
+    switch (cols) {
+    case 1: return ba_fill32_kernel<KIND, AFFINE, 1>;
+    case 2: return ba_fill32_kernel<KIND, AFFINE, 2>;
+    case 3: return ba_fill32_kernel<KIND, AFFINE, 3>;
+    case 4: return ba_fill32_kernel<KIND, AFFINE, 4>;
+    case 5: return ba_fill32_kernel<KIND, AFFINE, 5>;
+    case 6: return ba_fill32_kernel<KIND, AFFINE, 6>;
+    case 7: return ba_fill32_kernel<KIND, AFFINE, 7>;
+    default: return ba_fill32_kernel<KIND, AFFINE, 8>;
+    }
+}
+
+FillFn pick_fill(int kind, int affine, int cols)
+{
+    if (affine) {
+        if (kind == KIND_SW) return fill_for_cols<KIND_SW, true>(cols);
+        if (kind == KIND_NW) return fill_for_cols<KIND_NW, true>(cols);
+        return fill_for_cols<KIND_FIT, true>(cols);
+    }
+    if (kind == KIND_SW) return fill_for_cols<KIND_SW, false>(cols);
+    if (kind == KIND_NW) return fill_for_cols<KIND_NW, false>(cols);
+    return fill_for_cols<KIND_FIT, false>(cols);
+}
+
+template <bool WRITE>
+WalkFn pick_walk(int kind, int affine)
+{
+    if (affine) {
+        if (kind == KIND_SW) return ba_walk_kernel<KIND_SW, true, WRITE>;
+        if (kind == KIND_NW) return ba_walk_kernel<KIND_NW, true, WRITE>;
+        return ba_walk_kernel<KIND_FIT, true, WRITE>;
+    }
+    if (kind == KIND_SW) return ba_walk_kernel<KIND_SW, false, WRITE>;
+    if (kind == KIND_NW) return ba_walk_kernel<KIND_NW, false, WRITE>;
+    return ba_walk_kernel<KIND_FIT, false, WRITE>;
+}
+
+}  // namespace
+
+struct ba_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    bool have_scoring = false;
+    DeviceScoring h_sc;
+    DeviceScoring *d_sc = nullptr;
+    int64_t opt_arena_bytes = 0;
+    // grow-only device buffers
+    DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
+    DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
+    std::vector<PinnedBlock> pinned;
+};
+
+namespace {
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            char b_[512];                                                             \
+            snprintf(b_, sizeof b_, "%s:%d: %s: %s", __FILE__, __LINE__, #call,       \
+                     cudaGetErrorString(e_));                                         \
+            ctx->err = b_;                                                            \
+            return (e_ == cudaErrorMemoryAllocation) ? BA_ERR_NOMEM : BA_ERR_CUDA;    \
+        }                                                                             \
+    } while (0)
+
+int ensure(ba_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return BA_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        want = bytes;
+        CK(cudaMalloc(&b.p, want));
+    }
+    b.cap = want;
+    return BA_OK;
+}
+
+void *pinned_get(ba_ctx *ctx, size_t bytes)
+{
+    if (bytes == 0) bytes = 8;
+    int bestk = -1;
+    for (size_t k = 0; k < ctx->pinned.size(); k++) {
+        PinnedBlock &b = ctx->pinned[k];
+        if (!b.used && b.cap >= bytes && (bestk < 0 || b.cap < ctx->pinned[bestk].cap)) bestk = (int)k;
+    }
+    if (bestk >= 0) {
+        ctx->pinned[bestk].used = true;
+        return ctx->pinned[bestk].p;
+    }
+    void *p = nullptr;
+    size_t cap = bytes + bytes / 4;
+    if (cudaMallocHost(&p, cap) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    ctx->pinned.push_back({p, cap, true});
+    return p;
+}
+
+void pinned_put(ba_ctx *ctx, void *p)
+{
+    for (auto &b : ctx->pinned)
+        if (b.p == p) b.used = false;
+}
+
+// seg_base = exclusive prefix sum of seg_count (int32 -> int64)
+int exclusive_scan(ba_ctx *ctx, void *tmp, size_t &tmp_bytes, const int32_t *in, int64_t *out, int n,
+                   cudaStream_t st)
+{
+#ifdef BA_EMULATE
+    (void)st;
+    if (!tmp) {
+        tmp_bytes = 16;
+        return BA_OK;
+    }
+    int64_t acc = 0;
+    for (int k = 0; k < n; k++) {
+        out[k] = acc;
+        acc += in[k];
+    }
+    (void)ctx;
+    return BA_OK;
+#else
+    auto itr = thrust::make_transform_iterator(in, ToInt64());
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, itr, out, n, st));
+    return BA_OK;
+#endif
+}
+
+int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int stride,
+               const int64_t *d_ref_off, const int32_t *d_ref_len, const int64_t *d_qry_off,
+               const int32_t *d_qry_len, const int32_t *h_ref_len, const int32_t *h_qry_len,
+               int64_t n, cudaStream_t st, ba_result *out)
+{
+    const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+    int64_t launches = 0;
+
+    // ---- result arrays (pinned, pooled)
+    out->n = n;
+    out->status = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
+    out->err_pos = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
+    out->seg_start = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
+    out->seg_count = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
+    out->segs = nullptr;
+    out->n_segs = 0;
+    if (!out->status || !out->err_pos || !out->seg_start || !out->seg_count) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    if (n == 0) return BA_OK;
+
+    CK(cudaEventRecord(ctx->ev[1], st));
+
+    // ---- encode + validate
+    int rc;
+    if ((rc = ensure(ctx, ctx->enc, (size_t)letters_bytes + 16)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->status, sizeof(int32_t) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->err_pos, sizeof(int64_t) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->start, sizeof(PairStart) * (size_t)n)) != BA_OK) return rc;
+    uint8_t *d_enc = (uint8_t *)ctx->enc.p;
+    int32_t *d_status = (int32_t *)ctx->status.p;
+    int64_t *d_err_pos = (int64_t *)ctx->err_pos.p;
+    PairStart *d_start = (PairStart *)ctx->start.p;
+    if (letters_bytes > 0) {
+        int64_t blocks = (letters_bytes / 16 + 255) / 256;
+        if (blocks < 1) blocks = 1;
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        BA_LAUNCH(ba_encode_kernel, (unsigned)blocks, 256, st, d_letters, d_enc, letters_bytes, ctx->d_sc);
+        launches++;
+    }
+    {
+        int64_t blocks = (n + 7) / 8;
+        if (blocks > ctx->sm_count * 32) blocks = ctx->sm_count * 32;
+        BA_LAUNCH(ba_validate_kernel, (unsigned)blocks, 256, st, d_enc, stride, d_ref_off, d_ref_len, d_qry_off,
+                  d_qry_len, n, kind, affine, d_status, d_err_pos);
+        launches++;
+    }
+    CK(cudaGetLastError());
+
+    // ---- plan
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    int64_t arena_cap = ctx->opt_arena_bytes;
+    if (arena_cap <= 0) {
+        arena_cap = (int64_t)((double)(free_b + ctx->arena.cap) * 0.6);
+        const int64_t lim = 48LL << 30;
+        if (arena_cap > lim) arena_cap = lim;
+    }
+    Plan plan;
+    build_plan(h_ref_len, h_qry_len, n, kind, affine, arena_cap, plan);
+    out->cells = plan.cells;
+
+    int64_t max_items = 0, max_code = 0, max_aux = 0;
+    for (auto &w : plan.waves) {
+        max_items = std::max(max_items, w.count);
+        max_code = std::max(max_code, w.code_bytes);
+        max_aux = std::max(max_aux, w.aux_ints);
+    }
+    if ((rc = ensure(ctx, ctx->items, sizeof(WorkItem) * (size_t)max_items)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->aux_off, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->aux, sizeof(int32_t) * (size_t)(max_aux + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_count, sizeof(int32_t) * (size_t)max_items)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_base, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->arena, (size_t)max_code + 256)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 64)) != BA_OK) return rc;
+    size_t scan_bytes = 0;
+    if ((rc = exclusive_scan(ctx, nullptr, scan_bytes, (const int32_t *)ctx->seg_count.p,
+                             (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
+        return rc;
+    if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
+
+    // host staging for per-item results of a wave
+    int32_t *h_cnt = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
+    int64_t *h_base = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(max_items + 1));
+    if (!h_cnt || !h_base) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+
+    WalkFn walk_count = pick_walk<false>(kind, affine);
+    WalkFn walk_write = pick_walk<true>(kind, affine);
+
+    struct WaveOut {
+        int32_t *segs;
+        int64_t nsegs;
+    };
+    std::vector<WaveOut> wave_out;
+    int64_t seg_total = 0;
+    float ms_d2h = 0.f;
+
+    for (auto &w : plan.waves) {
+        WorkItem *d_items = (WorkItem *)ctx->items.p;
+        CK(cudaMemcpyAsync(d_items, plan.items.data() + w.first, sizeof(WorkItem) * (size_t)w.count,
+                           cudaMemcpyHostToDevice, st));
+        int64_t *d_aux_off = (int64_t *)ctx->aux_off.p;
+        if (kind == KIND_FIT)
+            CK(cudaMemcpyAsync(d_aux_off, plan.aux_off.data() + w.first, sizeof(int64_t) * (size_t)w.count,
+                               cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
+
+        // ---- fill
+        int li = 0;
+        for (auto &L : w.launches) {
+            FillFn fn = pick_fill(kind, affine, L.cols);
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BA_FILL_WARPS * 32, 0));
+            if (occ < 1) occ = 1;
+            int64_t blocks = (L.count + BA_FILL_WARPS - 1) / BA_FILL_WARPS;
+            int64_t maxb = (int64_t)ctx->sm_count * occ;
+            if (blocks > maxb) blocks = maxb;
+            int64_t bnd_stride = 0;
+            if (w.max_n_multipass > 0) {
+                bnd_stride = (int64_t)(affine ? 3 : 1) * ((int64_t)w.max_n_multipass + 2);
+                if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * blocks * BA_FILL_WARPS))) !=
+                    BA_OK)
+                    return rc;
+            }
+            FillParams fp;
+            fp.enc = d_enc;
+            fp.stride = stride;
+            fp.ref_off = d_ref_off;
+            fp.ref_len = d_ref_len;
+            fp.qry_off = d_qry_off;
+            fp.qry_len = d_qry_len;
+            fp.status = d_status;
+            fp.items = d_items + (L.first - w.first);
+            fp.n_items = (int)L.count;
+            fp.counter = (int *)ctx->counters.p + (li++ % 64);
+            fp.arena = (uint8_t *)ctx->arena.p;
+            fp.bnd = (int32_t *)ctx->bnd.p;
+            fp.bnd_stride = bnd_stride;
+            fp.start = d_start;
+            fp.aux = (int32_t *)ctx->aux.p;
+            fp.aux_off = d_aux_off + (L.first - w.first);
+            fp.sc = ctx->d_sc;
+            BA_LAUNCH(fn, (unsigned)blocks, BA_FILL_WARPS * 32, st, fp);
+            launches++;
+        }
+        CK(cudaGetLastError());
+
+        // ---- walk: count, scan, write
+        WalkParams wp;
+        wp.enc = d_enc;
+        wp.stride = stride;
+        wp.ref_off = d_ref_off;
+        wp.ref_len = d_ref_len;
+        wp.qry_off = d_qry_off;
+        wp.qry_len = d_qry_len;
+        wp.status = d_status;
+        wp.items = d_items;
+        wp.n_items = (int)w.count;
+        wp.arena = (const uint8_t *)ctx->arena.p;
+        wp.start = d_start;
+        wp.aux = (const int32_t *)ctx->aux.p;
+        wp.aux_off = d_aux_off;
+        wp.sc = ctx->d_sc;
+        wp.seg_count = (int32_t *)ctx->seg_count.p;
+        wp.seg_base = (const int64_t *)ctx->seg_base.p;
+        wp.segs = nullptr;
+        const unsigned wblocks = (unsigned)((w.count + 127) / 128);
+        BA_LAUNCH(walk_count, wblocks, 128, st, wp);
+        launches++;
+        {
+            size_t tb = ctx->scan_tmp.cap;
+            if ((rc = exclusive_scan(ctx, ctx->scan_tmp.p, tb, (const int32_t *)ctx->seg_count.p,
+                                     (int64_t *)ctx->seg_base.p, (int)w.count, st)) != BA_OK)
+                return rc;
+            launches += 2;
+        }
+        CK(cudaMemcpyAsync(h_cnt, ctx->seg_count.p, sizeof(int32_t) * (size_t)w.count, cudaMemcpyDeviceToHost,
+                           st));
+        CK(cudaMemcpyAsync(h_base, ctx->seg_base.p, sizeof(int64_t) * (size_t)w.count, cudaMemcpyDeviceToHost,
+                           st));
+        CK(cudaStreamSynchronize(st));
+        const int64_t wsegs = h_base[w.count - 1] + h_cnt[w.count - 1];
+        if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
+        wp.segs = (int32_t *)ctx->segs.p;
+        BA_LAUNCH(walk_write, wblocks, 128, st, wp);
+        launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[2], st));
+        int32_t *h_segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(wsegs + 1));
+        if (!h_segs) {
+            ctx->err = "pinned host allocation failed";
+            return BA_ERR_NOMEM;
+        }
+        CK(cudaMemcpyAsync(h_segs, ctx->segs.p, sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        ms_d2h += ms;
+        for (int64_t k = 0; k < w.count; k++) {
+            const int32_t p = plan.items[(size_t)(w.first + k)].pair;
+            out->seg_start[p] = seg_total + h_base[k];
+            out->seg_count[p] = h_cnt[k];
+        }
+        wave_out.push_back({h_segs, wsegs});
+        seg_total += wsegs;
+    }
+
+    // ---- gather
+    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaMemcpyAsync(out->status, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->err_pos, d_err_pos, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f, all = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        ms_d2h += ms;
+        CK(cudaEventElapsedTime(&all, ctx->ev[1], ctx->ev[3]));
+        out->ms_d2h = ms_d2h;
+        out->ms_kernels = all - ms_d2h;
+    }
+    if (wave_out.size() == 1) {
+        out->segs = wave_out[0].segs;
+    } else {
+        out->segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(seg_total + 1));
+        if (!out->segs) {
+            ctx->err = "pinned host allocation failed";
+            return BA_ERR_NOMEM;
+        }
+        int64_t o = 0;
+        for (auto &wo : wave_out) {
+            memcpy(out->segs + 5 * o, wo.segs, sizeof(int32_t) * 5 * (size_t)wo.nsegs);
+            o += wo.nsegs;
+            pinned_put(ctx, wo.segs);
+        }
+    }
+    out->n_segs = seg_total;
+    out->gpu_launches = launches;
+    pinned_put(ctx, h_cnt);
+    pinned_put(ctx, h_base);
+    return BA_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int ba_abi_version(void) { return BA_ABI_VERSION; }
+
+const char *ba_build_info(void)
+{
+    return "libbiogoalign sm_100a (fill32 exact-code kernels; nvcc " __DATE__ ")";
+}
+
+int ba_create(int device, ba_ctx **out)
+{
+    if (!out) return BA_ERR_ARG;
+    *out = nullptr;
+    ba_ctx *ctx = new ba_ctx();
+    ctx->device = device;
+    auto fail = [&](cudaError_t e, const char *what) {
+        // keep the ctx alive so the caller can read ba_last_error(); it holds no device state
+        char b[256];
+        snprintf(b, sizeof b, "%s: %s", what, cudaGetErrorString(e));
+        ctx->err = b;
+        *out = ctx;
+        return BA_ERR_CUDA;
+    };
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) {
+        ctx->err = "libbiogoalign is built for sm_100a (B200) only";
+        *out = ctx;
+        return BA_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
+    for (int k = 0; k < 4; k++) {
+        e = cudaEventCreate(&ctx->ev[k]);
+        if (e != cudaSuccess) return fail(e, "cudaEventCreate");
+    }
+    e = cudaMalloc((void **)&ctx->d_sc, sizeof(DeviceScoring));
+    if (e != cudaSuccess) return fail(e, "cudaMalloc");
+    *out = ctx;
+    return BA_OK;
+}
+
+void ba_destroy(ba_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    DevBuf *bufs[] = {&ctx->letters, &ctx->enc,  &ctx->ref_off,   &ctx->ref_len,  &ctx->qry_off, &ctx->qry_len,
+                      &ctx->status,  &ctx->err_pos, &ctx->start,  &ctx->items,    &ctx->aux_off, &ctx->aux,
+                      &ctx->bnd,     &ctx->seg_count, &ctx->seg_base, &ctx->segs, &ctx->arena,   &ctx->scan_tmp,
+                      &ctx->counters};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (auto &b : ctx->pinned) cudaFreeHost(b.p);
+    if (ctx->d_sc) cudaFree(ctx->d_sc);
+    for (int k = 0; k < 4; k++)
+        if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *ba_last_error(const ba_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
+{
+    if (!ctx || !key) return BA_ERR_ARG;
+    if (!strcmp(key, "arena_bytes")) {
+        ctx->opt_arena_bytes = value;
+        return BA_OK;
+    }
+    ctx->err = std::string("unknown option: ") + key;
+    return BA_ERR_ARG;
+}
+
+int ba_set_scoring(ba_ctx *ctx, int kind, int affine, const int64_t *la, int let, int alpha_len,
+                   int64_t gap_open, const int32_t *index)
+{
+    if (!ctx || !la || !index || let < 1 || kind < BA_SW || kind > BA_FITTED) return BA_ERR_ARG;
+    if (!ctx->d_sc) {
+        ctx->err = "context has no device (ba_create failed)";
+        return BA_ERR_CUDA;
+    }
+    // align/sw_letters.go:70-72 (absent in fitted_letters.go:71-78)
+    if (kind != BA_FITTED && let < alpha_len) {
+        ctx->err = "align: scoring matrix size does not match alphabet length";
+        return BA_ERR_MATRIX_SIZE;
+    }
+    if (let > BA_MAX_LET) {
+        ctx->err = "scoring matrix larger than 32x32 is not supported";
+        return BA_ERR_RANGE;
+    }
+    int64_t maxabs = 0;
+    for (int k = 0; k < let * let; k++) {
+        int64_t a = la[k] < 0 ? -la[k] : la[k];
+        if (a > maxabs) maxabs = a;
+    }
+    const int64_t ago = gap_open < 0 ? -gap_open : gap_open;
+    if (maxabs > (1 << 20) || ago > (1 << 20)) {
+        ctx->err = "scoring values exceed the 32-bit device range";
+        return BA_ERR_RANGE;
+    }
+    DeviceScoring &s = ctx->h_sc;
+    memset(&s, 0, sizeof s);
+    for (int k = 0; k < let * let; k++) s.la[k] = (int32_t)la[k];
+    s.let = let;
+    s.gap_open = affine ? (int32_t)gap_open : 0;
+    s.alpha_len = alpha_len;
+    s.kind = kind;
+    s.affine = affine ? 1 : 0;
+    for (int k = 0; k < 256; k++) s.index[k] = (index[k] < 0 || index[k] > 253) ? 0xFF : (uint8_t)index[k];
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_sc, &s, sizeof s, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_scoring = true;
+    return BA_OK;
+}
+
+static int check_range(ba_ctx *ctx, const int32_t *ref_len, const int32_t *qry_len, int64_t n)
+{
+    int64_t maxabs = 0;
+    const DeviceScoring &s = ctx->h_sc;
+    for (int k = 0; k < s.let * s.let; k++) {
+        int64_t a = s.la[k] < 0 ? -(int64_t)s.la[k] : s.la[k];
+        if (a > maxabs) maxabs = a;
+    }
+    int64_t maxlen = 0;
+    for (int64_t p = 0; p < n; p++) {
+        if (ref_len[p] < 0 || qry_len[p] < 0) {
+            ctx->err = "negative sequence length";
+            return BA_ERR_ARG;
+        }
+        int64_t l = (int64_t)ref_len[p] + qry_len[p];
+        if (l > maxlen) maxlen = l;
+    }
+    const int64_t ago = s.gap_open < 0 ? -(int64_t)s.gap_open : s.gap_open;
+    const int64_t bound = ago + (maxlen + 2) * maxabs;
+    if (bound * BA_SCALE >= (1LL << 26)) {
+        ctx->err = "score bound exceeds the 32-bit device lanes";
+        return BA_ERR_RANGE;
+    }
+    return BA_OK;
+}
+
+int ba_align_batch_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int stride,
+                          const int64_t *d_ref_off, const int32_t *d_ref_len, const int64_t *d_qry_off,
+                          const int32_t *d_qry_len, const int32_t *h_ref_len, const int32_t *h_qry_len,
+                          int64_t n, void *cuda_stream, ba_result *out)
+{
+    if (!ctx || !out || n < 0 || (stride != 1 && stride != 2)) return BA_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (!ctx->have_scoring) {
+        ctx->err = "ba_set_scoring has not been called";
+        return BA_ERR_NO_SCORING;
+    }
+    if (n > 0 && (!d_ref_off || !d_ref_len || !d_qry_off || !d_qry_len || !h_ref_len || !h_qry_len))
+        return BA_ERR_ARG;
+    if (n > 0x7fffffff) return BA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_range(ctx, h_ref_len, h_qry_len, n);
+    if (rc != BA_OK) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    rc = run_device(ctx, d_letters, letters_bytes, stride, d_ref_off, d_ref_len, d_qry_off, d_qry_len,
+                    h_ref_len, h_qry_len, n, st, out);
+    out->ms_h2d = 0.f;
+    if (rc != BA_OK) ba_free_result(ctx, out);
+    return rc;
+}
+
+int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_t *ref_off,
+                   const int32_t *ref_len, const int64_t *qry_off, const int32_t *qry_len, int64_t n,
+                   ba_result *out)
+{
+    if (!ctx || !out || n < 0 || (stride != 1 && stride != 2)) return BA_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (!ctx->have_scoring) {
+        ctx->err = "ba_set_scoring has not been called";
+        return BA_ERR_NO_SCORING;
+    }
+    if (n > 0 && (!ref_off || !ref_len || !qry_off || !qry_len)) return BA_ERR_ARG;
+    if (n > 0x7fffffff) return BA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_range(ctx, ref_len, qry_len, n);
+    if (rc != BA_OK) return rc;
+    int64_t letters_bytes = 0;
+    for (int64_t p = 0; p < n; p++) {
+        if (ref_off[p] < 0 || qry_off[p] < 0) {
+            ctx->err = "negative sequence offset";
+            return BA_ERR_ARG;
+        }
+        int64_t e1 = ref_len[p] ? ref_off[p] + ((int64_t)ref_len[p] - 1) * stride + 1 : 0;
+        int64_t e2 = qry_len[p] ? qry_off[p] + ((int64_t)qry_len[p] - 1) * stride + 1 : 0;
+        if (e1 > letters_bytes) letters_bytes = e1;
+        if (e2 > letters_bytes) letters_bytes = e2;
+    }
+    if (letters_bytes > 0 && !letters) return BA_ERR_ARG;
+    cudaStream_t st = ctx->stream;
+    if ((rc = ensure(ctx, ctx->letters, (size_t)letters_bytes + 16)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->ref_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->qry_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->ref_len, sizeof(int32_t) * (size_t)(n + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->qry_len, sizeof(int32_t) * (size_t)(n + 1))) != BA_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    if (letters_bytes > 0)
+        CK(cudaMemcpyAsync(ctx->letters.p, letters, (size_t)letters_bytes, cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->ref_off.p, ref_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->qry_off.p, qry_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ref_len.p, ref_len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->qry_len.p, qry_len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    rc = run_device(ctx, (const uint8_t *)ctx->letters.p, letters_bytes, stride, (const int64_t *)ctx->ref_off.p,
+                    (const int32_t *)ctx->ref_len.p, (const int64_t *)ctx->qry_off.p,
+                    (const int32_t *)ctx->qry_len.p, ref_len, qry_len, n, st, out);
+    if (rc != BA_OK) {
+        ba_free_result(ctx, out);
+        return rc;
+    }
+    if (n > 0) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        out->ms_h2d = ms;
+    }
+    return BA_OK;
+}
+
+void ba_free_result(ba_ctx *ctx, ba_result *res)
+{
+    if (!ctx || !res) return;
+    if (res->status) pinned_put(ctx, res->status);
+    if (res->err_pos) pinned_put(ctx, res->err_pos);
+    if (res->seg_start) pinned_put(ctx, res->seg_start);
+    if (res->seg_count) pinned_put(ctx, res->seg_count);
+    if (res->segs) pinned_put(ctx, res->segs);
+    memset(res, 0, sizeof *res);
+}
+
+void *ba_alloc_host(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void ba_free_host(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

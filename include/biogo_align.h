@@ -1,0 +1,142 @@
+/*
+ * biogo_align.h -- C ABI of libbiogoalign.so, the B200 (sm_100a) replacement for the
+ * dynamic-programming hot path of biogo's `align` package.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no CUDA or torch types.
+ * The twelve unexported Go methods
+ *     (a SW|NW|Fitted|SWAffine|NWAffine|FittedAffine) alignLetters / alignQLetters
+ *     (align/sw_letters.go:68, sw_qletters.go:68, nw_letters.go:75, nw_qletters.go:75,
+ *      fitted_letters.go:70, fitted_qletters.go:70, sw_affine_letters.go:85,
+ *      sw_affine_qletters.go:85, nw_affine_letters.go:98, nw_affine_qletters.go:98,
+ *      fitted_affine_letters.go:93, fitted_affine_qletters.go:93)
+ * each become one ba_align_batch() call with n == 1; the new AlignBatch entry point is
+ * the same call with n > 1.  The cgo stub a maintainer would add is in INTEGRATION.md.
+ *
+ * There is no CPU fallback: every entry point that needs the GPU returns BA_ERR_CUDA
+ * (with ba_last_error() text) when no sm_100 device/driver is usable.
+ */
+#ifndef BIOGO_ALIGN_H
+#define BIOGO_ALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BA_ABI_VERSION 1
+
+/* Aligner kind: align/sw.go:18, align/nw.go:16, align/fitted.go:16 (and *_affine.go:16). */
+enum { BA_SW = 0, BA_NW = 1, BA_FITTED = 2 };
+
+/* Call status (return value of the ba_* functions). */
+enum {
+    BA_OK = 0,
+    BA_ERR_ARG = -1,          /* bad argument (null pointer, negative size, unknown kind) */
+    BA_ERR_CUDA = -2,         /* CUDA runtime/driver failure; no CPU fallback exists */
+    BA_ERR_MATRIX_SIZE = -3,  /* align.ErrMatrixWrongSize{Size,Len} (align/align.go:66-73); SW/NW kinds only */
+    BA_ERR_RANGE = -4,        /* score bound does not fit the 32-bit device lanes */
+    BA_ERR_NOMEM = -5,        /* host or device allocation failed */
+    BA_ERR_NO_SCORING = -6    /* ba_align_batch before ba_set_scoring */
+};
+
+/* Per-pair status (ba_result.status[k]). */
+enum {
+    BA_PAIR_OK = 0,
+    BA_PAIR_ILLEGAL_REF = 1,  /* "align: illegal letter %q at position %d in rSeq"; err_pos[k] = position */
+    BA_PAIR_ILLEGAL_QRY = 2,  /* "... in qSeq" */
+    BA_PAIR_PANIC = 3,        /* the Go code panics on this input (index out of range: empty or
+                                 illegal-letter input in the NW/Fitted border set-up) */
+    BA_PAIR_NO_PATH = 4       /* "align: ... internal error: no path" (never expected) */
+};
+
+typedef struct ba_ctx ba_ctx;
+
+/*
+ * Result of one batch.  All arrays are owned by the library (pinned host memory) and
+ * stay valid until ba_free_result().  Segment k (0 <= k < seg_count[p]) of pair p is
+ *     segs[5*(seg_start[p]+k) .. +5] = { a.start, a.end, b.start, b.end, score }
+ * in final order (already reversed like align/sw_letters.go:188-190), 0-based half-open
+ * slice coordinates; a = reference, b = query.  This is featPair (align/align.go:121-124).
+ * Pairs are laid out in the scheduler's work order, so seg_start is NOT monotone in p.
+ */
+typedef struct {
+    int64_t n;           /* number of pairs */
+    int32_t *status;     /* [n] BA_PAIR_* */
+    int64_t *err_pos;    /* [n] letter position for BA_PAIR_ILLEGAL_*, else -1 */
+    int64_t *seg_start;  /* [n] first segment of pair p inside segs (in segments) */
+    int32_t *seg_count;  /* [n] number of segments of pair p (0 unless BA_PAIR_OK) */
+    int32_t *segs;       /* [5*n_segs] */
+    int64_t n_segs;
+    /* device-side timing of this call, CUDA events on the launching stream (ms) */
+    float ms_h2d, ms_kernels, ms_d2h;
+    int64_t cells;        /* sum of len(ref)*len(query) over the batch */
+    int64_t gpu_launches; /* kernels launched for this batch */
+} ba_result;
+
+/* Context: one per (host thread, device).  Thread-compatible: calls on ONE ctx must be
+ * serialised by the caller; different ctxs may be used concurrently. */
+int ba_create(int device, ba_ctx **out);
+void ba_destroy(ba_ctx *ctx);
+const char *ba_last_error(const ba_ctx *ctx);
+
+/*
+ * Module (1): scoring upload.  Replaces the matrix check/flatten at the top of every
+ * alignLetters (e.g. align/sw_letters.go:69-79) and alpha.LetterIndex()
+ * (alphabet/alphabet.go:255).
+ *   kind      BA_SW / BA_NW / BA_FITTED
+ *   affine    0 = Linear [][]int, 1 = Affine{Matrix, GapOpen} (align/align.go:34-40)
+ *   la        the square matrix flattened row-major, let*let Go ints
+ *   alpha_len alphabet.Len(); let < alpha_len is BA_ERR_MATRIX_SIZE for SW and NW kinds
+ *             (absent in Fitted/FittedAffine: align/fitted_letters.go:71-78)
+ *   index     alphabet.Index, 256 entries, negative = letter not in the alphabet
+ * The matrix is copied; callers may mutate theirs afterwards.
+ */
+int ba_set_scoring(ba_ctx *ctx, int kind, int affine, const int64_t *la, int let,
+                   int alpha_len, int64_t gap_open, const int32_t *index);
+
+/*
+ * Modules (2)+(3): DP fill + traceback for n independent pairs.
+ *   letters   one contiguous HOST buffer holding every sequence
+ *   stride    1 = alphabet.Letters, 2 = alphabet.QLetters ({L,Q} pairs; Q is ignored,
+ *             align/sw_qletters.go is sw_letters.go with x -> x.L)
+ *   *_off     BYTE offsets of element 0 of each sequence inside `letters`
+ *   *_len     lengths in letters
+ * Inputs are read-only and not retained after return.
+ */
+int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride,
+                   const int64_t *ref_off, const int32_t *ref_len,
+                   const int64_t *qry_off, const int32_t *qry_len,
+                   int64_t n, ba_result *out);
+
+/*
+ * Same, with the packed inputs already resident in DEVICE memory (all five pointers are
+ * device pointers; letters_bytes = size of the letters buffer).  `cuda_stream` is a
+ * cudaStream_t cast to void* (NULL = the library's own stream).  Used by bench.py to
+ * time the kernels alone; results are still gathered to the host in `out`.
+ */
+int ba_align_batch_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int stride,
+                          const int64_t *d_ref_off, const int32_t *d_ref_len,
+                          const int64_t *d_qry_off, const int32_t *d_qry_len,
+                          const int32_t *h_ref_len, const int32_t *h_qry_len,
+                          int64_t n, void *cuda_stream, ba_result *out);
+
+void ba_free_result(ba_ctx *ctx, ba_result *res);
+
+/* Pinned host allocation so a caller (cgo, ctypes) can pack straight into DMA-able memory. */
+void *ba_alloc_host(size_t bytes);
+void ba_free_host(void *p);
+
+/* Tunables (optional). key: "arena_bytes" (traceback-code arena per wave, default 48 GiB
+ * or 60 % of free HBM), "force_path" (0 auto, 1 = 32-bit exact-code kernels only). */
+int ba_set_option(ba_ctx *ctx, const char *key, int64_t value);
+
+/* Build/ABI information. */
+int ba_abi_version(void);
+const char *ba_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOGO_ALIGN_H */
