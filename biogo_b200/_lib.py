@@ -40,8 +40,11 @@ class BaResult(C.Structure):
         ("ms_h2d", C.c_float),
         ("ms_kernels", C.c_float),
         ("ms_d2h", C.c_float),
+        ("ms_fill", C.c_float),
         ("cells", C.c_int64),
         ("gpu_launches", C.c_int64),
+        ("fill_launches", C.c_int64),
+        ("code_bytes", C.c_int64),
     ]
 
 
@@ -101,12 +104,17 @@ def load(path: str | None = None):
 class BatchResult:
     """numpy views of a ba_result, copied out so the pinned buffers can be recycled."""
 
-    __slots__ = ("n", "status", "err_pos", "seg_start", "seg_count", "segs", "ms_h2d", "ms_kernels",
-                 "ms_d2h", "cells", "gpu_launches")
+    __slots__ = ("n", "status", "err_pos", "seg_start", "seg_count", "segs", "stats")
 
     def pairs(self, p: int):
         s, c = int(self.seg_start[p]), int(self.seg_count[p])
         return self.segs[s : s + c]
+
+
+def _stats(res: BaResult) -> dict:
+    return {k: (float(getattr(res, k)) if k.startswith("ms_") else int(getattr(res, k)))
+            for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_fill", "cells", "gpu_launches", "fill_launches",
+                      "code_bytes", "n_segs")}
 
 
 def _as_array(ptr, n, dtype):
@@ -172,8 +180,7 @@ class Context:
         out.seg_count = _as_array(res.seg_count, n, np.int32)
         ns = int(res.n_segs)
         out.segs = _as_array(res.segs, 5 * ns, np.int32).reshape(ns, 5)
-        out.ms_h2d, out.ms_kernels, out.ms_d2h = float(res.ms_h2d), float(res.ms_kernels), float(res.ms_d2h)
-        out.cells, out.gpu_launches = int(res.cells), int(res.gpu_launches)
+        out.stats = _stats(res)
         self.lib.ba_free_result(self._h, C.byref(res))
         return out
 
@@ -192,8 +199,7 @@ class Context:
         self._check(rc)
         if collect:
             return self._collect(res)
-        stats = (float(res.ms_h2d), float(res.ms_kernels), float(res.ms_d2h), int(res.cells),
-                 int(res.gpu_launches), int(res.n_segs))
+        stats = _stats(res)
         self.lib.ba_free_result(self._h, C.byref(res))
         return stats
 
@@ -211,7 +217,6 @@ class Context:
         self._check(rc)
         if collect:
             return self._collect(res)
-        stats = (float(res.ms_h2d), float(res.ms_kernels), float(res.ms_d2h), int(res.cells),
-                 int(res.gpu_launches), int(res.n_segs))
+        stats = _stats(res)
         self.lib.ba_free_result(self._h, C.byref(res))
         return stats

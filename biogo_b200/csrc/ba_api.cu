@@ -94,7 +94,7 @@ struct ba_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     bool have_scoring = false;
     DeviceScoring h_sc;
@@ -195,7 +195,8 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
                int64_t n, cudaStream_t st, ba_result *out)
 {
     const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
-    int64_t launches = 0;
+    int64_t launches = 0, fill_launches = 0, code_bytes = 0;
+    float ms_fill = 0.f;
 
     // ---- result arrays (pinned, pooled)
     out->n = n;
@@ -301,6 +302,7 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
 
         // ---- fill
+        CK(cudaEventRecord(ctx->ev[4], st));
         int li = 0;
         for (auto &L : w.launches) {
             FillFn fn = pick_fill(kind, affine, L.cols);
@@ -337,8 +339,11 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
             fp.sc = ctx->d_sc;
             BA_LAUNCH(fn, (unsigned)blocks, BA_FILL_WARPS * 32, st, fp);
             launches++;
+            fill_launches++;
         }
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[5], st));
+        code_bytes += w.code_bytes;
 
         // ---- walk: count, scan, write
         WalkParams wp;
@@ -392,6 +397,8 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
         ms_d2h += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+        ms_fill += ms;
         for (int64_t k = 0; k < w.count; k++) {
             const int32_t p = plan.items[(size_t)(w.first + k)].pair;
             out->seg_start[p] = seg_total + h_base[k];
@@ -432,6 +439,9 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
     }
     out->n_segs = seg_total;
     out->gpu_launches = launches;
+    out->fill_launches = fill_launches;
+    out->code_bytes = code_bytes;
+    out->ms_fill = ms_fill;
     pinned_put(ctx, h_cnt);
     pinned_put(ctx, h_base);
     return BA_OK;
@@ -476,7 +486,7 @@ int ba_create(int device, ba_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 6; k++) {
         e = cudaEventCreate(&ctx->ev[k]);
         if (e != cudaSuccess) return fail(e, "cudaEventCreate");
     }
@@ -498,7 +508,7 @@ void ba_destroy(ba_ctx *ctx)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
     if (ctx->d_sc) cudaFree(ctx->d_sc);
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 6; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -71,8 +71,11 @@ typedef struct {
     int64_t n_segs;
     /* device-side timing of this call, CUDA events on the launching stream (ms) */
     float ms_h2d, ms_kernels, ms_d2h;
+    float ms_fill;        /* DP fill kernels only (the dominant kernel family) */
     int64_t cells;        /* sum of len(ref)*len(query) over the batch */
     int64_t gpu_launches; /* kernels launched for this batch */
+    int64_t fill_launches;/* of which DP fill kernels */
+    int64_t code_bytes;   /* traceback bytes the fill kernels wrote to HBM */
 } ba_result;
 
 /* Context: one per (host thread, device).  Thread-compatible: calls on ONE ctx must be

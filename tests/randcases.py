@@ -1,0 +1,39 @@
+"""Seeded random batches shared by the emulator (CPU) and GPU parity tests."""
+import random
+
+import golden_vectors as gv
+
+DNA_LETTERS = b"ACGT"
+
+
+def rand_matrix(rng, n=5):
+    style = rng.randrange(3)
+    if style == 0:
+        return gv.match(rng.choice([-1, -2, 0, -3]), rng.choice([1, 2, 3]), rng.choice([-1, -2, 0]), n)
+    if style == 1:
+        return [[rng.randint(-4, 4) for _ in range(n)] for _ in range(n)]
+    M = gv.match(rng.choice([-2, -4]), 5, -4, n)
+    return M
+
+
+def rand_pairs(rng, count, lens_r, lens_q, related=0.5, dirty=0.2, alpha=DNA_LETTERS, dirty_alpha=b"ACGT-acgtN"):
+    pairs = []
+    for _ in range(count):
+        n, m = rng.choice(lens_r), rng.choice(lens_q)
+        al = dirty_alpha if rng.random() < dirty else alpha
+        r = bytes(rng.choice(al) for _ in range(n))
+        if rng.random() < related and n > 0 and m > 0:
+            q = bytearray(r[:m]) if m <= n else bytearray(r + bytes(rng.choice(alpha) for _ in range(m - n)))
+            for x in range(len(q)):
+                u = rng.random()
+                if u < 0.10:
+                    q[x] = rng.choice(alpha)
+            if len(q) > 4 and rng.random() < 0.5:
+                cut = rng.randrange(1, len(q) - 1)
+                q = q[:cut] + q[cut + rng.randrange(1, 3):] + bytes(rng.choice(alpha) for _ in range(2))
+                q = q[:m]
+            q = bytes(q)
+        else:
+            q = bytes(rng.choice(al) for _ in range(m))
+        pairs.append((r, q))
+    return pairs

@@ -1,0 +1,105 @@
+"""Kernel LOGIC parity on the CPU: the unmodified kernel sources (biogo_b200/csrc/*.cuh) and
+host scheduler (ba_api.cu) are compiled with g++ against tests/emu/cuda_emu.h and run through
+the same C ABI, then compared bit-exactly with the oracle.  This is test infrastructure for the
+container that has no GPU; the `-m gpu` tests repeat the comparison on the real sm_100a build."""
+import random
+
+import numpy as np
+import pytest
+
+import golden_vectors as gv
+import helpers
+import randcases
+from biogo_b200 import matrix
+from helpers import O
+
+DNA_IDX = O.build_index("-acgt")
+PROT_IDX = O.build_index("-abcdefghijklmnpqrstvwxyz*")
+
+
+@pytest.mark.parametrize("vec", gv.GOLDEN, ids=[v[0] for v in gv.GOLDEN])
+def test_golden_through_emulated_kernels(emu_ctx, vec):
+    name, kind, affine, M, go, ref, qry, want, _ = vec
+    pk = helpers.pack([(ref.encode(), qry.encode())])
+    res = helpers.run_lib(emu_ctx, kind, affine, M, go, DNA_IDX, 5, pk)
+    assert int(res.status[0]) == 0
+    assert O.format_pairs(res.pairs(0)) == want
+
+
+@pytest.mark.parametrize("vec", gv.DERIVED, ids=[v[0] for v in gv.DERIVED])
+def test_derived_through_emulated_kernels(emu_ctx, vec):
+    name, kind, affine, alpha, M, go, ref, qry, want = vec
+    if alpha == "protein":
+        M, idx, alen = matrix.with_gap(matrix.BLOSUM62, -1), PROT_IDX, 26
+    else:
+        idx, alen = DNA_IDX, 5
+    res = helpers.run_lib(emu_ctx, kind, affine, M, go, idx, alen, helpers.pack([(ref.encode(), qry.encode())]))
+    assert O.format_pairs(res.pairs(0)) == want
+
+
+@pytest.mark.parametrize("kind,affine", helpers.KINDS, ids=[helpers.KIND_NAMES[k] for k in helpers.KINDS])
+def test_random_small_batches(emu_ctx, kind, affine):
+    rng = random.Random(100 + kind + 10 * affine)
+    for trial in range(12):
+        M = randcases.rand_matrix(rng)
+        go = rng.choice([0, -1, -2, -5, 1])
+        stride = rng.choice([1, 2])
+        pairs = randcases.rand_pairs(rng, 24, [0, 1, 2, 3, 5, 8, 13, 30, 60], [0, 1, 2, 3, 5, 9, 17, 33, 40, 70, 100])
+        pk = helpers.pack(pairs, stride)
+        res = helpers.run_lib(emu_ctx, kind, affine, M, go, DNA_IDX, 5, pk, stride)
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, go, DNA_IDX, pk, stride),
+                        f"{helpers.KIND_NAMES[(kind, affine)]} trial {trial} M={M} go={go} stride={stride}")
+
+
+@pytest.mark.parametrize("kind,affine", helpers.KINDS, ids=[helpers.KIND_NAMES[k] for k in helpers.KINDS])
+def test_multi_pass_and_wide_lanes(emu_ctx, kind, affine):
+    """queries of 129..600 letters: 5..8 columns per lane and more than one 256-column pass."""
+    rng = random.Random(500 + kind + 10 * affine)
+    M = gv.match(-1, 2, -1) if not affine else gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 6, [40, 90, 300], [129, 200, 256, 257, 300, 600], related=0.7, dirty=0.0)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(emu_ctx, kind, affine, M, -3, DNA_IDX, 5, pk)
+    helpers.compare(res, helpers.run_oracle(kind, affine, M, -3, DNA_IDX, pk),
+                    f"{helpers.KIND_NAMES[(kind, affine)]} multipass")
+
+
+def test_protein_blosum62(emu_ctx):
+    rng = random.Random(9)
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    M = matrix.with_gap(matrix.BLOSUM62, -1)
+    pairs = randcases.rand_pairs(rng, 16, [20, 45, 80], [20, 45, 80], related=0.8, dirty=0.15, alpha=aa,
+                                 dirty_alpha=aa + b"BZX*J-acdu")
+    pk = helpers.pack(pairs)
+    for kind, affine in helpers.KINDS:
+        res = helpers.run_lib(emu_ctx, kind, affine, M, -10, PROT_IDX, 26, pk)
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, -10, PROT_IDX, pk), f"protein {kind} {affine}")
+
+
+def test_waves_when_the_arena_is_small(emu_ctx):
+    """A tiny traceback arena forces several waves; results must not change."""
+    rng = random.Random(3)
+    pairs = randcases.rand_pairs(rng, 40, [30, 60], [20, 50, 90], dirty=0.0)
+    pk = helpers.pack(pairs)
+    M = gv.match(-1, 1, -1)
+    emu_ctx.set_option("arena_bytes", 20000)
+    try:
+        res = helpers.run_lib(emu_ctx, 0, True, M, -5, DNA_IDX, 5, pk)
+    finally:
+        emu_ctx.set_option("arena_bytes", 0)
+    helpers.compare(res, helpers.run_oracle(0, True, M, -5, DNA_IDX, pk), "waves")
+
+
+def test_empty_batch_and_range_error(emu_ctx):
+    from biogo_b200 import _lib
+
+    M = gv.match(-1, 1, -1)
+    res = helpers.run_lib(emu_ctx, 0, True, M, -5, DNA_IDX, 5, helpers.pack([]))
+    assert res.n == 0 and len(res.segs) == 0
+    big = [[1 << 22] * 5 for _ in range(5)]
+    with pytest.raises(_lib.AlignError) as e:
+        emu_ctx.set_scoring(0, False, np.array(big, np.int64).reshape(-1), 5, 5, 0, DNA_IDX)
+    assert e.value.code == _lib.BA_ERR_RANGE
+    with pytest.raises(_lib.AlignError) as e:   # SW/NW reject a matrix smaller than the alphabet
+        emu_ctx.set_scoring(0, False, np.zeros(16, np.int64), 4, 5, 0, DNA_IDX)
+    assert e.value.code == _lib.BA_ERR_MATRIX_SIZE
+    emu_ctx.set_scoring(2, False, np.zeros(16, np.int64), 4, 5, 0, DNA_IDX)  # Fitted has no such check

@@ -1,0 +1,201 @@
+"""Parity tests proper: the sm_100a CUDA path, through the C ABI, against the oracle."""
+import random
+
+import numpy as np
+import pytest
+
+import golden_vectors as gv
+import helpers
+import randcases
+from biogo_b200 import align, alphabet, feat, matrix, seq, synth
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+
+DNA_IDX = O.build_index("-acgt")
+PROT_IDX = O.build_index("-abcdefghijklmnpqrstvwxyz*")
+CLS = {(0, False): align.SW, (1, False): align.NW, (2, False): align.Fitted,
+       (0, True): align.SWAffine, (1, True): align.NWAffine, (2, True): align.FittedAffine}
+
+
+@pytest.mark.parametrize("vec", gv.GOLDEN, ids=[v[0] for v in gv.GOLDEN])
+def test_reference_golden_vectors_like_the_go_examples(gpu_ctx, vec):
+    """Reads like align/sw_example_test.go: build Seqs, Align, print, Format."""
+    name, kind, affine, M, go, ref, qry, want, fmt = vec
+    a = CLS[(kind, affine)](Matrix=M, GapOpen=go) if affine else CLS[(kind, affine)](M)
+    sa = seq.Seq(Seq=alphabet.BytesToLetters(ref.encode()), Alpha=alphabet.DNAgapped)
+    sb = seq.Seq(Seq=alphabet.BytesToLetters(qry.encode()), Alpha=alphabet.DNAgapped)
+    aln, err = a.Align(sa, sb)
+    assert err is None
+    assert feat.Sprint(aln) == want
+    if fmt is not None:
+        fa = align.Format(sa, sb, aln, "-")
+        assert (str(fa[0]), str(fa[1])) == fmt
+    # the same through QLetters (quality ignored)
+    qa = seq.QSeq(Seq=alphabet.QLetters(ref.encode(), 40), Alpha=alphabet.DNAgapped)
+    qb = seq.QSeq(Seq=alphabet.QLetters(qry.encode(), 40), Alpha=alphabet.DNAgapped)
+    aln2, err = a.Align(qa, qb)
+    assert err is None and feat.Sprint(aln2) == want
+
+
+@pytest.mark.parametrize("vec", gv.DERIVED, ids=[v[0] for v in gv.DERIVED])
+def test_derived_anchors(gpu_ctx, vec):
+    name, kind, affine, alpha, M, go, ref, qry, want = vec
+    if alpha == "protein":
+        M, idx, alen = matrix.with_gap(matrix.BLOSUM62, -1), PROT_IDX, 26
+    else:
+        idx, alen = DNA_IDX, 5
+    res = helpers.run_lib(gpu_ctx, kind, affine, M, go, idx, alen, helpers.pack([(ref.encode(), qry.encode())]))
+    assert O.format_pairs(res.pairs(0)) == want
+
+
+@pytest.mark.parametrize("kind,affine", helpers.KINDS, ids=[helpers.KIND_NAMES[k] for k in helpers.KINDS])
+def test_random_batches_all_kinds(gpu_ctx, kind, affine):
+    rng = random.Random(1000 + kind + 10 * affine)
+    for trial in range(30):
+        M = randcases.rand_matrix(rng)
+        go = rng.choice([0, -1, -2, -5, 1])
+        stride = rng.choice([1, 2])
+        pairs = randcases.rand_pairs(rng, 200, [0, 1, 2, 3, 5, 8, 13, 30, 60, 150],
+                                     [0, 1, 2, 3, 5, 9, 17, 31, 32, 33, 64, 65, 100, 129, 200, 256])
+        pk = helpers.pack(pairs, stride)
+        res = helpers.run_lib(gpu_ctx, kind, affine, M, go, DNA_IDX, 5, pk, stride)
+        assert res.stats["gpu_launches"] > 0
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, go, DNA_IDX, pk, stride, 16),
+                        f"{helpers.KIND_NAMES[(kind, affine)]} trial {trial} M={M} go={go} stride={stride}")
+
+
+@pytest.mark.parametrize("kind,affine", helpers.KINDS, ids=[helpers.KIND_NAMES[k] for k in helpers.KINDS])
+def test_long_queries_multi_pass(gpu_ctx, kind, affine):
+    rng = random.Random(2000 + kind + 10 * affine)
+    M = gv.match(-1, 2, -1) if not affine else gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 60, [100, 700, 1500, 3000], [257, 300, 512, 513, 1000, 2500], related=0.8,
+                                 dirty=0.0)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(gpu_ctx, kind, affine, M, -4, DNA_IDX, 5, pk)
+    helpers.compare(res, helpers.run_oracle(kind, affine, M, -4, DNA_IDX, pk, 1, 8),
+                    f"{helpers.KIND_NAMES[(kind, affine)]} long")
+
+
+def test_protein_blosum62_all_kinds(gpu_ctx):
+    rng = random.Random(9)
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    M = matrix.with_gap(matrix.BLOSUM62, -1)
+    pairs = randcases.rand_pairs(rng, 400, [20, 45, 80, 300], [20, 45, 80, 300], related=0.8, dirty=0.1, alpha=aa,
+                                 dirty_alpha=aa + b"BZX*J-acdu")
+    pk = helpers.pack(pairs)
+    for kind, affine in helpers.KINDS:
+        res = helpers.run_lib(gpu_ctx, kind, affine, M, -10, PROT_IDX, 26, pk)
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, -10, PROT_IDX, pk, 1, 16), f"protein {kind} {affine}")
+
+
+@pytest.mark.parametrize("num,n", [(1, 3000), (2, 2000), (3, 3000), (5, 300)])
+def test_baseline_config_shapes_against_oracle(gpu_ctx, num, n):
+    """Seeded sub-samples of BASELINE configs 1, 2, 3, 5 at their real shapes."""
+    w = synth.config(num, n)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    go = w.gap_open if w.affine else 0
+    res = helpers.run_lib(gpu_ctx, w.kind, w.affine, w.matrix, go, w.alpha.LetterIndex(), w.alpha.Len(), pk, w.stride)
+    helpers.compare(res, helpers.run_oracle(w.kind, w.affine, w.matrix, go, w.alpha.LetterIndex(), pk, w.stride, 16),
+                    w.name)
+
+
+def test_config4_long_pair_full_size(gpu_ctx):
+    """One 10 kb x 12 kb FittedAffine pair (120 M cells; the oracle needs 2.9 GB for it)."""
+    w = synth.config(4, 1)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    res = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    helpers.compare(res, helpers.run_oracle(w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), pk, 1, 1),
+                    w.name)
+
+
+def _rescore(w, res, p):
+    """Oracle-free property: segments tile the path contiguously and their scores re-add from
+    the letters and the matrix."""
+    r, q = w.pair(p)
+    idx = w.alpha.LetterIndex()
+    M, go = w.matrix, (w.gap_open if w.affine else 0)
+    segs = res.pairs(p)
+    total = 0
+    for k, (a0, a1, b0, b1, sc) in enumerate(segs.tolist()):
+        assert 0 <= a0 <= a1 <= len(r) and 0 <= b0 <= b1 <= len(q)
+        if k:
+            assert (a0, b0) == (segs[k - 1][1], segs[k - 1][3])
+        if a1 - a0 == b1 - b0:
+            s = sum(M[idx[r[a0 + x]]][idx[q[b0 + x]]] for x in range(a1 - a0))
+        elif a1 == a0:
+            s = sum(M[0][idx[q[x]]] for x in range(b0, b1)) + (go if b1 > b0 else 0)
+        else:
+            assert b1 == b0
+            s = sum(M[idx[r[x]]][0] for x in range(a0, a1)) + (go if a1 > a0 else 0)
+        assert s == sc, (p, k, segs.tolist())
+        total += sc
+    return total
+
+
+def test_full_size_shard_properties(gpu_ctx):
+    """BASELINE config 2 at bench size (one GPU's shard of 125 000 pairs): every pair OK,
+    segment chains consistent, and a checksum that is stable from run to run."""
+    w = synth.config(2, 125_000)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    res = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    assert res.n == w.n and int(np.count_nonzero(res.status)) == 0
+    assert res.stats["cells"] == w.cells
+    rng = random.Random(5)
+    for p in rng.sample(range(w.n), 300):
+        assert _rescore(w, res, p) > 50  # a 250 bp read with 5 % errors aligns with a clearly positive score
+    res2 = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    for p in rng.sample(range(w.n), 2000):
+        assert np.array_equal(res.pairs(p), res2.pairs(p))
+    # oracle on a seeded subsample of the same shard
+    sub = np.array(sorted(rng.sample(range(w.n), 1500)))
+    ws = w.subset(sub)
+    orc = helpers.run_oracle(w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(),
+                             (ws.letters, ws.ref_off, ws.ref_len, ws.qry_off, ws.qry_len), 1, 16)
+    for k, p in enumerate(sub):
+        want = orc[3][orc[2][k]:orc[2][k + 1]]
+        assert np.array_equal(res.pairs(int(p)).astype(np.int64), want), p
+
+
+def test_small_arena_waves_match(gpu_ctx):
+    w = synth.config(2, 600)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    full = helpers.run_lib(gpu_ctx, 0, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    gpu_ctx.set_option("arena_bytes", 40 << 20)
+    try:
+        waves = helpers.run_lib(gpu_ctx, 0, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    finally:
+        gpu_ctx.set_option("arena_bytes", 0)
+    for p in range(w.n):
+        assert np.array_equal(full.pairs(p), waves.pairs(p))
+
+
+def test_align_batch_host_mirror(gpu_ctx):
+    rng = random.Random(11)
+    pairs = randcases.rand_pairs(rng, 50, [10, 40, 90], [10, 40, 90])
+    a = align.NWAffine(Matrix=gv.match(-1, 1, -1), GapOpen=-3)
+    refs = [seq.Seq(Seq=r, Alpha=alphabet.DNAgapped) for r, _ in pairs]
+    qrys = [seq.Seq(Seq=q, Alpha=alphabet.DNAgapped) for _, q in pairs]
+    sc = O.Scoring(1, True, gv.match(-1, 1, -1), -3, DNA_IDX)
+    try:
+        alns, errs = a.AlignBatch(refs, qrys)
+    except align.GoPanic:
+        alns = None
+    n_ok = 0
+    for k, (r, q) in enumerate(pairs):
+        st, segs, ep = O.align(sc, r, q)
+        if alns is None:
+            continue
+        if st == 0:
+            assert errs[k] is None and [p.astuple() for p in alns[k]] == segs
+            n_ok += 1
+    # single Align calls agree and panics surface as GoPanic
+    for r, q in pairs[:10]:
+        st, segs, ep = O.align(sc, r, q)
+        sa, sb = seq.Seq(Seq=r, Alpha=alphabet.DNAgapped), seq.Seq(Seq=q, Alpha=alphabet.DNAgapped)
+        if st == 3:
+            with pytest.raises(align.GoPanic):
+                a.Align(sa, sb)
+        else:
+            aln, err = a.Align(sa, sb)
+            assert err is None and [p.astuple() for p in aln] == segs
