@@ -45,6 +45,7 @@ class BaResult(C.Structure):
         ("gpu_launches", C.c_int64),
         ("fill_launches", C.c_int64),
         ("code_bytes", C.c_int64),
+        ("pairs_fast16", C.c_int64),
     ]
 
 
@@ -114,7 +115,7 @@ class BatchResult:
 def _stats(res: BaResult) -> dict:
     return {k: (float(getattr(res, k)) if k.startswith("ms_") else int(getattr(res, k)))
             for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_fill", "cells", "gpu_launches", "fill_launches",
-                      "code_bytes", "n_segs")}
+                      "code_bytes", "pairs_fast16", "n_segs")}
 
 
 def _as_array(ptr, n, dtype):

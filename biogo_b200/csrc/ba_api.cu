@@ -18,6 +18,8 @@
 #endif
 #include "ba_fill32.cuh"
 #include "ba_walk.cuh"
+#include "ba_fill16.cuh"
+#include "ba_trace16.cuh"
 #include "ba_plan.h"
 
 // One spelling for kernel launches so the same scheduler source also drives the CPU
@@ -103,6 +105,8 @@ struct ba_ctx {
     // grow-only device buffers
     DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
+    DevBuf flags, slot_off, slot_cap, slots, seg_clip;
+    int64_t opt_force_path = 0, opt_slot_cap = 0;
     std::vector<PinnedBlock> pinned;
 };
 
@@ -189,69 +193,92 @@ int exclusive_scan(ba_ctx *ctx, void *tmp, size_t &tmp_bytes, const int32_t *in,
 #endif
 }
 
-int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int stride,
-               const int64_t *d_ref_off, const int32_t *d_ref_len, const int64_t *d_qry_off,
-               const int32_t *d_qry_len, const int32_t *h_ref_len, const int32_t *h_qry_len,
-               int64_t n, cudaStream_t st, ba_result *out)
-{
-    const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+// ---- everything the two execution paths share for one ba_align_batch call
+struct Batch {
+    const uint8_t *d_enc;
+    int stride;
+    const int64_t *d_ref_off, *d_qry_off;
+    const int32_t *d_ref_len, *d_qry_len;
+    const int32_t *h_ref_len, *h_qry_len;
+    int64_t n;
+    cudaStream_t st;
+    int32_t *d_status;
+    PairStart *d_start;
+    ba_result *out;
+    struct WaveOut {
+        int32_t *segs;
+        int64_t nsegs;
+    };
+    std::vector<WaveOut> wave_out;
+    int64_t seg_total = 0;
+    float ms_d2h = 0.f, ms_fill = 0.f;
     int64_t launches = 0, fill_launches = 0, code_bytes = 0;
-    float ms_fill = 0.f;
+};
 
-    // ---- result arrays (pinned, pooled)
-    out->n = n;
-    out->status = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
-    out->err_pos = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
-    out->seg_start = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
-    out->seg_count = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
-    out->segs = nullptr;
-    out->n_segs = 0;
-    if (!out->status || !out->err_pos || !out->seg_start || !out->seg_count) {
+int64_t arena_budget(ba_ctx *ctx, int64_t &cap)
+{
+    size_t free_b = 0, total_b = 0;
+    cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
+    if (e != cudaSuccess) return -1;
+    cap = ctx->opt_arena_bytes;
+    if (cap <= 0) {
+        cap = (int64_t)((double)(free_b + ctx->arena.cap) * 0.6);
+        const int64_t lim = 48LL << 30;
+        if (cap > lim) cap = lim;
+    }
+    return 0;
+}
+
+// D2H of one wave's compact segments + per-item (count, base), then the host-side scatter of
+// seg_start/seg_count by pair id.  `skip_overflow`: items whose count exceeds their slot
+// capacity are left for the exact path and reported through `overflow`.
+int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, int32_t *h_cnt, int64_t *h_base,
+                int64_t wsegs, const int32_t *d_segs, const int32_t *h_raw_cnt, std::vector<int32_t> *overflow)
+{
+    cudaStream_t st = B.st;
+    int32_t *h_segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(wsegs + 1));
+    if (!h_segs) {
         ctx->err = "pinned host allocation failed";
         return BA_ERR_NOMEM;
     }
-    if (n == 0) return BA_OK;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    if (wsegs > 0)
+        CK(cudaMemcpyAsync(h_segs, d_segs, sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    B.ms_d2h += ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    B.ms_fill += ms;
+    for (int64_t k = 0; k < w.count; k++) {
+        const int32_t p = plan.items[(size_t)(w.first + k)].pair;
+        if (overflow && h_raw_cnt[k] > plan.slot_cap[(size_t)(w.first + k)]) {
+            overflow->push_back(p);
+            continue;
+        }
+        B.out->seg_start[p] = B.seg_total + h_base[k];
+        B.out->seg_count[p] = h_cnt[k];
+    }
+    B.wave_out.push_back({h_segs, wsegs});
+    B.seg_total += wsegs;
+    return BA_OK;
+}
 
-    CK(cudaEventRecord(ctx->ev[1], st));
-
-    // ---- encode + validate
+// ---- path A: 32-bit exact-code fill + two-pass walk (all kinds, any matrix) ---------------
+int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
+{
+    if (nids == 0) return BA_OK;
+    const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+    cudaStream_t st = B.st;
     int rc;
-    if ((rc = ensure(ctx, ctx->enc, (size_t)letters_bytes + 16)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->status, sizeof(int32_t) * (size_t)n)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->err_pos, sizeof(int64_t) * (size_t)n)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->start, sizeof(PairStart) * (size_t)n)) != BA_OK) return rc;
-    uint8_t *d_enc = (uint8_t *)ctx->enc.p;
-    int32_t *d_status = (int32_t *)ctx->status.p;
-    int64_t *d_err_pos = (int64_t *)ctx->err_pos.p;
-    PairStart *d_start = (PairStart *)ctx->start.p;
-    if (letters_bytes > 0) {
-        int64_t blocks = (letters_bytes / 16 + 255) / 256;
-        if (blocks < 1) blocks = 1;
-        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-        BA_LAUNCH(ba_encode_kernel, (unsigned)blocks, 256, st, d_letters, d_enc, letters_bytes, ctx->d_sc);
-        launches++;
-    }
-    {
-        int64_t blocks = (n + 7) / 8;
-        if (blocks > ctx->sm_count * 32) blocks = ctx->sm_count * 32;
-        BA_LAUNCH(ba_validate_kernel, (unsigned)blocks, 256, st, d_enc, stride, d_ref_off, d_ref_len, d_qry_off,
-                  d_qry_len, n, kind, affine, d_status, d_err_pos);
-        launches++;
-    }
-    CK(cudaGetLastError());
-
-    // ---- plan
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    int64_t arena_cap = ctx->opt_arena_bytes;
-    if (arena_cap <= 0) {
-        arena_cap = (int64_t)((double)(free_b + ctx->arena.cap) * 0.6);
-        const int64_t lim = 48LL << 30;
-        if (arena_cap > lim) arena_cap = lim;
+    int64_t arena_cap = 0;
+    if (arena_budget(ctx, arena_cap) != 0) {
+        ctx->err = "cudaMemGetInfo failed";
+        return BA_ERR_CUDA;
     }
     Plan plan;
-    build_plan(h_ref_len, h_qry_len, n, kind, affine, arena_cap, plan);
-    out->cells = plan.cells;
+    build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, affine, false, arena_cap, plan);
 
     int64_t max_items = 0, max_code = 0, max_aux = 0;
     for (auto &w : plan.waves) {
@@ -271,25 +298,14 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
                              (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
         return rc;
     if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
-
-    // host staging for per-item results of a wave
     int32_t *h_cnt = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
     int64_t *h_base = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(max_items + 1));
     if (!h_cnt || !h_base) {
         ctx->err = "pinned host allocation failed";
         return BA_ERR_NOMEM;
     }
-
     WalkFn walk_count = pick_walk<false>(kind, affine);
     WalkFn walk_write = pick_walk<true>(kind, affine);
-
-    struct WaveOut {
-        int32_t *segs;
-        int64_t nsegs;
-    };
-    std::vector<WaveOut> wave_out;
-    int64_t seg_total = 0;
-    float ms_d2h = 0.f;
 
     for (auto &w : plan.waves) {
         WorkItem *d_items = (WorkItem *)ctx->items.p;
@@ -320,44 +336,44 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
                     return rc;
             }
             FillParams fp;
-            fp.enc = d_enc;
-            fp.stride = stride;
-            fp.ref_off = d_ref_off;
-            fp.ref_len = d_ref_len;
-            fp.qry_off = d_qry_off;
-            fp.qry_len = d_qry_len;
-            fp.status = d_status;
+            fp.enc = B.d_enc;
+            fp.stride = B.stride;
+            fp.ref_off = B.d_ref_off;
+            fp.ref_len = B.d_ref_len;
+            fp.qry_off = B.d_qry_off;
+            fp.qry_len = B.d_qry_len;
+            fp.status = B.d_status;
             fp.items = d_items + (L.first - w.first);
             fp.n_items = (int)L.count;
             fp.counter = (int *)ctx->counters.p + (li++ % 64);
             fp.arena = (uint8_t *)ctx->arena.p;
             fp.bnd = (int32_t *)ctx->bnd.p;
             fp.bnd_stride = bnd_stride;
-            fp.start = d_start;
+            fp.start = B.d_start;
             fp.aux = (int32_t *)ctx->aux.p;
             fp.aux_off = d_aux_off + (L.first - w.first);
             fp.sc = ctx->d_sc;
             BA_LAUNCH(fn, (unsigned)blocks, BA_FILL_WARPS * 32, st, fp);
-            launches++;
-            fill_launches++;
+            B.launches++;
+            B.fill_launches++;
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[5], st));
-        code_bytes += w.code_bytes;
+        B.code_bytes += w.code_bytes;
 
         // ---- walk: count, scan, write
         WalkParams wp;
-        wp.enc = d_enc;
-        wp.stride = stride;
-        wp.ref_off = d_ref_off;
-        wp.ref_len = d_ref_len;
-        wp.qry_off = d_qry_off;
-        wp.qry_len = d_qry_len;
-        wp.status = d_status;
+        wp.enc = B.d_enc;
+        wp.stride = B.stride;
+        wp.ref_off = B.d_ref_off;
+        wp.ref_len = B.d_ref_len;
+        wp.qry_off = B.d_qry_off;
+        wp.qry_len = B.d_qry_len;
+        wp.status = B.d_status;
         wp.items = d_items;
         wp.n_items = (int)w.count;
         wp.arena = (const uint8_t *)ctx->arena.p;
-        wp.start = d_start;
+        wp.start = B.d_start;
         wp.aux = (const int32_t *)ctx->aux.p;
         wp.aux_off = d_aux_off;
         wp.sc = ctx->d_sc;
@@ -366,13 +382,13 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         wp.segs = nullptr;
         const unsigned wblocks = (unsigned)((w.count + 127) / 128);
         BA_LAUNCH(walk_count, wblocks, 128, st, wp);
-        launches++;
+        B.launches++;
         {
             size_t tb = ctx->scan_tmp.cap;
             if ((rc = exclusive_scan(ctx, ctx->scan_tmp.p, tb, (const int32_t *)ctx->seg_count.p,
                                      (int64_t *)ctx->seg_base.p, (int)w.count, st)) != BA_OK)
                 return rc;
-            launches += 2;
+            B.launches += 2;
         }
         CK(cudaMemcpyAsync(h_cnt, ctx->seg_count.p, sizeof(int32_t) * (size_t)w.count, cudaMemcpyDeviceToHost,
                            st));
@@ -383,67 +399,349 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
         wp.segs = (int32_t *)ctx->segs.p;
         BA_LAUNCH(walk_write, wblocks, 128, st, wp);
-        launches++;
+        B.launches++;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[2], st));
-        int32_t *h_segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(wsegs + 1));
-        if (!h_segs) {
+        if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, nullptr,
+                              nullptr)) != BA_OK)
+            return rc;
+    }
+    pinned_put(ctx, h_cnt);
+    pinned_put(ctx, h_base);
+    return BA_OK;
+}
+
+// ---- path B: packed 16-bit DPX fill + checkpointed tile traceback (SWAffine, DNA-like) ------
+typedef void (*Fill16Fn)(Fill16Params);
+template <bool MULTI>
+Fill16Fn pick_fill16_m(int cols)
+{
+    switch (cols) {
+    case 1: return ba_fill16_sw_kernel<1, MULTI>;
+    case 2: return ba_fill16_sw_kernel<2, MULTI>;
+    case 3: return ba_fill16_sw_kernel<3, MULTI>;
+    case 4: return ba_fill16_sw_kernel<4, MULTI>;
+    case 5: return ba_fill16_sw_kernel<5, MULTI>;
+    case 6: return ba_fill16_sw_kernel<6, MULTI>;
+    case 7: return ba_fill16_sw_kernel<7, MULTI>;
+    default: return ba_fill16_sw_kernel<8, MULTI>;
+    }
+}
+Fill16Fn pick_fill16(int cols, bool multi)
+{
+    // only the widest class can need more than one pass
+    if (multi && cols == BA_MAX_COLS) return ba_fill16_sw_kernel<BA_MAX_COLS, true>;
+    return pick_fill16_m<false>(cols);
+}
+
+// Scoring-level eligibility of the packed path (conditions C1..C3 of ba_fill16.cuh).
+bool fast16_scoring_ok(const DeviceScoring &s, int &maxsub)
+{
+    if (s.kind != KIND_SW || !s.affine || s.let < 5) return false;
+    const int er = s.la[1 * s.let], eq = s.la[1];
+    maxsub = -1000000;
+    for (int a = 1; a <= 4; a++) {
+        if (s.la[a * s.let] != er || s.la[a] != eq) return false;
+        for (int b = 1; b <= 4; b++) {
+            const int v = s.la[a * s.let + b];
+            if (v < -127 || v > 127) return false;
+            if (v > maxsub) maxsub = v;
+        }
+    }
+    if (er > 0 || eq > 0 || er < -127 || eq < -127) return false;
+    if (s.gap_open + er + maxsub >= 0 || s.gap_open + eq + maxsub >= 0) return false;
+    if (s.gap_open + er < -4000 || s.gap_open + eq < -4000) return false;
+    if (maxsub <= 0) return false;
+    return true;
+}
+
+int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vector<int32_t> &overflow)
+{
+    if (nids == 0) return BA_OK;
+    cudaStream_t st = B.st;
+    int rc;
+    int64_t arena_cap = 0;
+    if (arena_budget(ctx, arena_cap) != 0) {
+        ctx->err = "cudaMemGetInfo failed";
+        return BA_ERR_CUDA;
+    }
+    Plan plan;
+    build_plan(ids, nids, B.h_ref_len, B.h_qry_len, KIND_SW, 1, true, arena_cap, plan);
+    if (ctx->opt_slot_cap > 0) {  // test hook: force the overflow -> exact-path fallback
+        for (auto &w : plan.waves) {
+            w.slots = 0;
+            for (int64_t k = 0; k < w.count; k++) {
+                plan.slot_off[(size_t)(w.first + k)] = w.slots;
+                plan.slot_cap[(size_t)(w.first + k)] = (int32_t)ctx->opt_slot_cap;
+                w.slots += ctx->opt_slot_cap;
+            }
+        }
+    }
+    int64_t max_items = 0, max_code = 0, max_slots = 0;
+    for (auto &w : plan.waves) {
+        max_items = std::max(max_items, w.count);
+        max_code = std::max(max_code, w.code_bytes);
+        max_slots = std::max(max_slots, w.slots);
+    }
+    if ((rc = ensure(ctx, ctx->items, sizeof(WorkItem) * (size_t)max_items)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->slot_off, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->slot_cap, sizeof(int32_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->slots, sizeof(int32_t) * 5 * (size_t)(max_slots + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_count, sizeof(int32_t) * (size_t)max_items)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_clip, sizeof(int32_t) * (size_t)max_items)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_base, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->arena, (size_t)max_code + 256)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 64)) != BA_OK) return rc;
+    size_t scan_bytes = 0;
+    if ((rc = exclusive_scan(ctx, nullptr, scan_bytes, (const int32_t *)ctx->seg_clip.p,
+                             (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
+        return rc;
+    if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
+    int32_t *h_cnt = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
+    int32_t *h_raw = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
+    int64_t *h_base = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(max_items + 1));
+    if (!h_cnt || !h_raw || !h_base) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+
+    for (auto &w : plan.waves) {
+        WorkItem *d_items = (WorkItem *)ctx->items.p;
+        CK(cudaMemcpyAsync(d_items, plan.items.data() + w.first, sizeof(WorkItem) * (size_t)w.count,
+                           cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->slot_off.p, plan.slot_off.data() + w.first, sizeof(int64_t) * (size_t)w.count,
+                           cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->slot_cap.p, plan.slot_cap.data() + w.first, sizeof(int32_t) * (size_t)w.count,
+                           cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
+
+        // ---- fill (values + checkpoints)
+        CK(cudaEventRecord(ctx->ev[4], st));
+        int li = 0;
+        for (auto &L : w.launches) {
+            const bool multi = (L.cols == BA_MAX_COLS) && w.max_n_multipass > 0;
+            Fill16Fn fn = pick_fill16(L.cols, multi);
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BA16_WARPS * 32, 0));
+            if (occ < 1) occ = 1;
+            int64_t blocks = (L.count + BA16_GROUPS - 1) / BA16_GROUPS;
+            int64_t maxb = (int64_t)ctx->sm_count * occ;
+            if (blocks > maxb) blocks = maxb;
+            int64_t bnd_stride = 0;
+            if (multi) {
+                bnd_stride = 3 * ((int64_t)w.max_n_multipass + 2);
+                if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * blocks * BA16_GROUPS))) != BA_OK)
+                    return rc;
+            }
+            Fill16Params fp;
+            fp.enc = B.d_enc;
+            fp.stride = B.stride;
+            fp.ref_off = B.d_ref_off;
+            fp.ref_len = B.d_ref_len;
+            fp.qry_off = B.d_qry_off;
+            fp.qry_len = B.d_qry_len;
+            fp.status = B.d_status;
+            fp.items = d_items + (L.first - w.first);
+            fp.n_items = (int)L.count;
+            fp.counter = (int *)ctx->counters.p + (li++ % 64);
+            fp.arena = (uint8_t *)ctx->arena.p;
+            fp.bnd = (int32_t *)ctx->bnd.p;
+            fp.bnd_stride = bnd_stride;
+            fp.sc = ctx->d_sc;
+            BA_LAUNCH(fn, (unsigned)blocks, BA16_WARPS * 32, st, fp);
+            B.launches++;
+            B.fill_launches++;
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[5], st));
+        B.code_bytes += w.code_bytes;
+
+        // ---- tile traceback into slots, clip, scan, compact
+        Trace16Params tp;
+        tp.enc = B.d_enc;
+        tp.stride = B.stride;
+        tp.ref_off = B.d_ref_off;
+        tp.ref_len = B.d_ref_len;
+        tp.qry_off = B.d_qry_off;
+        tp.qry_len = B.d_qry_len;
+        tp.status = B.d_status;
+        tp.items = d_items;
+        tp.n_items = (int)w.count;
+        tp.arena = (const uint8_t *)ctx->arena.p;
+        tp.sc = ctx->d_sc;
+        tp.seg_count = (int32_t *)ctx->seg_count.p;
+        tp.slot_off = (const int64_t *)ctx->slot_off.p;
+        tp.slot_cap = (const int32_t *)ctx->slot_cap.p;
+        tp.slots = (int32_t *)ctx->slots.p;
+        const unsigned tblocks = (unsigned)((w.count + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
+        BA_LAUNCH(ba_trace16_kernel<KIND_SW>, tblocks, BA_TRACE_THREADS, st, tp);
+        const unsigned cblocks = (unsigned)((w.count + 255) / 256);
+        BA_LAUNCH(ba_clip_counts_kernel, cblocks, 256, st, (const int32_t *)ctx->seg_count.p,
+                  (const int32_t *)ctx->slot_cap.p, (int32_t *)ctx->seg_clip.p, (int)w.count);
+        B.launches += 2;
+        {
+            size_t tb = ctx->scan_tmp.cap;
+            if ((rc = exclusive_scan(ctx, ctx->scan_tmp.p, tb, (const int32_t *)ctx->seg_clip.p,
+                                     (int64_t *)ctx->seg_base.p, (int)w.count, st)) != BA_OK)
+                return rc;
+            B.launches += 2;
+        }
+        CK(cudaMemcpyAsync(h_cnt, ctx->seg_clip.p, sizeof(int32_t) * (size_t)w.count, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_raw, ctx->seg_count.p, sizeof(int32_t) * (size_t)w.count, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_base, ctx->seg_base.p, sizeof(int64_t) * (size_t)w.count, cudaMemcpyDeviceToHost,
+                           st));
+        CK(cudaStreamSynchronize(st));
+        const int64_t wsegs = h_base[w.count - 1] + h_cnt[w.count - 1];
+        if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
+        BA_LAUNCH(ba_compact_kernel, cblocks, 256, st, (const int32_t *)ctx->slots.p,
+                  (const int64_t *)ctx->slot_off.p, (const int32_t *)ctx->slot_cap.p,
+                  (const int32_t *)ctx->seg_count.p, (const int64_t *)ctx->seg_base.p, (int32_t *)ctx->segs.p,
+                  (int)w.count);
+        B.launches++;
+        CK(cudaGetLastError());
+        if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, h_raw,
+                              &overflow)) != BA_OK)
+            return rc;
+    }
+    pinned_put(ctx, h_cnt);
+    pinned_put(ctx, h_raw);
+    pinned_put(ctx, h_base);
+    return BA_OK;
+}
+
+int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int stride,
+               const int64_t *d_ref_off, const int32_t *d_ref_len, const int64_t *d_qry_off,
+               const int32_t *d_qry_len, const int32_t *h_ref_len, const int32_t *h_qry_len,
+               int64_t n, cudaStream_t st, ba_result *out)
+{
+    const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+
+    // ---- result arrays (pinned, pooled)
+    out->n = n;
+    out->status = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
+    out->err_pos = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
+    out->seg_start = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
+    out->seg_count = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
+    out->segs = nullptr;
+    out->n_segs = 0;
+    if (!out->status || !out->err_pos || !out->seg_start || !out->seg_count) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    if (n == 0) return BA_OK;
+
+    CK(cudaEventRecord(ctx->ev[1], st));
+
+    Batch B;
+    B.stride = stride;
+    B.d_ref_off = d_ref_off;
+    B.d_qry_off = d_qry_off;
+    B.d_ref_len = d_ref_len;
+    B.d_qry_len = d_qry_len;
+    B.h_ref_len = h_ref_len;
+    B.h_qry_len = h_qry_len;
+    B.n = n;
+    B.st = st;
+    B.out = out;
+
+    // ---- encode + validate
+    int rc;
+    if ((rc = ensure(ctx, ctx->enc, (size_t)letters_bytes + 16)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->status, sizeof(int32_t) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->err_pos, sizeof(int64_t) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->start, sizeof(PairStart) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->flags, (size_t)n + 16)) != BA_OK) return rc;
+    uint8_t *d_enc = (uint8_t *)ctx->enc.p;
+    B.d_enc = d_enc;
+    B.d_status = (int32_t *)ctx->status.p;
+    B.d_start = (PairStart *)ctx->start.p;
+    int64_t *d_err_pos = (int64_t *)ctx->err_pos.p;
+    int maxsub = 0;
+    const bool fast16 = ctx->opt_force_path != 1 && fast16_scoring_ok(ctx->h_sc, maxsub);
+    if (letters_bytes > 0) {
+        int64_t blocks = (letters_bytes / 16 + 255) / 256;
+        if (blocks < 1) blocks = 1;
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        BA_LAUNCH(ba_encode_kernel, (unsigned)blocks, 256, st, d_letters, d_enc, letters_bytes, ctx->d_sc);
+        B.launches++;
+    }
+    {
+        int64_t blocks = (n + 7) / 8;
+        if (blocks > ctx->sm_count * 32) blocks = ctx->sm_count * 32;
+        BA_LAUNCH(ba_validate_kernel, (unsigned)blocks, 256, st, d_enc, stride, d_ref_off, d_ref_len, d_qry_off,
+                  d_qry_len, n, kind, affine, B.d_status, d_err_pos, fast16 ? (uint8_t *)ctx->flags.p : nullptr);
+        B.launches++;
+    }
+    CK(cudaGetLastError());
+
+    int64_t cells = 0;
+    for (int64_t p = 0; p < n; p++) cells += (int64_t)h_ref_len[p] * (int64_t)h_qry_len[p];
+    out->cells = cells;
+
+    // ---- split the batch between the two paths
+    std::vector<int32_t> slow;
+    if (fast16) {
+        uint8_t *h_flags = (uint8_t *)pinned_get(ctx, (size_t)n + 16);
+        if (!h_flags) {
             ctx->err = "pinned host allocation failed";
             return BA_ERR_NOMEM;
         }
-        CK(cudaMemcpyAsync(h_segs, ctx->segs.p, sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, (size_t)n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-        ms_d2h += ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
-        ms_fill += ms;
-        for (int64_t k = 0; k < w.count; k++) {
-            const int32_t p = plan.items[(size_t)(w.first + k)].pair;
-            out->seg_start[p] = seg_total + h_base[k];
-            out->seg_count[p] = h_cnt[k];
+        std::vector<int32_t> fast;
+        fast.reserve((size_t)n);
+        for (int64_t p = 0; p < n; p++) {
+            const int64_t lo = std::min(h_ref_len[p], h_qry_len[p]);
+            const bool ok = h_flags[p] && lo > 0 && lo * maxsub < 32000 && h_ref_len[p] < (1 << 19);
+            (ok ? fast : slow).push_back((int32_t)p);
         }
-        wave_out.push_back({h_segs, wsegs});
-        seg_total += wsegs;
+        pinned_put(ctx, h_flags);
+        const size_t nslow0 = slow.size();
+        if ((rc = run_path16(ctx, B, fast.data(), (int64_t)fast.size(), slow)) != BA_OK) return rc;
+        out->pairs_fast16 = (int64_t)fast.size() - (int64_t)(slow.size() - nslow0);
+        if ((rc = run_path32(ctx, B, slow.data(), (int64_t)slow.size())) != BA_OK) return rc;
+    } else {
+        if ((rc = run_path32(ctx, B, nullptr, n)) != BA_OK) return rc;
     }
 
     // ---- gather
     CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaMemcpyAsync(out->status, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->status, B.d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out->err_pos, d_err_pos, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[3], st));
     CK(cudaStreamSynchronize(st));
     {
         float ms = 0.f, all = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-        ms_d2h += ms;
+        B.ms_d2h += ms;
         CK(cudaEventElapsedTime(&all, ctx->ev[1], ctx->ev[3]));
-        out->ms_d2h = ms_d2h;
-        out->ms_kernels = all - ms_d2h;
+        out->ms_d2h = B.ms_d2h;
+        out->ms_kernels = all - B.ms_d2h;
     }
-    if (wave_out.size() == 1) {
-        out->segs = wave_out[0].segs;
+    if (B.wave_out.size() == 1) {
+        out->segs = B.wave_out[0].segs;
     } else {
-        out->segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(seg_total + 1));
+        out->segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(B.seg_total + 1));
         if (!out->segs) {
             ctx->err = "pinned host allocation failed";
             return BA_ERR_NOMEM;
         }
         int64_t o = 0;
-        for (auto &wo : wave_out) {
+        for (auto &wo : B.wave_out) {
             memcpy(out->segs + 5 * o, wo.segs, sizeof(int32_t) * 5 * (size_t)wo.nsegs);
             o += wo.nsegs;
             pinned_put(ctx, wo.segs);
         }
     }
-    out->n_segs = seg_total;
-    out->gpu_launches = launches;
-    out->fill_launches = fill_launches;
-    out->code_bytes = code_bytes;
-    out->ms_fill = ms_fill;
-    pinned_put(ctx, h_cnt);
-    pinned_put(ctx, h_base);
+    for (int64_t p = 0; p < n; p++)
+        if (out->status[p] != 0) {
+            out->seg_start[p] = 0;
+            out->seg_count[p] = 0;
+        }
+    out->n_segs = B.seg_total;
+    out->gpu_launches = B.launches;
+    out->fill_launches = B.fill_launches;
+    out->code_bytes = B.code_bytes;
+    out->ms_fill = B.ms_fill;
     return BA_OK;
 }
 
@@ -456,7 +754,7 @@ int ba_abi_version(void) { return BA_ABI_VERSION; }
 
 const char *ba_build_info(void)
 {
-    return "libbiogoalign sm_100a (fill32 exact-code kernels; nvcc " __DATE__ ")";
+    return "libbiogoalign sm_100a (fill16 DPX + checkpointed trace, fill32 exact-code kernels; nvcc " __DATE__ ")";
 }
 
 int ba_create(int device, ba_ctx **out)
@@ -503,7 +801,7 @@ void ba_destroy(ba_ctx *ctx)
     DevBuf *bufs[] = {&ctx->letters, &ctx->enc,  &ctx->ref_off,   &ctx->ref_len,  &ctx->qry_off, &ctx->qry_len,
                       &ctx->status,  &ctx->err_pos, &ctx->start,  &ctx->items,    &ctx->aux_off, &ctx->aux,
                       &ctx->bnd,     &ctx->seg_count, &ctx->seg_base, &ctx->segs, &ctx->arena,   &ctx->scan_tmp,
-                      &ctx->counters};
+                      &ctx->counters, &ctx->flags,  &ctx->slot_off,  &ctx->slot_cap, &ctx->slots, &ctx->seg_clip};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
@@ -521,6 +819,14 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     if (!ctx || !key) return BA_ERR_ARG;
     if (!strcmp(key, "arena_bytes")) {
         ctx->opt_arena_bytes = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "slot_cap")) {
+        ctx->opt_slot_cap = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "force_path")) {
+        ctx->opt_force_path = value;
         return BA_OK;
     }
     ctx->err = std::string("unknown option: ") + key;

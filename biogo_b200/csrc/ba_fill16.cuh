@@ -1,0 +1,301 @@
+// ba_fill16.cuh -- packed 16-bit DPX fill for SWAffine with checkpointed traceback.
+//
+// Why a second fill kernel: ba_fill32 derives every cell's exact tie-break code, which costs
+// ~50 issue slots per cell and makes it ALU-issue bound (profiles/r01_fill32_ncu_summary.txt).
+// The walk only ever visits O(r+c) cells, so this kernel computes VALUES ONLY -- seven DPX /
+// packed-integer instructions per TWO cells -- and stores sparse checkpoints of the table:
+//   * the right-most column of every 32*COLS/32-wide strip, every row        (M, L)
+//   * one row of every strip every 16 steps                                   (M, U)
+// ba_trace16 (ba_trace16.cuh) then re-derives the exact codes only for the 16-row x COLS-column
+// tiles the traceback actually crosses, with the very same affine_cell<> as ba_fill32.
+//
+// Layout: a warp holds two pairs, one per 16-lane group.  Each lane carries TWO virtual
+// threads in the halves of its 32-bit registers: low half = virtual thread t (strip t of the
+// pass), high half = virtual thread t+16.  Virtual thread v handles row i at step s = i-1+v, so
+// one warp shuffle (rotate within the group) hands the boundary column from strip v to v+1
+// for both halves at once; lane 0 re-routes lane 15's low half into its own high half.
+//
+// Exactness conditions checked by the host before this path is chosen (else ba_fill32):
+//   C1  every gap entry la[R][0] (resp. la[0][Q]) is one value er <= 0 (eq <= 0) for letters 1..4
+//   C2  go + er + max(sub) < 0 and go + eq + max(sub) < 0   => every cell that attains the table
+//       maximum has max3(diag) == diag M, i.e. qualifies for bíogo's best-cell rule
+//       (align/sw_affine_letters.go:126-134), so "last cell in row-major order with the maximum
+//       score" is the reference's start cell; U and L may skip the clamp at 0 inside the
+//       recurrence (it is re-applied when checkpoints are written)
+//   C3  letters restricted to alphabet indices 1..4 and |la| < 128: the substitution score of
+//       a packed cell pair is ONE PRMT (byte permute with sign replication) of two 4-byte row
+//       profiles
+//   C4  min(n, m) * max(sub) < 2^15 - 256
+#pragma once
+
+#include "ba_common.cuh"
+
+#define BA16_PROF_RING 1024          // ring of row profiles per group (entries)
+#define BA16_PROF_CHUNK 512          // rows loaded per refill
+#define BA16_WARPS 4                 // warps per CTA
+#define BA16_GROUPS (2 * BA16_WARPS) // pairs in flight per CTA
+
+struct Fill16Params {
+    const uint8_t *enc;
+    int stride;
+    const int64_t *ref_off;
+    const int32_t *ref_len;
+    const int64_t *qry_off;
+    const int32_t *qry_len;
+    const int32_t *status;
+    const WorkItem *items;
+    int n_items;
+    int *counter;
+    uint8_t *arena;          // checkpoints, WorkItem.code_off bytes into it
+    int32_t *bnd;            // inter-pass boundary, bnd_stride ints per group
+    int64_t bnd_stride;
+    const DeviceScoring *sc;
+};
+
+// ---- packed helpers ---------------------------------------------------------------------
+__device__ __forceinline__ unsigned ba_prmt(unsigned a, unsigned b, unsigned s)
+{
+#ifdef BA_EMULATE
+    return emu_prmt(a, b, s);
+#else
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+#endif
+}
+__device__ __forceinline__ unsigned pack16(int lo, int hi)
+{
+    return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+}
+__device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
+
+// Checkpoint geometry shared with ba_trace16 ------------------------------------------------
+// One pass of one pair occupies, in this order:
+//   colck: nsteps x 16 lanes x {M,L}      (8 bytes per lane-step; both halves packed)
+//   rowck: nper  x 16 lanes x COLS x {M,U} (8 bytes per column)
+// with nsteps = n + 31 and nper = nsteps / 16 (periods that end inside the pass).
+__host__ __device__ inline int64_t ba16_colck_bytes(int64_t n) { return (n + 31) * 16 * 8; }
+__host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + 31) / 16; }
+__host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, int cols) { return ba16_nper(n) * 16 * cols * 8; }
+__host__ __device__ inline int64_t ba16_pass_bytes(int64_t n, int cols)
+{
+    return ba16_colck_bytes(n) + ba16_rowck_bytes(n, cols);
+}
+// After the passes: one candidate record per (pass, lane): {packed best score of the two
+// strips, packed last period attaining it} -- the start-cell candidates of ba_trace16.
+__host__ __device__ inline int64_t ba16_npass(int cols, int64_t m) { return (m + 32LL * cols - 1) / (32LL * cols); }
+__host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m)
+{
+    if (n <= 0 || m <= 0) return 0;
+    const int64_t np = ba16_npass(cols, m);
+    return np * ba16_pass_bytes(n, cols) + np * 16 * 8;
+}
+// Columns are RIGHT-aligned: strip (pass, v) covers table columns
+//   jshift + pass*W + v*COLS + 1 .. + COLS   with jshift = m - npass*W  (<= 0),
+// so the last strip ends exactly at column m and the padding falls on columns <= 0, which
+// behave as the all-zero SW border (substitution 0 or -1 keeps M at 0 there).
+
+// MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
+// inter-pass boundary code is compiled out of the common single-pass instance).
+template <int COLS, bool MULTI>
+__global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Params P)
+{
+    // row profiles: ring[group][i & (RING-1)] = 4 substitution bytes of the letter of row i
+    __shared__ unsigned ring[BA16_GROUPS][BA16_PROF_RING];
+    __shared__ unsigned proftab[8];  // letter index -> {sub(R,1), sub(R,2), sub(R,3), sub(R,4)} as int8
+    const int let = P.sc->let;
+    if (threadIdx.x < 8) {
+        unsigned w = 0x80808080u;  // virtual row: -128 against everything
+        const int R = threadIdx.x;
+        if (R >= 1 && R <= 4 && R < let) {
+            w = 0;
+            for (int q = 1; q <= 4; q++) w |= ((unsigned)(P.sc->la[R * let + q]) & 0xffu) << (8 * (q - 1));
+        }
+        proftab[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int er = P.sc->la[1 * let];  // C1: identical for letters 1..4
+    const int eq = P.sc->la[1];
+    const int go = P.sc->gap_open;
+    const unsigned erp = pack16(er, er), eqp = pack16(eq, eq);
+    const unsigned goerp = pack16(go + er, go + er), goeqp = pack16(go + eq, go + eq);
+
+    const int lane = threadIdx.x & 31;
+    const int t = lane & 15;                       // lane inside the group
+    const int grp = (threadIdx.x >> 4);            // group inside the CTA
+    const int group_global = blockIdx.x * BA16_GROUPS + grp;
+    unsigned *myring = ring[grp];
+    int32_t *bnd = P.bnd + (int64_t)group_global * P.bnd_stride;
+    constexpr int W = 32 * COLS;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned fixsel = (t == 0) ? 0x5410u : 0x7654u;  // lane 0: {boundary.lo, neighbour.lo}
+
+    for (;;) {
+        // each warp takes two consecutive items (one per group)
+        int it0 = 0;
+        if (lane == 0) it0 = atomicAdd(P.counter, 2);
+        it0 = __shfl_sync(FULL, it0, 0);
+        if (it0 >= P.n_items) break;
+        const int it = it0 + (lane >> 4);
+        const bool have = it < P.n_items;
+        WorkItem item;
+        item.pair = 0;
+        item.cols = COLS;
+        item.code_off = 0;
+        if (have) item = P.items[it];
+        const int p = item.pair;
+        int n = have ? P.ref_len[p] : 0, m = have ? P.qry_len[p] : 0;
+        if (have && P.status[p] != 0) n = 0;
+        const bool live = have && n > 0 && m > 0;
+        if (!live) {
+            n = 0;
+            m = 0;
+        }
+        const uint8_t *rptr = P.enc + (live ? P.ref_off[p] : 0);
+        const uint8_t *qptr = P.enc + (live ? P.qry_off[p] : 0);
+        const int stride = P.stride;
+        const int npass = live ? (m + W - 1) / W : 0;
+        const int nsteps = live ? n + 31 : 0;
+        // loop bounds must be warp-uniform (shuffles): take the larger group
+        const int nsteps_w = max(nsteps, __shfl_xor_sync(FULL, nsteps, 16));
+        const int npass_w = MULTI ? max(npass, __shfl_xor_sync(FULL, npass, 16)) : 1;
+        const int64_t pass_bytes = ba16_pass_bytes(n, COLS);
+
+
+        for (int pass = 0; pass < npass_w; pass++) {
+            const bool pass_live = live && pass < npass;
+            const int jbase = pass * W;
+            const int jshift = m - npass * W;
+            // ---- per-column constants: PRMT selectors (columns <= 0: sign-select => sub in {0,-1})
+            unsigned sel[COLS];
+#pragma unroll
+            for (int k = 0; k < COLS; k++) {
+                const int jl = jshift + jbase + t * COLS + k + 1, jh = jl + 16 * COLS;
+                unsigned nl = 0x88u, nh = 0xCC00u;  // virtual column: both bytes = sign of a profile byte
+                if (pass_live && jl >= 1) {
+                    const unsigned q = (unsigned)qptr[(int64_t)(jl - 1) * stride] - 1u;
+                    nl = q | ((q | 8u) << 4);
+                }
+                if (pass_live && jh >= 1) {
+                    const unsigned q = 4u + (unsigned)qptr[(int64_t)(jh - 1) * stride] - 1u;
+                    nh = (q << 8) | ((q | 8u) << 12);
+                }
+                sel[k] = nl | nh;
+            }
+            // ---- (re)load the profile ring: rows -31..0 virtual, rows 1.. from the reference
+            for (int x = t; x < 32; x += 16) myring[(x - 31) & (BA16_PROF_RING - 1)] = 0x80808080u;
+            __syncwarp();
+
+            unsigned Mu[COLS], Uu[COLS], Hu[COLS];
+#pragma unroll
+            for (int k = 0; k < COLS; k++) Mu[k] = Uu[k] = Hu[k] = 0;
+            unsigned outM = 0, outL = 0, outH = 0, sdiagH = 0;
+            unsigned bmax = 0;  // running max of the current 16-step period
+            // per virtual thread: best value of this pass and the LAST period attaining it
+            unsigned vbest = pack16(1, 1);
+            int per_lo = -1, per_hi = -1;
+            uint8_t *ck = P.arena + item.code_off + (int64_t)pass * pass_bytes;
+            uint2 *colck = (uint2 *)ck + t;
+            uint2 *rowck = (uint2 *)(ck + ba16_colck_bytes(n)) + (int64_t)t * COLS;
+
+            for (int s = 0; s < nsteps_w; s++, colck += 16) {
+                if ((s & (BA16_PROF_CHUNK - 1)) == 0) {
+                    // rows s+1 .. s+CHUNK enter the ring (lanes of the group share the load)
+                    __syncwarp();
+                    for (int x = t; x < BA16_PROF_CHUNK; x += 16) {
+                        const int i = s + 1 + x;
+                        unsigned w = 0x80808080u;
+                        if (pass_live && i <= n) w = proftab[rptr[(int64_t)(i - 1) * stride] & 7];
+                        myring[i & (BA16_PROF_RING - 1)] = w;
+                    }
+                    __syncwarp();
+                }
+                const int ilo = s + 1 - t;
+                const unsigned profA = myring[ilo & (BA16_PROF_RING - 1)];
+                const unsigned profB = myring[(ilo + BA16_PROF_RING - 16) & (BA16_PROF_RING - 1)];
+
+                // boundary column of the left neighbour strip (rotate inside the 16-lane group)
+                unsigned rM = __shfl_sync(FULL, outM, (t + 15) & 15, 16);
+                unsigned rL = __shfl_sync(FULL, outL, (t + 15) & 15, 16);
+                unsigned rH = __shfl_sync(FULL, outH, (t + 15) & 15, 16);
+                unsigned bM = 0, bL = 0, bH = 0;  // pass 0: DP column 0 is all zero for SW
+                if (MULTI && pass > 0) {  // warp-uniform
+                    if (t == 0 && ilo >= 1 && ilo <= n) {
+                        bM = (unsigned)bnd[3 * ilo + 0];
+                        bL = (unsigned)bnd[3 * ilo + 1];
+                        bH = (unsigned)bnd[3 * ilo + 2];
+                    }
+                }
+                rM = ba_prmt(bM, rM, fixsel);
+                rL = ba_prmt(bL, rL, fixsel);
+                rH = ba_prmt(bH, rH, fixsel);
+
+                unsigned Ml = rM, Ll = rL, Hd = sdiagH;
+#pragma unroll
+                for (int k = 0; k < COLS; k++) {
+                    const unsigned sub = ba_prmt(profA, profB, sel[k]);
+                    const unsigned Mn = __viaddmax_s16x2_relu(Hd, sub, erp);  // erp <= 0: same as max(.,0)
+                    const unsigned c1 = __vadd2(Uu[k], erp);
+                    const unsigned Un = __viaddmax_s16x2(Mu[k], goerp, c1);
+                    const unsigned c2 = __vadd2(Ll, eqp);
+                    const unsigned Ln = __viaddmax_s16x2(Ml, goeqp, c2);
+                    Hd = Hu[k];
+                    Hu[k] = __vimax3_s16x2(Mn, Un, Ln);
+                    Mu[k] = Mn;
+                    Uu[k] = Un;
+                    Ml = Mn;
+                    Ll = Ln;
+                }
+#pragma unroll
+                for (int k = 0; k + 1 < COLS; k += 2) bmax = __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
+                if (COLS & 1) bmax = __vmaxs2(bmax, Mu[COLS - 1]);
+                sdiagH = rH;
+                outM = Mu[COLS - 1];
+                outL = Ll;
+                outH = Hu[COLS - 1];
+
+                if (pass_live && s < nsteps) {
+                    // column checkpoint: (M, clamped L) of my last column, every step
+                    *colck = make_uint2(outM, __vimax_s16x2_relu(outL, erp));
+                    if (MULTI && t == 15 && pass + 1 < npass) {
+                        const int ihi = ilo - 16;
+                        if (ihi >= 1 && ihi <= n) {
+                            bnd[3 * ihi + 0] = hi16(outM) & 0xffff;
+                            bnd[3 * ihi + 1] = hi16(outL) & 0xffff;
+                            bnd[3 * ihi + 2] = hi16(outH) & 0xffff;
+                        }
+                    }
+                }
+                if ((s & 15) == 15) {
+                    const int e = s >> 4;
+                    if (pass_live && s < nsteps) {
+#pragma unroll
+                        for (int k = 0; k < COLS; k++)
+                            rowck[(int64_t)e * 16 * COLS + k] = make_uint2(Mu[k], __vimax_s16x2_relu(Uu[k], erp));
+                    }
+                    // best tracking at period granularity ('>=' keeps the LAST period)
+                    bool ph, pl;
+                    vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
+                    if (pl) per_lo = e;
+                    if (ph) per_hi = e;
+                    bmax = 0;
+                }
+            }
+            // the tail period (fewer than 16 steps) still counts for the best cell
+            if (nsteps_w & 15) {
+                const int e = nsteps_w >> 4;
+                bool ph, pl;
+                vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
+                if (pl) per_lo = e;
+                if (ph) per_hi = e;
+            }
+            if (pass_live) {
+                uint2 *cand = (uint2 *)(P.arena + item.code_off + (int64_t)npass * pass_bytes) + pass * 16 + t;
+                *cand = make_uint2(vbest, pack16(per_lo, per_hi));
+            }
+            __syncwarp();
+        }
+
+    }
+}

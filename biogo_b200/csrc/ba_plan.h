@@ -6,61 +6,77 @@
 #include <vector>
 
 #include "ba_common.cuh"
+#include "ba_fill16.cuh"
 
 namespace {
 
 struct Plan {
     std::vector<WorkItem> items;        // all items, grouped by class then size
-    std::vector<int64_t> aux_off;       // per item (Fitted kinds)
+    std::vector<int64_t> aux_off;       // per item (Fitted kinds, 32-bit path)
+    std::vector<int64_t> slot_off;      // per item (16-bit path): first segment slot
+    std::vector<int32_t> slot_cap;      // per item (16-bit path)
     struct Launch {
         int cols;
         int64_t first, count;           // item range
     };
     struct Wave {
         int64_t first, count;           // item range
-        int64_t code_bytes, aux_ints;
+        int64_t code_bytes, aux_ints, slots;
         std::vector<Launch> launches;
         int max_n_multipass;            // largest n among pairs needing >1 pass (0 = none)
     };
     std::vector<Wave> waves;
-    int64_t cells = 0;
 };
 
-int cols_for(int m)
+inline int cols_for(int m)
 {
     if (m <= 0) return 1;
     int c = (m + 31) / 32;
     return c > BA_MAX_COLS ? BA_MAX_COLS : c;
 }
 
-// Length-bucketed work list: pairs are grouped by the number of columns a lane owns
-// (the template instance they need), ordered largest-first inside a group so the
-// dynamic work counter balances the tail, then cut into waves whose codes fit the arena.
-void build_plan(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int kind, int affine,
-                int64_t arena_cap, Plan &plan)
+// capacity of the per-pair segment slot buffer of the 16-bit path; pairs that emit more are
+// re-run on the exact two-pass path
+inline int32_t slot_cap_for(int n, int m)
+{
+    int64_t c = ((int64_t)n + m) / 12 + 12;
+    const int64_t hi = (int64_t)n + m + 2;
+    return (int32_t)(c < hi ? c : hi);
+}
+
+// Length-bucketed work list over the pairs `ids`: grouped by the number of columns a lane
+// owns (the template instance they need), largest-first inside a group so the dynamic work
+// counter balances the tail, then cut into waves whose traceback data fits the arena.
+// mode16: checkpoint bytes of ba_fill16 instead of the code bytes of ba_fill32.
+inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len, const int32_t *qry_len, int kind,
+                       int affine, bool mode16, int64_t arena_cap, Plan &plan)
 {
     std::vector<std::vector<int32_t>> by_class(BA_MAX_COLS + 1);
     std::vector<char> uniform(BA_MAX_COLS + 1, 1);
     std::vector<int64_t> first_cells(BA_MAX_COLS + 1, -1);
-    plan.cells = 0;
-    for (int64_t p = 0; p < n; p++) {
+    for (int64_t x = 0; x < nids; x++) {
+        const int32_t p = ids ? ids[x] : (int32_t)x;
         const int c = cols_for(qry_len[p]);
         const int64_t cells = (int64_t)ref_len[p] * (int64_t)qry_len[p];
-        plan.cells += cells;
         if (first_cells[c] < 0)
             first_cells[c] = cells;
         else if (first_cells[c] != cells)
             uniform[c] = 0;
-        by_class[c].push_back((int32_t)p);
+        by_class[c].push_back(p);
     }
-    plan.items.reserve((size_t)n);
-    const bool need_aux = (kind == KIND_FIT);
-    if (need_aux) plan.aux_off.reserve((size_t)n);
+    plan.items.reserve((size_t)nids);
+    const bool need_aux = (kind == KIND_FIT) && !mode16;
+    if (need_aux) plan.aux_off.reserve((size_t)nids);
+    if (mode16) {
+        plan.slot_off.reserve((size_t)nids);
+        plan.slot_cap.reserve((size_t)nids);
+    }
     Plan::Wave wave;
     wave.first = 0;
     wave.count = 0;
     wave.code_bytes = 0;
     wave.aux_ints = 0;
+    wave.slots = 0;
     wave.max_n_multipass = 0;
     auto flush = [&]() {
         if (wave.count > 0) plan.waves.push_back(wave);
@@ -68,6 +84,7 @@ void build_plan(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int k
         wave.count = 0;
         wave.code_bytes = 0;
         wave.aux_ints = 0;
+        wave.slots = 0;
         wave.max_n_multipass = 0;
         wave.launches.clear();
     };
@@ -84,7 +101,8 @@ void build_plan(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int k
         L.first = wave.first + wave.count;
         L.count = 0;
         for (int32_t p : v) {
-            int64_t cb = ba_code_bytes(affine, c, ref_len[p], qry_len[p]);
+            int64_t cb = mode16 ? ba16_ck_bytes(c, ref_len[p], qry_len[p])
+                                : ba_code_bytes(affine, c, ref_len[p], qry_len[p]);
             cb = (cb + 255) & ~(int64_t)255;
             if (wave.count > 0 && wave.code_bytes + cb > arena_cap) {
                 if (L.count > 0) wave.launches.push_back(L);
@@ -101,6 +119,12 @@ void build_plan(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int k
                 plan.aux_off.push_back(wave.aux_ints);
                 wave.aux_ints += (int64_t)ref_len[p] + 1;
             }
+            if (mode16) {
+                const int32_t cap = slot_cap_for(ref_len[p], qry_len[p]);
+                plan.slot_off.push_back(wave.slots);
+                plan.slot_cap.push_back(cap);
+                wave.slots += cap;
+            }
             wave.code_bytes += cb;
             wave.count++;
             L.count++;
@@ -110,6 +134,5 @@ void build_plan(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int k
     }
     flush();
 }
-
 
 }  // namespace

@@ -1,0 +1,345 @@
+// ba_trace16.cuh -- traceback for the checkpointed fill (ba_fill16.cuh).
+//
+// One thread per pair.  The walk needs bíogo's layer-independent candidate order at every
+// visited cell (align/sw_affine_letters.go:171-275), i.e. exact VALUES around the path.  The
+// fill stored only sparse checkpoints, so this kernel re-derives the table tile by tile:
+// a tile is the part of one column strip between two of its row checkpoints (16 rows x
+// COLS columns).  For the tile under the walk it rebuilds the boundary (top row from the row
+// checkpoint, left column from the column checkpoints, the missing third layer by its own
+// one-dimensional recurrence), recomputes the needed cells with the very same
+// affine_cell<KIND>() that ba_fill32 uses, keeps their 8-bit codes in shared memory and walks
+// them with the same rules as ba_walk_kernel until the path leaves the tile.
+#pragma once
+
+#include "ba_common.cuh"
+#include "ba_fill16.cuh"
+#include "ba_fill32.cuh"
+#include "ba_walk.cuh"
+
+#define BA_TRACE_THREADS 128
+#define BA_TILE_ROWS 16
+
+struct Trace16Params {
+    const uint8_t *enc;
+    int stride;
+    const int64_t *ref_off;
+    const int32_t *ref_len;
+    const int64_t *qry_off;
+    const int32_t *qry_len;
+    int32_t *status;
+    const WorkItem *items;
+    int n_items;
+    const uint8_t *arena;
+    const DeviceScoring *sc;
+    int32_t *seg_count;        // per item: segments emitted (may exceed the slot capacity)
+    const int64_t *slot_off;   // per item: first slot, in segments
+    const int32_t *slot_cap;   // per item
+    int32_t *slots;            // 5 ints per segment, in EMISSION order (reverse of final)
+};
+
+struct CkView {
+    const uint8_t *base;
+    int n, m, cols, npass, jshift;
+    int64_t pass_bytes, colck_bytes;
+    // (M, clamped L) of the last column of global strip g at row r
+    __device__ __forceinline__ void col_ml(int g, int r, int &M, int &L) const
+    {
+        const int pass = g >> 5, v = g & 31;
+        const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
+                                         ((int64_t)(r - 1 + v) * 16 + (v & 15)) * 8);
+        M = p[v >> 4];
+        L = p[2 + (v >> 4)];
+    }
+    // (M, clamped U) of column k of global strip g at its checkpoint row of period e
+    __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const
+    {
+        const int pass = g >> 5, v = g & 31;
+        const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
+                                         (((int64_t)e * 16 + (v & 15)) * cols + k) * 8);
+        M = p[v >> 4];
+        U = p[2 + (v >> 4)];
+    }
+    __device__ __forceinline__ int strip_of(int j) const { return (j - jshift - 1) / cols; }
+    __device__ __forceinline__ int left_col(int g) const { return jshift + g * cols; }
+};
+
+// Recompute the tile of strip g, period e, for rows rt+1 .. imax and columns up to jmax, and
+// store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).  When `want`
+// is >= 0 the last cell in row-major order whose M equals `want` (scaled) is reported.
+template <int KIND>
+__device__ void trace16_tile(const CkView &ck, const DeviceScoring *sc, const uint8_t *rs, const uint8_t *qs,
+                             int stride, int g, int e, int imax, int jmax, uint8_t *tile, int want, int &fi,
+                             int &fj)
+{
+    const int let = sc->let;
+    const int32_t *la = sc->la;
+    const int go = sc->gap_open * BA_SCALE;
+    const int v = g & 31;
+    const int rt = max(16 * e - v, 0);          // top boundary row (0 = DP border)
+    const int c0 = ck.left_col(g);
+    const int cL = max(c0, 0);                  // effective left boundary column (0 = DP border)
+    const int kfirst = cL - c0;                 // first real column of the strip
+    const int klast = jmax - c0 - 1;            // last needed column (inclusive)
+
+    // ---- corner (rt, cL) and the U layer of the left boundary column
+    Cell3 corner;
+    corner.M = corner.U = corner.L = 0;         // SW border
+    int leftU = 0;                              // U at (row, cL), advanced row by row
+    if (cL > 0) {
+        const int gl = g - 1;                   // strip whose last column is cL
+        const int vl = gl & 31;
+        // U of column cL is checkpointed (with M) only at strip gl's own rows; start from the
+        // closest one at or above rt and run U's recurrence down the column on the stored M.
+        int r0 = rt - ((rt + vl) & 15);         // largest row <= rt with (r0 + vl) % 16 == 0
+        int u = 0;
+        if (r0 >= 1) {
+            int mm;
+            ck.row_mu(gl, (r0 + vl) / 16 - 1, ck.cols - 1, mm, u);
+            u *= BA_SCALE;
+        } else {
+            r0 = 0;                             // DP border row: U = 0 for SW
+        }
+        for (int r = r0 + 1; r <= rt; r++) {
+            int mp = 0, lp;
+            if (r - 1 >= 1) ck.col_ml(gl, r - 1, mp, lp);
+            const int er = la[(int)rs[(int64_t)(r - 1) * stride] * let] * BA_SCALE;
+            u = max(max(mp * BA_SCALE + go + er, u + er), 0);
+        }
+        leftU = u;
+        if (rt >= 1) {
+            int mm, ll;
+            ck.col_ml(gl, rt, mm, ll);
+            corner.M = mm * BA_SCALE;
+            corner.L = ll * BA_SCALE;
+            corner.U = u;
+        }
+    }
+
+    // ---- top boundary row rt for my columns
+    Cell3 Pv[BA_MAX_COLS];
+    {
+        int lM = corner.M, lL = corner.L;
+#pragma unroll
+        for (int k = 0; k < BA_MAX_COLS; k++) {
+            Pv[k].M = Pv[k].U = Pv[k].L = 0;
+            if (k >= kfirst && k <= klast && rt >= 1) {
+                int mm, uu;
+                ck.row_mu(g, e - 1, k, mm, uu);
+                const int eq = la[(int)qs[(int64_t)(c0 + k) * stride]] * BA_SCALE;
+                Pv[k].M = mm * BA_SCALE;
+                Pv[k].U = uu * BA_SCALE;
+                Pv[k].L = max(max(lM + go + eq, lL + eq), 0);
+                lM = Pv[k].M;
+                lL = Pv[k].L;
+            }
+        }
+    }
+
+    // ---- rows rt+1 .. imax
+    Cell3 dprev = corner;  // (row-1, cL)
+    for (int r = rt + 1; r <= imax; r++) {
+        const int R = rs[(int64_t)(r - 1) * stride];
+        const int er = la[R * let] * BA_SCALE;
+        const int goer = go + er;
+        Cell3 left;
+        left.M = left.U = left.L = 0;
+        if (cL > 0) {
+            int mm, ll;
+            ck.col_ml(g - 1, r, mm, ll);
+            // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er, 0)
+            leftU = max(max(dprev.M + goer, leftU + er), 0);
+            left.M = mm * BA_SCALE;
+            left.L = ll * BA_SCALE;
+            left.U = leftU;
+        }
+        Cell3 d = dprev, l = left;
+        uint8_t *trow = tile + (size_t)((r - rt - 1) * BA_MAX_COLS) * BA_TRACE_THREADS;
+#pragma unroll
+        for (int k = 0; k < BA_MAX_COLS; k++) {
+            if (k >= kfirst && k <= klast) {
+                const int Q = qs[(int64_t)(c0 + k) * stride];
+                const int eq = la[Q] * BA_SCALE;
+                unsigned code;
+                int dm;
+                const Cell3 old = Pv[k];
+                const Cell3 nw = affine_cell<KIND>(d, old, l, la[R * let + Q] * BA_SCALE, er, goer, eq, go + eq,
+                                                   code, dm);
+                trow[(size_t)k * BA_TRACE_THREADS] = (uint8_t)code;
+                if (want >= 0 && nw.M == want) {
+                    fi = r;
+                    fj = c0 + k + 1;
+                }
+                Pv[k] = nw;
+                d = old;
+                l = nw;
+            }
+        }
+        dprev = left;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BA_TRACE_THREADS) ba_trace16_kernel(Trace16Params P)
+{
+    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= P.n_items) return;
+    uint8_t *tile = tiles + threadIdx.x;
+    const WorkItem item = P.items[it];
+    const int p = item.pair;
+    if (P.status[p] != 0) {
+        P.seg_count[it] = 0;
+        return;
+    }
+    const int n = P.ref_len[p], m = P.qry_len[p];
+    const uint8_t *rs = P.enc + P.ref_off[p];
+    const uint8_t *qs = P.enc + P.qry_off[p];
+    const int stride = P.stride;
+    const DeviceScoring *sc = P.sc;
+    const int let = sc->let;
+    const int32_t *la = sc->la;
+    const int go = sc->gap_open;
+
+    CkView ck;
+    ck.base = P.arena + item.code_off;
+    ck.n = n;
+    ck.m = m;
+    ck.cols = item.cols;
+    ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
+    ck.jshift = m - ck.npass * 32 * item.cols;
+    ck.pass_bytes = ba16_pass_bytes(n, item.cols);
+    ck.colck_bytes = ba16_colck_bytes(n);
+
+    int32_t *out = P.slots + 5 * P.slot_off[it];
+    const int cap = P.slot_cap[it];
+    int nseg = 0;
+#define T16_EMIT(a0, a1, b0, b1, sc_)     \
+    do {                                  \
+        if (nseg < cap) {                 \
+            int32_t *o_ = out + 5 * nseg; \
+            o_[0] = (a0);                 \
+            o_[1] = (a1);                 \
+            o_[2] = (b0);                 \
+            o_[3] = (b1);                 \
+            o_[4] = (sc_);                \
+        }                                 \
+        nseg++;                           \
+    } while (0)
+
+    // ---- start cell (SW): the last cell in row-major order holding the table maximum
+    int i = 0, j = 0, cur = 0;
+    if (n > 0 && m > 0) {
+        const uint2 *cand = (const uint2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
+        int S = 0;
+        for (int x = 0; x < ck.npass * 16; x++) {
+            const uint2 c = cand[x];
+            if (lo16(c.y) >= 0) S = max(S, lo16(c.x));
+            if (hi16(c.y) >= 0) S = max(S, hi16(c.x));
+        }
+        if (S > 0) {
+            for (int x = 0; x < ck.npass * 16; x++) {
+                const uint2 c = cand[x];
+                for (int h = 0; h < 2; h++) {
+                    const int e = h ? hi16(c.y) : lo16(c.y);
+                    const int sv = h ? hi16(c.x) : lo16(c.x);
+                    if (e < 0 || sv != S) continue;
+                    const int g = (x >> 4) * 32 + (x & 15) + 16 * h;
+                    const int v = g & 31;
+                    const int rlast = min(n, 16 * e + 16 - v);
+                    const int clast = ck.left_col(g) + ck.cols;
+                    if (rlast < 1 || clast < 1) continue;
+                    if (rlast < i || (rlast == i && clast < j)) continue;  // cannot come later
+                    int fi = 0, fj = 0;
+                    trace16_tile<KIND>(ck, sc, rs, qs, stride, g, e, rlast, clast, tile, S * BA_SCALE, fi, fj);
+                    if (fi > i || (fi == i && fj > j)) {
+                        i = fi;
+                        j = fj;
+                    }
+                }
+            }
+            cur = S;
+        }
+    }
+
+    int maxI = i, maxJ = j, score = 0, last = MV_DIAG, layer = 0;
+    bool bad = false;
+    while (i > 0 && j > 0 && !bad) {
+        if (KIND == KIND_SW && cur == 0) break;
+        const int g = ck.strip_of(j);
+        const int v = g & 31;
+        const int e = (i + v - 1) >> 4;
+        const int rt = max(16 * e - v, 0);
+        const int c0 = max(ck.left_col(g), 0);
+        int fi, fj;
+        trace16_tile<KIND>(ck, sc, rs, qs, stride, g, e, i, j, tile, -1, fi, fj);
+        const int cbase = ck.left_col(g);
+        while (i > rt && j > c0) {
+            if (KIND == KIND_SW && cur == 0) break;
+            const int R = rs[(int64_t)(i - 1) * stride], Q = qs[(int64_t)(j - 1) * stride];
+            const unsigned code = tile[(size_t)((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
+            const bool corner = (i == n && j == m);
+            const unsigned f = (layer == 0) ? (code & 7u) : (layer == 1) ? ((code >> 3) & 3u) : (code >> 5);
+            const int er = la[R * let], eq = la[Q];
+            int move, nl = 0, delta;
+            switch (f) {
+            case 1: move = MV_UP;   nl = 1; delta = er;      break;
+            case 2: move = MV_LEFT; nl = 2; delta = eq;      break;
+            case 3: move = MV_UP;   nl = 0; delta = go + er; break;
+            case 4: move = MV_LEFT; nl = 0; delta = go + eq; break;
+            case 5: move = MV_DIAG; nl = (KIND == KIND_SW) ? 0 : 1; delta = la[R * let + Q]; break;
+            case 6: move = MV_DIAG; nl = (KIND == KIND_SW) ? 1 : 2; delta = la[R * let + Q]; break;
+            case 7: move = MV_DIAG; nl = (KIND == KIND_SW) ? 2 : 0; delta = la[R * let + Q]; break;
+            default: move = MV_DIAG; delta = 0; bad = true; break;
+            }
+            if (bad) break;
+            if (last != move && (move == MV_DIAG || !corner)) {
+                T16_EMIT(i, maxI, j, maxJ, score);
+                maxI = i;
+                maxJ = j;
+                score = 0;
+            }
+            score += delta;
+            if (KIND == KIND_SW) cur -= delta;
+            if (move != MV_LEFT) i--;
+            if (move != MV_UP) j--;
+            layer = nl;
+            last = move;
+        }
+        if (KIND == KIND_SW && cur == 0) break;
+    }
+    T16_EMIT(i, maxI, j, maxJ, score);
+#undef T16_EMIT
+    if (bad) {
+        P.status[p] = 4;  // BA_PAIR_NO_PATH
+        nseg = 0;
+    }
+    P.seg_count[it] = nseg;
+}
+
+// Reverse the emission-order slots of every item into its final, compact place.
+__global__ void ba_compact_kernel(const int32_t *__restrict__ slots, const int64_t *__restrict__ slot_off,
+                                  const int32_t *__restrict__ slot_cap, const int32_t *__restrict__ seg_count,
+                                  const int64_t *__restrict__ seg_base, int32_t *__restrict__ segs, int n_items)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int cnt = seg_count[it];
+    if (cnt > slot_cap[it]) return;  // overflow: the host re-runs this pair on the exact two-pass path
+    const int32_t *src = slots + 5 * slot_off[it];
+    int32_t *dst = segs + 5 * seg_base[it];
+    for (int k = 0; k < cnt; k++) {
+        const int32_t *s = src + 5 * (cnt - 1 - k);
+#pragma unroll
+        for (int x = 0; x < 5; x++) dst[5 * k + x] = s[x];
+    }
+}
+
+// seg_count clipped to what actually gets compacted (overflowed items contribute 0)
+__global__ void ba_clip_counts_kernel(const int32_t *__restrict__ seg_count, const int32_t *__restrict__ slot_cap,
+                                      int32_t *__restrict__ clipped, int n_items)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int c = seg_count[it];
+    clipped[it] = (c > slot_cap[it]) ? 0 : c;
+}

@@ -62,7 +62,8 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
                                    const int64_t *__restrict__ ref_off, const int32_t *__restrict__ ref_len,
                                    const int64_t *__restrict__ qry_off, const int32_t *__restrict__ qry_len,
                                    int64_t npairs, int kind, int affine,
-                                   int32_t *__restrict__ status, int64_t *__restrict__ err_pos)
+                                   int32_t *__restrict__ status, int64_t *__restrict__ err_pos,
+                                   uint8_t *__restrict__ acgt_only)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -73,18 +74,21 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
         const uint8_t *q = enc + qry_off[p];
         int bad_r = 0x7fffffff, bad_q = 0x7fffffff;  // first illegal position
         int oob = 0;                                 // any index beyond the matrix
+        int other = 0;                               // any letter outside alphabet indices 1..4
         for (int base = 0; base < n && bad_r == 0x7fffffff; base += 32) {
             int x = base + lane;
-            uint8_t v = (x < n) ? r[(int64_t)x * stride] : 0;
+            uint8_t v = (x < n) ? r[(int64_t)x * stride] : 1;
             unsigned b = __ballot_sync(0xffffffffu, v == 0xFF);
             oob |= __any_sync(0xffffffffu, v == 0xFE);
+            other |= __any_sync(0xffffffffu, v < 1 || v > 4);
             if (b) bad_r = base + __ffs(b) - 1;
         }
         for (int base = 0; base < m && bad_q == 0x7fffffff; base += 32) {
             int x = base + lane;
-            uint8_t v = (x < m) ? q[(int64_t)x * stride] : 0;
+            uint8_t v = (x < m) ? q[(int64_t)x * stride] : 1;
             unsigned b = __ballot_sync(0xffffffffu, v == 0xFF);
             oob |= __any_sync(0xffffffffu, v == 0xFE);
+            other |= __any_sync(0xffffffffu, v < 1 || v > 4);
             if (b) bad_q = base + __ffs(b) - 1;
         }
         const bool hr = bad_r != 0x7fffffff, hq = bad_q != 0x7fffffff;
@@ -115,6 +119,8 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
         if (lane == 0) {
             status[p] = st;
             err_pos[p] = ep;
+            // the scan above stops at the first illegal letter, which makes st != 0 anyway
+            if (acgt_only) acgt_only[p] = (st == 0 && !other) ? 1 : 0;
         }
     }
 }

@@ -76,6 +76,7 @@ typedef struct {
     int64_t gpu_launches; /* kernels launched for this batch */
     int64_t fill_launches;/* of which DP fill kernels */
     int64_t code_bytes;   /* traceback bytes the fill kernels wrote to HBM */
+    int64_t pairs_fast16; /* pairs served by the packed 16-bit DPX path (the rest: 32-bit exact-code path) */
 } ba_result;
 
 /* Context: one per (host thread, device).  Thread-compatible: calls on ONE ctx must be
@@ -132,7 +133,8 @@ void *ba_alloc_host(size_t bytes);
 void ba_free_host(void *p);
 
 /* Tunables (optional). key: "arena_bytes" (traceback-code arena per wave, default 48 GiB
- * or 60 % of free HBM), "force_path" (0 auto, 1 = 32-bit exact-code kernels only). */
+ * or 60 % of free HBM), "force_path" (0 auto, 1 = 32-bit exact-code kernels only), "slot_cap"
+ * (test hook: segment slots per pair on the 16-bit path, 0 = automatic). */
 int ba_set_option(ba_ctx *ctx, const char *key, int64_t value);
 
 /* Build/ABI information. */

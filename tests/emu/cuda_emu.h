@@ -229,19 +229,22 @@ using std::max;
 using std::min;
 
 template <typename T>
-static inline T __shfl_up_sync(unsigned, T v, int d)
+static inline T __shfl_up_sync(unsigned, T v, int d, int width = 32)
 {
-    int l = emu::my_lane();
-    return emu::exchange(v, l >= d ? l - d : -1);
+    const int l = emu::my_lane();
+    const int base = l & ~(width - 1);
+    return emu::exchange(v, (l - base) >= d ? l - d : -1);
 }
 template <typename T>
-static inline T __shfl_sync(unsigned, T v, int src)
+static inline T __shfl_sync(unsigned, T v, int src, int width = 32)
 {
-    return emu::exchange(v, src & 31);
+    const int base = emu::my_lane() & ~(width - 1);
+    return emu::exchange(v, base + (src & (width - 1)));
 }
 template <typename T>
-static inline T __shfl_xor_sync(unsigned, T v, int m)
+static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32)
 {
+    (void)width;
     return emu::exchange(v, emu::my_lane() ^ m);
 }
 static inline unsigned __ballot_sync(unsigned, bool pred)
@@ -351,4 +354,40 @@ static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, 
 {
     *n = 1;
     return cudaSuccess;
+}
+
+// ---- packed 16-bit SIMD-in-a-word intrinsics (scalar restatements) and PRMT
+static inline short emu_lo(unsigned v) { return (short)(v & 0xffffu); }
+static inline short emu_hi(unsigned v) { return (short)(v >> 16); }
+static inline unsigned emu_pk(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+static inline unsigned __vadd2(unsigned a, unsigned b) { return emu_pk(emu_lo(a) + emu_lo(b), emu_hi(a) + emu_hi(b)); }
+static inline unsigned __vmaxs2(unsigned a, unsigned b)
+{
+    return emu_pk(std::max(emu_lo(a), emu_lo(b)), std::max(emu_hi(a), emu_hi(b)));
+}
+static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vmaxs2(a, b), c); }
+static inline unsigned __vimax_s16x2_relu(unsigned a, unsigned b) { return __vmaxs2(__vmaxs2(a, b), 0u); }
+static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }
+static inline unsigned __viaddmax_s16x2_relu(unsigned a, unsigned b, unsigned c)
+{
+    return __vmaxs2(__vmaxs2(__vadd2(a, b), c), 0u);
+}
+static inline unsigned __vibmax_s16x2(unsigned a, unsigned b, bool *ph, bool *pl)
+{
+    *ph = emu_hi(a) >= emu_hi(b);
+    *pl = emu_lo(a) >= emu_lo(b);
+    return __vmaxs2(a, b);
+}
+// prmt.b32 (default mode): selector nibble bit 3 replicates the sign of the selected byte
+static inline unsigned emu_prmt(unsigned a, unsigned b, unsigned s)
+{
+    const uint64_t src = ((uint64_t)b << 32) | a;
+    unsigned r = 0;
+    for (int k = 0; k < 4; k++) {
+        const unsigned nib = (s >> (4 * k)) & 0xf;
+        unsigned byte = (unsigned)(src >> (8 * (nib & 7))) & 0xff;
+        if (nib & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * k);
+    }
+    return r;
 }

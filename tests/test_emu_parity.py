@@ -103,3 +103,49 @@ def test_empty_batch_and_range_error(emu_ctx):
         emu_ctx.set_scoring(0, False, np.zeros(16, np.int64), 4, 5, 0, DNA_IDX)
     assert e.value.code == _lib.BA_ERR_MATRIX_SIZE
     emu_ctx.set_scoring(2, False, np.zeros(16, np.int64), 4, 5, 0, DNA_IDX)  # Fitted has no such check
+
+
+def _fast_batch(rng, count, lens_r, lens_q):
+    pairs = randcases.rand_pairs(rng, count, lens_r, lens_q, related=0.85, dirty=0.0)
+    return [(r, q) for r, q in pairs]
+
+
+@pytest.mark.parametrize("params", [(-1, 1, -1, -5), (-1, 2, -1, -3), (-2, 5, -4, -10), (0, 1, -1, -2)],
+                         ids=["m1", "m2", "nuc4like", "gap0"])
+def test_fast16_path_swaffine(emu_ctx, params):
+    """The packed 16-bit DPX fill + checkpointed tile traceback (ba_fill16 / ba_trace16)."""
+    gap, ma, mi, go = params
+    rng = random.Random(hash(params) & 0xffff)
+    M = gv.match(gap, ma, mi)
+    pairs = _fast_batch(rng, 40, [1, 2, 7, 15, 16, 17, 31, 33, 48, 64, 90, 130],
+                        [1, 2, 5, 8, 9, 16, 31, 32, 33, 40, 64, 65, 95, 100, 160])
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(emu_ctx, 0, True, M, go, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] == len(pairs)
+    helpers.compare(res, helpers.run_oracle(0, True, M, go, DNA_IDX, pk), f"fast16 {params}")
+
+
+def test_fast16_multi_pass_mixed_and_overflow(emu_ctx):
+    rng = random.Random(77)
+    M = gv.match(-1, 1, -1)
+    pairs = _fast_batch(rng, 10, [60, 200, 300], [257, 300, 520])                 # > 256 columns: several passes
+    pairs += randcases.rand_pairs(rng, 12, [20, 50], [20, 50], dirty=1.0)          # gap letters / N -> 32-bit path
+    pairs += _fast_batch(rng, 12, [30, 80], [30, 80])
+    pk = helpers.pack(pairs, 2)
+    res = helpers.run_lib(emu_ctx, 0, True, M, -5, DNA_IDX, 5, pk, 2)
+    assert 0 < res.stats["pairs_fast16"] < len(pairs)
+    orc = helpers.run_oracle(0, True, M, -5, DNA_IDX, pk, 2)
+    helpers.compare(res, orc, "fast16 mixed")
+    emu_ctx.set_option("slot_cap", 2)   # almost every pair overflows its segment slots -> exact path
+    try:
+        res2 = helpers.run_lib(emu_ctx, 0, True, M, -5, DNA_IDX, 5, pk, 2)
+    finally:
+        emu_ctx.set_option("slot_cap", 0)
+    helpers.compare(res2, orc, "fast16 overflow fallback")
+    emu_ctx.set_option("force_path", 1)
+    try:
+        res3 = helpers.run_lib(emu_ctx, 0, True, M, -5, DNA_IDX, 5, pk, 2)
+    finally:
+        emu_ctx.set_option("force_path", 0)
+    assert res3.stats["pairs_fast16"] == 0
+    helpers.compare(res3, orc, "forced 32-bit path")

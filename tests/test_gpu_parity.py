@@ -199,3 +199,42 @@ def test_align_batch_host_mirror(gpu_ctx):
         else:
             aln, err = a.Align(sa, sb)
             assert err is None and [p.astuple() for p in aln] == segs
+
+
+@pytest.mark.parametrize("params", [(-1, 1, -1, -5), (-1, 2, -1, -3), (-2, 5, -4, -10), (0, 1, -1, -2)],
+                         ids=["m1", "m2", "nuc4like", "gap0"])
+def test_fast16_path_random(gpu_ctx, params):
+    """Packed 16-bit DPX fill + checkpointed tile traceback against the oracle."""
+    gap, ma, mi, go = params
+    rng = random.Random(hash(params) & 0xffff)
+    M = gv.match(gap, ma, mi)
+    pairs = randcases.rand_pairs(rng, 1500, [1, 2, 7, 15, 16, 17, 31, 33, 48, 64, 90, 130, 400, 1000],
+                                 [1, 2, 5, 8, 9, 16, 31, 32, 33, 40, 64, 65, 95, 100, 160, 250, 256, 257, 300, 700],
+                                 related=0.85, dirty=0.02)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(gpu_ctx, 0, True, M, go, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] > 0.9 * len(pairs)
+    helpers.compare(res, helpers.run_oracle(0, True, M, go, DNA_IDX, pk, 1, 16), f"fast16 {params}")
+
+
+def test_fast16_and_exact_paths_agree_on_config2(gpu_ctx):
+    w = synth.config(2, 4000)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    fast = helpers.run_lib(gpu_ctx, 0, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    assert fast.stats["pairs_fast16"] == w.n
+    gpu_ctx.set_option("force_path", 1)
+    try:
+        exact = helpers.run_lib(gpu_ctx, 0, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    finally:
+        gpu_ctx.set_option("force_path", 0)
+    assert exact.stats["pairs_fast16"] == 0
+    for p in range(w.n):
+        assert np.array_equal(fast.pairs(p), exact.pairs(p)), p
+    gpu_ctx.set_option("slot_cap", 3)
+    try:
+        ovf = helpers.run_lib(gpu_ctx, 0, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    finally:
+        gpu_ctx.set_option("slot_cap", 0)
+    assert 0 < ovf.stats["pairs_fast16"] < w.n
+    for p in range(w.n):
+        assert np.array_equal(ovf.pairs(p), exact.pairs(p)), p
