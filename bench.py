@@ -219,8 +219,8 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    agg = {"ms_fill": 0.0, "ms_kernels": 0.0, "ms_d2h": 0.0, "gpu_launches": 0, "fill_launches": 0,
-           "code_bytes": 0, "n_segs": 0}
+    agg = {"ms_fill": 0.0, "ms_trace": 0.0, "ms_host": 0.0, "ms_kernels": 0.0, "ms_d2h": 0.0, "gpu_launches": 0,
+           "fill_launches": 0, "code_bytes": 0, "n_segs": 0, "pairs_fast16": 0}
     for _ in range(args.steps):
         s = step_device()
         for k in agg:
@@ -273,8 +273,10 @@ def main():
         ach = agg["code_bytes"] / fill_s / 1e9 if fill_s > 0 else 0.0
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "ba_fill32_kernel (DP fill + traceback-code stores)",
+                "kernel": ("ba_fill16_sw_kernel (packed DPX fill + checkpoint stores)" if agg["pairs_fast16"]
+                           else "ba_fill32_kernel (DP fill + traceback-code stores)"),
                 "algorithmic_bytes_per_cell": (1.0 if w.affine else 0.25),
+                "stored_bytes_per_cell": agg["code_bytes"] / (cells_step * args.steps),
                 "fill_ms_per_step": agg["ms_fill"] / args.steps,
                 "fill_share_of_step": agg["ms_fill"] / ms if ms > 0 else None,
                 "fill_gcups": cells_step * args.steps / fill_s / 1e9 if fill_s > 0 else None}
@@ -296,6 +298,9 @@ def main():
                        "l2": "inputs + traceback codes per step exceed the 126 MB L2",
                        "seed": "splitmix64 0xB10600+config (+rank<<20)"},
             "roofline": roof, "clocks": clocks,
+            "breakdown_ms_per_step": {"fill": agg["ms_fill"] / args.steps, "trace": agg["ms_trace"] / args.steps,
+                                      "d2h": agg["ms_d2h"] / args.steps, "host_plan_scatter": agg["ms_host"] / args.steps,
+                                      "pairs_on_dpx16_path": agg["pairs_fast16"] // args.steps},
             "gpu_launches": int(agg["gpu_launches"]),
         }
         if e2e:

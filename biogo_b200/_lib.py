@@ -41,6 +41,8 @@ class BaResult(C.Structure):
         ("ms_kernels", C.c_float),
         ("ms_d2h", C.c_float),
         ("ms_fill", C.c_float),
+        ("ms_trace", C.c_float),
+        ("ms_host", C.c_float),
         ("cells", C.c_int64),
         ("gpu_launches", C.c_int64),
         ("fill_launches", C.c_int64),
@@ -114,7 +116,7 @@ class BatchResult:
 
 def _stats(res: BaResult) -> dict:
     return {k: (float(getattr(res, k)) if k.startswith("ms_") else int(getattr(res, k)))
-            for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_fill", "cells", "gpu_launches", "fill_launches",
+            for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_fill", "ms_trace", "ms_host", "cells", "gpu_launches", "fill_launches",
                       "code_bytes", "pairs_fast16", "n_segs")}
 
 

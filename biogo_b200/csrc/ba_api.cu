@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -96,7 +97,7 @@ struct ba_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     bool have_scoring = false;
     DeviceScoring h_sc;
@@ -211,9 +212,18 @@ struct Batch {
     };
     std::vector<WaveOut> wave_out;
     int64_t seg_total = 0;
-    float ms_d2h = 0.f, ms_fill = 0.f;
+    float ms_d2h = 0.f, ms_fill = 0.f, ms_trace = 0.f;
+    double host_s = 0.0;
     int64_t launches = 0, fill_launches = 0, code_bytes = 0;
 };
+
+static bool g_timing = getenv("BA_TIMING") != nullptr;
+#define BA_TSEC(name, t0) do { if (g_timing) fprintf(stderr, "[ba timing] %-22s %8.3f ms\n", name, (now_s() - (t0)) * 1e3); } while (0)
+
+static inline double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 int64_t arena_budget(ba_ctx *ctx, int64_t &cap)
 {
@@ -251,9 +261,12 @@ int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, in
     B.ms_d2h += ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
     B.ms_fill += ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+    B.ms_trace += ms;
+    const double t0 = now_s();
     for (int64_t k = 0; k < w.count; k++) {
-        const int32_t p = plan.items[(size_t)(w.first + k)].pair;
-        if (overflow && h_raw_cnt[k] > plan.slot_cap[(size_t)(w.first + k)]) {
+        const int32_t p = plan.items[w.first + k].pair;
+        if (overflow && (h_raw_cnt[k] < 0 || h_raw_cnt[k] > plan.slot_cap[w.first + k])) {
             overflow->push_back(p);
             continue;
         }
@@ -262,6 +275,8 @@ int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, in
     }
     B.wave_out.push_back({h_segs, wsegs});
     B.seg_total += wsegs;
+    BA_TSEC("gather scatter", t0);
+    B.host_s += now_s() - t0;
     return BA_OK;
 }
 
@@ -278,7 +293,15 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
         return BA_ERR_CUDA;
     }
     Plan plan;
+    const double tp0 = now_s();
+    plan.items = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)nids);
+    plan.aux_off = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)nids);
+    if (!plan.items || !plan.aux_off) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
     build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, affine, false, arena_cap, plan);
+    B.host_s += now_s() - tp0;
 
     int64_t max_items = 0, max_code = 0, max_aux = 0;
     for (auto &w : plan.waves) {
@@ -309,11 +332,11 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
 
     for (auto &w : plan.waves) {
         WorkItem *d_items = (WorkItem *)ctx->items.p;
-        CK(cudaMemcpyAsync(d_items, plan.items.data() + w.first, sizeof(WorkItem) * (size_t)w.count,
+        CK(cudaMemcpyAsync(d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count,
                            cudaMemcpyHostToDevice, st));
         int64_t *d_aux_off = (int64_t *)ctx->aux_off.p;
         if (kind == KIND_FIT)
-            CK(cudaMemcpyAsync(d_aux_off, plan.aux_off.data() + w.first, sizeof(int64_t) * (size_t)w.count,
+            CK(cudaMemcpyAsync(d_aux_off, plan.aux_off + w.first, sizeof(int64_t) * (size_t)w.count,
                                cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
 
@@ -401,12 +424,15 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
         BA_LAUNCH(walk_write, wblocks, 128, st, wp);
         B.launches++;
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[6], st));
         if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, nullptr,
                               nullptr)) != BA_OK)
             return rc;
     }
     pinned_put(ctx, h_cnt);
     pinned_put(ctx, h_base);
+    pinned_put(ctx, plan.items);
+    pinned_put(ctx, plan.aux_off);
     return BA_OK;
 }
 
@@ -465,13 +491,25 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         return BA_ERR_CUDA;
     }
     Plan plan;
+    const double tp0 = now_s();
+    plan.items = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)nids);
+    plan.slot_off = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)nids);
+    plan.slot_cap = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)nids);
+    if (!plan.items || !plan.slot_off || !plan.slot_cap) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    const double tp1 = now_s();
     build_plan(ids, nids, B.h_ref_len, B.h_qry_len, KIND_SW, 1, true, arena_cap, plan);
+    BA_TSEC("plan16 pinned_get", tp0);
+    BA_TSEC("plan16 build", tp1);
+    B.host_s += now_s() - tp0;
     if (ctx->opt_slot_cap > 0) {  // test hook: force the overflow -> exact-path fallback
         for (auto &w : plan.waves) {
             w.slots = 0;
             for (int64_t k = 0; k < w.count; k++) {
-                plan.slot_off[(size_t)(w.first + k)] = w.slots;
-                plan.slot_cap[(size_t)(w.first + k)] = (int32_t)ctx->opt_slot_cap;
+                plan.slot_off[w.first + k] = w.slots;
+                plan.slot_cap[w.first + k] = (int32_t)ctx->opt_slot_cap;
                 w.slots += ctx->opt_slot_cap;
             }
         }
@@ -506,11 +544,11 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
 
     for (auto &w : plan.waves) {
         WorkItem *d_items = (WorkItem *)ctx->items.p;
-        CK(cudaMemcpyAsync(d_items, plan.items.data() + w.first, sizeof(WorkItem) * (size_t)w.count,
+        CK(cudaMemcpyAsync(d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count,
                            cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->slot_off.p, plan.slot_off.data() + w.first, sizeof(int64_t) * (size_t)w.count,
+        CK(cudaMemcpyAsync(ctx->slot_off.p, plan.slot_off + w.first, sizeof(int64_t) * (size_t)w.count,
                            cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->slot_cap.p, plan.slot_cap.data() + w.first, sizeof(int32_t) * (size_t)w.count,
+        CK(cudaMemcpyAsync(ctx->slot_cap.p, plan.slot_cap + w.first, sizeof(int32_t) * (size_t)w.count,
                            cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
 
@@ -540,6 +578,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
             fp.qry_off = B.d_qry_off;
             fp.qry_len = B.d_qry_len;
             fp.status = B.d_status;
+            fp.acgt_only = (const uint8_t *)ctx->flags.p;
             fp.items = d_items + (L.first - w.first);
             fp.n_items = (int)L.count;
             fp.counter = (int *)ctx->counters.p + (li++ % 64);
@@ -564,6 +603,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         tp.qry_off = B.d_qry_off;
         tp.qry_len = B.d_qry_len;
         tp.status = B.d_status;
+        tp.acgt_only = (const uint8_t *)ctx->flags.p;
         tp.items = d_items;
         tp.n_items = (int)w.count;
         tp.arena = (const uint8_t *)ctx->arena.p;
@@ -598,6 +638,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
                   (int)w.count);
         B.launches++;
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[6], st));
         if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, h_raw,
                               &overflow)) != BA_OK)
             return rc;
@@ -605,6 +646,9 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
     pinned_put(ctx, h_cnt);
     pinned_put(ctx, h_raw);
     pinned_put(ctx, h_base);
+    pinned_put(ctx, plan.items);
+    pinned_put(ctx, plan.slot_off);
+    pinned_put(ctx, plan.slot_cap);
     return BA_OK;
 }
 
@@ -673,28 +717,28 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
     }
     CK(cudaGetLastError());
 
+    const double th0 = now_s();
     int64_t cells = 0;
     for (int64_t p = 0; p < n; p++) cells += (int64_t)h_ref_len[p] * (int64_t)h_qry_len[p];
     out->cells = cells;
+    BA_TSEC("cells loop", th0);
+    B.host_s += now_s() - th0;
 
     // ---- split the batch between the two paths
     std::vector<int32_t> slow;
     if (fast16) {
-        uint8_t *h_flags = (uint8_t *)pinned_get(ctx, (size_t)n + 16);
-        if (!h_flags) {
-            ctx->err = "pinned host allocation failed";
-            return BA_ERR_NOMEM;
-        }
-        CK(cudaMemcpyAsync(h_flags, ctx->flags.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        // size eligibility is known on the host; letter eligibility (ACGT only) is decided on the
+        // device: ineligible pairs come back from the traceback marked for the exact path
+        const double ts0 = now_s();
         std::vector<int32_t> fast;
         fast.reserve((size_t)n);
         for (int64_t p = 0; p < n; p++) {
             const int64_t lo = std::min(h_ref_len[p], h_qry_len[p]);
-            const bool ok = h_flags[p] && lo > 0 && lo * maxsub < 32000 && h_ref_len[p] < (1 << 19);
+            const bool ok = lo > 0 && lo * maxsub < 32000 && h_ref_len[p] < (1 << 19);
             (ok ? fast : slow).push_back((int32_t)p);
         }
-        pinned_put(ctx, h_flags);
+        BA_TSEC("partition", ts0);
+        B.host_s += now_s() - ts0;
         const size_t nslow0 = slow.size();
         if ((rc = run_path16(ctx, B, fast.data(), (int64_t)fast.size(), slow)) != BA_OK) return rc;
         out->pairs_fast16 = (int64_t)fast.size() - (int64_t)(slow.size() - nslow0);
@@ -742,6 +786,8 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
     out->fill_launches = B.fill_launches;
     out->code_bytes = B.code_bytes;
     out->ms_fill = B.ms_fill;
+    out->ms_trace = B.ms_trace;
+    out->ms_host = (float)(B.host_s * 1e3);
     return BA_OK;
 }
 
@@ -784,7 +830,7 @@ int ba_create(int device, ba_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 8; k++) {
         e = cudaEventCreate(&ctx->ev[k]);
         if (e != cudaSuccess) return fail(e, "cudaEventCreate");
     }
@@ -806,7 +852,7 @@ void ba_destroy(ba_ctx *ctx)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
     if (ctx->d_sc) cudaFree(ctx->d_sc);
-    for (int k = 0; k < 6; k++)
+    for (int k = 0; k < 8; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

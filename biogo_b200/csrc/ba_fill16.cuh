@@ -5,7 +5,7 @@
 // The walk only ever visits O(r+c) cells, so this kernel computes VALUES ONLY -- seven DPX /
 // packed-integer instructions per TWO cells -- and stores sparse checkpoints of the table:
 //   * the right-most column of every 32*COLS/32-wide strip, every row        (M, L)
-//   * one row of every strip every 16 steps                                   (M, U)
+//   * one row of every strip every BA16_PERIOD steps                          (M, U)
 // ba_trace16 (ba_trace16.cuh) then re-derives the exact codes only for the 16-row x COLS-column
 // tiles the traceback actually crosses, with the very same affine_cell<> as ba_fill32.
 //
@@ -33,6 +33,8 @@
 #define BA16_PROF_RING 1024          // ring of row profiles per group (entries)
 #define BA16_PROF_CHUNK 512          // rows loaded per refill
 #define BA16_WARPS 4                 // warps per CTA
+#define BA16_PERIOD 8                // steps between two row checkpoints (= tile rows of ba_trace16)
+#define BA16_PSHIFT 3
 #define BA16_GROUPS (2 * BA16_WARPS) // pairs in flight per CTA
 
 struct Fill16Params {
@@ -43,6 +45,7 @@ struct Fill16Params {
     const int64_t *qry_off;
     const int32_t *qry_len;
     const int32_t *status;
+    const uint8_t *acgt_only;  // per pair: letters are all alphabet indices 1..4 (else: exact path)
     const WorkItem *items;
     int n_items;
     int *counter;
@@ -74,9 +77,9 @@ __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); 
 // One pass of one pair occupies, in this order:
 //   colck: nsteps x 16 lanes x {M,L}      (8 bytes per lane-step; both halves packed)
 //   rowck: nper  x 16 lanes x COLS x {M,U} (8 bytes per column)
-// with nsteps = n + 31 and nper = nsteps / 16 (periods that end inside the pass).
+// with nsteps = n + 31 and nper = nsteps / BA16_PERIOD (periods that end inside the pass).
 __host__ __device__ inline int64_t ba16_colck_bytes(int64_t n) { return (n + 31) * 16 * 8; }
-__host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + 31) / 16; }
+__host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + 31) / BA16_PERIOD; }
 __host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, int cols) { return ba16_nper(n) * 16 * cols * 8; }
 __host__ __device__ inline int64_t ba16_pass_bytes(int64_t n, int cols)
 {
@@ -102,7 +105,7 @@ template <int COLS, bool MULTI>
 __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Params P)
 {
     // row profiles: ring[group][i & (RING-1)] = 4 substitution bytes of the letter of row i
-    __shared__ unsigned ring[BA16_GROUPS][BA16_PROF_RING];
+    __shared__ unsigned ring[BA16_GROUPS][BA16_PROF_RING + 16];  // +16: the two groups of a warp hit disjoint banks
     __shared__ unsigned proftab[8];  // letter index -> {sub(R,1), sub(R,2), sub(R,3), sub(R,4)} as int8
     const int let = P.sc->let;
     if (threadIdx.x < 8) {
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
         if (have) item = P.items[it];
         const int p = item.pair;
         int n = have ? P.ref_len[p] : 0, m = have ? P.qry_len[p] : 0;
-        if (have && P.status[p] != 0) n = 0;
+        if (have && (P.status[p] != 0 || !P.acgt_only[p])) n = 0;
         const bool live = have && n > 0 && m > 0;
         if (!live) {
             n = 0;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
 #pragma unroll
             for (int k = 0; k < COLS; k++) Mu[k] = Uu[k] = Hu[k] = 0;
             unsigned outM = 0, outL = 0, outH = 0, sdiagH = 0;
-            unsigned bmax = 0;  // running max of the current 16-step period
+            unsigned bmax = 0;  // running max of the current period
             // per virtual thread: best value of this pass and the LAST period attaining it
             unsigned vbest = pack16(1, 1);
             int per_lo = -1, per_hi = -1;
@@ -199,6 +202,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
             uint2 *colck = (uint2 *)ck + t;
             uint2 *rowck = (uint2 *)(ck + ba16_colck_bytes(n)) + (int64_t)t * COLS;
 
+            // byte offsets of my two rows inside the profile ring, advanced by one entry per step
+            unsigned rolo = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;
+            unsigned rohi = (unsigned)((1 - t - 16) & (BA16_PROF_RING - 1)) * 4u;
+#pragma unroll 2
             for (int s = 0; s < nsteps_w; s++, colck += 16) {
                 if ((s & (BA16_PROF_CHUNK - 1)) == 0) {
                     // rows s+1 .. s+CHUNK enter the ring (lanes of the group share the load)
@@ -212,8 +219,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     __syncwarp();
                 }
                 const int ilo = s + 1 - t;
-                const unsigned profA = myring[ilo & (BA16_PROF_RING - 1)];
-                const unsigned profB = myring[(ilo + BA16_PROF_RING - 16) & (BA16_PROF_RING - 1)];
+                const unsigned profA = *(const unsigned *)((const char *)myring + rolo);
+                const unsigned profB = *(const unsigned *)((const char *)myring + rohi);
+                rolo = (rolo + 4u) & (BA16_PROF_RING * 4u - 1u);
+                rohi = (rohi + 4u) & (BA16_PROF_RING * 4u - 1u);
 
                 // boundary column of the left neighbour strip (rotate inside the 16-lane group)
                 unsigned rM = __shfl_sync(FULL, outM, (t + 15) & 15, 16);
@@ -267,8 +276,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                         }
                     }
                 }
-                if ((s & 15) == 15) {
-                    const int e = s >> 4;
+                if ((s & (BA16_PERIOD - 1)) == BA16_PERIOD - 1) {
+                    const int e = s >> BA16_PSHIFT;
                     if (pass_live && s < nsteps) {
 #pragma unroll
                         for (int k = 0; k < COLS; k++)
@@ -282,9 +291,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     bmax = 0;
                 }
             }
-            // the tail period (fewer than 16 steps) still counts for the best cell
-            if (nsteps_w & 15) {
-                const int e = nsteps_w >> 4;
+            // the tail period (a partial one) still counts for the best cell
+            if (nsteps_w & (BA16_PERIOD - 1)) {
+                const int e = nsteps_w >> BA16_PSHIFT;
                 bool ph, pl;
                 vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
                 if (pl) per_lo = e;

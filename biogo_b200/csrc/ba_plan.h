@@ -11,10 +11,11 @@
 namespace {
 
 struct Plan {
-    std::vector<WorkItem> items;        // all items, grouped by class then size
-    std::vector<int64_t> aux_off;       // per item (Fitted kinds, 32-bit path)
-    std::vector<int64_t> slot_off;      // per item (16-bit path): first segment slot
-    std::vector<int32_t> slot_cap;      // per item (16-bit path)
+    // per-item arrays live in caller-provided (pinned) buffers of `nids` entries each
+    WorkItem *items = nullptr;          // all items, grouped by class then size
+    int64_t *aux_off = nullptr;         // per item (Fitted kinds, 32-bit path)
+    int64_t *slot_off = nullptr;        // per item (16-bit path): first segment slot
+    int32_t *slot_cap = nullptr;        // per item (16-bit path)
     struct Launch {
         int cols;
         int64_t first, count;           // item range
@@ -51,26 +52,43 @@ inline int32_t slot_cap_for(int n, int m)
 inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len, const int32_t *qry_len, int kind,
                        int affine, bool mode16, int64_t arena_cap, Plan &plan)
 {
-    std::vector<std::vector<int32_t>> by_class(BA_MAX_COLS + 1);
-    std::vector<char> uniform(BA_MAX_COLS + 1, 1);
-    std::vector<int64_t> first_cells(BA_MAX_COLS + 1, -1);
+    // pass 1: class sizes and whether a class is uniform (then no sort is needed)
+    int64_t cnt[BA_MAX_COLS + 1] = {0};
+    int64_t first_cells[BA_MAX_COLS + 1];
+    bool uniform[BA_MAX_COLS + 1];
+    for (int c = 0; c <= BA_MAX_COLS; c++) {
+        first_cells[c] = -1;
+        uniform[c] = true;
+    }
+    std::vector<uint8_t> cls((size_t)nids);
     for (int64_t x = 0; x < nids; x++) {
         const int32_t p = ids ? ids[x] : (int32_t)x;
         const int c = cols_for(qry_len[p]);
+        cls[(size_t)x] = (uint8_t)c;
         const int64_t cells = (int64_t)ref_len[p] * (int64_t)qry_len[p];
         if (first_cells[c] < 0)
             first_cells[c] = cells;
         else if (first_cells[c] != cells)
-            uniform[c] = 0;
-        by_class[c].push_back(p);
+            uniform[c] = false;
+        cnt[c]++;
     }
-    plan.items.reserve((size_t)nids);
+    // pass 2: pair ids grouped by class (widest first), written into one array
+    std::vector<int32_t> order((size_t)nids);
+    int64_t start[BA_MAX_COLS + 2];
+    {
+        int64_t acc = 0;
+        for (int c = BA_MAX_COLS; c >= 1; c--) {
+            start[c] = acc;
+            acc += cnt[c];
+        }
+        int64_t fill[BA_MAX_COLS + 1];
+        for (int c = 1; c <= BA_MAX_COLS; c++) fill[c] = start[c];
+        for (int64_t x = 0; x < nids; x++) {
+            const int32_t p = ids ? ids[x] : (int32_t)x;
+            order[(size_t)fill[cls[(size_t)x]]++] = p;
+        }
+    }
     const bool need_aux = (kind == KIND_FIT) && !mode16;
-    if (need_aux) plan.aux_off.reserve((size_t)nids);
-    if (mode16) {
-        plan.slot_off.reserve((size_t)nids);
-        plan.slot_cap.reserve((size_t)nids);
-    }
     Plan::Wave wave;
     wave.first = 0;
     wave.count = 0;
@@ -88,11 +106,12 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         wave.max_n_multipass = 0;
         wave.launches.clear();
     };
+    int64_t w = 0;  // next item slot
     for (int c = BA_MAX_COLS; c >= 1; c--) {
-        auto &v = by_class[c];
-        if (v.empty()) continue;
+        if (cnt[c] == 0) continue;
+        int32_t *v = order.data() + start[c];
         if (!uniform[c]) {
-            std::stable_sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
+            std::stable_sort(v, v + cnt[c], [&](int32_t a, int32_t b) {
                 return (int64_t)ref_len[a] * qry_len[a] > (int64_t)ref_len[b] * qry_len[b];
             });
         }
@@ -100,10 +119,19 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         L.cols = c;
         L.first = wave.first + wave.count;
         L.count = 0;
-        for (int32_t p : v) {
-            int64_t cb = mode16 ? ba16_ck_bytes(c, ref_len[p], qry_len[p])
-                                : ba_code_bytes(affine, c, ref_len[p], qry_len[p]);
-            cb = (cb + 255) & ~(int64_t)255;
+        int memo_n = -1, memo_m = -1;   // batches are often uniform: reuse the per-shape numbers
+        int64_t memo_cb = 0;
+        int32_t memo_cap = 0;
+        for (int64_t x = 0; x < cnt[c]; x++) {
+            const int32_t p = v[x];
+            if (ref_len[p] != memo_n || qry_len[p] != memo_m) {
+                memo_n = ref_len[p];
+                memo_m = qry_len[p];
+                memo_cb = mode16 ? ba16_ck_bytes(c, memo_n, memo_m) : ba_code_bytes(affine, c, memo_n, memo_m);
+                memo_cb = (memo_cb + 255) & ~(int64_t)255;
+                memo_cap = slot_cap_for(memo_n, memo_m);
+            }
+            const int64_t cb = memo_cb;
             if (wave.count > 0 && wave.code_bytes + cb > arena_cap) {
                 if (L.count > 0) wave.launches.push_back(L);
                 flush();
@@ -114,17 +142,18 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             it.pair = p;
             it.cols = c;
             it.code_off = wave.code_bytes;
-            plan.items.push_back(it);
+            plan.items[w] = it;
             if (need_aux) {
-                plan.aux_off.push_back(wave.aux_ints);
+                plan.aux_off[w] = wave.aux_ints;
                 wave.aux_ints += (int64_t)ref_len[p] + 1;
             }
             if (mode16) {
-                const int32_t cap = slot_cap_for(ref_len[p], qry_len[p]);
-                plan.slot_off.push_back(wave.slots);
-                plan.slot_cap.push_back(cap);
+                const int32_t cap = memo_cap;
+                plan.slot_off[w] = wave.slots;
+                plan.slot_cap[w] = cap;
                 wave.slots += cap;
             }
+            w++;
             wave.code_bytes += cb;
             wave.count++;
             L.count++;

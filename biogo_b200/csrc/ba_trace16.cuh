@@ -17,7 +17,7 @@
 #include "ba_walk.cuh"
 
 #define BA_TRACE_THREADS 128
-#define BA_TILE_ROWS 16
+#define BA_TILE_ROWS BA16_PERIOD
 
 struct Trace16Params {
     const uint8_t *enc;
@@ -27,11 +27,12 @@ struct Trace16Params {
     const int64_t *qry_off;
     const int32_t *qry_len;
     int32_t *status;
+    const uint8_t *acgt_only;  // per pair eligibility (see ba_fill16)
     const WorkItem *items;
     int n_items;
     const uint8_t *arena;
     const DeviceScoring *sc;
-    int32_t *seg_count;        // per item: segments emitted (may exceed the slot capacity)
+    int32_t *seg_count;        // per item: segments emitted (may exceed the slot capacity); -1 = not eligible
     const int64_t *slot_off;   // per item: first slot, in segments
     const int32_t *slot_cap;   // per item
     int32_t *slots;            // 5 ints per segment, in EMISSION order (reverse of final)
@@ -66,35 +67,45 @@ struct CkView {
 // Recompute the tile of strip g, period e, for rows rt+1 .. imax and columns up to jmax, and
 // store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).  When `want`
 // is >= 0 the last cell in row-major order whose M equals `want` (scaled) is reported.
+// S is the scoring matrix scaled by BA_SCALE in shared memory (row stride `let`).
 template <int KIND>
-__device__ void trace16_tile(const CkView &ck, const DeviceScoring *sc, const uint8_t *rs, const uint8_t *qs,
-                             int stride, int g, int e, int imax, int jmax, uint8_t *tile, int want, int &fi,
-                             int &fj)
+__device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
+                                             const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
+                                             uint8_t *tile, int want, int &fi, int &fj)
 {
-    const int let = sc->let;
-    const int32_t *la = sc->la;
-    const int go = sc->gap_open * BA_SCALE;
     const int v = g & 31;
-    const int rt = max(16 * e - v, 0);          // top boundary row (0 = DP border)
+    const int rt = max(BA16_PERIOD * e - v, 0); // top boundary row (0 = DP border)
     const int c0 = ck.left_col(g);
     const int cL = max(c0, 0);                  // effective left boundary column (0 = DP border)
     const int kfirst = cL - c0;                 // first real column of the strip
     const int klast = jmax - c0 - 1;            // last needed column (inclusive)
 
+    // ---- per-column constants of this tile
+    int qo[BA_MAX_COLS], eqv[BA_MAX_COLS];
+#pragma unroll
+    for (int k = 0; k < BA_MAX_COLS; k++) {
+        qo[k] = 0;
+        eqv[k] = 0;
+        if (k >= kfirst && k <= klast) {
+            qo[k] = qs[(c0 + k) * stride];
+            eqv[k] = S[qo[k]];
+        }
+    }
+
     // ---- corner (rt, cL) and the U layer of the left boundary column
     Cell3 corner;
     corner.M = corner.U = corner.L = 0;         // SW border
     int leftU = 0;                              // U at (row, cL), advanced row by row
+    const int gl = g - 1;                       // strip whose last column is cL
     if (cL > 0) {
-        const int gl = g - 1;                   // strip whose last column is cL
         const int vl = gl & 31;
         // U of column cL is checkpointed (with M) only at strip gl's own rows; start from the
         // closest one at or above rt and run U's recurrence down the column on the stored M.
-        int r0 = rt - ((rt + vl) & 15);         // largest row <= rt with (r0 + vl) % 16 == 0
+        int r0 = rt - ((rt + vl) & (BA16_PERIOD - 1));  // largest row <= rt with (r0 + vl) % PERIOD == 0
         int u = 0;
         if (r0 >= 1) {
             int mm;
-            ck.row_mu(gl, (r0 + vl) / 16 - 1, ck.cols - 1, mm, u);
+            ck.row_mu(gl, (r0 + vl) / BA16_PERIOD - 1, ck.cols - 1, mm, u);
             u *= BA_SCALE;
         } else {
             r0 = 0;                             // DP border row: U = 0 for SW
@@ -102,7 +113,7 @@ __device__ void trace16_tile(const CkView &ck, const DeviceScoring *sc, const ui
         for (int r = r0 + 1; r <= rt; r++) {
             int mp = 0, lp;
             if (r - 1 >= 1) ck.col_ml(gl, r - 1, mp, lp);
-            const int er = la[(int)rs[(int64_t)(r - 1) * stride] * let] * BA_SCALE;
+            const int er = S[(int)rs[(r - 1) * stride] * let];
             u = max(max(mp * BA_SCALE + go + er, u + er), 0);
         }
         leftU = u;
@@ -125,10 +136,9 @@ __device__ void trace16_tile(const CkView &ck, const DeviceScoring *sc, const ui
             if (k >= kfirst && k <= klast && rt >= 1) {
                 int mm, uu;
                 ck.row_mu(g, e - 1, k, mm, uu);
-                const int eq = la[(int)qs[(int64_t)(c0 + k) * stride]] * BA_SCALE;
                 Pv[k].M = mm * BA_SCALE;
                 Pv[k].U = uu * BA_SCALE;
-                Pv[k].L = max(max(lM + go + eq, lL + eq), 0);
+                Pv[k].L = max(max(lM + go + eqv[k], lL + eqv[k]), 0);
                 lM = Pv[k].M;
                 lL = Pv[k].L;
             }
@@ -137,15 +147,16 @@ __device__ void trace16_tile(const CkView &ck, const DeviceScoring *sc, const ui
 
     // ---- rows rt+1 .. imax
     Cell3 dprev = corner;  // (row-1, cL)
-    for (int r = rt + 1; r <= imax; r++) {
-        const int R = rs[(int64_t)(r - 1) * stride];
-        const int er = la[R * let] * BA_SCALE;
+    uint8_t *trow = tile;
+    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * BA_TRACE_THREADS) {
+        const int *Srow = S + (int)rs[(r - 1) * stride] * let;
+        const int er = Srow[0];
         const int goer = go + er;
         Cell3 left;
         left.M = left.U = left.L = 0;
         if (cL > 0) {
             int mm, ll;
-            ck.col_ml(g - 1, r, mm, ll);
+            ck.col_ml(gl, r, mm, ll);
             // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er, 0)
             leftU = max(max(dprev.M + goer, leftU + er), 0);
             left.M = mm * BA_SCALE;
@@ -153,18 +164,14 @@ __device__ void trace16_tile(const CkView &ck, const DeviceScoring *sc, const ui
             left.U = leftU;
         }
         Cell3 d = dprev, l = left;
-        uint8_t *trow = tile + (size_t)((r - rt - 1) * BA_MAX_COLS) * BA_TRACE_THREADS;
 #pragma unroll
         for (int k = 0; k < BA_MAX_COLS; k++) {
             if (k >= kfirst && k <= klast) {
-                const int Q = qs[(int64_t)(c0 + k) * stride];
-                const int eq = la[Q] * BA_SCALE;
                 unsigned code;
                 int dm;
                 const Cell3 old = Pv[k];
-                const Cell3 nw = affine_cell<KIND>(d, old, l, la[R * let + Q] * BA_SCALE, er, goer, eq, go + eq,
-                                                   code, dm);
-                trow[(size_t)k * BA_TRACE_THREADS] = (uint8_t)code;
+                const Cell3 nw = affine_cell<KIND>(d, old, l, Srow[qo[k]], er, goer, eqv[k], go + eqv[k], code, dm);
+                trow[k * BA_TRACE_THREADS] = (uint8_t)code;
                 if (want >= 0 && nw.M == want) {
                     fi = r;
                     fj = c0 + k + 1;
@@ -179,9 +186,15 @@ __device__ void trace16_tile(const CkView &ck, const DeviceScoring *sc, const ui
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(BA_TRACE_THREADS) ba_trace16_kernel(Trace16Params P)
+__global__ void __launch_bounds__(BA_TRACE_THREADS, 4) ba_trace16_kernel(Trace16Params P)
 {
     __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    __shared__ int S[BA_MAX_LET * BA_MAX_LET];
+    {
+        const int ll = P.sc->let;
+        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] * BA_SCALE;
+    }
+    __syncthreads();
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= P.n_items) return;
     uint8_t *tile = tiles + threadIdx.x;
@@ -191,14 +204,18 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS) ba_trace16_kernel(Trace16Par
         P.seg_count[it] = 0;
         return;
     }
+    if (!P.acgt_only[p]) {
+        P.seg_count[it] = -1;  // the host re-runs this pair on the exact path
+        return;
+    }
     const int n = P.ref_len[p], m = P.qry_len[p];
     const uint8_t *rs = P.enc + P.ref_off[p];
     const uint8_t *qs = P.enc + P.qry_off[p];
     const int stride = P.stride;
     const DeviceScoring *sc = P.sc;
     const int let = sc->let;
-    const int32_t *la = sc->la;
     const int go = sc->gap_open;
+    const int go8 = go * BA_SCALE;
 
     CkView ck;
     ck.base = P.arena + item.code_off;
@@ -230,34 +247,34 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS) ba_trace16_kernel(Trace16Par
     int i = 0, j = 0, cur = 0;
     if (n > 0 && m > 0) {
         const uint2 *cand = (const uint2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
-        int S = 0;
+        int Smax = 0;
         for (int x = 0; x < ck.npass * 16; x++) {
             const uint2 c = cand[x];
-            if (lo16(c.y) >= 0) S = max(S, lo16(c.x));
-            if (hi16(c.y) >= 0) S = max(S, hi16(c.x));
+            if (lo16(c.y) >= 0) Smax = max(Smax, lo16(c.x));
+            if (hi16(c.y) >= 0) Smax = max(Smax, hi16(c.x));
         }
-        if (S > 0) {
+        if (Smax > 0) {
             for (int x = 0; x < ck.npass * 16; x++) {
                 const uint2 c = cand[x];
                 for (int h = 0; h < 2; h++) {
                     const int e = h ? hi16(c.y) : lo16(c.y);
                     const int sv = h ? hi16(c.x) : lo16(c.x);
-                    if (e < 0 || sv != S) continue;
+                    if (e < 0 || sv != Smax) continue;
                     const int g = (x >> 4) * 32 + (x & 15) + 16 * h;
                     const int v = g & 31;
-                    const int rlast = min(n, 16 * e + 16 - v);
+                    const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
                     const int clast = ck.left_col(g) + ck.cols;
                     if (rlast < 1 || clast < 1) continue;
                     if (rlast < i || (rlast == i && clast < j)) continue;  // cannot come later
                     int fi = 0, fj = 0;
-                    trace16_tile<KIND>(ck, sc, rs, qs, stride, g, e, rlast, clast, tile, S * BA_SCALE, fi, fj);
+                    trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, Smax * BA_SCALE, fi, fj);
                     if (fi > i || (fi == i && fj > j)) {
                         i = fi;
                         j = fj;
                     }
                 }
             }
-            cur = S;
+            cur = Smax;
         }
     }
 
@@ -267,28 +284,28 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS) ba_trace16_kernel(Trace16Par
         if (KIND == KIND_SW && cur == 0) break;
         const int g = ck.strip_of(j);
         const int v = g & 31;
-        const int e = (i + v - 1) >> 4;
-        const int rt = max(16 * e - v, 0);
+        const int e = (i + v - 1) >> BA16_PSHIFT;
+        const int rt = max(BA16_PERIOD * e - v, 0);
         const int c0 = max(ck.left_col(g), 0);
         int fi, fj;
-        trace16_tile<KIND>(ck, sc, rs, qs, stride, g, e, i, j, tile, -1, fi, fj);
+        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, -1, fi, fj);
         const int cbase = ck.left_col(g);
         while (i > rt && j > c0) {
             if (KIND == KIND_SW && cur == 0) break;
-            const int R = rs[(int64_t)(i - 1) * stride], Q = qs[(int64_t)(j - 1) * stride];
-            const unsigned code = tile[(size_t)((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
+            const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
+            const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
             const bool corner = (i == n && j == m);
             const unsigned f = (layer == 0) ? (code & 7u) : (layer == 1) ? ((code >> 3) & 3u) : (code >> 5);
-            const int er = la[R * let], eq = la[Q];
+            const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
             int move, nl = 0, delta;
             switch (f) {
             case 1: move = MV_UP;   nl = 1; delta = er;      break;
             case 2: move = MV_LEFT; nl = 2; delta = eq;      break;
             case 3: move = MV_UP;   nl = 0; delta = go + er; break;
             case 4: move = MV_LEFT; nl = 0; delta = go + eq; break;
-            case 5: move = MV_DIAG; nl = (KIND == KIND_SW) ? 0 : 1; delta = la[R * let + Q]; break;
-            case 6: move = MV_DIAG; nl = (KIND == KIND_SW) ? 1 : 2; delta = la[R * let + Q]; break;
-            case 7: move = MV_DIAG; nl = (KIND == KIND_SW) ? 2 : 0; delta = la[R * let + Q]; break;
+            case 5: move = MV_DIAG; nl = (KIND == KIND_SW) ? 0 : 1; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
+            case 6: move = MV_DIAG; nl = (KIND == KIND_SW) ? 1 : 2; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
+            case 7: move = MV_DIAG; nl = (KIND == KIND_SW) ? 2 : 0; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
             default: move = MV_DIAG; delta = 0; bad = true; break;
             }
             if (bad) break;
@@ -324,7 +341,7 @@ __global__ void ba_compact_kernel(const int32_t *__restrict__ slots, const int64
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
     const int cnt = seg_count[it];
-    if (cnt > slot_cap[it]) return;  // overflow: the host re-runs this pair on the exact two-pass path
+    if (cnt < 0 || cnt > slot_cap[it]) return;  // not eligible / overflow: re-run on the exact two-pass path
     const int32_t *src = slots + 5 * slot_off[it];
     int32_t *dst = segs + 5 * seg_base[it];
     for (int k = 0; k < cnt; k++) {
@@ -341,5 +358,5 @@ __global__ void ba_clip_counts_kernel(const int32_t *__restrict__ seg_count, con
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
     const int c = seg_count[it];
-    clipped[it] = (c > slot_cap[it]) ? 0 : c;
+    clipped[it] = (c < 0 || c > slot_cap[it]) ? 0 : c;
 }

@@ -72,6 +72,8 @@ typedef struct {
     /* device-side timing of this call, CUDA events on the launching stream (ms) */
     float ms_h2d, ms_kernels, ms_d2h;
     float ms_fill;        /* DP fill kernels only (the dominant kernel family) */
+    float ms_trace;       /* traceback kernels (walk / tile trace + compaction) */
+    float ms_host;        /* host wall time inside the call spent planning/scattering (GPU idle) */
     int64_t cells;        /* sum of len(ref)*len(query) over the batch */
     int64_t gpu_launches; /* kernels launched for this batch */
     int64_t fill_launches;/* of which DP fill kernels */

@@ -129,7 +129,8 @@ def test_fast16_multi_pass_mixed_and_overflow(emu_ctx):
     rng = random.Random(77)
     M = gv.match(-1, 1, -1)
     pairs = _fast_batch(rng, 10, [60, 200, 300], [257, 300, 520])                 # > 256 columns: several passes
-    pairs += randcases.rand_pairs(rng, 12, [20, 50], [20, 50], dirty=1.0)          # gap letters / N -> 32-bit path
+    pairs += randcases.rand_pairs(rng, 6, [20, 50], [20, 50], dirty=1.0)           # N: illegal-letter errors
+    pairs += randcases.rand_pairs(rng, 8, [20, 50], [20, 50], dirty=1.0, dirty_alpha=b"ACGT-acgt")  # gap letters -> exact path
     pairs += _fast_batch(rng, 12, [30, 80], [30, 80])
     pk = helpers.pack(pairs, 2)
     res = helpers.run_lib(emu_ctx, 0, True, M, -5, DNA_IDX, 5, pk, 2)
