@@ -76,7 +76,7 @@ __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); 
 // Checkpoint geometry shared with ba_trace16 ------------------------------------------------
 // One pass of one pair occupies, in this order:
 //   colck: nsteps x 16 lanes x {M,L}      (8 bytes per lane-step; both halves packed)
-//   rowck: nper  x 16 lanes x COLS x {M,U} (8 bytes per column)
+//   rowck: nper  x COLS x 16 lanes x {M,U} (8 bytes per lane; one coalesced 128-byte row per column)
 // with nsteps = n + 31 and nper = nsteps / BA16_PERIOD (periods that end inside the pass).
 __host__ __device__ inline int64_t ba16_colck_bytes(int64_t n) { return (n + 31) * 16 * 8; }
 __host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + 31) / BA16_PERIOD; }
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
             int per_lo = -1, per_hi = -1;
             uint8_t *ck = P.arena + item.code_off + (int64_t)pass * pass_bytes;
             uint2 *colck = (uint2 *)ck + t;
-            uint2 *rowck = (uint2 *)(ck + ba16_colck_bytes(n)) + (int64_t)t * COLS;
+            uint2 *rowck = (uint2 *)(ck + ba16_colck_bytes(n)) + t;  // [period][column k][lane]: lanes contiguous
 
             // byte offsets of my two rows inside the profile ring, advanced by one entry per step
             unsigned rolo = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     if (pass_live && s < nsteps) {
 #pragma unroll
                         for (int k = 0; k < COLS; k++)
-                            rowck[(int64_t)e * 16 * COLS + k] = make_uint2(Mu[k], __vimax_s16x2_relu(Uu[k], erp));
+                            rowck[((int64_t)e * COLS + k) * 16] = make_uint2(Mu[k], __vimax_s16x2_relu(Uu[k], erp));
                     }
                     // best tracking at period granularity ('>=' keeps the LAST period)
                     bool ph, pl;

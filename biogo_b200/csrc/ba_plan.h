@@ -52,6 +52,57 @@ inline int32_t slot_cap_for(int n, int m)
 inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len, const int32_t *qry_len, int kind,
                        int affine, bool mode16, int64_t arena_cap, Plan &plan)
 {
+    const bool need_aux = (kind == KIND_FIT) && !mode16;
+    // fast path: every pair has the same shape (the common batch): closed-form plan
+    if (nids > 0) {
+        const int32_t p0 = ids ? ids[0] : 0;
+        const int n0 = ref_len[p0], m0 = qry_len[p0];
+        bool same = true;
+        for (int64_t x = 1; x < nids && same; x++) {
+            const int32_t p = ids ? ids[x] : (int32_t)x;
+            same = (ref_len[p] == n0) & (qry_len[p] == m0);
+        }
+        if (same) {
+            const int c = cols_for(m0);
+            int64_t cb = mode16 ? ba16_ck_bytes(c, n0, m0) : ba_code_bytes(affine, c, n0, m0);
+            cb = (cb + 255) & ~(int64_t)255;
+            const int32_t cap = slot_cap_for(n0, m0);
+            int64_t per_wave = cb > 0 ? arena_cap / cb : nids;
+            if (per_wave < 1) per_wave = 1;
+            if (per_wave > nids) per_wave = nids;
+            for (int64_t first = 0; first < nids; first += per_wave) {
+                const int64_t count = std::min(per_wave, nids - first);
+                Plan::Wave w;
+                w.first = first;
+                w.count = count;
+                w.code_bytes = count * cb;
+                w.aux_ints = need_aux ? count * ((int64_t)n0 + 1) : 0;
+                w.slots = mode16 ? count * (int64_t)cap : 0;
+                w.max_n_multipass = (m0 > 32 * c) ? n0 : 0;
+                Plan::Launch L;
+                L.cols = c;
+                L.first = first;
+                L.count = count;
+                w.launches.push_back(L);
+                for (int64_t k = 0; k < count; k++) {
+                    WorkItem it;
+                    it.pair = ids ? ids[first + k] : (int32_t)(first + k);
+                    it.cols = c;
+                    it.code_off = k * cb;
+                    plan.items[first + k] = it;
+                }
+                if (need_aux)
+                    for (int64_t k = 0; k < count; k++) plan.aux_off[first + k] = k * ((int64_t)n0 + 1);
+                if (mode16)
+                    for (int64_t k = 0; k < count; k++) {
+                        plan.slot_off[first + k] = k * (int64_t)cap;
+                        plan.slot_cap[first + k] = cap;
+                    }
+                plan.waves.push_back(w);
+            }
+            return;
+        }
+    }
     // pass 1: class sizes and whether a class is uniform (then no sort is needed)
     int64_t cnt[BA_MAX_COLS + 1] = {0};
     int64_t first_cells[BA_MAX_COLS + 1];
@@ -88,7 +139,6 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             order[(size_t)fill[cls[(size_t)x]]++] = p;
         }
     }
-    const bool need_aux = (kind == KIND_FIT) && !mode16;
     Plan::Wave wave;
     wave.first = 0;
     wave.count = 0;

@@ -56,7 +56,7 @@ struct CkView {
     {
         const int pass = g >> 5, v = g & 31;
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
-                                         (((int64_t)e * 16 + (v & 15)) * cols + k) * 8);
+                                         (((int64_t)e * cols + k) * 16 + (v & 15)) * 8);
         M = p[v >> 4];
         U = p[2 + (v >> 4)];
     }

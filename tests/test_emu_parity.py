@@ -150,3 +150,18 @@ def test_fast16_multi_pass_mixed_and_overflow(emu_ctx):
         emu_ctx.set_option("force_path", 0)
     assert res3.stats["pairs_fast16"] == 0
     helpers.compare(res3, orc, "forced 32-bit path")
+
+
+def test_uniform_batch_closed_form_plan_and_waves(emu_ctx):
+    """All pairs of one shape take the planner's closed-form path; a small arena forces waves."""
+    rng = random.Random(21)
+    pairs = randcases.rand_pairs(rng, 30, [70], [40], related=0.8, dirty=0.0)
+    pk = helpers.pack(pairs)
+    M = gv.match(-1, 1, -1)
+    for kind, affine in ((0, True), (1, True), (2, False)):
+        emu_ctx.set_option("arena_bytes", 60000)
+        try:
+            res = helpers.run_lib(emu_ctx, kind, affine, M, -5, DNA_IDX, 5, pk)
+        finally:
+            emu_ctx.set_option("arena_bytes", 0)
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, -5, DNA_IDX, pk), f"uniform waves {kind} {affine}")
