@@ -30,8 +30,8 @@
 
 #include "ba_common.cuh"
 
-#define BA16_PROF_RING 1024          // ring of row profiles per group (entries)
-#define BA16_PROF_CHUNK 512          // rows loaded per refill
+#define BA16_PROF_RING 512           // ring of row profiles per group (entries)
+#define BA16_PROF_CHUNK 256          // rows loaded per refill
 #define BA16_WARPS 4                 // warps per CTA
 #define BA16_PERIOD 8                // steps between two row checkpoints (= tile rows of ba_trace16)
 #define BA16_PSHIFT 3
@@ -74,13 +74,21 @@ __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffff
 __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
 
 // Checkpoint geometry shared with ba_trace16 ------------------------------------------------
-// One pass of one pair occupies, in this order:
-//   colck: nsteps x 16 lanes x {M,L}      (8 bytes per lane-step; both halves packed)
-//   rowck: nper  x COLS x 16 lanes x {M,U} (8 bytes per lane; one coalesced 128-byte row per column)
-// with nsteps = n + 31 and nper = nsteps / BA16_PERIOD (periods that end inside the pass).
-__host__ __device__ inline int64_t ba16_colck_bytes(int64_t n) { return (n + 31) * 16 * 8; }
-__host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + 31) / BA16_PERIOD; }
-__host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, int cols) { return ba16_nper(n) * 16 * cols * 8; }
+// Everything is organised in 32-byte SECTORS, one per (period e, virtual thread v), so that
+// the traceback thread of a pair fetches a whole tile boundary with one or two DRAM sectors:
+//   colck[e][v] = 8 steps   x {M, L} int16 : last column of strip v at steps 8e .. 8e+7
+//   rowck[e][v] = 8 columns x {M, U} int16 : row of strip v processed at step 8e+7
+// A period is BA16_PERIOD = 8 steps; one pass of one pair holds nper = ceil((n+31)/8) periods of
+// 32 sectors for each of the two arrays (about 1 byte per DP cell for 8-column strips).
+// The fill stages both through shared memory and writes each period as fully coalesced
+// 16-byte stores.
+__host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + 31 + BA16_PERIOD - 1) / BA16_PERIOD; }
+__host__ __device__ inline int64_t ba16_colck_bytes(int64_t n) { return ba16_nper(n) * 32 * 32; }
+__host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, int cols)
+{
+    (void)cols;
+    return ba16_nper(n) * 32 * 32;
+}
 __host__ __device__ inline int64_t ba16_pass_bytes(int64_t n, int cols)
 {
     return ba16_colck_bytes(n) + ba16_rowck_bytes(n, cols);
@@ -99,6 +107,26 @@ __host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m)
 // so the last strip ends exactly at column m and the padding falls on columns <= 0, which
 // behave as the all-zero SW border (substitution 0 or -1 keeps M at 0 there).
 
+#define BA16_STAGE_ROW 17  // padded row length (entries) of the staging buffers
+
+// Write one period of staged checkpoints: buf[j][lane] = {packed A, packed B} for j = 0..7 (step
+// or column), lanes 0..15; the low halves belong to virtual thread `lane`, the high halves to
+// `lane+16`.  Output: 32 sectors of 32 bytes, sector v = 8 x {A.half, B.half}; lane t writes the
+// 16-byte chunks t, 16+t, 32+t, 48+t, i.e. every store instruction covers 256 contiguous bytes.
+__device__ __forceinline__ void ba16_flush_period(const uint2 *buf, uint4 *gdst, int t)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int c = q * 16 + t;
+        const int v = c >> 1, hh = c & 1;
+        const unsigned selw = (v & 16) ? 0x7632u : 0x5410u;
+        const uint2 *src = buf + (4 * hh) * BA16_STAGE_ROW + (v & 15);
+        const uint2 e0 = src[0], e1 = src[BA16_STAGE_ROW], e2 = src[2 * BA16_STAGE_ROW], e3 = src[3 * BA16_STAGE_ROW];
+        gdst[c] = make_uint4(ba_prmt(e0.x, e0.y, selw), ba_prmt(e1.x, e1.y, selw), ba_prmt(e2.x, e2.y, selw),
+                             ba_prmt(e3.x, e3.y, selw));
+    }
+}
+
 // MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
 // inter-pass boundary code is compiled out of the common single-pass instance).
 template <int COLS, bool MULTI>
@@ -107,6 +135,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
     // row profiles: ring[group][i & (RING-1)] = 4 substitution bytes of the letter of row i
     __shared__ unsigned ring[BA16_GROUPS][BA16_PROF_RING + 16];  // +16: the two groups of a warp hit disjoint banks
     __shared__ unsigned proftab[8];  // letter index -> {sub(R,1), sub(R,2), sub(R,3), sub(R,4)} as int8
+    __shared__ uint2 colbuf[BA16_GROUPS][8 * BA16_STAGE_ROW];  // staged column checkpoints of the period
+    __shared__ uint2 rowbuf[BA16_GROUPS][8 * BA16_STAGE_ROW];  // staged row checkpoint
     const int let = P.sc->let;
     if (threadIdx.x < 8) {
         unsigned w = 0x80808080u;  // virtual row: -128 against everything
@@ -129,6 +159,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
     const int grp = (threadIdx.x >> 4);            // group inside the CTA
     const int group_global = blockIdx.x * BA16_GROUPS + grp;
     unsigned *myring = ring[grp];
+    uint2 *mycol = colbuf[grp];
+    uint2 *myrow = rowbuf[grp];
     int32_t *bnd = P.bnd + (int64_t)group_global * P.bnd_stride;
     constexpr int W = 32 * COLS;
     const unsigned FULL = 0xffffffffu;
@@ -199,14 +231,14 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
             unsigned vbest = pack16(1, 1);
             int per_lo = -1, per_hi = -1;
             uint8_t *ck = P.arena + item.code_off + (int64_t)pass * pass_bytes;
-            uint2 *colck = (uint2 *)ck + t;
-            uint2 *rowck = (uint2 *)(ck + ba16_colck_bytes(n)) + t;  // [period][column k][lane]: lanes contiguous
+            uint4 *colck = (uint4 *)ck;                              // [period][64 chunks of 16 bytes]
+            uint4 *rowck = (uint4 *)(ck + ba16_colck_bytes(n));
 
             // byte offsets of my two rows inside the profile ring, advanced by one entry per step
             unsigned rolo = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;
             unsigned rohi = (unsigned)((1 - t - 16) & (BA16_PROF_RING - 1)) * 4u;
 #pragma unroll 2
-            for (int s = 0; s < nsteps_w; s++, colck += 16) {
+            for (int s = 0; s < nsteps_w; s++) {
                 if ((s & (BA16_PROF_CHUNK - 1)) == 0) {
                     // rows s+1 .. s+CHUNK enter the ring (lanes of the group share the load)
                     __syncwarp();
@@ -264,25 +296,25 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                 outL = Ll;
                 outH = Hu[COLS - 1];
 
-                if (pass_live && s < nsteps) {
-                    // column checkpoint: (M, clamped L) of my last column, every step
-                    *colck = make_uint2(outM, __vimax_s16x2_relu(outL, erp));
-                    if (MULTI && t == 15 && pass + 1 < npass) {
-                        const int ihi = ilo - 16;
-                        if (ihi >= 1 && ihi <= n) {
-                            bnd[3 * ihi + 0] = hi16(outM) & 0xffff;
-                            bnd[3 * ihi + 1] = hi16(outL) & 0xffff;
-                            bnd[3 * ihi + 2] = hi16(outH) & 0xffff;
-                        }
+                // column checkpoint: (M, clamped L) of my last column, staged for this period
+                mycol[(s & 7) * BA16_STAGE_ROW + t] = make_uint2(outM, __vimax_s16x2_relu(outL, erp));
+                if (MULTI && pass_live && s < nsteps && t == 15 && pass + 1 < npass) {
+                    const int ihi = ilo - 16;
+                    if (ihi >= 1 && ihi <= n) {
+                        bnd[3 * ihi + 0] = hi16(outM) & 0xffff;
+                        bnd[3 * ihi + 1] = hi16(outL) & 0xffff;
+                        bnd[3 * ihi + 2] = hi16(outH) & 0xffff;
                     }
                 }
                 if ((s & (BA16_PERIOD - 1)) == BA16_PERIOD - 1) {
                     const int e = s >> BA16_PSHIFT;
-                    if (pass_live && s < nsteps) {
 #pragma unroll
-                        for (int k = 0; k < COLS; k++)
-                            rowck[((int64_t)e * COLS + k) * 16] = make_uint2(Mu[k], __vimax_s16x2_relu(Uu[k], erp));
-                    }
+                    for (int k = 0; k < COLS; k++)
+                        myrow[k * BA16_STAGE_ROW + t] = make_uint2(Mu[k], __vimax_s16x2_relu(Uu[k], erp));
+                    __syncwarp();
+                    if (pass_live && (e << BA16_PSHIFT) < nsteps) ba16_flush_period(mycol, colck + (int64_t)e * 64, t);
+                    if (pass_live && s < nsteps) ba16_flush_period(myrow, rowck + (int64_t)e * 64, t);
+                    __syncwarp();
                     // best tracking at period granularity ('>=' keeps the LAST period)
                     bool ph, pl;
                     vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
@@ -291,7 +323,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     bmax = 0;
                 }
             }
-            // the tail period (a partial one) still counts for the best cell
+            // the tail period (a partial one): its column checkpoints, and the best cell
+            __syncwarp();
+            if ((nsteps_w & (BA16_PERIOD - 1)) != 0 && pass_live &&
+                ((nsteps_w >> BA16_PSHIFT) << BA16_PSHIFT) < nsteps)
+                ba16_flush_period(mycol, colck + (int64_t)(nsteps_w >> BA16_PSHIFT) * 64, t);
             if (nsteps_w & (BA16_PERIOD - 1)) {
                 const int e = nsteps_w >> BA16_PSHIFT;
                 bool ph, pl;

@@ -10,8 +10,8 @@
 #include <cstdlib>
 #include <vector>
 
-#define NCH 8
-#define ITERS 4096
+#define NCH 16
+#define ITERS 8192
 
 enum Op {
     OP_VIMAX3_S16X2, OP_VIADDMAX_S16X2_RELU, OP_VIADD_16X2, OP_VIMAX3_S32, OP_VIADDMAX_S32, OP_VIMIN3_U32,
@@ -99,7 +99,7 @@ void run(int sms, unsigned *d_out, long long *d_cyc, int clock_khz)
     cudaDeviceSynchronize();
     float best = 1e30f;
     double cyc_avg = 0;
-    for (int rep = 0; rep < 5; rep++) {
+    for (int rep = 0; rep < 12; rep++) {
         cudaEventRecord(e0);
         bench_kernel<OP><<<blocks, threads>>>(d_out, d_cyc, 0x00030005u, 0x00010002u);
         cudaEventRecord(e1);

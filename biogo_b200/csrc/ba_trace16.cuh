@@ -42,23 +42,24 @@ struct CkView {
     const uint8_t *base;
     int n, m, cols, npass, jshift;
     int64_t pass_bytes, colck_bytes;
-    // (M, clamped L) of the last column of global strip g at row r
+    // (M, clamped L) of the last column of global strip g at row r: sector (period, v), step slot
     __device__ __forceinline__ void col_ml(int g, int r, int &M, int &L) const
     {
         const int pass = g >> 5, v = g & 31;
+        const int st = r - 1 + v;
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
-                                         ((int64_t)(r - 1 + v) * 16 + (v & 15)) * 8);
-        M = p[v >> 4];
-        L = p[2 + (v >> 4)];
+                                         ((int64_t)((st >> BA16_PSHIFT) * 32 + v) * 8 + (st & (BA16_PERIOD - 1))) * 4);
+        M = p[0];
+        L = p[1];
     }
     // (M, clamped U) of column k of global strip g at its checkpoint row of period e
     __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const
     {
         const int pass = g >> 5, v = g & 31;
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
-                                         (((int64_t)e * cols + k) * 16 + (v & 15)) * 8);
-        M = p[v >> 4];
-        U = p[2 + (v >> 4)];
+                                         ((int64_t)(e * 32 + v) * 8 + k) * 4);
+        M = p[0];
+        U = p[1];
     }
     __device__ __forceinline__ int strip_of(int j) const { return (j - jshift - 1) / cols; }
     __device__ __forceinline__ int left_col(int g) const { return jshift + g * cols; }
