@@ -561,7 +561,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
             int occ = 1;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BA16_WARPS * 32, 0));
             if (occ < 1) occ = 1;
-            int64_t blocks = (L.count + BA16_GROUPS - 1) / BA16_GROUPS;
+            int64_t blocks = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
             int64_t maxb = (int64_t)ctx->sm_count * occ;
             if (blocks > maxb) blocks = maxb;
             int64_t bnd_stride = 0;
@@ -593,6 +593,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[5], st));
         B.code_bytes += w.code_bytes;
+        BA_TSEC("P16 fill launched", tp0);
 
         // ---- tile traceback into slots, clip, scan, compact
         Trace16Params tp;
@@ -629,7 +630,9 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         CK(cudaMemcpyAsync(h_raw, ctx->seg_count.p, sizeof(int32_t) * (size_t)w.count, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_base, ctx->seg_base.p, sizeof(int64_t) * (size_t)w.count, cudaMemcpyDeviceToHost,
                            st));
+        BA_TSEC("P16 trace launched", tp0);
         CK(cudaStreamSynchronize(st));
+        BA_TSEC("P16 counts synced", tp0);
         const int64_t wsegs = h_base[w.count - 1] + h_cnt[w.count - 1];
         if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
         BA_LAUNCH(ba_compact_kernel, cblocks, 256, st, (const int32_t *)ctx->slots.p,
@@ -642,6 +645,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, h_raw,
                               &overflow)) != BA_OK)
             return rc;
+        BA_TSEC("P16 wave gathered", tp0);
     }
     pinned_put(ctx, h_cnt);
     pinned_put(ctx, h_raw);
@@ -658,6 +662,7 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
                int64_t n, cudaStream_t st, ba_result *out)
 {
     const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+    const double t_call = now_s();
 
     // ---- result arrays (pinned, pooled)
     out->n = n;
@@ -716,6 +721,7 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         B.launches++;
     }
     CK(cudaGetLastError());
+    BA_TSEC("T result+enc launch", t_call);
 
     const double th0 = now_s();
     int64_t cells = 0;
@@ -747,6 +753,7 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         if ((rc = run_path32(ctx, B, nullptr, n)) != BA_OK) return rc;
     }
 
+    BA_TSEC("T paths done", t_call);
     // ---- gather
     CK(cudaEventRecord(ctx->ev[2], st));
     CK(cudaMemcpyAsync(out->status, B.d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -788,6 +795,7 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
     out->ms_fill = B.ms_fill;
     out->ms_trace = B.ms_trace;
     out->ms_host = (float)(B.host_s * 1e3);
+    BA_TSEC("T call total", t_call);
     return BA_OK;
 }
 

@@ -9,11 +9,11 @@
 // ba_trace16 (ba_trace16.cuh) then re-derives the exact codes only for the 16-row x COLS-column
 // tiles the traceback actually crosses, with the very same affine_cell<> as ba_fill32.
 //
-// Layout: a warp holds two pairs, one per 16-lane group.  Each lane carries TWO virtual
-// threads in the halves of its 32-bit registers: low half = virtual thread t (strip t of the
-// pass), high half = virtual thread t+16.  Virtual thread v handles row i at step s = i-1+v, so
-// one warp shuffle (rotate within the group) hands the boundary column from strip v to v+1
-// for both halves at once; lane 0 re-routes lane 15's low half into its own high half.
+// Layout: a warp holds FOUR pairs, two per 16-lane group: the low 16-bit halves of every
+// register belong to pair A, the high halves to pair B (two pairs of the same size class,
+// neighbours in the sorted work list).  Lane t owns 2*COLS consecutive columns of a 32*COLS wide
+// pass (two "strips" of COLS columns: 2t and 2t+1) and handles row i at step s = i-1+t; one
+// SHFL.UP per boundary register hands the right-most column to lane t+1 for both pairs at once.
 //
 // Exactness conditions checked by the host before this path is chosen (else ba_fill32):
 //   C1  every gap entry la[R][0] (resp. la[0][Q]) is one value er <= 0 (eq <= 0) for letters 1..4
@@ -32,10 +32,11 @@
 
 #define BA16_PROF_RING 512           // ring of row profiles per group (entries)
 #define BA16_PROF_CHUNK 256          // rows loaded per refill
-#define BA16_WARPS 4                 // warps per CTA
+#define BA16_WARPS 2                 // warps per CTA
 #define BA16_PERIOD 8                // steps between two row checkpoints (= tile rows of ba_trace16)
 #define BA16_PSHIFT 3
-#define BA16_GROUPS (2 * BA16_WARPS) // pairs in flight per CTA
+#define BA16_GROUPS (2 * BA16_WARPS) // 16-lane groups per CTA (two pairs each)
+#define BA16_SKEW 15                 // steps of systolic skew: nsteps = n + BA16_SKEW
 
 struct Fill16Params {
     const uint8_t *enc;
@@ -74,15 +75,15 @@ __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffff
 __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
 
 // Checkpoint geometry shared with ba_trace16 ------------------------------------------------
-// Everything is organised in 32-byte SECTORS, one per (period e, virtual thread v), so that
-// the traceback thread of a pair fetches a whole tile boundary with one or two DRAM sectors:
-//   colck[e][v] = 8 steps   x {M, L} int16 : last column of strip v at steps 8e .. 8e+7
-//   rowck[e][v] = 8 columns x {M, U} int16 : row of strip v processed at step 8e+7
-// A period is BA16_PERIOD = 8 steps; one pass of one pair holds nper = ceil((n+31)/8) periods of
-// 32 sectors for each of the two arrays (about 1 byte per DP cell for 8-column strips).
-// The fill stages both through shared memory and writes each period as fully coalesced
-// 16-byte stores.
-__host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + 31 + BA16_PERIOD - 1) / BA16_PERIOD; }
+// Everything is organised in 32-byte SECTORS, one per (period e, strip g), so that the
+// traceback thread of a pair fetches a whole tile boundary with one or two DRAM sectors:
+//   colck[e][g] = 8 steps   x {M, L} int16 : last column of strip g at steps 8e .. 8e+7
+//   rowck[e][g] = 8 columns x {M, U} int16 : row of strip g processed at step 8e+7
+// A period is BA16_PERIOD = 8 steps; strip g belongs to lane g>>1, which handles row i at step
+// i-1+(g>>1).  One pass of one pair holds nper = ceil((n+15)/8) periods of 32 sectors for each
+// of the two arrays (about 1 byte per DP cell for 8-column strips).  The fill stages both
+// through shared memory and writes every period as fully coalesced 16-byte stores.
+__host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + BA16_SKEW + BA16_PERIOD - 1) / BA16_PERIOD; }
 __host__ __device__ inline int64_t ba16_colck_bytes(int64_t n) { return ba16_nper(n) * 32 * 32; }
 __host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, int cols)
 {
@@ -93,8 +94,8 @@ __host__ __device__ inline int64_t ba16_pass_bytes(int64_t n, int cols)
 {
     return ba16_colck_bytes(n) + ba16_rowck_bytes(n, cols);
 }
-// After the passes: one candidate record per (pass, lane): {packed best score of the two
-// strips, packed last period attaining it} -- the start-cell candidates of ba_trace16.
+// After the passes: one candidate record per (pass, lane): {best score of the lane's two
+// strips, last period attaining it} -- the start-cell candidates of ba_trace16.
 __host__ __device__ inline int64_t ba16_npass(int cols, int64_t m) { return (m + 32LL * cols - 1) / (32LL * cols); }
 __host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m)
 {
@@ -102,28 +103,28 @@ __host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m)
     const int64_t np = ba16_npass(cols, m);
     return np * ba16_pass_bytes(n, cols) + np * 16 * 8;
 }
-// Columns are RIGHT-aligned: strip (pass, v) covers table columns
-//   jshift + pass*W + v*COLS + 1 .. + COLS   with jshift = m - npass*W  (<= 0),
+// Columns are RIGHT-aligned: strip g of pass p covers table columns
+//   jshift + p*W + g*COLS + 1 .. + COLS   with W = 32*COLS, jshift = m - npass*W  (<= 0),
 // so the last strip ends exactly at column m and the padding falls on columns <= 0, which
 // behave as the all-zero SW border (substitution 0 or -1 keeps M at 0 there).
 
-#define BA16_STAGE_ROW 17  // padded row length (entries) of the staging buffers
+// Staging buffers (shared memory): per pair one period = 32 sectors of 8 words; lane t owns the
+// 16 words of its two strips (2t, 2t+1) = four 16-byte chunks, stored rotated by t so that both
+// the per-lane stores and the chunk-ordered flush loads are (nearly) bank-conflict free.
+#define BA16_STAGE_WORDS (32 * 8)
+__device__ __forceinline__ int ba16_stage_word(int t, int chunk /*0..3*/)
+{
+    return 16 * t + 4 * ((chunk + t) & 3);
+}
 
-// Write one period of staged checkpoints: buf[j][lane] = {packed A, packed B} for j = 0..7 (step
-// or column), lanes 0..15; the low halves belong to virtual thread `lane`, the high halves to
-// `lane+16`.  Output: 32 sectors of 32 bytes, sector v = 8 x {A.half, B.half}; lane t writes the
-// 16-byte chunks t, 16+t, 32+t, 48+t, i.e. every store instruction covers 256 contiguous bytes.
-__device__ __forceinline__ void ba16_flush_period(const uint2 *buf, uint4 *gdst, int t)
+// Copy one staged period to global memory.  Lane t writes the 16-byte chunks t, 16+t, 32+t, 48+t
+// (sector-major order), so each store instruction covers 256 contiguous bytes.
+__device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gdst, int t)
 {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int c = q * 16 + t;
-        const int v = c >> 1, hh = c & 1;
-        const unsigned selw = (v & 16) ? 0x7632u : 0x5410u;
-        const uint2 *src = buf + (4 * hh) * BA16_STAGE_ROW + (v & 15);
-        const uint2 e0 = src[0], e1 = src[BA16_STAGE_ROW], e2 = src[2 * BA16_STAGE_ROW], e3 = src[3 * BA16_STAGE_ROW];
-        gdst[c] = make_uint4(ba_prmt(e0.x, e0.y, selw), ba_prmt(e1.x, e1.y, selw), ba_prmt(e2.x, e2.y, selw),
-                             ba_prmt(e3.x, e3.y, selw));
+        gdst[c] = *(const uint4 *)(buf + ba16_stage_word(c >> 2, c & 3));
     }
 }
 
@@ -132,11 +133,12 @@ __device__ __forceinline__ void ba16_flush_period(const uint2 *buf, uint4 *gdst,
 template <int COLS, bool MULTI>
 __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Params P)
 {
-    // row profiles: ring[group][i & (RING-1)] = 4 substitution bytes of the letter of row i
-    __shared__ unsigned ring[BA16_GROUPS][BA16_PROF_RING + 16];  // +16: the two groups of a warp hit disjoint banks
+    constexpr int NC = 2 * COLS;  // columns per lane
+    // row profiles: ring[group][pair][i & (RING-1)] = 4 substitution bytes of the letter of row i
+    __shared__ unsigned ring[BA16_GROUPS][2][BA16_PROF_RING + 8];
     __shared__ unsigned proftab[8];  // letter index -> {sub(R,1), sub(R,2), sub(R,3), sub(R,4)} as int8
-    __shared__ uint2 colbuf[BA16_GROUPS][8 * BA16_STAGE_ROW];  // staged column checkpoints of the period
-    __shared__ uint2 rowbuf[BA16_GROUPS][8 * BA16_STAGE_ROW];  // staged row checkpoint
+    __shared__ __align__(16) unsigned colbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged column checkpoints
+    __shared__ __align__(16) unsigned rowbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged row checkpoint
     const int let = P.sc->let;
     if (threadIdx.x < 8) {
         unsigned w = 0x80808080u;  // virtual row: -128 against everything
@@ -158,189 +160,222 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
     const int t = lane & 15;                       // lane inside the group
     const int grp = (threadIdx.x >> 4);            // group inside the CTA
     const int group_global = blockIdx.x * BA16_GROUPS + grp;
-    unsigned *myring = ring[grp];
-    uint2 *mycol = colbuf[grp];
-    uint2 *myrow = rowbuf[grp];
-    int32_t *bnd = P.bnd + (int64_t)group_global * P.bnd_stride;
+    unsigned *ringA = ring[grp][0], *ringB = ring[grp][1];
+    unsigned *colA = colbuf[grp][0], *colB = colbuf[grp][1];
+    unsigned *rowA = rowbuf[grp][0], *rowB = rowbuf[grp][1];
+    unsigned *bnd = (unsigned *)P.bnd + (int64_t)group_global * P.bnd_stride;
     constexpr int W = 32 * COLS;
     const unsigned FULL = 0xffffffffu;
-    const unsigned fixsel = (t == 0) ? 0x5410u : 0x7654u;  // lane 0: {boundary.lo, neighbour.lo}
 
     for (;;) {
-        // each warp takes two consecutive items (one per group)
+        // each warp takes four consecutive items: two (pairs A and B) per 16-lane group
         int it0 = 0;
-        if (lane == 0) it0 = atomicAdd(P.counter, 2);
+        if (lane == 0) it0 = atomicAdd(P.counter, 4);
         it0 = __shfl_sync(FULL, it0, 0);
         if (it0 >= P.n_items) break;
-        const int it = it0 + (lane >> 4);
-        const bool have = it < P.n_items;
-        WorkItem item;
-        item.pair = 0;
-        item.cols = COLS;
-        item.code_off = 0;
-        if (have) item = P.items[it];
-        const int p = item.pair;
-        int n = have ? P.ref_len[p] : 0, m = have ? P.qry_len[p] : 0;
-        if (have && (P.status[p] != 0 || !P.acgt_only[p])) n = 0;
-        const bool live = have && n > 0 && m > 0;
-        if (!live) {
-            n = 0;
-            m = 0;
+        const int itA = it0 + 2 * (lane >> 4), itB = itA + 1;
+        int nA = 0, mA = 0, nB = 0, mB = 0, pA = 0, pB = 0;
+        int64_t offA = 0, offB = 0;
+        bool liveA = false, liveB = false;
+        if (itA < P.n_items) {
+            const WorkItem item = P.items[itA];
+            pA = item.pair;
+            offA = item.code_off;
+            nA = P.ref_len[pA];
+            mA = P.qry_len[pA];
+            liveA = P.status[pA] == 0 && P.acgt_only[pA] && nA > 0 && mA > 0;
         }
-        const uint8_t *rptr = P.enc + (live ? P.ref_off[p] : 0);
-        const uint8_t *qptr = P.enc + (live ? P.qry_off[p] : 0);
+        if (itB < P.n_items) {
+            const WorkItem item = P.items[itB];
+            pB = item.pair;
+            offB = item.code_off;
+            nB = P.ref_len[pB];
+            mB = P.qry_len[pB];
+            liveB = P.status[pB] == 0 && P.acgt_only[pB] && nB > 0 && mB > 0;
+        }
+        if (!liveA) nA = mA = 0;
+        if (!liveB) nB = mB = 0;
+        const uint8_t *rA = P.enc + (liveA ? P.ref_off[pA] : 0), *qA = P.enc + (liveA ? P.qry_off[pA] : 0);
+        const uint8_t *rB = P.enc + (liveB ? P.ref_off[pB] : 0), *qB = P.enc + (liveB ? P.qry_off[pB] : 0);
         const int stride = P.stride;
-        const int npass = live ? (m + W - 1) / W : 0;
-        const int nsteps = live ? n + 31 : 0;
-        // loop bounds must be warp-uniform (shuffles): take the larger group
-        const int nsteps_w = max(nsteps, __shfl_xor_sync(FULL, nsteps, 16));
-        const int npass_w = MULTI ? max(npass, __shfl_xor_sync(FULL, npass, 16)) : 1;
-        const int64_t pass_bytes = ba16_pass_bytes(n, COLS);
-
+        const int npassA = liveA ? (mA + W - 1) / W : 0, npassB = liveB ? (mB + W - 1) / W : 0;
+        const int nstepsA = liveA ? nA + BA16_SKEW : 0, nstepsB = liveB ? nB + BA16_SKEW : 0;
+        // loop bounds must be warp-uniform (shuffles): take the largest of the four pairs
+        int nsteps_w = max(nstepsA, nstepsB), npass_w = max(npassA, npassB);
+        nsteps_w = max(nsteps_w, __shfl_xor_sync(FULL, nsteps_w, 16));
+        npass_w = MULTI ? max(npass_w, __shfl_xor_sync(FULL, npass_w, 16)) : 1;
+        const int64_t passbA = ba16_pass_bytes(nA, COLS), passbB = ba16_pass_bytes(nB, COLS);
+        const int jshiftA = mA - npassA * W, jshiftB = mB - npassB * W;
+        // rows staged between passes: only pairs that really have a next pass (bounds the scratch)
+        const int nbnd = max(npassA > 1 ? nA : 0, npassB > 1 ? nB : 0);
 
         for (int pass = 0; pass < npass_w; pass++) {
-            const bool pass_live = live && pass < npass;
-            const int jbase = pass * W;
-            const int jshift = m - npass * W;
+            const bool plA = liveA && pass < npassA, plB = liveB && pass < npassB;
             // ---- per-column constants: PRMT selectors (columns <= 0: sign-select => sub in {0,-1})
-            unsigned sel[COLS];
+            unsigned sel[NC];
 #pragma unroll
-            for (int k = 0; k < COLS; k++) {
-                const int jl = jshift + jbase + t * COLS + k + 1, jh = jl + 16 * COLS;
+            for (int k = 0; k < NC; k++) {
+                const int ja = jshiftA + pass * W + t * NC + k + 1, jb = jshiftB + pass * W + t * NC + k + 1;
                 unsigned nl = 0x88u, nh = 0xCC00u;  // virtual column: both bytes = sign of a profile byte
-                if (pass_live && jl >= 1) {
-                    const unsigned q = (unsigned)qptr[(int64_t)(jl - 1) * stride] - 1u;
+                if (plA && ja >= 1) {
+                    const unsigned q = (unsigned)qA[(int64_t)(ja - 1) * stride] - 1u;
                     nl = q | ((q | 8u) << 4);
                 }
-                if (pass_live && jh >= 1) {
-                    const unsigned q = 4u + (unsigned)qptr[(int64_t)(jh - 1) * stride] - 1u;
+                if (plB && jb >= 1) {
+                    const unsigned q = 4u + (unsigned)qB[(int64_t)(jb - 1) * stride] - 1u;
                     nh = (q << 8) | ((q | 8u) << 12);
                 }
                 sel[k] = nl | nh;
             }
-            // ---- (re)load the profile ring: rows -31..0 virtual, rows 1.. from the reference
-            for (int x = t; x < 32; x += 16) myring[(x - 31) & (BA16_PROF_RING - 1)] = 0x80808080u;
+            // ---- profile rings: rows -15..0 virtual, rows 1.. loaded in chunks inside the step loop
+            ringA[(t - 15) & (BA16_PROF_RING - 1)] = 0x80808080u;
+            ringB[(t - 15) & (BA16_PROF_RING - 1)] = 0x80808080u;
             __syncwarp();
 
-            unsigned Mu[COLS], Uu[COLS], Hu[COLS];
+            unsigned Mu[NC], Uu[NC], Hu[NC];
 #pragma unroll
-            for (int k = 0; k < COLS; k++) Mu[k] = Uu[k] = Hu[k] = 0;
+            for (int k = 0; k < NC; k++) Mu[k] = Uu[k] = Hu[k] = 0;
             unsigned outM = 0, outL = 0, outH = 0, sdiagH = 0;
             unsigned bmax = 0;  // running max of the current period
-            // per virtual thread: best value of this pass and the LAST period attaining it
+            // per lane (both pairs packed): best value of this pass and the LAST period attaining it
             unsigned vbest = pack16(1, 1);
             int per_lo = -1, per_hi = -1;
-            uint8_t *ck = P.arena + item.code_off + (int64_t)pass * pass_bytes;
-            uint4 *colck = (uint4 *)ck;                              // [period][64 chunks of 16 bytes]
-            uint4 *rowck = (uint4 *)(ck + ba16_colck_bytes(n));
+            uint4 *colckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA);
+            uint4 *rowckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA + ba16_colck_bytes(nA));
+            uint4 *colckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB);
+            uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB));
+            unsigned ro = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;  // byte offset of my row in the rings
 
-            // byte offsets of my two rows inside the profile ring, advanced by one entry per step
-            unsigned rolo = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;
-            unsigned rohi = (unsigned)((1 - t - 16) & (BA16_PROF_RING - 1)) * 4u;
-#pragma unroll 2
-            for (int s = 0; s < nsteps_w; s++) {
-                if ((s & (BA16_PROF_CHUNK - 1)) == 0) {
-                    // rows s+1 .. s+CHUNK enter the ring (lanes of the group share the load)
+            int stw[4];  // word offsets of my four staging chunks
+#pragma unroll
+            for (int c = 0; c < 4; c++) stw[c] = ba16_stage_word(t, c);
+            const int nper_w = (nsteps_w + BA16_PERIOD - 1) >> BA16_PSHIFT;
+            for (int e = 0; e < nper_w; e++) {
+                if ((e & (BA16_PROF_CHUNK / BA16_PERIOD - 1)) == 0) {
+                    // rows 8e+1 .. 8e+CHUNK enter the rings (lanes of the group share the load)
                     __syncwarp();
                     for (int x = t; x < BA16_PROF_CHUNK; x += 16) {
-                        const int i = s + 1 + x;
-                        unsigned w = 0x80808080u;
-                        if (pass_live && i <= n) w = proftab[rptr[(int64_t)(i - 1) * stride] & 7];
-                        myring[i & (BA16_PROF_RING - 1)] = w;
+                        const int i = 8 * e + 1 + x;
+                        unsigned wa = 0x80808080u, wb = 0x80808080u;
+                        if (plA && i <= nA) wa = proftab[rA[(int64_t)(i - 1) * stride] & 7];
+                        if (plB && i <= nB) wb = proftab[rB[(int64_t)(i - 1) * stride] & 7];
+                        ringA[i & (BA16_PROF_RING - 1)] = wa;
+                        ringB[i & (BA16_PROF_RING - 1)] = wb;
                     }
                     __syncwarp();
                 }
-                const int ilo = s + 1 - t;
-                const unsigned profA = *(const unsigned *)((const char *)myring + rolo);
-                const unsigned profB = *(const unsigned *)((const char *)myring + rohi);
-                rolo = (rolo + 4u) & (BA16_PROF_RING * 4u - 1u);
-                rohi = (rohi + 4u) & (BA16_PROF_RING * 4u - 1u);
+#pragma unroll
+                for (int j = 0; j < BA16_PERIOD; j++) {
+                    const int s = 8 * e + j;
+                const int i = s + 1 - t;
+                const unsigned profA = *(const unsigned *)((const char *)ringA + ro);
+                const unsigned profB = *(const unsigned *)((const char *)ringB + ro);
+                ro = (ro + 4u) & (BA16_PROF_RING * 4u - 1u);
 
-                // boundary column of the left neighbour strip (rotate inside the 16-lane group)
-                unsigned rM = __shfl_sync(FULL, outM, (t + 15) & 15, 16);
-                unsigned rL = __shfl_sync(FULL, outL, (t + 15) & 15, 16);
-                unsigned rH = __shfl_sync(FULL, outH, (t + 15) & 15, 16);
-                unsigned bM = 0, bL = 0, bH = 0;  // pass 0: DP column 0 is all zero for SW
-                if (MULTI && pass > 0) {  // warp-uniform
-                    if (t == 0 && ilo >= 1 && ilo <= n) {
-                        bM = (unsigned)bnd[3 * ilo + 0];
-                        bL = (unsigned)bnd[3 * ilo + 1];
-                        bH = (unsigned)bnd[3 * ilo + 2];
+                // boundary column of the left neighbour lane; lane 0: DP column 0 (all zero for SW)
+                // or the staged last column of the previous pass
+                unsigned rM = __shfl_up_sync(FULL, outM, 1, 16);
+                unsigned rL = __shfl_up_sync(FULL, outL, 1, 16);
+                unsigned rH = __shfl_up_sync(FULL, outH, 1, 16);
+                if (t == 0) {
+                    rM = rL = rH = 0;
+                    if (MULTI && pass > 0 && i >= 1 && i <= nbnd) {
+                        rM = bnd[3 * i + 0];
+                        rL = bnd[3 * i + 1];
+                        rH = bnd[3 * i + 2];
                     }
                 }
-                rM = ba_prmt(bM, rM, fixsel);
-                rL = ba_prmt(bL, rL, fixsel);
-                rH = ba_prmt(bH, rH, fixsel);
 
-                unsigned Ml = rM, Ll = rL, Hd = sdiagH;
+                // Three sweeps, each updating its array in place (no register rotation):
+                //  U from the previous row's (M, U); M from the previous row's H; then L along the
+                //  row and H = max3 for the next row's diagonal.
 #pragma unroll
-                for (int k = 0; k < COLS; k++) {
-                    const unsigned sub = ba_prmt(profA, profB, sel[k]);
-                    const unsigned Mn = __viaddmax_s16x2_relu(Hd, sub, erp);  // erp <= 0: same as max(.,0)
-                    const unsigned c1 = __vadd2(Uu[k], erp);
-                    const unsigned Un = __viaddmax_s16x2(Mu[k], goerp, c1);
-                    const unsigned c2 = __vadd2(Ll, eqp);
-                    const unsigned Ln = __viaddmax_s16x2(Ml, goeqp, c2);
-                    Hd = Hu[k];
-                    Hu[k] = __vimax3_s16x2(Mn, Un, Ln);
-                    Mu[k] = Mn;
-                    Uu[k] = Un;
-                    Ml = Mn;
-                    Ll = Ln;
+                for (int k = 0; k < NC; k++) Uu[k] = __viaddmax_s16x2(Mu[k], goerp, __vadd2(Uu[k], erp));
+                {
+                    unsigned Hd = sdiagH;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        const unsigned sub = ba_prmt(profA, profB, sel[k]);
+                        Mu[k] = __viaddmax_s16x2_relu(Hd, sub, erp);  // erp <= 0: same as max(.,0)
+                        Hd = Hu[k];
+                    }
+                }
+                unsigned Ml = rM, Ll = rL;
+                unsigned mc0 = 0, lc0 = 0;  // boundary column of my first strip
+#pragma unroll
+                for (int k = 0; k < NC; k++) {
+                    Ll = __viaddmax_s16x2(Ml, goeqp, __vadd2(Ll, eqp));
+                    Ml = Mu[k];
+                    Hu[k] = __vimax3_s16x2(Ml, Uu[k], Ll);
+                    if (k == COLS - 1) {
+                        mc0 = Ml;
+                        lc0 = Ll;
+                    }
                 }
 #pragma unroll
-                for (int k = 0; k + 1 < COLS; k += 2) bmax = __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
-                if (COLS & 1) bmax = __vmaxs2(bmax, Mu[COLS - 1]);
+                for (int k = 0; k + 1 < NC; k += 2) bmax = __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
                 sdiagH = rH;
-                outM = Mu[COLS - 1];
+                outM = Mu[NC - 1];
                 outL = Ll;
-                outH = Hu[COLS - 1];
+                outH = Hu[NC - 1];
 
-                // column checkpoint: (M, clamped L) of my last column, staged for this period
-                mycol[(s & 7) * BA16_STAGE_ROW + t] = make_uint2(outM, __vimax_s16x2_relu(outL, erp));
-                if (MULTI && pass_live && s < nsteps && t == 15 && pass + 1 < npass) {
-                    const int ihi = ilo - 16;
-                    if (ihi >= 1 && ihi <= n) {
-                        bnd[3 * ihi + 0] = hi16(outM) & 0xffff;
-                        bnd[3 * ihi + 1] = hi16(outL) & 0xffff;
-                        bnd[3 * ihi + 2] = hi16(outH) & 0xffff;
+                // column checkpoints (M, clamped L) of my two strips, staged per pair for this period
+                {
+                    const unsigned l0 = __vimax_s16x2_relu(lc0, erp), l1 = __vimax_s16x2_relu(outL, erp);
+                    const int w0 = stw[j >> 2] + (j & 3);        // strip 2t: chunks 0,1
+                    const int w1 = stw[2 + (j >> 2)] + (j & 3);  // strip 2t+1: chunks 2,3
+                    colA[w0] = ba_prmt(mc0, l0, 0x5410u);
+                    colB[w0] = ba_prmt(mc0, l0, 0x7632u);
+                    colA[w1] = ba_prmt(outM, l1, 0x5410u);
+                    colB[w1] = ba_prmt(outM, l1, 0x7632u);
+                }
+                if (MULTI && t == 15 && i >= 1 && i <= nbnd) {
+                    bnd[3 * i + 0] = outM;
+                    bnd[3 * i + 1] = outL;
+                    bnd[3 * i + 2] = outH;
+                }
+                }
+                // ---- end of the period: row checkpoint, flush both arrays, best-cell bookkeeping
+                {
+                    unsigned wa[4 * 4], wb[4 * 4];  // four chunks of four words per pair
+#pragma unroll
+                    for (int x = 0; x < 16; x++) wa[x] = wb[x] = 0;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        const unsigned u = __vimax_s16x2_relu(Uu[k], erp);
+                        const int x = (k >= COLS ? 8 + (k - COLS) : k);  // word inside my 16-word region
+                        wa[x] = ba_prmt(Mu[k], u, 0x5410u);
+                        wb[x] = ba_prmt(Mu[k], u, 0x7632u);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int w = ba16_stage_word(t, c);
+                        *(uint4 *)(rowA + w) = make_uint4(wa[4 * c], wa[4 * c + 1], wa[4 * c + 2], wa[4 * c + 3]);
+                        *(uint4 *)(rowB + w) = make_uint4(wb[4 * c], wb[4 * c + 1], wb[4 * c + 2], wb[4 * c + 3]);
                     }
                 }
-                if ((s & (BA16_PERIOD - 1)) == BA16_PERIOD - 1) {
-                    const int e = s >> BA16_PSHIFT;
-#pragma unroll
-                    for (int k = 0; k < COLS; k++)
-                        myrow[k * BA16_STAGE_ROW + t] = make_uint2(Mu[k], __vimax_s16x2_relu(Uu[k], erp));
-                    __syncwarp();
-                    if (pass_live && (e << BA16_PSHIFT) < nsteps) ba16_flush_period(mycol, colck + (int64_t)e * 64, t);
-                    if (pass_live && s < nsteps) ba16_flush_period(myrow, rowck + (int64_t)e * 64, t);
-                    __syncwarp();
-                    // best tracking at period granularity ('>=' keeps the LAST period)
-                    bool ph, pl;
-                    vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
-                    if (pl) per_lo = e;
-                    if (ph) per_hi = e;
-                    bmax = 0;
-                }
-            }
-            // the tail period (a partial one): its column checkpoints, and the best cell
-            __syncwarp();
-            if ((nsteps_w & (BA16_PERIOD - 1)) != 0 && pass_live &&
-                ((nsteps_w >> BA16_PSHIFT) << BA16_PSHIFT) < nsteps)
-                ba16_flush_period(mycol, colck + (int64_t)(nsteps_w >> BA16_PSHIFT) * 64, t);
-            if (nsteps_w & (BA16_PERIOD - 1)) {
-                const int e = nsteps_w >> BA16_PSHIFT;
+                __syncwarp();
+                if (plA && (e << BA16_PSHIFT) < nstepsA) ba16_flush_period(colA, colckA + (int64_t)e * 64, t);
+                if (plB && (e << BA16_PSHIFT) < nstepsB) ba16_flush_period(colB, colckB + (int64_t)e * 64, t);
+                if (plA && 8 * e + 7 < nstepsA) ba16_flush_period(rowA, rowckA + (int64_t)e * 64, t);
+                if (plB && 8 * e + 7 < nstepsB) ba16_flush_period(rowB, rowckB + (int64_t)e * 64, t);
+                __syncwarp();
+                // best tracking at period granularity ('>=' keeps the LAST period)
                 bool ph, pl;
                 vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
                 if (pl) per_lo = e;
                 if (ph) per_hi = e;
+                bmax = 0;
             }
-            if (pass_live) {
-                uint2 *cand = (uint2 *)(P.arena + item.code_off + (int64_t)npass * pass_bytes) + pass * 16 + t;
-                *cand = make_uint2(vbest, pack16(per_lo, per_hi));
+            if (plA) {
+                int2 *cand = (int2 *)(P.arena + offA + (int64_t)npassA * passbA) + pass * 16 + t;
+                *cand = make_int2(lo16(vbest), per_lo);
+            }
+            if (plB) {
+                int2 *cand = (int2 *)(P.arena + offB + (int64_t)npassB * passbB) + pass * 16 + t;
+                *cand = make_int2(hi16(vbest), per_hi);
             }
             __syncwarp();
         }
-
     }
 }

@@ -42,22 +42,26 @@ struct CkView {
     const uint8_t *base;
     int n, m, cols, npass, jshift;
     int64_t pass_bytes, colck_bytes;
-    // (M, clamped L) of the last column of global strip g at row r: sector (period, v), step slot
+    // Strip g (global index: pass*32 + strip) belongs to lane (g & 31) >> 1 of the fill, which
+    // handles row i at step i-1+lane.
+    __device__ __forceinline__ static int lane_of(int g) { return (g & 31) >> 1; }
+    // (M, clamped L) of the last column of strip g at row r: sector (period, strip), step slot
     __device__ __forceinline__ void col_ml(int g, int r, int &M, int &L) const
     {
-        const int pass = g >> 5, v = g & 31;
-        const int st = r - 1 + v;
+        const int pass = g >> 5;
+        const int st = r - 1 + lane_of(g);
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
-                                         ((int64_t)((st >> BA16_PSHIFT) * 32 + v) * 8 + (st & (BA16_PERIOD - 1))) * 4);
+                                         ((int64_t)((st >> BA16_PSHIFT) * 32 + (g & 31)) * 8 +
+                                          (st & (BA16_PERIOD - 1))) * 4);
         M = p[0];
         L = p[1];
     }
-    // (M, clamped U) of column k of global strip g at its checkpoint row of period e
+    // (M, clamped U) of column k of strip g at its checkpoint row of period e
     __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const
     {
-        const int pass = g >> 5, v = g & 31;
+        const int pass = g >> 5;
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
-                                         ((int64_t)(e * 32 + v) * 8 + k) * 4);
+                                         ((int64_t)(e * 32 + (g & 31)) * 8 + k) * 4);
         M = p[0];
         U = p[1];
     }
@@ -74,7 +78,7 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                              uint8_t *tile, int want, int &fi, int &fj)
 {
-    const int v = g & 31;
+    const int v = CkView::lane_of(g);
     const int rt = max(BA16_PERIOD * e - v, 0); // top boundary row (0 = DP border)
     const int c0 = ck.left_col(g);
     const int cL = max(c0, 0);                  // effective left boundary column (0 = DP border)
@@ -99,7 +103,7 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
     int leftU = 0;                              // U at (row, cL), advanced row by row
     const int gl = g - 1;                       // strip whose last column is cL
     if (cL > 0) {
-        const int vl = gl & 31;
+        const int vl = CkView::lane_of(gl);
         // U of column cL is checkpointed (with M) only at strip gl's own rows; start from the
         // closest one at or above rt and run U's recurrence down the column on the stored M.
         int r0 = rt - ((rt + vl) & (BA16_PERIOD - 1));  // largest row <= rt with (r0 + vl) % PERIOD == 0
@@ -247,22 +251,20 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, 4) ba_trace16_kernel(Trace16
     // ---- start cell (SW): the last cell in row-major order holding the table maximum
     int i = 0, j = 0, cur = 0;
     if (n > 0 && m > 0) {
-        const uint2 *cand = (const uint2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
+        const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
         int Smax = 0;
         for (int x = 0; x < ck.npass * 16; x++) {
-            const uint2 c = cand[x];
-            if (lo16(c.y) >= 0) Smax = max(Smax, lo16(c.x));
-            if (hi16(c.y) >= 0) Smax = max(Smax, hi16(c.x));
+            const int2 c = cand[x];
+            if (c.y >= 0) Smax = max(Smax, c.x);
         }
         if (Smax > 0) {
             for (int x = 0; x < ck.npass * 16; x++) {
-                const uint2 c = cand[x];
-                for (int h = 0; h < 2; h++) {
-                    const int e = h ? hi16(c.y) : lo16(c.y);
-                    const int sv = h ? hi16(c.x) : lo16(c.x);
-                    if (e < 0 || sv != Smax) continue;
-                    const int g = (x >> 4) * 32 + (x & 15) + 16 * h;
-                    const int v = g & 31;
+                const int2 c = cand[x];
+                if (c.y < 0 || c.x != Smax) continue;
+                const int e = c.y;
+                for (int h = 0; h < 2; h++) {  // the lane's two strips
+                    const int g = (x >> 4) * 32 + 2 * (x & 15) + h;
+                    const int v = CkView::lane_of(g);
                     const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
                     const int clast = ck.left_col(g) + ck.cols;
                     if (rlast < 1 || clast < 1) continue;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, 4) ba_trace16_kernel(Trace16
     while (i > 0 && j > 0 && !bad) {
         if (KIND == KIND_SW && cur == 0) break;
         const int g = ck.strip_of(j);
-        const int v = g & 31;
+        const int v = CkView::lane_of(g);
         const int e = (i + v - 1) >> BA16_PSHIFT;
         const int rt = max(BA16_PERIOD * e - v, 0);
         const int c0 = max(ck.left_col(g), 0);

@@ -211,6 +211,7 @@ inline T exchange(T v, int src_lane)
 #define __restrict__
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 #define threadIdx (emu::g_threadIdx())
 #define blockIdx (emu::g_blockIdx())
 #define blockDim (emu::g_blockDim())
@@ -223,6 +224,10 @@ struct uint4 {
     unsigned x, y, z, w;
 };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+struct int2 {
+    int x, y;
+};
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 using std::max;
