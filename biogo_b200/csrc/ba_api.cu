@@ -108,6 +108,8 @@ struct ba_ctx {
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
     DevBuf flags, slot_off, slot_cap, slots, seg_clip;
     int64_t opt_force_path = 0, opt_slot_cap = 0;
+    int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
+    std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
 };
 
@@ -227,6 +229,14 @@ static inline double now_s()
 
 int64_t arena_budget(ba_ctx *ctx, int64_t &cap)
 {
+    if (ctx->opt_arena_bytes > 0) {
+        cap = ctx->opt_arena_bytes;
+        return 0;
+    }
+    if (ctx->cached_arena_cap > 0) {
+        cap = ctx->cached_arena_cap;
+        return 0;
+    }
     size_t free_b = 0, total_b = 0;
     cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
     if (e != cudaSuccess) return -1;
@@ -236,7 +246,23 @@ int64_t arena_budget(ba_ctx *ctx, int64_t &cap)
         const int64_t lim = 48LL << 30;
         if (cap > lim) cap = lim;
     }
+    ctx->cached_arena_cap = cap;
     return 0;
+}
+
+template <typename Fn>
+int cached_occupancy(ba_ctx *ctx, Fn fn, int threads, int &occ)
+{
+    for (auto &e : ctx->occ_cache)
+        if (e.first == (const void *)fn) {
+            occ = e.second;
+            return BA_OK;
+        }
+    occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0));
+    if (occ < 1) occ = 1;
+    ctx->occ_cache.push_back({(const void *)fn, occ});
+    return BA_OK;
 }
 
 // D2H of one wave's compact segments + per-item (count, base), then the host-side scatter of
@@ -346,8 +372,7 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
         for (auto &L : w.launches) {
             FillFn fn = pick_fill(kind, affine, L.cols);
             int occ = 1;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BA_FILL_WARPS * 32, 0));
-            if (occ < 1) occ = 1;
+            if ((rc = cached_occupancy(ctx, fn, BA_FILL_WARPS * 32, occ)) != BA_OK) return rc;
             int64_t blocks = (L.count + BA_FILL_WARPS - 1) / BA_FILL_WARPS;
             int64_t maxb = (int64_t)ctx->sm_count * occ;
             if (blocks > maxb) blocks = maxb;
@@ -559,8 +584,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
             const bool multi = (L.cols == BA_MAX_COLS) && w.max_n_multipass > 0;
             Fill16Fn fn = pick_fill16(L.cols, multi);
             int occ = 1;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BA16_WARPS * 32, 0));
-            if (occ < 1) occ = 1;
+            if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
             int64_t blocks = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
             int64_t maxb = (int64_t)ctx->sm_count * occ;
             if (blocks > maxb) blocks = maxb;

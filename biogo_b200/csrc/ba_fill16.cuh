@@ -108,23 +108,31 @@ __host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m)
 // so the last strip ends exactly at column m and the padding falls on columns <= 0, which
 // behave as the all-zero SW border (substitution 0 or -1 keeps M at 0 there).
 
-// Staging buffers (shared memory): per pair one period = 32 sectors of 8 words; lane t owns the
-// 16 words of its two strips (2t, 2t+1) = four 16-byte chunks, stored rotated by t so that both
-// the per-lane stores and the chunk-ordered flush loads are (nearly) bank-conflict free.
-#define BA16_STAGE_WORDS (32 * 8)
+// Staging buffers (shared memory): per pair one period = 32 sectors of 8 words = 64 chunks of
+// 16 bytes.  Lane t owns the four chunks of its two strips (2t: chunks 0,1; 2t+1: chunks 2,3),
+// i.e. the global chunks 4t .. 4t+3.  Layout: chunk plane c (padded to 72 words) x lane x 4 words,
+// so the 16-byte row stores, the per-step 4-byte column stores and the chunk-ordered 16-byte
+// flush loads are all bank-conflict free; the column stores additionally rotate the word inside
+// the chunk by one for lanes 8..15 (undone at flush time, where that is a compile-time fact).
+#define BA16_STAGE_PLANE 72
+#define BA16_STAGE_WORDS (4 * BA16_STAGE_PLANE)
 __device__ __forceinline__ int ba16_stage_word(int t, int chunk /*0..3*/)
 {
-    return 16 * t + 4 * ((chunk + t) & 3);
+    return chunk * BA16_STAGE_PLANE + 4 * t;
 }
 
 // Copy one staged period to global memory.  Lane t writes the 16-byte chunks t, 16+t, 32+t, 48+t
 // (sector-major order), so each store instruction covers 256 contiguous bytes.
+// ROTATED: the buffer was filled by the per-step column stores (word rotation for lanes >= 8).
+template <bool ROTATED>
 __device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gdst, int t)
 {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int c = q * 16 + t;
-        gdst[c] = *(const uint4 *)(buf + ba16_stage_word(c >> 2, c & 3));
+        const int c = q * 16 + t;               // global chunk: owner lane c>>2 (= 4q + t/4), its chunk c&3
+        uint4 v = *(const uint4 *)(buf + ba16_stage_word(c >> 2, c & 3));
+        if (ROTATED && q >= 2) v = make_uint4(v.y, v.z, v.w, v.x);  // owner lane >= 8
+        gdst[c] = v;
     }
 }
 
@@ -246,9 +254,13 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
             uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB));
             unsigned ro = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;  // byte offset of my row in the rings
 
-            int stw[4];  // word offsets of my four staging chunks
+            // staging addresses of my column-checkpoint words: [half of the period][word], pair A,
+            // strip 2t; strip 2t+1 is two chunk planes further, pair B one buffer further
+            unsigned *cst[2][4];
 #pragma unroll
-            for (int c = 0; c < 4; c++) stw[c] = ba16_stage_word(t, c);
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) cst[c][jj] = colA + ba16_stage_word(t, c) + ((jj + (t >> 3)) & 3);
             const int nper_w = (nsteps_w + BA16_PERIOD - 1) >> BA16_PSHIFT;
             for (int e = 0; e < nper_w; e++) {
                 if ((e & (BA16_PROF_CHUNK / BA16_PERIOD - 1)) == 0) {
@@ -322,12 +334,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                 // column checkpoints (M, clamped L) of my two strips, staged per pair for this period
                 {
                     const unsigned l0 = __vimax_s16x2_relu(lc0, erp), l1 = __vimax_s16x2_relu(outL, erp);
-                    const int w0 = stw[j >> 2] + (j & 3);        // strip 2t: chunks 0,1
-                    const int w1 = stw[2 + (j >> 2)] + (j & 3);  // strip 2t+1: chunks 2,3
-                    colA[w0] = ba_prmt(mc0, l0, 0x5410u);
-                    colB[w0] = ba_prmt(mc0, l0, 0x7632u);
-                    colA[w1] = ba_prmt(outM, l1, 0x5410u);
-                    colB[w1] = ba_prmt(outM, l1, 0x7632u);
+                    unsigned *w = cst[j >> 2][j & 3];
+                    w[0] = ba_prmt(mc0, l0, 0x5410u);
+                    w[BA16_STAGE_WORDS] = ba_prmt(mc0, l0, 0x7632u);
+                    w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, l1, 0x5410u);
+                    w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, l1, 0x7632u);
                 }
                 if (MULTI && t == 15 && i >= 1 && i <= nbnd) {
                     bnd[3 * i + 0] = outM;
@@ -355,10 +366,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     }
                 }
                 __syncwarp();
-                if (plA && (e << BA16_PSHIFT) < nstepsA) ba16_flush_period(colA, colckA + (int64_t)e * 64, t);
-                if (plB && (e << BA16_PSHIFT) < nstepsB) ba16_flush_period(colB, colckB + (int64_t)e * 64, t);
-                if (plA && 8 * e + 7 < nstepsA) ba16_flush_period(rowA, rowckA + (int64_t)e * 64, t);
-                if (plB && 8 * e + 7 < nstepsB) ba16_flush_period(rowB, rowckB + (int64_t)e * 64, t);
+                if (plA && (e << BA16_PSHIFT) < nstepsA) ba16_flush_period<true>(colA, colckA + (int64_t)e * 64, t);
+                if (plB && (e << BA16_PSHIFT) < nstepsB) ba16_flush_period<true>(colB, colckB + (int64_t)e * 64, t);
+                if (plA && 8 * e + 7 < nstepsA) ba16_flush_period<false>(rowA, rowckA + (int64_t)e * 64, t);
+                if (plB && 8 * e + 7 < nstepsB) ba16_flush_period<false>(rowB, rowckB + (int64_t)e * 64, t);
                 __syncwarp();
                 // best tracking at period granularity ('>=' keeps the LAST period)
                 bool ph, pl;
