@@ -191,7 +191,7 @@ def main():
 
     pairs = args.pairs_per_gpu or DEFAULT_PAIRS[args.config]
     w = synth.config(args.config, pairs, shard=rank)
-    ctx = _lib.Context(local_rank)
+    ctx = _lib.Context(local_rank, os.environ.get("BA_LIB_PATH") or None)  # override: kernel-variant experiments
     ctx.set_scoring(w.kind, w.affine, np.array(w.matrix, np.int64).reshape(-1), len(w.matrix), w.alpha.Len(),
                     w.gap_open if w.affine else 0, w.alpha.LetterIndex())
 

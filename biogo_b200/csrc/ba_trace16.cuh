@@ -17,6 +17,9 @@
 #include "ba_walk.cuh"
 
 #define BA_TRACE_THREADS 128
+#ifndef BA_TRACE_MINB
+#define BA_TRACE_MINB 4   // resident CTAs per SM the register allocation is tuned for
+#endif
 #define BA_TILE_ROWS BA16_PERIOD
 
 struct Trace16Params {
@@ -191,7 +194,7 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(BA_TRACE_THREADS, 4) ba_trace16_kernel(Trace16Params P)
+__global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_kernel(Trace16Params P)
 {
     __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
     __shared__ int S[BA_MAX_LET * BA_MAX_LET];
