@@ -463,50 +463,94 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
 
 // ---- path B: packed 16-bit DPX fill + checkpointed tile traceback (SWAffine, DNA-like) ------
 typedef void (*Fill16Fn)(Fill16Params);
-template <bool MULTI>
-Fill16Fn pick_fill16_m(int cols)
+template <int KIND, bool MULTI, bool GSUB>
+Fill16Fn pick_fill16_c(int cols)
 {
     switch (cols) {
-    case 1: return ba_fill16_sw_kernel<1, MULTI>;
-    case 2: return ba_fill16_sw_kernel<2, MULTI>;
-    case 3: return ba_fill16_sw_kernel<3, MULTI>;
-    case 4: return ba_fill16_sw_kernel<4, MULTI>;
-    case 5: return ba_fill16_sw_kernel<5, MULTI>;
-    case 6: return ba_fill16_sw_kernel<6, MULTI>;
-    case 7: return ba_fill16_sw_kernel<7, MULTI>;
-    default: return ba_fill16_sw_kernel<8, MULTI>;
+    case 1: return ba_fill16_kernel<KIND, 1, MULTI, GSUB>;
+    case 2: return ba_fill16_kernel<KIND, 2, MULTI, GSUB>;
+    case 3: return ba_fill16_kernel<KIND, 3, MULTI, GSUB>;
+    case 4: return ba_fill16_kernel<KIND, 4, MULTI, GSUB>;
+    case 5: return ba_fill16_kernel<KIND, 5, MULTI, GSUB>;
+    case 6: return ba_fill16_kernel<KIND, 6, MULTI, GSUB>;
+    case 7: return ba_fill16_kernel<KIND, 7, MULTI, GSUB>;
+    default: return ba_fill16_kernel<KIND, 8, MULTI, GSUB>;
     }
 }
-Fill16Fn pick_fill16(int cols, bool multi)
+template <int KIND>
+Fill16Fn pick_fill16_k(int cols, bool multi, bool gsub)
 {
-    // only the widest class can need more than one pass
-    if (multi && cols == BA_MAX_COLS) return ba_fill16_sw_kernel<BA_MAX_COLS, true>;
-    return pick_fill16_m<false>(cols);
+    if (gsub) return multi ? pick_fill16_c<KIND, true, true>(cols) : pick_fill16_c<KIND, false, true>(cols);
+    return multi ? pick_fill16_c<KIND, true, false>(cols) : pick_fill16_c<KIND, false, false>(cols);
+}
+Fill16Fn pick_fill16(int kind, int cols, bool multi, bool gsub)
+{
+    if (kind == KIND_SW) return pick_fill16_k<KIND_SW>(cols, multi, gsub);
+    if (kind == KIND_NW) return pick_fill16_k<KIND_NW>(cols, multi, gsub);
+    return pick_fill16_k<KIND_FIT>(cols, multi, gsub);
+}
+typedef void (*Trace16Fn)(Trace16Params);
+Trace16Fn pick_trace16(int kind)
+{
+    if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW>;
+    if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW>;
+    return ba_trace16_kernel<KIND_FIT>;
 }
 
-// Scoring-level eligibility of the packed path (conditions C1..C3 of ba_fill16.cuh).
-bool fast16_scoring_ok(const DeviceScoring &s, int &maxsub)
+// Scoring-level eligibility of the packed 16-bit path (ba_fill16.cuh):
+//   affine gaps; uniform gap entries over the non-gap letters (C1); for SW additionally
+//   non-positive gaps and go + gap + max(sub) < 0 (C2).  `gsub`: the alphabet is not the
+//   5-letter gapped nucleotide one, so substitution scores come from shared-memory tables
+//   instead of PRMT profiles.  maxsub / maxabs feed the per-pair 16-bit range checks.
+struct Fast16 {
+    bool ok = false, gsub = false;
+    int maxsub = 0, maxabs = 0;
+};
+Fast16 fast16_scoring(const DeviceScoring &s)
 {
-    if (s.kind != KIND_SW || !s.affine || s.let < 5) return false;
+    Fast16 f;
+    if (!s.affine || s.let < 2 || s.let > BA_MAX_LET) return f;
+    f.gsub = (s.let != 5);
     const int er = s.la[1 * s.let], eq = s.la[1];
-    maxsub = -1000000;
-    for (int a = 1; a <= 4; a++) {
-        if (s.la[a * s.let] != er || s.la[a] != eq) return false;
-        for (int b = 1; b <= 4; b++) {
+    int maxsub = -1000000, maxabs = 0;
+    for (int a = 1; a < s.let; a++) {
+        if (s.la[a * s.let] != er || s.la[a] != eq) return f;
+        for (int b = 1; b < s.let; b++) {
             const int v = s.la[a * s.let + b];
-            if (v < -127 || v > 127) return false;
-            if (v > maxsub) maxsub = v;
+            if (v < -127 || v > 127) return f;
+            maxsub = std::max(maxsub, v);
+            maxabs = std::max(maxabs, v < 0 ? -v : v);
         }
     }
-    if (er > 0 || eq > 0 || er < -127 || eq < -127) return false;
-    if (s.gap_open + er + maxsub >= 0 || s.gap_open + eq + maxsub >= 0) return false;
-    if (s.gap_open + er < -4000 || s.gap_open + eq < -4000) return false;
-    if (maxsub <= 0) return false;
+    if (er < -127 || er > 127 || eq < -127 || eq > 127) return f;
+    if (s.gap_open < -4000 || s.gap_open > 4000) return f;
+    maxabs = std::max(maxabs, std::max(er < 0 ? -er : er, eq < 0 ? -eq : eq));
+    if (s.kind == KIND_SW) {
+        if (er > 0 || eq > 0 || maxsub <= 0) return f;
+        if (s.gap_open + er + maxsub >= 0 || s.gap_open + eq + maxsub >= 0) return f;
+    }
+    f.maxsub = maxsub;
+    f.maxabs = maxabs;
+    f.ok = true;
+    return f;
+}
+// Per-pair 16-bit range check.
+bool fast16_pair_ok(const DeviceScoring &s, const Fast16 &f, int n, int m)
+{
+    const int64_t lo = std::min(n, m), hi = std::max(n, m);
+    if (lo <= 0 || n >= (1 << 19)) return false;
+    if (lo * std::max(f.maxsub, 0) >= 30000) return false;
+    if (s.kind != KIND_SW) {
+        const int64_t ago = s.gap_open < 0 ? -(int64_t)s.gap_open : s.gap_open;
+        if ((hi + 3) * f.maxabs + 2 * ago > 14000) return false;
+    }
     return true;
 }
 
-int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vector<int32_t> &overflow)
+int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsub, std::vector<int32_t> &overflow)
 {
+    const int kind = ctx->h_sc.kind;
+    const int flag_mask = gsub ? 2 : 1;
     if (nids == 0) return BA_OK;
     cudaStream_t st = B.st;
     int rc;
@@ -525,7 +569,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         return BA_ERR_NOMEM;
     }
     const double tp1 = now_s();
-    build_plan(ids, nids, B.h_ref_len, B.h_qry_len, KIND_SW, 1, true, arena_cap, plan);
+    build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, 1, true, arena_cap, plan);
     BA_TSEC("plan16 pinned_get", tp0);
     BA_TSEC("plan16 build", tp1);
     B.host_s += now_s() - tp0;
@@ -581,8 +625,8 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         CK(cudaEventRecord(ctx->ev[4], st));
         int li = 0;
         for (auto &L : w.launches) {
-            const bool multi = (L.cols == BA_MAX_COLS) && w.max_n_multipass > 0;
-            Fill16Fn fn = pick_fill16(L.cols, multi);
+            const bool multi = w.max_n_multipass > 0;
+            Fill16Fn fn = pick_fill16(kind, L.cols, multi, gsub);
             int occ = 1;
             if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
             int64_t blocks = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
@@ -603,6 +647,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
             fp.qry_len = B.d_qry_len;
             fp.status = B.d_status;
             fp.acgt_only = (const uint8_t *)ctx->flags.p;
+            fp.flag_mask = flag_mask;
             fp.items = d_items + (L.first - w.first);
             fp.n_items = (int)L.count;
             fp.counter = (int *)ctx->counters.p + (li++ % 64);
@@ -629,6 +674,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         tp.qry_len = B.d_qry_len;
         tp.status = B.d_status;
         tp.acgt_only = (const uint8_t *)ctx->flags.p;
+        tp.flag_mask = flag_mask;
         tp.items = d_items;
         tp.n_items = (int)w.count;
         tp.arena = (const uint8_t *)ctx->arena.p;
@@ -638,7 +684,8 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, std::vec
         tp.slot_cap = (const int32_t *)ctx->slot_cap.p;
         tp.slots = (int32_t *)ctx->slots.p;
         const unsigned tblocks = (unsigned)((w.count + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
-        BA_LAUNCH(ba_trace16_kernel<KIND_SW>, tblocks, BA_TRACE_THREADS, st, tp);
+        Trace16Fn tfn = pick_trace16(kind);
+        BA_LAUNCH(tfn, tblocks, BA_TRACE_THREADS, st, tp);
         const unsigned cblocks = (unsigned)((w.count + 255) / 256);
         BA_LAUNCH(ba_clip_counts_kernel, cblocks, 256, st, (const int32_t *)ctx->seg_count.p,
                   (const int32_t *)ctx->slot_cap.p, (int32_t *)ctx->seg_clip.p, (int)w.count);
@@ -728,8 +775,8 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
     B.d_status = (int32_t *)ctx->status.p;
     B.d_start = (PairStart *)ctx->start.p;
     int64_t *d_err_pos = (int64_t *)ctx->err_pos.p;
-    int maxsub = 0;
-    const bool fast16 = ctx->opt_force_path != 1 && fast16_scoring_ok(ctx->h_sc, maxsub);
+    const Fast16 f16 = fast16_scoring(ctx->h_sc);
+    const bool fast16 = ctx->opt_force_path != 1 && f16.ok;
     if (letters_bytes > 0) {
         int64_t blocks = (letters_bytes / 16 + 255) / 256;
         if (blocks < 1) blocks = 1;
@@ -763,14 +810,13 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         std::vector<int32_t> fast;
         fast.reserve((size_t)n);
         for (int64_t p = 0; p < n; p++) {
-            const int64_t lo = std::min(h_ref_len[p], h_qry_len[p]);
-            const bool ok = lo > 0 && lo * maxsub < 32000 && h_ref_len[p] < (1 << 19);
+            const bool ok = fast16_pair_ok(ctx->h_sc, f16, h_ref_len[p], h_qry_len[p]);
             (ok ? fast : slow).push_back((int32_t)p);
         }
         BA_TSEC("partition", ts0);
         B.host_s += now_s() - ts0;
         const size_t nslow0 = slow.size();
-        if ((rc = run_path16(ctx, B, fast.data(), (int64_t)fast.size(), slow)) != BA_OK) return rc;
+        if ((rc = run_path16(ctx, B, fast.data(), (int64_t)fast.size(), f16.gsub, slow)) != BA_OK) return rc;
         out->pairs_fast16 = (int64_t)fast.size() - (int64_t)(slow.size() - nslow0);
         if ((rc = run_path32(ctx, B, slow.data(), (int64_t)slow.size())) != BA_OK) return rc;
     } else {

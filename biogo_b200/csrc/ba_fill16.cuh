@@ -1,4 +1,4 @@
-// ba_fill16.cuh -- packed 16-bit DPX fill for SWAffine with checkpointed traceback.
+// ba_fill16.cuh -- packed 16-bit DPX fill for the affine aligners with checkpointed traceback.
 //
 // Why a second fill kernel: ba_fill32 derives every cell's exact tie-break code, which costs
 // ~50 issue slots per cell and makes it ALU-issue bound (profiles/r01_fill32_ncu_summary.txt).
@@ -37,6 +37,7 @@
 #define BA16_PSHIFT 3
 #define BA16_GROUPS (2 * BA16_WARPS) // 16-lane groups per CTA (two pairs each)
 #define BA16_SKEW 15                 // steps of systolic skew: nsteps = n + BA16_SKEW
+#define BA16_NEG (-20000)            // "minus infinity" of the NW/Fitted kernels (finite values stay above -14000)
 
 struct Fill16Params {
     const uint8_t *enc;
@@ -46,7 +47,8 @@ struct Fill16Params {
     const int64_t *qry_off;
     const int32_t *qry_len;
     const int32_t *status;
-    const uint8_t *acgt_only;  // per pair: letters are all alphabet indices 1..4 (else: exact path)
+    const uint8_t *acgt_only;  // per pair letter flags: bit0 = all indices in 1..4, bit1 = no index 0
+    int flag_mask;             // which of those bits this launch requires (else: exact path)
     const WorkItem *items;
     int n_items;
     int *counter;
@@ -138,31 +140,48 @@ __device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gd
 
 // MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
 // inter-pass boundary code is compiled out of the common single-pass instance).
-template <int COLS, bool MULTI>
-__global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Params P)
+// KIND: KIND_SW (right-aligned columns, zero borders, clamps, best-cell candidates) or KIND_NW /
+// KIND_FIT (left-aligned, -inf/gap borders, no clamps).  GSUB: substitution scores from two
+// shared-memory tables (any alphabet, e.g. Protein) instead of the 4-letter PRMT profiles.
+template <int KIND, int COLS, bool MULTI, bool GSUB>
+__global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params P)
 {
     constexpr int NC = 2 * COLS;  // columns per lane
     // row profiles: ring[group][pair][i & (RING-1)] = 4 substitution bytes of the letter of row i
     __shared__ unsigned ring[BA16_GROUPS][2][BA16_PROF_RING + 8];
-    __shared__ unsigned proftab[8];  // letter index -> {sub(R,1), sub(R,2), sub(R,3), sub(R,4)} as int8
+    __shared__ unsigned proftab[BA_MAX_LET + 1];  // PRMT: letter -> 4 sub bytes; GSUB: letter -> row byte offset
+    __shared__ unsigned subA[GSUB ? (BA_MAX_LET + 1) * BA_MAX_LET : 1];  // GSUB: sub & 0xffff  (pair A half)
+    __shared__ unsigned subB[GSUB ? (BA_MAX_LET + 1) * BA_MAX_LET : 1];  // GSUB: sub << 16     (pair B half)
     __shared__ __align__(16) unsigned colbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged column checkpoints
     __shared__ __align__(16) unsigned rowbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged row checkpoint
     const int let = P.sc->let;
-    if (threadIdx.x < 8) {
-        unsigned w = 0x80808080u;  // virtual row: -128 against everything
-        const int R = threadIdx.x;
-        if (R >= 1 && R <= 4 && R < let) {
-            w = 0;
-            for (int q = 1; q <= 4; q++) w |= ((unsigned)(P.sc->la[R * let + q]) & 0xffu) << (8 * (q - 1));
+    if (!GSUB) {
+        if (threadIdx.x < 8) {
+            unsigned w = 0x80808080u;  // virtual row: -128 against everything
+            const int R = threadIdx.x;
+            if (R >= 1 && R <= 4 && R < let) {
+                w = 0;
+                for (int q = 1; q <= 4; q++) w |= ((unsigned)(P.sc->la[R * let + q]) & 0xffu) << (8 * (q - 1));
+            }
+            proftab[threadIdx.x] = w;
         }
-        proftab[threadIdx.x] = w;
+    } else {
+        // row `let` is the virtual letter: -128 against everything
+        for (int x = threadIdx.x; x < (let + 1) * let; x += blockDim.x) {
+            const int v = (x < let * let) ? P.sc->la[x] : -128;
+            subA[x] = (unsigned)v & 0xffffu;
+            subB[x] = (unsigned)v << 16;
+        }
+        for (int x = threadIdx.x; x <= BA_MAX_LET; x += blockDim.x) proftab[x] = (unsigned)(min(x, let) * let * 4);
     }
+    const unsigned VROW = GSUB ? (unsigned)(let * let * 4) : 0x80808080u;  // ring entry of a virtual row
     __syncthreads();
     const int er = P.sc->la[1 * let];  // C1: identical for letters 1..4
     const int eq = P.sc->la[1];
     const int go = P.sc->gap_open;
     const unsigned erp = pack16(er, er), eqp = pack16(eq, eq);
     const unsigned goerp = pack16(go + er, go + er), goeqp = pack16(go + eq, go + eq);
+    const unsigned NEGP = pack16(BA16_NEG, BA16_NEG);
 
     const int lane = threadIdx.x & 31;
     const int t = lane & 15;                       // lane inside the group
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
             offA = item.code_off;
             nA = P.ref_len[pA];
             mA = P.qry_len[pA];
-            liveA = P.status[pA] == 0 && P.acgt_only[pA] && nA > 0 && mA > 0;
+            liveA = P.status[pA] == 0 && (P.acgt_only[pA] & P.flag_mask) == P.flag_mask && nA > 0 && mA > 0;
         }
         if (itB < P.n_items) {
             const WorkItem item = P.items[itB];
@@ -199,7 +218,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
             offB = item.code_off;
             nB = P.ref_len[pB];
             mB = P.qry_len[pB];
-            liveB = P.status[pB] == 0 && P.acgt_only[pB] && nB > 0 && mB > 0;
+            liveB = P.status[pB] == 0 && (P.acgt_only[pB] & P.flag_mask) == P.flag_mask && nB > 0 && mB > 0;
         }
         if (!liveA) nA = mA = 0;
         if (!liveB) nB = mB = 0;
@@ -213,37 +232,65 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
         nsteps_w = max(nsteps_w, __shfl_xor_sync(FULL, nsteps_w, 16));
         npass_w = MULTI ? max(npass_w, __shfl_xor_sync(FULL, npass_w, 16)) : 1;
         const int64_t passbA = ba16_pass_bytes(nA, COLS), passbB = ba16_pass_bytes(nB, COLS);
-        const int jshiftA = mA - npassA * W, jshiftB = mB - npassB * W;
+        const int jshiftA = (KIND == KIND_SW) ? mA - npassA * W : 0, jshiftB = (KIND == KIND_SW) ? mB - npassB * W : 0;
         // rows staged between passes: only pairs that really have a next pass (bounds the scratch)
         const int nbnd = max(npassA > 1 ? nA : 0, npassB > 1 ? nB : 0);
 
         for (int pass = 0; pass < npass_w; pass++) {
             const bool plA = liveA && pass < npassA, plB = liveB && pass < npassB;
-            // ---- per-column constants: PRMT selectors (columns <= 0: sign-select => sub in {0,-1})
+            // ---- per-column constants.  PRMT path: byte selectors (virtual columns <= 0 of SW:
+            // sign-select => sub in {0,-1}).  GSUB path: byte offsets of the query letters in a
+            // table row (SW virtual columns use letter 0 = gap: any finite entry keeps M <= 0 only
+            // approximately, so SW+GSUB clamps them through the profile row instead -- see below).
             unsigned sel[NC];
+            unsigned qb4[GSUB ? NC : 1];
 #pragma unroll
             for (int k = 0; k < NC; k++) {
                 const int ja = jshiftA + pass * W + t * NC + k + 1, jb = jshiftB + pass * W + t * NC + k + 1;
-                unsigned nl = 0x88u, nh = 0xCC00u;  // virtual column: both bytes = sign of a profile byte
-                if (plA && ja >= 1) {
-                    const unsigned q = (unsigned)qA[(int64_t)(ja - 1) * stride] - 1u;
-                    nl = q | ((q | 8u) << 4);
+                const bool oka = plA && ja >= 1 && ja <= mA, okb = plB && jb >= 1 && jb <= mB;
+                if (!GSUB) {
+                    unsigned nl = 0x88u, nh = 0xCC00u;  // virtual column: both bytes = sign of a profile byte
+                    if (KIND != KIND_SW) {
+                        nl = 0x80u;                     // padding column of NW/Fitted: any letter will do
+                        nh = 0xC400u;
+                    }
+                    if (oka) {
+                        const unsigned q = (unsigned)qA[(int64_t)(ja - 1) * stride] - 1u;
+                        nl = q | ((q | 8u) << 4);
+                    }
+                    if (okb) {
+                        const unsigned q = 4u + (unsigned)qB[(int64_t)(jb - 1) * stride] - 1u;
+                        nh = (q << 8) | ((q | 8u) << 12);
+                    }
+                    sel[k] = nl | nh;
+                } else {
+                    sel[k] = oka ? 4u * (unsigned)qA[(int64_t)(ja - 1) * stride] : 0u;
+                    qb4[k] = okb ? 4u * (unsigned)qB[(int64_t)(jb - 1) * stride] : 0u;
                 }
-                if (plB && jb >= 1) {
-                    const unsigned q = 4u + (unsigned)qB[(int64_t)(jb - 1) * stride] - 1u;
-                    nh = (q << 8) | ((q | 8u) << 12);
-                }
-                sel[k] = nl | nh;
             }
             // ---- profile rings: rows -15..0 virtual, rows 1.. loaded in chunks inside the step loop
-            ringA[(t - 15) & (BA16_PROF_RING - 1)] = 0x80808080u;
-            ringB[(t - 15) & (BA16_PROF_RING - 1)] = 0x80808080u;
+            ringA[(t - 15) & (BA16_PROF_RING - 1)] = VROW;
+            ringB[(t - 15) & (BA16_PROF_RING - 1)] = VROW;
             __syncwarp();
 
             unsigned Mu[NC], Uu[NC], Hu[NC];
-#pragma unroll
-            for (int k = 0; k < NC; k++) Mu[k] = Uu[k] = Hu[k] = 0;
             unsigned outM = 0, outL = 0, outH = 0, sdiagH = 0;
+#pragma unroll
+            for (int k = 0; k < NC; k++) {
+                if (KIND == KIND_SW) {
+                    Mu[k] = Uu[k] = Hu[k] = 0;
+                } else {
+                    // row 0: M = U = -inf, L = go + j*eq (nw_affine_letters.go:119-131); H = L
+                    const int j = pass * W + t * NC + k + 1;
+                    Mu[k] = Uu[k] = NEGP;
+                    Hu[k] = pack16(go + j * eq, go + j * eq);
+                }
+            }
+            if (KIND != KIND_SW) {
+                const int j0 = pass * W + t * NC;  // the column left of my first one: H[0][j0]
+                sdiagH = (j0 == 0) ? 0u : pack16(go + j0 * eq, go + j0 * eq);
+                outM = outL = NEGP;
+            }
             unsigned bmax = 0;  // running max of the current period
             // per lane (both pairs packed): best value of this pass and the LAST period attaining it
             unsigned vbest = pack16(1, 1);
@@ -253,6 +300,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
             uint4 *colckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB);
             uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB));
             unsigned ro = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;  // byte offset of my row in the rings
+            unsigned mc0 = 0, lc0 = 0;  // boundary column of my first strip (M, L) at the current row
 
             // staging addresses of my column-checkpoint words: [half of the period][word], pair A,
             // strip 2t; strip 2t+1 is two chunk planes further, pair B one buffer further
@@ -268,9 +316,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     __syncwarp();
                     for (int x = t; x < BA16_PROF_CHUNK; x += 16) {
                         const int i = 8 * e + 1 + x;
-                        unsigned wa = 0x80808080u, wb = 0x80808080u;
-                        if (plA && i <= nA) wa = proftab[rA[(int64_t)(i - 1) * stride] & 7];
-                        if (plB && i <= nB) wb = proftab[rB[(int64_t)(i - 1) * stride] & 7];
+                        unsigned wa = VROW, wb = VROW;
+                        if (plA && i <= nA) wa = proftab[rA[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
+                        if (plB && i <= nB) wb = proftab[rB[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
                         ringA[i & (BA16_PROF_RING - 1)] = wa;
                         ringB[i & (BA16_PROF_RING - 1)] = wb;
                     }
@@ -290,7 +338,14 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                 unsigned rL = __shfl_up_sync(FULL, outL, 1, 16);
                 unsigned rH = __shfl_up_sync(FULL, outH, 1, 16);
                 if (t == 0) {
-                    rM = rL = rH = 0;
+                    if (KIND == KIND_SW) {
+                        rM = rL = rH = 0;
+                    } else {
+                        // DP column 0: M = L = -inf; U = go + i*er (NW, nw_affine_letters.go:132-142)
+                        // or 0 (Fitted, fitted_affine_letters.go:123-132); H = U
+                        rM = rL = NEGP;
+                        rH = (KIND == KIND_NW) ? pack16(go + i * er, go + i * er) : 0u;
+                    }
                     if (MULTI && pass > 0 && i >= 1 && i <= nbnd) {
                         rM = bnd[3 * i + 0];
                         rL = bnd[3 * i + 1];
@@ -298,6 +353,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     }
                 }
 
+                // NW/Fitted: a lane whose first row has not come yet keeps its row-0 border state
+                if (KIND == KIND_SW || i >= 1) {
                 // Three sweeps, each updating its array in place (no register rotation):
                 //  U from the previous row's (M, U); M from the previous row's H; then L along the
                 //  row and H = max3 for the next row's diagonal.
@@ -307,13 +364,20 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     unsigned Hd = sdiagH;
 #pragma unroll
                     for (int k = 0; k < NC; k++) {
-                        const unsigned sub = ba_prmt(profA, profB, sel[k]);
-                        Mu[k] = __viaddmax_s16x2_relu(Hd, sub, erp);  // erp <= 0: same as max(.,0)
+                        unsigned sub;
+                        if (!GSUB)
+                            sub = ba_prmt(profA, profB, sel[k]);
+                        else
+                            sub = *(const unsigned *)((const char *)subA + profA + sel[k]) |
+                                  *(const unsigned *)((const char *)subB + profB + qb4[k]);
+                        if (KIND == KIND_SW)
+                            Mu[k] = __viaddmax_s16x2_relu(Hd, sub, erp);  // erp <= 0: same as max(.,0)
+                        else
+                            Mu[k] = __vadd2(Hd, sub);
                         Hd = Hu[k];
                     }
                 }
                 unsigned Ml = rM, Ll = rL;
-                unsigned mc0 = 0, lc0 = 0;  // boundary column of my first strip
 #pragma unroll
                 for (int k = 0; k < NC; k++) {
                     Ll = __viaddmax_s16x2(Ml, goeqp, __vadd2(Ll, eqp));
@@ -324,16 +388,21 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                         lc0 = Ll;
                     }
                 }
-#pragma unroll
-                for (int k = 0; k + 1 < NC; k += 2) bmax = __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
                 sdiagH = rH;
                 outM = Mu[NC - 1];
                 outL = Ll;
                 outH = Hu[NC - 1];
+                }
+                if (KIND == KIND_SW) {
+#pragma unroll
+                for (int k = 0; k + 1 < NC; k += 2) bmax = __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
+                }
 
                 // column checkpoints (M, clamped L) of my two strips, staged per pair for this period
                 {
-                    const unsigned l0 = __vimax_s16x2_relu(lc0, erp), l1 = __vimax_s16x2_relu(outL, erp);
+                    // SW re-applies the clamp its recurrence deferred; NW/Fitted store raw values
+                    const unsigned l0 = (KIND == KIND_SW) ? __vimax_s16x2_relu(lc0, erp) : lc0;
+                    const unsigned l1 = (KIND == KIND_SW) ? __vimax_s16x2_relu(outL, erp) : outL;
                     unsigned *w = cst[j >> 2][j & 3];
                     w[0] = ba_prmt(mc0, l0, 0x5410u);
                     w[BA16_STAGE_WORDS] = ba_prmt(mc0, l0, 0x7632u);
@@ -353,7 +422,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                     for (int x = 0; x < 16; x++) wa[x] = wb[x] = 0;
 #pragma unroll
                     for (int k = 0; k < NC; k++) {
-                        const unsigned u = __vimax_s16x2_relu(Uu[k], erp);
+                        const unsigned u = (KIND == KIND_SW) ? __vimax_s16x2_relu(Uu[k], erp) : Uu[k];
                         const int x = (k >= COLS ? 8 + (k - COLS) : k);  // word inside my 16-word region
                         wa[x] = ba_prmt(Mu[k], u, 0x5410u);
                         wb[x] = ba_prmt(Mu[k], u, 0x7632u);
@@ -371,18 +440,20 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_sw_kernel(Fill16Par
                 if (plA && 8 * e + 7 < nstepsA) ba16_flush_period<false>(rowA, rowckA + (int64_t)e * 64, t);
                 if (plB && 8 * e + 7 < nstepsB) ba16_flush_period<false>(rowB, rowckB + (int64_t)e * 64, t);
                 __syncwarp();
-                // best tracking at period granularity ('>=' keeps the LAST period)
-                bool ph, pl;
-                vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
-                if (pl) per_lo = e;
-                if (ph) per_hi = e;
-                bmax = 0;
+                if (KIND == KIND_SW) {
+                    // best tracking at period granularity ('>=' keeps the LAST period)
+                    bool ph, pl;
+                    vbest = __vibmax_s16x2(bmax, vbest, &ph, &pl);
+                    if (pl) per_lo = e;
+                    if (ph) per_hi = e;
+                    bmax = 0;
+                }
             }
-            if (plA) {
+            if (KIND == KIND_SW && plA) {
                 int2 *cand = (int2 *)(P.arena + offA + (int64_t)npassA * passbA) + pass * 16 + t;
                 *cand = make_int2(lo16(vbest), per_lo);
             }
-            if (plB) {
+            if (KIND == KIND_SW && plB) {
                 int2 *cand = (int2 *)(P.arena + offB + (int64_t)npassB * passbB) + pass * 16 + t;
                 *cand = make_int2(hi16(vbest), per_hi);
             }

@@ -29,10 +29,13 @@ struct Plan {
     std::vector<Wave> waves;
 };
 
+// Columns per lane (32-bit path) / per strip (16-bit path): the narrowest class that covers the
+// query in the fewest passes, e.g. m = 300 -> two passes of 32*5 = 160 columns instead of 2 x 256.
 inline int cols_for(int m)
 {
     if (m <= 0) return 1;
-    int c = (m + 31) / 32;
+    const int npass = (m + 32 * BA_MAX_COLS - 1) / (32 * BA_MAX_COLS);
+    const int c = (m + 32 * npass - 1) / (32 * npass);
     return c > BA_MAX_COLS ? BA_MAX_COLS : c;
 }
 

@@ -30,7 +30,8 @@ struct Trace16Params {
     const int64_t *qry_off;
     const int32_t *qry_len;
     int32_t *status;
-    const uint8_t *acgt_only;  // per pair eligibility (see ba_fill16)
+    const uint8_t *acgt_only;  // per pair letter flags (see ba_fill16)
+    int flag_mask;
     const WorkItem *items;
     int n_items;
     const uint8_t *arena;
@@ -72,14 +73,52 @@ struct CkView {
     __device__ __forceinline__ int left_col(int g) const { return jshift + g * cols; }
 };
 
+// What the caller wants to learn from a tile besides its codes.
+struct TileProbe {
+    int want = -1;              // SW: report the last cell (row-major) whose M equals this scaled value
+    int fi = 0, fj = 0;
+    int col = -1;               // Fitted: track the last row maximising M in this table column
+    int best = INT32_MIN, besti = 0;
+    int ci = -1, cj = -1;       // NW: capture the three layer values of this cell
+    int cM = 0, cU = 0, cL = 0;
+};
+
+// DP border values in the scaled domain (uniform gap entries: condition C1 of ba_fill16.cuh).
+template <int KIND>
+__device__ __forceinline__ Cell3 border_row0(int j, int go, int eq)
+{
+    Cell3 c;
+    if (KIND == KIND_SW) {
+        c.M = c.U = c.L = 0;
+    } else if (j == 0) {
+        c.M = 0;                // table[0] = {0, minInt, minInt}
+        c.U = c.L = BA_NEG;
+    } else {
+        c.M = c.U = BA_NEG;     // nw_affine_letters.go:119-131
+        c.L = go + j * eq;
+    }
+    return c;
+}
+template <int KIND>
+__device__ __forceinline__ Cell3 border_col0(int i, int go, int er)
+{
+    Cell3 c;
+    if (KIND == KIND_SW) {
+        c.M = c.U = c.L = 0;
+    } else {
+        c.M = c.L = BA_NEG;     // nw_affine_letters.go:132-142 / fitted_affine_letters.go:123-132
+        c.U = (KIND == KIND_NW) ? go + i * er : 0;
+    }
+    return c;
+}
+
 // Recompute the tile of strip g, period e, for rows rt+1 .. imax and columns up to jmax, and
-// store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).  When `want`
-// is >= 0 the last cell in row-major order whose M equals `want` (scaled) is reported.
+// store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).
 // S is the scoring matrix scaled by BA_SCALE in shared memory (row stride `let`).
 template <int KIND>
 __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
-                                             uint8_t *tile, int want, int &fi, int &fj)
+                                             uint8_t *tile, TileProbe &pb)
 {
     const int v = CkView::lane_of(g);
     const int rt = max(BA16_PERIOD * e - v, 0); // top boundary row (0 = DP border)
@@ -87,6 +126,7 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
     const int cL = max(c0, 0);                  // effective left boundary column (0 = DP border)
     const int kfirst = cL - c0;                 // first real column of the strip
     const int klast = jmax - c0 - 1;            // last needed column (inclusive)
+    const int er_u = S[let], eq_u = S[1];       // uniform gap entries (letters >= 1)
 
     // ---- per-column constants of this tile
     int qo[BA_MAX_COLS], eqv[BA_MAX_COLS];
@@ -101,28 +141,34 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
     }
 
     // ---- corner (rt, cL) and the U layer of the left boundary column
-    Cell3 corner;
-    corner.M = corner.U = corner.L = 0;         // SW border
-    int leftU = 0;                              // U at (row, cL), advanced row by row
+    Cell3 corner = (rt == 0) ? border_row0<KIND>(cL, go, eq_u) : border_col0<KIND>(rt, go, er_u);
+    int leftU = corner.U;                       // U at (row, cL), advanced row by row
     const int gl = g - 1;                       // strip whose last column is cL
     if (cL > 0) {
         const int vl = CkView::lane_of(gl);
         // U of column cL is checkpointed (with M) only at strip gl's own rows; start from the
         // closest one at or above rt and run U's recurrence down the column on the stored M.
         int r0 = rt - ((rt + vl) & (BA16_PERIOD - 1));  // largest row <= rt with (r0 + vl) % PERIOD == 0
-        int u = 0;
+        int u;
         if (r0 >= 1) {
             int mm;
             ck.row_mu(gl, (r0 + vl) / BA16_PERIOD - 1, ck.cols - 1, mm, u);
             u *= BA_SCALE;
         } else {
-            r0 = 0;                             // DP border row: U = 0 for SW
+            r0 = 0;                             // DP border row
+            u = border_row0<KIND>(cL, go, eq_u).U;
         }
         for (int r = r0 + 1; r <= rt; r++) {
-            int mp = 0, lp;
-            if (r - 1 >= 1) ck.col_ml(gl, r - 1, mp, lp);
+            int mp, lp;
+            if (r - 1 >= 1) {
+                ck.col_ml(gl, r - 1, mp, lp);
+                mp *= BA_SCALE;
+            } else {
+                mp = border_row0<KIND>(cL, go, eq_u).M;
+            }
             const int er = S[(int)rs[(r - 1) * stride] * let];
-            u = max(max(mp * BA_SCALE + go + er, u + er), 0);
+            u = max(mp + go + er, u + er);
+            if (KIND == KIND_SW) u = max(u, 0);
         }
         leftU = u;
         if (rt >= 1) {
@@ -141,14 +187,19 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
 #pragma unroll
         for (int k = 0; k < BA_MAX_COLS; k++) {
             Pv[k].M = Pv[k].U = Pv[k].L = 0;
-            if (k >= kfirst && k <= klast && rt >= 1) {
-                int mm, uu;
-                ck.row_mu(g, e - 1, k, mm, uu);
-                Pv[k].M = mm * BA_SCALE;
-                Pv[k].U = uu * BA_SCALE;
-                Pv[k].L = max(max(lM + go + eqv[k], lL + eqv[k]), 0);
-                lM = Pv[k].M;
-                lL = Pv[k].L;
+            if (k >= kfirst && k <= klast) {
+                if (rt >= 1) {
+                    int mm, uu;
+                    ck.row_mu(g, e - 1, k, mm, uu);
+                    Pv[k].M = mm * BA_SCALE;
+                    Pv[k].U = uu * BA_SCALE;
+                    Pv[k].L = max(lM + go + eqv[k], lL + eqv[k]);
+                    if (KIND == KIND_SW) Pv[k].L = max(Pv[k].L, 0);
+                    lM = Pv[k].M;
+                    lL = Pv[k].L;
+                } else {
+                    Pv[k] = border_row0<KIND>(c0 + k + 1, go, eq_u);
+                }
             }
         }
     }
@@ -161,15 +212,17 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
         const int er = Srow[0];
         const int goer = go + er;
         Cell3 left;
-        left.M = left.U = left.L = 0;
         if (cL > 0) {
             int mm, ll;
             ck.col_ml(gl, r, mm, ll);
-            // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er, 0)
-            leftU = max(max(dprev.M + goer, leftU + er), 0);
+            // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er [, 0])
+            leftU = max(dprev.M + goer, leftU + er);
+            if (KIND == KIND_SW) leftU = max(leftU, 0);
             left.M = mm * BA_SCALE;
             left.L = ll * BA_SCALE;
             left.U = leftU;
+        } else {
+            left = border_col0<KIND>(r, go, er_u);
         }
         Cell3 d = dprev, l = left;
 #pragma unroll
@@ -180,9 +233,19 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
                 const Cell3 old = Pv[k];
                 const Cell3 nw = affine_cell<KIND>(d, old, l, Srow[qo[k]], er, goer, eqv[k], go + eqv[k], code, dm);
                 trow[k * BA_TRACE_THREADS] = (uint8_t)code;
-                if (want >= 0 && nw.M == want) {
-                    fi = r;
-                    fj = c0 + k + 1;
+                const int col = c0 + k + 1;
+                if (KIND == KIND_SW && pb.want >= 0 && nw.M == pb.want) {
+                    pb.fi = r;
+                    pb.fj = col;
+                }
+                if (KIND == KIND_FIT && col == pb.col && nw.M >= pb.best) {
+                    pb.best = nw.M;
+                    pb.besti = r;
+                }
+                if (KIND == KIND_NW && r == pb.ci && col == pb.cj) {
+                    pb.cM = nw.M;
+                    pb.cU = nw.U;
+                    pb.cL = nw.L;
                 }
                 Pv[k] = nw;
                 d = old;
@@ -212,7 +275,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         P.seg_count[it] = 0;
         return;
     }
-    if (!P.acgt_only[p]) {
+    if ((P.acgt_only[p] & P.flag_mask) != P.flag_mask) {
         P.seg_count[it] = -1;  // the host re-runs this pair on the exact path
         return;
     }
@@ -231,7 +294,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
     ck.m = m;
     ck.cols = item.cols;
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
-    ck.jshift = m - ck.npass * 32 * item.cols;
+    ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
     ck.pass_bytes = ba16_pass_bytes(n, item.cols);
     ck.colck_bytes = ba16_colck_bytes(n);
 
@@ -251,9 +314,11 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         nseg++;                           \
     } while (0)
 
-    // ---- start cell (SW): the last cell in row-major order holding the table maximum
-    int i = 0, j = 0, cur = 0;
-    if (n > 0 && m > 0) {
+    // ---- start cell
+    int i = 0, j = 0, cur = 0, layer = 0;
+    if (KIND == KIND_SW && n > 0 && m > 0) {
+        // the last cell in row-major order holding the table maximum (sw_affine_letters.go:126-134
+        // under condition C2 of ba_fill16.cuh)
         const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
         int Smax = 0;
         for (int x = 0; x < ck.npass * 16; x++) {
@@ -272,19 +337,52 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
                     const int clast = ck.left_col(g) + ck.cols;
                     if (rlast < 1 || clast < 1) continue;
                     if (rlast < i || (rlast == i && clast < j)) continue;  // cannot come later
-                    int fi = 0, fj = 0;
-                    trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, Smax * BA_SCALE, fi, fj);
-                    if (fi > i || (fi == i && fj > j)) {
-                        i = fi;
-                        j = fj;
+                    TileProbe pb;
+                    pb.want = Smax * BA_SCALE;
+                    trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
+                        i = pb.fi;
+                        j = pb.fj;
                     }
                 }
             }
             cur = Smax;
         }
     }
+    if (KIND == KIND_NW) {
+        // start at (r-1, c-1) in the layer with the largest value, strict '>' scanning M, U, L
+        // (nw_affine_letters.go:183-192)
+        i = n;
+        j = m;
+        const int g = ck.strip_of(j);
+        TileProbe pb;
+        pb.ci = i;
+        pb.cj = j;
+        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+                           tile, pb);
+        int best = pb.cM;
+        if (pb.cU > best) {
+            best = pb.cU;
+            layer = 1;
+        }
+        if (pb.cL > best) layer = 2;
+    }
+    if (KIND == KIND_FIT) {
+        // j = c-1; i = last row maximising M in the last column (fitted_affine_letters.go:170-181)
+        j = m;
+        const int g = ck.strip_of(j);
+        const int v = CkView::lane_of(g);
+        TileProbe pb;
+        pb.col = m;
+        for (int e = 0; BA16_PERIOD * e - v < n; e++) {
+            const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
+            if (rlast < 1) continue;
+            trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+        }
+        i = pb.besti;
+    }
 
-    int maxI = i, maxJ = j, score = 0, last = MV_DIAG, layer = 0;
+    int maxI = i, maxJ = j, score = 0, last = MV_DIAG;
     bool bad = false;
     while (i > 0 && j > 0 && !bad) {
         if (KIND == KIND_SW && cur == 0) break;
@@ -293,8 +391,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         const int e = (i + v - 1) >> BA16_PSHIFT;
         const int rt = max(BA16_PERIOD * e - v, 0);
         const int c0 = max(ck.left_col(g), 0);
-        int fi, fj;
-        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, -1, fi, fj);
+        TileProbe pb0;
+        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
         const int cbase = ck.left_col(g);
         while (i > rt && j > c0) {
             if (KIND == KIND_SW && cur == 0) break;
@@ -331,6 +429,15 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         if (KIND == KIND_SW && cur == 0) break;
     }
     T16_EMIT(i, maxI, j, maxJ, score);
+    if (KIND == KIND_NW && i != j) {
+        // nw_affine_letters.go:311-325: leading gap, its score is the border value
+        int b = go;
+        if (i == 0)
+            for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> BA_SCALE_SHIFT;
+        else
+            for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> BA_SCALE_SHIFT;
+        T16_EMIT(0, i, 0, j, b);
+    }
 #undef T16_EMIT
     if (bad) {
         P.status[p] = 4;  // BA_PAIR_NO_PATH

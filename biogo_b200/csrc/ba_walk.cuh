@@ -75,12 +75,14 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
         int bad_r = 0x7fffffff, bad_q = 0x7fffffff;  // first illegal position
         int oob = 0;                                 // any index beyond the matrix
         int other = 0;                               // any letter outside alphabet indices 1..4
+        int zero = 0;                                // any gap letter (alphabet index 0)
         for (int base = 0; base < n && bad_r == 0x7fffffff; base += 32) {
             int x = base + lane;
             uint8_t v = (x < n) ? r[(int64_t)x * stride] : 1;
             unsigned b = __ballot_sync(0xffffffffu, v == 0xFF);
             oob |= __any_sync(0xffffffffu, v == 0xFE);
             other |= __any_sync(0xffffffffu, v < 1 || v > 4);
+            zero |= __any_sync(0xffffffffu, v == 0);
             if (b) bad_r = base + __ffs(b) - 1;
         }
         for (int base = 0; base < m && bad_q == 0x7fffffff; base += 32) {
@@ -89,6 +91,7 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
             unsigned b = __ballot_sync(0xffffffffu, v == 0xFF);
             oob |= __any_sync(0xffffffffu, v == 0xFE);
             other |= __any_sync(0xffffffffu, v < 1 || v > 4);
+            zero |= __any_sync(0xffffffffu, v == 0);
             if (b) bad_q = base + __ffs(b) - 1;
         }
         const bool hr = bad_r != 0x7fffffff, hq = bad_q != 0x7fffffff;
@@ -120,7 +123,8 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
             status[p] = st;
             err_pos[p] = ep;
             // the scan above stops at the first illegal letter, which makes st != 0 anyway
-            if (acgt_only) acgt_only[p] = (st == 0 && !other) ? 1 : 0;
+            // bit0: only alphabet indices 1..4 (PRMT profiles); bit1: no gap letter (uniform gap entries)
+            if (acgt_only) acgt_only[p] = (st == 0) ? ((other ? 0 : 1) | (zero ? 0 : 2)) : 0;
         }
     }
 }

@@ -165,3 +165,25 @@ def test_uniform_batch_closed_form_plan_and_waves(emu_ctx):
         finally:
             emu_ctx.set_option("arena_bytes", 0)
         helpers.compare(res, helpers.run_oracle(kind, affine, M, -5, DNA_IDX, pk), f"uniform waves {kind} {affine}")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SWAffine", "NWAffine", "FittedAffine"])
+def test_fast16_all_affine_kinds_dna_and_protein(emu_ctx, kind):
+    """The packed 16-bit path for NWAffine / FittedAffine (borders, -inf, start cells) and for
+    a generic alphabet (Protein/BLOSUM62 through the shared-memory score tables)."""
+    rng = random.Random(900 + kind)
+    M = gv.match(-1, 2, -1)
+    pairs = randcases.rand_pairs(rng, 30, [1, 5, 17, 40, 90, 150], [1, 4, 16, 33, 64, 100, 257, 300], related=0.85,
+                                 dirty=0.0)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] >= len(pairs) - 3
+    helpers.compare(res, helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk), f"fast16 dna kind {kind}")
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    P = matrix.with_gap(matrix.BLOSUM62, -1)
+    ppairs = randcases.rand_pairs(rng, 24, [3, 20, 45, 80, 300], [2, 20, 45, 80, 300], related=0.8, dirty=0.15,
+                                  alpha=aa, dirty_alpha=aa + b"BZX*J-acdu")
+    ppk = helpers.pack(ppairs, 2)
+    res = helpers.run_lib(emu_ctx, kind, True, P, -10, PROT_IDX, 26, ppk, 2)
+    assert res.stats["pairs_fast16"] > 0
+    helpers.compare(res, helpers.run_oracle(kind, True, P, -10, PROT_IDX, ppk, 2), f"fast16 protein kind {kind}")

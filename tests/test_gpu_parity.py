@@ -238,3 +238,34 @@ def test_fast16_and_exact_paths_agree_on_config2(gpu_ctx):
     assert 0 < ovf.stats["pairs_fast16"] < w.n
     for p in range(w.n):
         assert np.array_equal(ovf.pairs(p), exact.pairs(p)), p
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SWAffine", "NWAffine", "FittedAffine"])
+def test_fast16_all_affine_kinds(gpu_ctx, kind):
+    rng = random.Random(3000 + kind)
+    M = gv.match(-1, 2, -1)
+    pairs = randcases.rand_pairs(rng, 1200, [1, 5, 17, 40, 90, 150, 400, 1000],
+                                 [1, 4, 16, 33, 64, 100, 160, 250, 257, 300, 700], related=0.85, dirty=0.02)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(gpu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] > 0.85 * len(pairs)
+    helpers.compare(res, helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk, 1, 16), f"fast16 dna kind {kind}")
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    P = matrix.with_gap(matrix.BLOSUM62, -1)
+    ppairs = randcases.rand_pairs(rng, 800, [3, 20, 45, 80, 300, 600], [2, 20, 45, 80, 300, 500], related=0.8,
+                                  dirty=0.1, alpha=aa, dirty_alpha=aa + b"BZX*J-acdu")
+    ppk = helpers.pack(ppairs, 2)
+    res = helpers.run_lib(gpu_ctx, kind, True, P, -10, PROT_IDX, 26, ppk, 2)
+    assert res.stats["pairs_fast16"] > 0.5 * len(ppairs)
+    helpers.compare(res, helpers.run_oracle(kind, True, P, -10, PROT_IDX, ppk, 2, 16), f"fast16 protein kind {kind}")
+
+
+def test_fitted_affine_long_pairs_fast_path(gpu_ctx):
+    """FittedAffine on kb-scale pairs (BASELINE config 4 scaled down): many passes per pair."""
+    rng = random.Random(41)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 24, [1500, 3000, 4000], [1200, 2500, 3300], related=1.0, dirty=0.0)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(gpu_ctx, 2, True, M, -5, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] == len(pairs)
+    helpers.compare(res, helpers.run_oracle(2, True, M, -5, DNA_IDX, pk, 1, 8), "fitted long")
