@@ -184,6 +184,6 @@ def test_fast16_all_affine_kinds_dna_and_protein(emu_ctx, kind):
     ppairs = randcases.rand_pairs(rng, 24, [3, 20, 45, 80, 300], [2, 20, 45, 80, 300], related=0.8, dirty=0.15,
                                   alpha=aa, dirty_alpha=aa + b"BZX*J-acdu")
     ppk = helpers.pack(ppairs, 2)
-    res = helpers.run_lib(emu_ctx, kind, True, P, -10, PROT_IDX, 26, ppk, 2)
+    res = helpers.run_lib(emu_ctx, kind, True, P, -12, PROT_IDX, 26, ppk, 2)
     assert res.stats["pairs_fast16"] > 0
-    helpers.compare(res, helpers.run_oracle(kind, True, P, -10, PROT_IDX, ppk, 2), f"fast16 protein kind {kind}")
+    helpers.compare(res, helpers.run_oracle(kind, True, P, -12, PROT_IDX, ppk, 2), f"fast16 protein kind {kind}")

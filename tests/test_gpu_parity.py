@@ -255,9 +255,9 @@ def test_fast16_all_affine_kinds(gpu_ctx, kind):
     ppairs = randcases.rand_pairs(rng, 800, [3, 20, 45, 80, 300, 600], [2, 20, 45, 80, 300, 500], related=0.8,
                                   dirty=0.1, alpha=aa, dirty_alpha=aa + b"BZX*J-acdu")
     ppk = helpers.pack(ppairs, 2)
-    res = helpers.run_lib(gpu_ctx, kind, True, P, -10, PROT_IDX, 26, ppk, 2)
+    res = helpers.run_lib(gpu_ctx, kind, True, P, -12, PROT_IDX, 26, ppk, 2)
     assert res.stats["pairs_fast16"] > 0.5 * len(ppairs)
-    helpers.compare(res, helpers.run_oracle(kind, True, P, -10, PROT_IDX, ppk, 2, 16), f"fast16 protein kind {kind}")
+    helpers.compare(res, helpers.run_oracle(kind, True, P, -12, PROT_IDX, ppk, 2, 16), f"fast16 protein kind {kind}")
 
 
 def test_fitted_affine_long_pairs_fast_path(gpu_ctx):
