@@ -269,3 +269,10 @@ def test_fitted_affine_long_pairs_fast_path(gpu_ctx):
     res = helpers.run_lib(gpu_ctx, 2, True, M, -5, DNA_IDX, 5, pk)
     assert res.stats["pairs_fast16"] == len(pairs)
     helpers.compare(res, helpers.run_oracle(2, True, M, -5, DNA_IDX, pk, 1, 8), "fitted long")
+
+
+def test_graft_entry_smoke(gpu_ctx):
+    """The driver's smoke(): one small invocation of every aligner kind, checked against the oracle."""
+    import __graft_entry__ as g
+
+    g.smoke()
