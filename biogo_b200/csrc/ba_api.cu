@@ -106,8 +106,8 @@ struct ba_ctx {
     // grow-only device buffers
     DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
-    DevBuf flags, slot_off, slot_cap, slots, seg_clip;
-    int64_t opt_force_path = 0, opt_slot_cap = 0;
+    DevBuf flags, slot_off, slot_cap, slots, seg_clip, tasks, prog;
+    int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
@@ -483,6 +483,21 @@ Fill16Fn pick_fill16_k(int cols, bool multi, bool gsub)
     if (gsub) return multi ? pick_fill16_c<KIND, true, true>(cols) : pick_fill16_c<KIND, false, true>(cols);
     return multi ? pick_fill16_c<KIND, true, false>(cols) : pick_fill16_c<KIND, false, false>(cols);
 }
+// LONG (inter-pass wavefront) instances exist for the two widest column classes only: pairs with
+// four or more passes always land there (ba_plan.h cols_for)
+template <int KIND>
+Fill16Fn pick_fill16_long_k(int cols, bool gsub)
+{
+    if (cols == 7)
+        return gsub ? ba_fill16_kernel<KIND, 7, true, true, true> : ba_fill16_kernel<KIND, 7, true, false, true>;
+    return gsub ? ba_fill16_kernel<KIND, 8, true, true, true> : ba_fill16_kernel<KIND, 8, true, false, true>;
+}
+Fill16Fn pick_fill16_long(int kind, int cols, bool gsub)
+{
+    if (kind == KIND_SW) return pick_fill16_long_k<KIND_SW>(cols, gsub);
+    if (kind == KIND_NW) return pick_fill16_long_k<KIND_NW>(cols, gsub);
+    return pick_fill16_long_k<KIND_FIT>(cols, gsub);
+}
 Fill16Fn pick_fill16(int kind, int cols, bool multi, bool gsub)
 {
     if (kind == KIND_SW) return pick_fill16_k<KIND_SW>(cols, multi, gsub);
@@ -603,6 +618,13 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                              (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
         return rc;
     if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
+    int32_t *h_long_err = (int32_t *)pinned_get(ctx, 64);
+    if (!h_long_err) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    memset(h_long_err, 0, 64);
+    std::vector<WorkItem *> long_tasks;
     int32_t *h_cnt = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
     int32_t *h_raw = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
     int64_t *h_base = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(max_items + 1));
@@ -626,18 +648,6 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         int li = 0;
         for (auto &L : w.launches) {
             const bool multi = w.max_n_multipass > 0;
-            Fill16Fn fn = pick_fill16(kind, L.cols, multi, gsub);
-            int occ = 1;
-            if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
-            int64_t blocks = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
-            int64_t maxb = (int64_t)ctx->sm_count * occ;
-            if (blocks > maxb) blocks = maxb;
-            int64_t bnd_stride = 0;
-            if (multi) {
-                bnd_stride = 3 * ((int64_t)w.max_n_multipass + 2);
-                if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * blocks * BA16_GROUPS))) != BA_OK)
-                    return rc;
-            }
             Fill16Params fp;
             fp.enc = B.d_enc;
             fp.stride = B.stride;
@@ -648,13 +658,91 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             fp.status = B.d_status;
             fp.acgt_only = (const uint8_t *)ctx->flags.p;
             fp.flag_mask = flag_mask;
-            fp.items = d_items + (L.first - w.first);
-            fp.n_items = (int)L.count;
             fp.counter = (int *)ctx->counters.p + (li++ % 64);
             fp.arena = (uint8_t *)ctx->arena.p;
+            fp.sc = ctx->d_sc;
+            fp.long_couples = fp.long_maxpass = 0;
+            fp.prog = fp.long_err = nullptr;
+
+            // ---- LONG: too few pairs to fill the GPU pair by pair, and many passes each: spread the
+            // passes of every pair over warps (wavefront).  Items of a launch are sorted by cells.
+            const int W16 = 32 * L.cols;
+            int maxp = 0, max_n = 0;
+            if (multi && L.cols >= 7 && ctx->opt_long_mode != 0) {
+                for (int64_t k = 0; k < L.count; k++) {
+                    const int32_t p = plan.items[L.first + k].pair;
+                    maxp = std::max(maxp, (B.h_qry_len[p] + W16 - 1) / W16);
+                    max_n = std::max(max_n, B.h_ref_len[p]);
+                }
+            }
+            Fill16Fn fn = pick_fill16(kind, L.cols, multi, gsub);
+            int occ = 1;
+            if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
+            int64_t maxb = (int64_t)ctx->sm_count * occ;
+            const int64_t pair_warps = (L.count + 3) / 4;
+            const bool use_long = maxp >= 4 && (ctx->opt_long_mode == 2 || pair_warps < maxb * BA16_WARPS) &&
+                                  (int64_t)maxp * (L.count + 4) < (1 << 22);
+            if (use_long) {
+                fn = pick_fill16_long(kind, L.cols, gsub);
+                if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
+                maxb = (int64_t)ctx->sm_count * occ;
+                const int64_t ncp = ((L.count + 3) / 4) * 2;         // couples per pass, even
+                const int64_t ntasks = (int64_t)maxp * 2 * ncp;
+                WorkItem *h_tasks = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)ntasks);
+                if (!h_tasks) {
+                    ctx->err = "pinned host allocation failed";
+                    return BA_ERR_NOMEM;
+                }
+                for (int ps = 0; ps < maxp; ps++)
+                    for (int64_t k = 0; k < 2 * ncp; k++) {
+                        WorkItem t;
+                        t.pair = -1;
+                        t.cols = L.cols;
+                        t.code_off = 0;
+                        if (k < L.count) {
+                            const WorkItem &it = plan.items[L.first + k];
+                            if (ps < (B.h_qry_len[it.pair] + W16 - 1) / W16) t = it;
+                        }
+                        h_tasks[(int64_t)ps * 2 * ncp + k] = t;
+                    }
+                const int64_t bnd_stride = 3 * ((int64_t)max_n + 2);
+                if ((rc = ensure(ctx, ctx->tasks, sizeof(WorkItem) * (size_t)ntasks)) != BA_OK) return rc;
+                if ((rc = ensure(ctx, ctx->prog, sizeof(int) * (size_t)(ncp * maxp + 1))) != BA_OK) return rc;
+                if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * ncp))) != BA_OK) return rc;
+                CK(cudaMemcpyAsync(ctx->tasks.p, h_tasks, sizeof(WorkItem) * (size_t)ntasks, cudaMemcpyHostToDevice,
+                                   st));
+                CK(cudaMemsetAsync(ctx->prog.p, 0, sizeof(int) * (size_t)(ncp * maxp + 1), st));
+                fp.items = (const WorkItem *)ctx->tasks.p;
+                fp.n_items = (int)ntasks;
+                fp.bnd = (int32_t *)ctx->bnd.p;
+                fp.bnd_stride = bnd_stride;
+                fp.long_couples = (int)ncp;
+                fp.long_maxpass = maxp;
+                fp.long_err = (int *)ctx->prog.p;
+                fp.prog = (int *)ctx->prog.p + 1;
+                int64_t blocks = (ntasks + 4 * BA16_WARPS - 1) / (4 * BA16_WARPS);
+                if (blocks > maxb) blocks = maxb;
+                BA_LAUNCH(fn, (unsigned)blocks, BA16_WARPS * 32, st, fp);
+                CK(cudaMemcpyAsync(h_long_err + (long_tasks.size() & 15), ctx->prog.p, sizeof(int), cudaMemcpyDeviceToHost,
+                                   st));
+                long_tasks.push_back(h_tasks);
+                B.out->wavefront_launches++;
+                B.launches++;
+                B.fill_launches++;
+                continue;
+            }
+            int64_t blocks = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
+            if (blocks > maxb) blocks = maxb;
+            int64_t bnd_stride = 0;
+            if (multi) {
+                bnd_stride = 3 * ((int64_t)w.max_n_multipass + 2);
+                if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * blocks * BA16_GROUPS))) != BA_OK)
+                    return rc;
+            }
+            fp.items = d_items + (L.first - w.first);
+            fp.n_items = (int)L.count;
             fp.bnd = (int32_t *)ctx->bnd.p;
             fp.bnd_stride = bnd_stride;
-            fp.sc = ctx->d_sc;
             BA_LAUNCH(fn, (unsigned)blocks, BA16_WARPS * 32, st, fp);
             B.launches++;
             B.fill_launches++;
@@ -704,6 +792,13 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         BA_TSEC("P16 trace launched", tp0);
         CK(cudaStreamSynchronize(st));
         BA_TSEC("P16 counts synced", tp0);
+        for (WorkItem *t : long_tasks) pinned_put(ctx, t);
+        long_tasks.clear();
+        for (int k = 0; k < 16; k++)
+            if (h_long_err[k] != 0) {
+                ctx->err = "fill16 wavefront: a pass waited too long for its left neighbour";
+                return BA_ERR_CUDA;
+            }
         const int64_t wsegs = h_base[w.count - 1] + h_cnt[w.count - 1];
         if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
         BA_LAUNCH(ba_compact_kernel, cblocks, 256, st, (const int32_t *)ctx->slots.p,
@@ -718,6 +813,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             return rc;
         BA_TSEC("P16 wave gathered", tp0);
     }
+    pinned_put(ctx, h_long_err);
     pinned_put(ctx, h_cnt);
     pinned_put(ctx, h_raw);
     pinned_put(ctx, h_base);
@@ -925,7 +1021,8 @@ void ba_destroy(ba_ctx *ctx)
     DevBuf *bufs[] = {&ctx->letters, &ctx->enc,  &ctx->ref_off,   &ctx->ref_len,  &ctx->qry_off, &ctx->qry_len,
                       &ctx->status,  &ctx->err_pos, &ctx->start,  &ctx->items,    &ctx->aux_off, &ctx->aux,
                       &ctx->bnd,     &ctx->seg_count, &ctx->seg_base, &ctx->segs, &ctx->arena,   &ctx->scan_tmp,
-                      &ctx->counters, &ctx->flags,  &ctx->slot_off,  &ctx->slot_cap, &ctx->slots, &ctx->seg_clip};
+                      &ctx->counters, &ctx->flags,  &ctx->slot_off,  &ctx->slot_cap, &ctx->slots, &ctx->seg_clip,
+                      &ctx->tasks,   &ctx->prog};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
@@ -947,6 +1044,10 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     }
     if (!strcmp(key, "slot_cap")) {
         ctx->opt_slot_cap = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "long_mode")) {  // 0 = never, 1 = automatic, 2 = whenever a launch has >= 4 passes
+        ctx->opt_long_mode = value;
         return BA_OK;
     }
     if (!strcmp(key, "force_path")) {

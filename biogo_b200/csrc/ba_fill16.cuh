@@ -53,8 +53,13 @@ struct Fill16Params {
     int n_items;
     int *counter;
     uint8_t *arena;          // checkpoints, WorkItem.code_off bytes into it
-    int32_t *bnd;            // inter-pass boundary, bnd_stride ints per group
+    int32_t *bnd;            // inter-pass boundary, bnd_stride ints per group (LONG: per couple)
     int64_t bnd_stride;
+    // LONG (wavefront over the passes of kb-scale pairs): items are (pair, pass) tasks in pass-major
+    // order, 2*long_couples per pass; prog[couple*long_maxpass + pass] = periods completed
+    int long_couples, long_maxpass;
+    int *prog;
+    int *long_err;           // set when a wait timed out (never expected)
     const DeviceScoring *sc;
 };
 
@@ -140,10 +145,25 @@ __device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gd
 
 // MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
 // inter-pass boundary code is compiled out of the common single-pass instance).
+#ifdef BA_EMULATE
+#define BA_SPIN_PAUSE() emu::yield()
+#define BA_LDCG(p) (*(p))
+#define BA_FENCE() ((void)0)
+#else
+#define BA_SPIN_PAUSE() __nanosleep(64)
+#define BA_LDCG(p) __ldcg(p)
+#define BA_FENCE() __threadfence()
+#endif
+
 // KIND: KIND_SW (right-aligned columns, zero borders, clamps, best-cell candidates) or KIND_NW /
 // KIND_FIT (left-aligned, -inf/gap borders, no clamps).  GSUB: substitution scores from two
 // shared-memory tables (any alphabet, e.g. Protein) instead of the 4-letter PRMT profiles.
-template <int KIND, int COLS, bool MULTI, bool GSUB>
+// LONG: intra-pair wavefront for kb-scale pairs -- every work item is ONE pass of a pair couple;
+// the passes of a couple run concurrently on different warps (anywhere on the GPU), each trailing
+// its left neighbour by three periods; the boundary column travels through a per-couple global
+// row buffer guarded by progress counters.  Items are claimed in pass-major order by a persistent
+// grid, so the pass a warp waits for is always held by a warp that is already running.
+template <int KIND, int COLS, bool MULTI, bool GSUB, bool LONG = false>
 __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params P)
 {
     constexpr int NC = 2 * COLS;  // columns per lane
@@ -190,7 +210,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     unsigned *ringA = ring[grp][0], *ringB = ring[grp][1];
     unsigned *colA = colbuf[grp][0], *colB = colbuf[grp][1];
     unsigned *rowA = rowbuf[grp][0], *rowB = rowbuf[grp][1];
-    unsigned *bnd = (unsigned *)P.bnd + (int64_t)group_global * P.bnd_stride;
+    unsigned *bnd = (unsigned *)P.bnd + (int64_t)group_global * P.bnd_stride;  // LONG: re-pointed per task
     constexpr int W = 32 * COLS;
     const unsigned FULL = 0xffffffffu;
 
@@ -201,24 +221,30 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
         it0 = __shfl_sync(FULL, it0, 0);
         if (it0 >= P.n_items) break;
         const int itA = it0 + 2 * (lane >> 4), itB = itA + 1;
+        int long_pass = 0, couple = 0;
+        if (LONG) {
+            long_pass = itA / (2 * P.long_couples);
+            couple = (itA % (2 * P.long_couples)) >> 1;
+            bnd = (unsigned *)P.bnd + (int64_t)couple * P.bnd_stride;
+        }
         int nA = 0, mA = 0, nB = 0, mB = 0, pA = 0, pB = 0;
         int64_t offA = 0, offB = 0;
         bool liveA = false, liveB = false;
         if (itA < P.n_items) {
             const WorkItem item = P.items[itA];
-            pA = item.pair;
+            pA = max(item.pair, 0);
             offA = item.code_off;
             nA = P.ref_len[pA];
             mA = P.qry_len[pA];
-            liveA = P.status[pA] == 0 && (P.acgt_only[pA] & P.flag_mask) == P.flag_mask && nA > 0 && mA > 0;
+            liveA = item.pair >= 0 && P.status[pA] == 0 && (P.acgt_only[pA] & P.flag_mask) == P.flag_mask && nA > 0 && mA > 0;
         }
         if (itB < P.n_items) {
             const WorkItem item = P.items[itB];
-            pB = item.pair;
+            pB = max(item.pair, 0);
             offB = item.code_off;
             nB = P.ref_len[pB];
             mB = P.qry_len[pB];
-            liveB = P.status[pB] == 0 && (P.acgt_only[pB] & P.flag_mask) == P.flag_mask && nB > 0 && mB > 0;
+            liveB = item.pair >= 0 && P.status[pB] == 0 && (P.acgt_only[pB] & P.flag_mask) == P.flag_mask && nB > 0 && mB > 0;
         }
         if (!liveA) nA = mA = 0;
         if (!liveB) nB = mB = 0;
@@ -236,8 +262,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
         // rows staged between passes: only pairs that really have a next pass (bounds the scratch)
         const int nbnd = max(npassA > 1 ? nA : 0, npassB > 1 ? nB : 0);
 
-        for (int pass = 0; pass < npass_w; pass++) {
+        for (int pass = (LONG ? long_pass : 0); pass < (LONG ? long_pass + 1 : npass_w); pass++) {
             const bool plA = liveA && pass < npassA, plB = liveB && pass < npassB;
+            // LONG: progress counters of this task and of the pass to its left
+            volatile int *prog_me = LONG ? P.prog + (int64_t)couple * P.long_maxpass + pass : nullptr;
+            volatile int *prog_left = (LONG && pass > 0) ? P.prog + (int64_t)couple * P.long_maxpass + pass - 1 : nullptr;
             // ---- per-column constants.  PRMT path: byte selectors (virtual columns <= 0 of SW:
             // sign-select => sub in {0,-1}).  GSUB path: byte offsets of the query letters in a
             // table row (SW virtual columns use letter 0 = gap: any finite entry keeps M <= 0 only
@@ -311,6 +340,21 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 for (int jj = 0; jj < 4; jj++) cst[c][jj] = colA + ba16_stage_word(t, c) + ((jj + (t >> 3)) & 3);
             const int nper_w = (nsteps_w + BA16_PERIOD - 1) >> BA16_PSHIFT;
             for (int e = 0; e < nper_w; e++) {
+                if (LONG && pass > 0) {
+                    // lane 0 reads boundary rows 8e+1 .. 8e+8 in this period; the left pass wrote rows
+                    // <= 8*e_left - 7 once it completed period e_left: wait for e_left >= e + 2
+                    if (t == 0 && (plA || plB)) {
+                        int spins = 0;
+                        while (*prog_left < e + 3) {
+                            BA_SPIN_PAUSE();
+                            if (++spins > (1 << 24)) {
+                                *P.long_err = 1;
+                                break;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
                 if ((e & (BA16_PROF_CHUNK / BA16_PERIOD - 1)) == 0) {
                     // rows 8e+1 .. 8e+CHUNK enter the rings (lanes of the group share the load)
                     __syncwarp();
@@ -347,9 +391,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         rH = (KIND == KIND_NW) ? pack16(go + i * er, go + i * er) : 0u;
                     }
                     if (MULTI && pass > 0 && i >= 1 && i <= nbnd) {
-                        rM = bnd[3 * i + 0];
-                        rL = bnd[3 * i + 1];
-                        rH = bnd[3 * i + 2];
+                        rM = BA_LDCG(bnd + 3 * i + 0);
+                        rL = BA_LDCG(bnd + 3 * i + 1);
+                        rH = BA_LDCG(bnd + 3 * i + 2);
                     }
                 }
 
@@ -409,7 +453,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, l1, 0x5410u);
                     w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, l1, 0x7632u);
                 }
-                if (MULTI && t == 15 && i >= 1 && i <= nbnd) {
+                if (MULTI && t == 15 && i >= 1 && i <= nbnd && pass + 1 < max(npassA, npassB)) {
                     bnd[3 * i + 0] = outM;
                     bnd[3 * i + 1] = outL;
                     bnd[3 * i + 2] = outH;
@@ -440,6 +484,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 if (plA && 8 * e + 7 < nstepsA) ba16_flush_period<false>(rowA, rowckA + (int64_t)e * 64, t);
                 if (plB && 8 * e + 7 < nstepsB) ba16_flush_period<false>(rowB, rowckB + (int64_t)e * 64, t);
                 __syncwarp();
+                if (LONG) {
+                    BA_FENCE();      // boundary rows of this period are visible before the counter moves
+                    __syncwarp();
+                    if (t == 0) *prog_me = e + 1;
+                }
                 if (KIND == KIND_SW) {
                     // best tracking at period granularity ('>=' keeps the LAST period)
                     bool ph, pl;
@@ -448,6 +497,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     if (ph) per_hi = e;
                     bmax = 0;
                 }
+            }
+            if (LONG) {
+                BA_FENCE();
+                __syncwarp();
+                if (t == 0) *prog_me = 0x3fffffff;  // finished: nobody waits on this pass any more
             }
             if (KIND == KIND_SW && plA) {
                 int2 *cand = (int2 *)(P.arena + offA + (int64_t)npassA * passbA) + pass * 16 + t;

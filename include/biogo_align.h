@@ -79,6 +79,7 @@ typedef struct {
     int64_t fill_launches;/* of which DP fill kernels */
     int64_t code_bytes;   /* traceback bytes the fill kernels wrote to HBM */
     int64_t pairs_fast16; /* pairs served by the packed 16-bit DPX path (the rest: 32-bit exact-code path) */
+    int64_t wavefront_launches; /* fill launches that spread the passes of long pairs over warps */
 } ba_result;
 
 /* Context: one per (host thread, device).  Thread-compatible: calls on ONE ctx must be

@@ -187,3 +187,34 @@ def test_fast16_all_affine_kinds_dna_and_protein(emu_ctx, kind):
     res = helpers.run_lib(emu_ctx, kind, True, P, -12, PROT_IDX, 26, ppk, 2)
     assert res.stats["pairs_fast16"] > 0
     helpers.compare(res, helpers.run_oracle(kind, True, P, -12, PROT_IDX, ppk, 2), f"fast16 protein kind {kind}")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SWAffine", "NWAffine", "FittedAffine"])
+def test_fast16_wavefront_over_passes(emu_ctx, kind):
+    """Long queries, few pairs: the passes of a pair run as a wavefront on different warps
+    (LONG mode of ba_fill16, boundary column handed over through global memory)."""
+    rng = random.Random(4100 + kind)
+    M = gv.match(-1, 2, -1)
+    # 4..7 passes (column classes 7 and 8), odd pair count, very different reference lengths
+    pairs = randcases.rand_pairs(rng, 7, [9, 40, 130, 260], [800, 1025, 1300, 1700], related=0.85, dirty=0.0)
+    pk = helpers.pack(pairs)
+    emu_ctx.set_option("long_mode", 2)
+    try:
+        res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+    finally:
+        emu_ctx.set_option("long_mode", 1)
+    assert res.stats["wavefront_launches"] >= 1
+    assert res.stats["pairs_fast16"] >= len(pairs) - 1
+    helpers.compare(res, helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk), f"wavefront kind {kind}")
+    if kind == 0:
+        aa = b"ACDEFGHIKLMNPQRSTVWY"
+        P = matrix.with_gap(matrix.BLOSUM62, -1)
+        ppairs = randcases.rand_pairs(rng, 3, [50, 120], [1030, 1290], related=0.8, dirty=0.0, alpha=aa)
+        ppk = helpers.pack(ppairs)
+        emu_ctx.set_option("long_mode", 2)
+        try:
+            res = helpers.run_lib(emu_ctx, kind, True, P, -12, PROT_IDX, 26, ppk)
+        finally:
+            emu_ctx.set_option("long_mode", 1)
+        assert res.stats["wavefront_launches"] >= 1
+        helpers.compare(res, helpers.run_oracle(kind, True, P, -12, PROT_IDX, ppk), "wavefront protein")

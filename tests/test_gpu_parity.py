@@ -276,3 +276,40 @@ def test_graft_entry_smoke(gpu_ctx):
     import __graft_entry__ as g
 
     g.smoke()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SWAffine", "NWAffine", "FittedAffine"])
+def test_wavefront_over_passes(gpu_ctx, kind):
+    """Few long pairs: the passes of each pair run concurrently on different warps, handing the
+    boundary column over through global memory (LONG mode of ba_fill16)."""
+    rng = random.Random(5100 + kind)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 13, [300, 1500, 3100], [900, 1025, 2500, 4100], related=0.9, dirty=0.0)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(gpu_ctx, kind, True, M, -5, DNA_IDX, 5, pk)
+    assert res.stats["wavefront_launches"] >= 1
+    orc = helpers.run_oracle(kind, True, M, -5, DNA_IDX, pk, 1, 8)
+    helpers.compare(res, orc, f"wavefront kind {kind}")
+    gpu_ctx.set_option("long_mode", 0)
+    try:
+        res0 = helpers.run_lib(gpu_ctx, kind, True, M, -5, DNA_IDX, 5, pk)
+    finally:
+        gpu_ctx.set_option("long_mode", 1)
+    assert res0.stats["wavefront_launches"] == 0
+    helpers.compare(res0, orc, f"no wavefront kind {kind}")
+
+
+def test_wavefront_with_more_tasks_than_resident_warps(gpu_ctx):
+    """Forced wavefront over a batch far larger than the GPU holds at once: passes are claimed in
+    pass-major order, so a waiting warp's left neighbour is always already running."""
+    rng = random.Random(5200)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 6000, [60, 150], [800, 1030, 1300], related=0.9, dirty=0.0)
+    pk = helpers.pack(pairs)
+    gpu_ctx.set_option("long_mode", 2)
+    try:
+        res = helpers.run_lib(gpu_ctx, 0, True, M, -5, DNA_IDX, 5, pk)
+    finally:
+        gpu_ctx.set_option("long_mode", 1)
+    assert res.stats["wavefront_launches"] >= 1
+    helpers.compare(res, helpers.run_oracle(0, True, M, -5, DNA_IDX, pk, 1, 16), "wavefront oversubscribed")
