@@ -107,7 +107,7 @@ struct ba_ctx {
     DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
     DevBuf flags, slot_off, slot_cap, slots, seg_clip, tasks, prog;
-    int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1;
+    int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
@@ -505,6 +505,12 @@ Fill16Fn pick_fill16(int kind, int cols, bool multi, bool gsub)
     return pick_fill16_k<KIND_FIT>(cols, multi, gsub);
 }
 typedef void (*Trace16Fn)(Trace16Params);
+Trace16Fn pick_trace16w(int kind)
+{
+    if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW>;
+    if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW>;
+    return ba_trace16w_kernel<KIND_FIT>;
+}
 Trace16Fn pick_trace16(int kind)
 {
     if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW>;
@@ -771,9 +777,19 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.slot_off = (const int64_t *)ctx->slot_off.p;
         tp.slot_cap = (const int32_t *)ctx->slot_cap.p;
         tp.slots = (int32_t *)ctx->slots.p;
-        const unsigned tblocks = (unsigned)((w.count + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
-        Trace16Fn tfn = pick_trace16(kind);
-        BA_LAUNCH(tfn, tblocks, BA_TRACE_THREADS, st, tp);
+        // one thread per pair when the batch fills the GPU that way, else one warp per pair
+        // (window of speculatively rebuilt tiles, see ba_trace16w_kernel)
+        const bool warp_trace = ctx->opt_trace_mode == 2 ||
+                                (ctx->opt_trace_mode == 1 &&
+                                 w.count * 32 <= (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS * 2);
+        if (warp_trace) {
+            const unsigned tb = (unsigned)((w.count + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
+            BA_LAUNCH(pick_trace16w(kind), tb, BA_TRACE_THREADS, st, tp);
+            B.out->warp_trace_launches++;
+        } else {
+            const unsigned tblocks = (unsigned)((w.count + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
+            BA_LAUNCH(pick_trace16(kind), tblocks, BA_TRACE_THREADS, st, tp);
+        }
         const unsigned cblocks = (unsigned)((w.count + 255) / 256);
         BA_LAUNCH(ba_clip_counts_kernel, cblocks, 256, st, (const int32_t *)ctx->seg_count.p,
                   (const int32_t *)ctx->slot_cap.p, (int32_t *)ctx->seg_clip.p, (int)w.count);
@@ -1048,6 +1064,10 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     }
     if (!strcmp(key, "long_mode")) {  // 0 = never, 1 = automatic, 2 = whenever a launch has >= 4 passes
         ctx->opt_long_mode = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "trace_mode")) {  // 0 = thread per pair, 1 = automatic, 2 = warp per pair
+        ctx->opt_trace_mode = value;
         return BA_OK;
     }
     if (!strcmp(key, "force_path")) {

@@ -446,6 +446,241 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
     P.seg_count[it] = nseg;
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-per-pair variant for batches too small to fill the GPU with one thread per pair
+// (kb-scale pairs, BASELINE config 4).  Same tiles, same walk; the 32 lanes
+//   * split the start-cell search (SW candidates / Fitted last-column periods), and
+//   * rebuild a WINDOW of 4 strips x 8 periods up-left of the walk position concurrently, one
+//     full tile per lane; then every lane walks the identical path through the cached tiles
+//     (all lanes read the same code byte: a shared-memory broadcast) until it leaves the window.
+// Lane 0 emits.  A window always contains the tile under the walk, so every round advances.
+#define BA_TW_STRIPS 4
+#define BA_TW_PERIODS 8
+template <int KIND>
+__global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_kernel(Trace16Params P)
+{
+    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    __shared__ int S[BA_MAX_LET * BA_MAX_LET];
+    {
+        const int ll = P.sc->let;
+        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] * BA_SCALE;
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int wbase = threadIdx.x & ~31;   // first thread of my warp: its 32 tile columns are the window
+    const int it = blockIdx.x * (BA_TRACE_THREADS / 32) + (threadIdx.x >> 5);
+    if (it >= P.n_items) return;           // warp-uniform
+    uint8_t *tile = tiles + threadIdx.x;
+    const WorkItem item = P.items[it];
+    const int p = item.pair;
+    if (P.status[p] != 0) {
+        if (lane == 0) P.seg_count[it] = 0;
+        return;
+    }
+    if ((P.acgt_only[p] & P.flag_mask) != P.flag_mask) {
+        if (lane == 0) P.seg_count[it] = -1;
+        return;
+    }
+    const int n = P.ref_len[p], m = P.qry_len[p];
+    const uint8_t *rs = P.enc + P.ref_off[p];
+    const uint8_t *qs = P.enc + P.qry_off[p];
+    const int stride = P.stride;
+    const int let = P.sc->let;
+    const int go = P.sc->gap_open;
+    const int go8 = go * BA_SCALE;
+
+    CkView ck;
+    ck.base = P.arena + item.code_off;
+    ck.n = n;
+    ck.m = m;
+    ck.cols = item.cols;
+    ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
+    ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
+    ck.pass_bytes = ba16_pass_bytes(n, item.cols);
+    ck.colck_bytes = ba16_colck_bytes(n);
+
+    int32_t *out = P.slots + 5 * P.slot_off[it];
+    const int cap = P.slot_cap[it];
+    int nseg = 0;
+#define T16W_EMIT(a0, a1, b0, b1, sc_)    \
+    do {                                  \
+        if (lane == 0 && nseg < cap) {    \
+            int32_t *o_ = out + 5 * nseg; \
+            o_[0] = (a0);                 \
+            o_[1] = (a1);                 \
+            o_[2] = (b0);                 \
+            o_[3] = (b1);                 \
+            o_[4] = (sc_);                \
+        }                                 \
+        nseg++;                           \
+    } while (0)
+
+    // ---- start cell (rules as in ba_trace16_kernel), searched by all lanes
+    int i = 0, j = 0, cur = 0, layer = 0;
+    if (KIND == KIND_SW && n > 0 && m > 0) {
+        const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
+        int Smax = 0;
+        for (int x = lane; x < ck.npass * 16; x += 32) {
+            const int2 c = cand[x];
+            if (c.y >= 0) Smax = max(Smax, c.x);
+        }
+        for (int o = 16; o; o >>= 1) Smax = max(Smax, __shfl_xor_sync(FULL, Smax, o));
+        if (Smax > 0) {
+            for (int x = lane; x < ck.npass * 16; x += 32) {
+                const int2 c = cand[x];
+                if (c.y < 0 || c.x != Smax) continue;
+                const int e = c.y;
+                for (int h = 0; h < 2; h++) {
+                    const int g = (x >> 4) * 32 + 2 * (x & 15) + h;
+                    const int v = CkView::lane_of(g);
+                    const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
+                    const int clast = ck.left_col(g) + ck.cols;
+                    if (rlast < 1 || clast < 1) continue;
+                    if (rlast < i || (rlast == i && clast < j)) continue;
+                    TileProbe pb;
+                    pb.want = Smax * BA_SCALE;
+                    trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
+                        i = pb.fi;
+                        j = pb.fj;
+                    }
+                }
+            }
+            // last cell in row-major order over the lanes
+            for (int o = 16; o; o >>= 1) {
+                const int oi = __shfl_xor_sync(FULL, i, o), oj = __shfl_xor_sync(FULL, j, o);
+                if (oi > i || (oi == i && oj > j)) {
+                    i = oi;
+                    j = oj;
+                }
+            }
+            cur = Smax;
+        }
+    }
+    if (KIND == KIND_NW) {
+        i = n;
+        j = m;
+        const int g = ck.strip_of(j);
+        TileProbe pb;
+        pb.ci = i;
+        pb.cj = j;
+        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+                           tile, pb);
+        int best = pb.cM;
+        if (pb.cU > best) {
+            best = pb.cU;
+            layer = 1;
+        }
+        if (pb.cL > best) layer = 2;
+    }
+    if (KIND == KIND_FIT) {
+        j = m;
+        const int g = ck.strip_of(j);
+        const int v = CkView::lane_of(g);
+        TileProbe pb;
+        pb.col = m;
+        for (int e = lane; BA16_PERIOD * e - v < n; e += 32) {
+            const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
+            if (rlast < 1) continue;
+            trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+        }
+        // last row attaining the maximum: larger value wins, ties go to the larger row
+        int best = pb.best, besti = pb.besti;
+        for (int o = 16; o; o >>= 1) {
+            const int ob = __shfl_xor_sync(FULL, best, o), oi = __shfl_xor_sync(FULL, besti, o);
+            if (ob > best || (ob == best && oi > besti)) {
+                best = ob;
+                besti = oi;
+            }
+        }
+        i = besti;
+    }
+    __syncwarp();
+
+    int maxI = i, maxJ = j, score = 0, last = MV_DIAG;
+    bool bad = false;
+    while (i > 0 && j > 0 && !bad) {
+        if (KIND == KIND_SW && cur == 0) break;
+        // ---- window anchored at (i, j): my tile is strip g_hi - ws, ws = lane / 8, period
+        // (period of row i in that strip) - lane % 8
+        const int g_hi = ck.strip_of(j);
+        const int i0 = i;
+        {
+            const int g = g_hi - (lane >> 3);
+            const int v = CkView::lane_of(g & 1023);  // (negative g is skipped below)
+            const int e = ((i0 + v - 1) >> BA16_PSHIFT) - (lane & 7);
+            const int clast = min(ck.left_col(g) + ck.cols, m);
+            const int rlast = min(min(n, BA16_PERIOD * e + BA16_PERIOD - v), i0);
+            const int rtop = max(BA16_PERIOD * e - v, 0);
+            if (g >= 0 && e >= 0 && clast >= 1 && rlast > rtop) {
+                TileProbe pb0;
+                trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
+            }
+        }
+        __syncwarp();
+        for (;;) {
+            if (i <= 0 || j <= 0) break;
+            if (KIND == KIND_SW && cur == 0) break;
+            const int g = ck.strip_of(j);
+            const int v = CkView::lane_of(g);
+            const int ws = g_hi - g;
+            const int we = ((i0 + v - 1) >> BA16_PSHIFT) - ((i + v - 1) >> BA16_PSHIFT);
+            if (ws >= BA_TW_STRIPS || we >= BA_TW_PERIODS) break;  // left the window: rebuild
+            const int rt = max(BA16_PERIOD * ((i + v - 1) >> BA16_PSHIFT) - v, 0);
+            const int cbase = ck.left_col(g);
+            const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
+            const unsigned code =
+                tiles[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS + wbase + ws * 8 + we];
+            const bool corner = (i == n && j == m);
+            const unsigned f = (layer == 0) ? (code & 7u) : (layer == 1) ? ((code >> 3) & 3u) : (code >> 5);
+            const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
+            int move, nl = 0, delta;
+            switch (f) {
+            case 1: move = MV_UP;   nl = 1; delta = er;      break;
+            case 2: move = MV_LEFT; nl = 2; delta = eq;      break;
+            case 3: move = MV_UP;   nl = 0; delta = go + er; break;
+            case 4: move = MV_LEFT; nl = 0; delta = go + eq; break;
+            case 5: move = MV_DIAG; nl = (KIND == KIND_SW) ? 0 : 1; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
+            case 6: move = MV_DIAG; nl = (KIND == KIND_SW) ? 1 : 2; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
+            case 7: move = MV_DIAG; nl = (KIND == KIND_SW) ? 2 : 0; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
+            default: move = MV_DIAG; delta = 0; bad = true; break;
+            }
+            if (bad) break;
+            if (last != move && (move == MV_DIAG || !corner)) {
+                T16W_EMIT(i, maxI, j, maxJ, score);
+                maxI = i;
+                maxJ = j;
+                score = 0;
+            }
+            score += delta;
+            if (KIND == KIND_SW) cur -= delta;
+            if (move != MV_LEFT) i--;
+            if (move != MV_UP) j--;
+            layer = nl;
+            last = move;
+        }
+        __syncwarp();
+    }
+    T16W_EMIT(i, maxI, j, maxJ, score);
+    if (KIND == KIND_NW && i != j) {
+        int b = go;
+        if (i == 0)
+            for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> BA_SCALE_SHIFT;
+        else
+            for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> BA_SCALE_SHIFT;
+        T16W_EMIT(0, i, 0, j, b);
+    }
+#undef T16W_EMIT
+    if (lane == 0) {
+        if (bad) {
+            P.status[p] = 4;  // BA_PAIR_NO_PATH
+            nseg = 0;
+        }
+        P.seg_count[it] = nseg;
+    }
+}
+
 // Reverse the emission-order slots of every item into its final, compact place.
 __global__ void ba_compact_kernel(const int32_t *__restrict__ slots, const int64_t *__restrict__ slot_off,
                                   const int32_t *__restrict__ slot_cap, const int32_t *__restrict__ seg_count,

@@ -80,6 +80,7 @@ typedef struct {
     int64_t code_bytes;   /* traceback bytes the fill kernels wrote to HBM */
     int64_t pairs_fast16; /* pairs served by the packed 16-bit DPX path (the rest: 32-bit exact-code path) */
     int64_t wavefront_launches; /* fill launches that spread the passes of long pairs over warps */
+    int64_t warp_trace_launches; /* traceback launches that used one warp per pair */
 } ba_result;
 
 /* Context: one per (host thread, device).  Thread-compatible: calls on ONE ctx must be
@@ -137,7 +138,9 @@ void ba_free_host(void *p);
 
 /* Tunables (optional). key: "arena_bytes" (traceback-code arena per wave, default 48 GiB
  * or 60 % of free HBM), "force_path" (0 auto, 1 = 32-bit exact-code kernels only), "slot_cap"
- * (test hook: segment slots per pair on the 16-bit path, 0 = automatic). */
+ * (test hook: segment slots per pair on the 16-bit path, 0 = automatic), "long_mode" (wavefront
+ * over the passes of kb-scale pairs: 0 never, 1 automatic, 2 whenever a launch has >= 4 passes),
+ * "trace_mode" (16-bit path traceback: 0 thread per pair, 1 automatic, 2 warp per pair). */
 int ba_set_option(ba_ctx *ctx, const char *key, int64_t value);
 
 /* Build/ABI information. */

@@ -218,3 +218,33 @@ def test_fast16_wavefront_over_passes(emu_ctx, kind):
             emu_ctx.set_option("long_mode", 1)
         assert res.stats["wavefront_launches"] >= 1
         helpers.compare(res, helpers.run_oracle(kind, True, P, -12, PROT_IDX, ppk), "wavefront protein")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SWAffine", "NWAffine", "FittedAffine"])
+def test_fast16_warp_per_pair_traceback(emu_ctx, kind):
+    """ba_trace16w_kernel: lanes split the start-cell search and rebuild a window of tiles."""
+    rng = random.Random(4300 + kind)
+    M = gv.match(-1, 2, -1)
+    pairs = randcases.rand_pairs(rng, 18, [1, 5, 17, 40, 90, 150, 260], [1, 4, 16, 33, 64, 100, 257, 300, 600],
+                                 related=0.85, dirty=0.0)
+    pairs += randcases.rand_pairs(rng, 4, [30, 200], [30, 200], related=0.0, dirty=0.0)   # unrelated: gappy paths
+    pk = helpers.pack(pairs)
+    orc = helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk)
+    emu_ctx.set_option("trace_mode", 2)
+    try:
+        res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+        assert res.stats["warp_trace_launches"] >= 1
+        helpers.compare(res, orc, f"warp trace kind {kind}")
+        emu_ctx.set_option("slot_cap", 2)
+        res2 = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+        helpers.compare(res2, orc, f"warp trace overflow kind {kind}")
+    finally:
+        emu_ctx.set_option("slot_cap", 0)
+        emu_ctx.set_option("trace_mode", 1)
+    emu_ctx.set_option("trace_mode", 0)
+    try:
+        res0 = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+    finally:
+        emu_ctx.set_option("trace_mode", 1)
+    assert res0.stats["warp_trace_launches"] == 0
+    helpers.compare(res0, orc, f"thread trace kind {kind}")

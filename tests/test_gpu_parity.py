@@ -313,3 +313,22 @@ def test_wavefront_with_more_tasks_than_resident_warps(gpu_ctx):
         gpu_ctx.set_option("long_mode", 1)
     assert res.stats["wavefront_launches"] >= 1
     helpers.compare(res, helpers.run_oracle(0, True, M, -5, DNA_IDX, pk, 1, 16), "wavefront oversubscribed")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SWAffine", "NWAffine", "FittedAffine"])
+def test_warp_per_pair_traceback_matches_thread_per_pair(gpu_ctx, kind):
+    rng = random.Random(5300 + kind)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 300, [1, 30, 250, 700, 1500], [1, 20, 150, 257, 600, 1300], related=0.85,
+                                 dirty=0.0)
+    pairs += randcases.rand_pairs(rng, 40, [100, 400], [100, 400], related=0.0, dirty=0.0)
+    pk = helpers.pack(pairs)
+    orc = helpers.run_oracle(kind, True, M, -5, DNA_IDX, pk, 1, 16)
+    for mode, want in ((2, True), (0, False)):
+        gpu_ctx.set_option("trace_mode", mode)
+        try:
+            res = helpers.run_lib(gpu_ctx, kind, True, M, -5, DNA_IDX, 5, pk)
+        finally:
+            gpu_ctx.set_option("trace_mode", 1)
+        assert (res.stats["warp_trace_launches"] >= 1) == want
+        helpers.compare(res, orc, f"trace_mode {mode} kind {kind}")
