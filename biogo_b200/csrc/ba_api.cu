@@ -462,65 +462,55 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
 }
 
 // ---- path B: packed 16-bit DPX fill + checkpointed tile traceback (SWAffine, DNA-like) ------
+}  // namespace
 typedef void (*Fill16Fn)(Fill16Params);
-template <int KIND, bool MULTI, bool GSUB>
-Fill16Fn pick_fill16_c(int cols)
+// the kernel instances live in ba_fill16_inst.cu, one translation unit per (kind, linear) family
+Fill16Fn ba_pick_fill16_0_0(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_1_0(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_2_0(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_0_1(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_1_1(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_2_1(int cols, bool multi, bool gsub, bool wavefront);
+namespace {
+Fill16Fn pick_fill16(int kind, bool lin, int cols, bool multi, bool gsub, bool wavefront)
 {
-    switch (cols) {
-    case 1: return ba_fill16_kernel<KIND, 1, MULTI, GSUB>;
-    case 2: return ba_fill16_kernel<KIND, 2, MULTI, GSUB>;
-    case 3: return ba_fill16_kernel<KIND, 3, MULTI, GSUB>;
-    case 4: return ba_fill16_kernel<KIND, 4, MULTI, GSUB>;
-    case 5: return ba_fill16_kernel<KIND, 5, MULTI, GSUB>;
-    case 6: return ba_fill16_kernel<KIND, 6, MULTI, GSUB>;
-    case 7: return ba_fill16_kernel<KIND, 7, MULTI, GSUB>;
-    default: return ba_fill16_kernel<KIND, 8, MULTI, GSUB>;
+    if (lin) {
+        if (kind == KIND_SW) return ba_pick_fill16_0_1(cols, multi, gsub, wavefront);
+        if (kind == KIND_NW) return ba_pick_fill16_1_1(cols, multi, gsub, wavefront);
+        return ba_pick_fill16_2_1(cols, multi, gsub, wavefront);
     }
-}
-template <int KIND>
-Fill16Fn pick_fill16_k(int cols, bool multi, bool gsub)
-{
-    if (gsub) return multi ? pick_fill16_c<KIND, true, true>(cols) : pick_fill16_c<KIND, false, true>(cols);
-    return multi ? pick_fill16_c<KIND, true, false>(cols) : pick_fill16_c<KIND, false, false>(cols);
-}
-// LONG (inter-pass wavefront) instances exist for the two widest column classes only: pairs with
-// four or more passes always land there (ba_plan.h cols_for)
-template <int KIND>
-Fill16Fn pick_fill16_long_k(int cols, bool gsub)
-{
-    if (cols == 7)
-        return gsub ? ba_fill16_kernel<KIND, 7, true, true, true> : ba_fill16_kernel<KIND, 7, true, false, true>;
-    return gsub ? ba_fill16_kernel<KIND, 8, true, true, true> : ba_fill16_kernel<KIND, 8, true, false, true>;
-}
-Fill16Fn pick_fill16_long(int kind, int cols, bool gsub)
-{
-    if (kind == KIND_SW) return pick_fill16_long_k<KIND_SW>(cols, gsub);
-    if (kind == KIND_NW) return pick_fill16_long_k<KIND_NW>(cols, gsub);
-    return pick_fill16_long_k<KIND_FIT>(cols, gsub);
-}
-Fill16Fn pick_fill16(int kind, int cols, bool multi, bool gsub)
-{
-    if (kind == KIND_SW) return pick_fill16_k<KIND_SW>(cols, multi, gsub);
-    if (kind == KIND_NW) return pick_fill16_k<KIND_NW>(cols, multi, gsub);
-    return pick_fill16_k<KIND_FIT>(cols, multi, gsub);
+    if (kind == KIND_SW) return ba_pick_fill16_0_0(cols, multi, gsub, wavefront);
+    if (kind == KIND_NW) return ba_pick_fill16_1_0(cols, multi, gsub, wavefront);
+    return ba_pick_fill16_2_0(cols, multi, gsub, wavefront);
 }
 typedef void (*Trace16Fn)(Trace16Params);
-Trace16Fn pick_trace16w(int kind)
+Trace16Fn pick_trace16w(int kind, bool lin)
 {
-    if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW>;
-    if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW>;
-    return ba_trace16w_kernel<KIND_FIT>;
+    if (lin) {
+        if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, true>;
+        if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, true>;
+        return ba_trace16w_kernel<KIND_FIT, true>;
+    }
+    if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, false>;
+    if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, false>;
+    return ba_trace16w_kernel<KIND_FIT, false>;
 }
-Trace16Fn pick_trace16(int kind)
+Trace16Fn pick_trace16(int kind, bool lin)
 {
-    if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW>;
-    if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW>;
-    return ba_trace16_kernel<KIND_FIT>;
+    if (lin) {
+        if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, true>;
+        if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, true>;
+        return ba_trace16_kernel<KIND_FIT, true>;
+    }
+    if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, false>;
+    if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, false>;
+    return ba_trace16_kernel<KIND_FIT, false>;
 }
 
 // Scoring-level eligibility of the packed 16-bit path (ba_fill16.cuh):
-//   affine gaps; uniform gap entries over the non-gap letters (C1); for SW additionally
-//   non-positive gaps and go + gap + max(sub) < 0 (C2).  `gsub`: the alphabet is not the
+//   uniform gap entries over the non-gap letters (C1); affine SW additionally needs
+//   non-positive gaps and go + gap + max(sub) < 0 (C2), linear SW strictly negative gaps (a cell
+//   holding the table maximum then always came through the diagonal).  `gsub`: the alphabet is not the
 //   5-letter gapped nucleotide one, so substitution scores come from shared-memory tables
 //   instead of PRMT profiles.  maxsub / maxabs feed the per-pair 16-bit range checks.
 struct Fast16 {
@@ -530,7 +520,8 @@ struct Fast16 {
 Fast16 fast16_scoring(const DeviceScoring &s)
 {
     Fast16 f;
-    if (!s.affine || s.let < 2 || s.let > BA_MAX_LET) return f;
+    if (s.let < 2 || s.let > BA_MAX_LET) return f;
+    const int64_t gap_open = s.affine ? s.gap_open : 0;
     f.gsub = (s.let != 5);
     const int er = s.la[1 * s.let], eq = s.la[1];
     int maxsub = -1000000, maxabs = 0;
@@ -544,12 +535,13 @@ Fast16 fast16_scoring(const DeviceScoring &s)
         }
     }
     if (er < -127 || er > 127 || eq < -127 || eq > 127) return f;
-    if (s.gap_open < -4000 || s.gap_open > 4000) return f;
+    if (gap_open < -4000 || gap_open > 4000) return f;
     maxabs = std::max(maxabs, std::max(er < 0 ? -er : er, eq < 0 ? -eq : eq));
-    if (s.kind == KIND_SW) {
+    if (s.kind == KIND_SW && s.affine) {
         if (er > 0 || eq > 0 || maxsub <= 0) return f;
-        if (s.gap_open + er + maxsub >= 0 || s.gap_open + eq + maxsub >= 0) return f;
+        if (gap_open + er + maxsub >= 0 || gap_open + eq + maxsub >= 0) return f;
     }
+    if (s.kind == KIND_SW && !s.affine && (er >= 0 || eq >= 0)) return f;
     f.maxsub = maxsub;
     f.maxabs = maxabs;
     f.ok = true;
@@ -562,7 +554,8 @@ bool fast16_pair_ok(const DeviceScoring &s, const Fast16 &f, int n, int m)
     if (lo <= 0 || n >= (1 << 19)) return false;
     if (lo * std::max(f.maxsub, 0) >= 30000) return false;
     if (s.kind != KIND_SW) {
-        const int64_t ago = s.gap_open < 0 ? -(int64_t)s.gap_open : s.gap_open;
+        const int64_t go = s.affine ? s.gap_open : 0;
+        const int64_t ago = go < 0 ? -go : go;
         if ((hi + 3) * f.maxabs + 2 * ago > 14000) return false;
     }
     return true;
@@ -571,6 +564,7 @@ bool fast16_pair_ok(const DeviceScoring &s, const Fast16 &f, int n, int m)
 int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsub, std::vector<int32_t> &overflow)
 {
     const int kind = ctx->h_sc.kind;
+    const bool lin = !ctx->h_sc.affine;
     const int flag_mask = gsub ? 2 : 1;
     if (nids == 0) return BA_OK;
     cudaStream_t st = B.st;
@@ -590,7 +584,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         return BA_ERR_NOMEM;
     }
     const double tp1 = now_s();
-    build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, 1, true, arena_cap, plan);
+    build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, lin ? 0 : 1, true, arena_cap, plan);
     BA_TSEC("plan16 pinned_get", tp0);
     BA_TSEC("plan16 build", tp1);
     B.host_s += now_s() - tp0;
@@ -667,8 +661,8 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             fp.counter = (int *)ctx->counters.p + (li++ % 64);
             fp.arena = (uint8_t *)ctx->arena.p;
             fp.sc = ctx->d_sc;
-            fp.long_couples = fp.long_maxpass = 0;
-            fp.prog = fp.long_err = nullptr;
+            fp.long_couples = 0;
+            fp.long_err = nullptr;
 
             // ---- LONG: too few pairs to fill the GPU pair by pair, and many passes each: spread the
             // passes of every pair over warps (wavefront).  Items of a launch are sorted by cells.
@@ -681,7 +675,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                     max_n = std::max(max_n, B.h_ref_len[p]);
                 }
             }
-            Fill16Fn fn = pick_fill16(kind, L.cols, multi, gsub);
+            Fill16Fn fn = pick_fill16(kind, lin, L.cols, multi, gsub, false);
             int occ = 1;
             if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
             int64_t maxb = (int64_t)ctx->sm_count * occ;
@@ -689,7 +683,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             const bool use_long = maxp >= 4 && (ctx->opt_long_mode == 2 || pair_warps < maxb * BA16_WARPS) &&
                                   (int64_t)maxp * (L.count + 4) < (1 << 22);
             if (use_long) {
-                fn = pick_fill16_long(kind, L.cols, gsub);
+                fn = pick_fill16(kind, lin, L.cols, true, gsub, true);
                 if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
                 maxb = (int64_t)ctx->sm_count * occ;
                 const int64_t ncp = ((L.count + 3) / 4) * 2;         // couples per pass, even
@@ -711,21 +705,21 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                         }
                         h_tasks[(int64_t)ps * 2 * ncp + k] = t;
                     }
-                const int64_t bnd_stride = 3 * ((int64_t)max_n + 2);
+                const int64_t bnd_stride = 4 * ((int64_t)max_n + 2);
                 if ((rc = ensure(ctx, ctx->tasks, sizeof(WorkItem) * (size_t)ntasks)) != BA_OK) return rc;
-                if ((rc = ensure(ctx, ctx->prog, sizeof(int) * (size_t)(ncp * maxp + 1))) != BA_OK) return rc;
+                if ((rc = ensure(ctx, ctx->prog, 64)) != BA_OK) return rc;
                 if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * ncp))) != BA_OK) return rc;
                 CK(cudaMemcpyAsync(ctx->tasks.p, h_tasks, sizeof(WorkItem) * (size_t)ntasks, cudaMemcpyHostToDevice,
                                    st));
-                CK(cudaMemsetAsync(ctx->prog.p, 0, sizeof(int) * (size_t)(ncp * maxp + 1), st));
+                CK(cudaMemsetAsync(ctx->prog.p, 0, 64, st));
+                // row tags start out invalid
+                CK(cudaMemsetAsync(ctx->bnd.p, 0, sizeof(int32_t) * (size_t)(bnd_stride * ncp), st));
                 fp.items = (const WorkItem *)ctx->tasks.p;
                 fp.n_items = (int)ntasks;
                 fp.bnd = (int32_t *)ctx->bnd.p;
                 fp.bnd_stride = bnd_stride;
                 fp.long_couples = (int)ncp;
-                fp.long_maxpass = maxp;
                 fp.long_err = (int *)ctx->prog.p;
-                fp.prog = (int *)ctx->prog.p + 1;
                 int64_t blocks = (ntasks + 4 * BA16_WARPS - 1) / (4 * BA16_WARPS);
                 if (blocks > maxb) blocks = maxb;
                 BA_LAUNCH(fn, (unsigned)blocks, BA16_WARPS * 32, st, fp);
@@ -741,7 +735,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             if (blocks > maxb) blocks = maxb;
             int64_t bnd_stride = 0;
             if (multi) {
-                bnd_stride = 3 * ((int64_t)w.max_n_multipass + 2);
+                bnd_stride = 4 * ((int64_t)w.max_n_multipass + 2);
                 if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * blocks * BA16_GROUPS))) != BA_OK)
                     return rc;
             }
@@ -784,11 +778,11 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                                  w.count * 32 <= (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS * 2);
         if (warp_trace) {
             const unsigned tb = (unsigned)((w.count + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-            BA_LAUNCH(pick_trace16w(kind), tb, BA_TRACE_THREADS, st, tp);
+            BA_LAUNCH(pick_trace16w(kind, lin), tb, BA_TRACE_THREADS, st, tp);
             B.out->warp_trace_launches++;
         } else {
             const unsigned tblocks = (unsigned)((w.count + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
-            BA_LAUNCH(pick_trace16(kind), tblocks, BA_TRACE_THREADS, st, tp);
+            BA_LAUNCH(pick_trace16(kind, lin), tblocks, BA_TRACE_THREADS, st, tp);
         }
         const unsigned cblocks = (unsigned)((w.count + 255) / 256);
         BA_LAUNCH(ba_clip_counts_kernel, cblocks, 256, st, (const int32_t *)ctx->seg_count.p,

@@ -53,12 +53,12 @@ struct Fill16Params {
     int n_items;
     int *counter;
     uint8_t *arena;          // checkpoints, WorkItem.code_off bytes into it
-    int32_t *bnd;            // inter-pass boundary, bnd_stride ints per group (LONG: per couple)
+    int32_t *bnd;            // inter-pass boundary rows (16 bytes each), bnd_stride ints per group (LONG: per couple)
     int64_t bnd_stride;
     // LONG (wavefront over the passes of kb-scale pairs): items are (pair, pass) tasks in pass-major
-    // order, 2*long_couples per pass; prog[couple*long_maxpass + pass] = periods completed
-    int long_couples, long_maxpass;
-    int *prog;
+    // order, 2*long_couples per pass; the boundary rows carry the writer's pass as a tag, so the
+    // reader needs neither flags nor fences (bnd is zeroed before the launch)
+    int long_couples;
     int *long_err;           // set when a wait timed out (never expected)
     const DeviceScoring *sc;
 };
@@ -148,22 +148,46 @@ __device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gd
 #ifdef BA_EMULATE
 #define BA_SPIN_PAUSE() emu::yield()
 #define BA_LDCG(p) (*(p))
-#define BA_FENCE() ((void)0)
 #else
 #define BA_SPIN_PAUSE() __nanosleep(64)
 #define BA_LDCG(p) __ldcg(p)
-#define BA_FENCE() __threadfence()
 #endif
+
+// Inter-pass boundary row: the last column's (M, L, H) of a pass for both pairs of a couple,
+// 16 bytes = two 64-bit words that each carry the writer's tag in their top 16 bits:
+//   w0 = M (A|B packed) | L_A << 32 | tag << 48      w1 = H (A|B packed) | L_B << 32 | tag << 48
+// A 64-bit access is single-copy atomic, so a reader that sees both tags sees the whole row.
+__device__ __forceinline__ ulonglong2 ba16_bnd_pack(unsigned M, unsigned L, unsigned H, unsigned tag)
+{
+    ulonglong2 w;
+    w.x = (unsigned long long)M | ((unsigned long long)((L & 0xffffu) | (tag << 16)) << 32);
+    w.y = (unsigned long long)H | ((unsigned long long)((L >> 16) | (tag << 16)) << 32);
+    return w;
+}
+__device__ __forceinline__ bool ba16_bnd_ready(const ulonglong2 &w, unsigned tag)
+{
+    return (unsigned)(w.x >> 48) == tag && (unsigned)(w.y >> 48) == tag;
+}
+__device__ __forceinline__ uint4 ba16_bnd_unpack(const ulonglong2 &w)
+{
+    const unsigned hx = (unsigned)(w.x >> 32), hy = (unsigned)(w.y >> 32);
+    return make_uint4((unsigned)w.x, (hx & 0xffffu) | (hy << 16), (unsigned)w.y, 0u);
+}
 
 // KIND: KIND_SW (right-aligned columns, zero borders, clamps, best-cell candidates) or KIND_NW /
 // KIND_FIT (left-aligned, -inf/gap borders, no clamps).  GSUB: substitution scores from two
 // shared-memory tables (any alphabet, e.g. Protein) instead of the 4-letter PRMT profiles.
 // LONG: intra-pair wavefront for kb-scale pairs -- every work item is ONE pass of a pair couple;
 // the passes of a couple run concurrently on different warps (anywhere on the GPU), each trailing
-// its left neighbour by three periods; the boundary column travels through a per-couple global
-// row buffer guarded by progress counters.  Items are claimed in pass-major order by a persistent
+// its left neighbour by about three periods; the boundary column travels through a per-couple
+// global row buffer whose rows are tagged with the writer's pass.  Items are claimed in pass-major order by a persistent
 // grid, so the pass a warp waits for is always held by a warp that is already running.
-template <int KIND, int COLS, bool MULTI, bool GSUB, bool LONG = false>
+// LIN: the linear-gap aligners (align/sw_letters.go, nw_letters.go, fitted_letters.go): one table T,
+// T = max3(diag + sub, up + er, left + eq) [clamped at 0 for SW]; it lives in the H registers, the
+// checkpoints carry it in their M field (the second field is zero).  SW needs er < 0 and eq < 0
+// so that every cell holding the table maximum came through the diagonal (best-cell rule,
+// align/sw_letters.go:110-114).
+template <int KIND, int COLS, bool MULTI, bool GSUB, bool LONG, bool LIN>
 __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params P)
 {
     constexpr int NC = 2 * COLS;  // columns per lane
@@ -174,6 +198,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     __shared__ unsigned subB[GSUB ? (BA_MAX_LET + 1) * BA_MAX_LET : 1];  // GSUB: sub << 16     (pair B half)
     __shared__ __align__(16) unsigned colbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged column checkpoints
     __shared__ __align__(16) unsigned rowbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged row checkpoint
+    __shared__ uint4 bbuf[MULTI ? BA16_GROUPS : 1][BA16_PERIOD];  // boundary rows (M, L, H) of the current period
     const int let = P.sc->let;
     if (!GSUB) {
         if (threadIdx.x < 8) {
@@ -198,7 +223,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     __syncthreads();
     const int er = P.sc->la[1 * let];  // C1: identical for letters 1..4
     const int eq = P.sc->la[1];
-    const int go = P.sc->gap_open;
+    const int go = LIN ? 0 : P.sc->gap_open;  // linear borders: j*eq and i*er
     const unsigned erp = pack16(er, er), eqp = pack16(eq, eq);
     const unsigned goerp = pack16(go + er, go + er), goeqp = pack16(go + eq, go + eq);
     const unsigned NEGP = pack16(BA16_NEG, BA16_NEG);
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     unsigned *ringA = ring[grp][0], *ringB = ring[grp][1];
     unsigned *colA = colbuf[grp][0], *colB = colbuf[grp][1];
     unsigned *rowA = rowbuf[grp][0], *rowB = rowbuf[grp][1];
-    unsigned *bnd = (unsigned *)P.bnd + (int64_t)group_global * P.bnd_stride;  // LONG: re-pointed per task
+    ulonglong2 *bnd = (ulonglong2 *)(P.bnd + (int64_t)group_global * P.bnd_stride);  // LONG: re-pointed per task
     constexpr int W = 32 * COLS;
     const unsigned FULL = 0xffffffffu;
 
@@ -225,7 +250,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
         if (LONG) {
             long_pass = itA / (2 * P.long_couples);
             couple = (itA % (2 * P.long_couples)) >> 1;
-            bnd = (unsigned *)P.bnd + (int64_t)couple * P.bnd_stride;
+            bnd = (ulonglong2 *)(P.bnd + (int64_t)couple * P.bnd_stride);
         }
         int nA = 0, mA = 0, nB = 0, mB = 0, pA = 0, pB = 0;
         int64_t offA = 0, offB = 0;
@@ -264,9 +289,29 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 
         for (int pass = (LONG ? long_pass : 0); pass < (LONG ? long_pass + 1 : npass_w); pass++) {
             const bool plA = liveA && pass < npassA, plB = liveB && pass < npassB;
-            // LONG: progress counters of this task and of the pass to its left
-            volatile int *prog_me = LONG ? P.prog + (int64_t)couple * P.long_maxpass + pass : nullptr;
-            volatile int *prog_left = (LONG && pass > 0) ? P.prog + (int64_t)couple * P.long_maxpass + pass - 1 : nullptr;
+            const bool rd_bnd = MULTI && pass > 0 && (plA || plB);               // my column 0 comes from bnd
+            const bool wr_bnd = MULTI && pass + 1 < max(npassA, npassB);          // the next pass reads my last column
+            // boundary rows are fetched one period ahead by lanes 0..7 of the group (row 8e+1+t)
+            ulonglong2 pre = make_ulonglong2(0ull, 0ull);
+#define BA16_BND_LAND(row_)                                                       \
+    do {                                                                          \
+        if (LONG) {                                                               \
+            int spins_ = 0;                                                       \
+            while (!ba16_bnd_ready(pre, (unsigned)pass)) {                        \
+                BA_SPIN_PAUSE();                                                  \
+                if (++spins_ > (1 << 22) || *(volatile int *)P.long_err != 0) {   \
+                    *P.long_err = 1;                                              \
+                    break;                                                        \
+                }                                                                 \
+                pre = BA_LDCG(bnd + (row_));                                      \
+            }                                                                     \
+        }                                                                         \
+        bbuf[grp][t] = ba16_bnd_unpack(pre);                                      \
+    } while (0)
+            if (rd_bnd && t < BA16_PERIOD && 1 + t <= nbnd) {
+                pre = BA_LDCG(bnd + 1 + t);
+                BA16_BND_LAND(1 + t);
+            }
             // ---- per-column constants.  PRMT path: byte selectors (virtual columns <= 0 of SW:
             // sign-select => sub in {0,-1}).  GSUB path: byte offsets of the query letters in a
             // table row (SW virtual columns use letter 0 = gap: any finite entry keeps M <= 0 only
@@ -340,21 +385,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 for (int jj = 0; jj < 4; jj++) cst[c][jj] = colA + ba16_stage_word(t, c) + ((jj + (t >> 3)) & 3);
             const int nper_w = (nsteps_w + BA16_PERIOD - 1) >> BA16_PSHIFT;
             for (int e = 0; e < nper_w; e++) {
-                if (LONG && pass > 0) {
-                    // lane 0 reads boundary rows 8e+1 .. 8e+8 in this period; the left pass wrote rows
-                    // <= 8*e_left - 7 once it completed period e_left: wait for e_left >= e + 2
-                    if (t == 0 && (plA || plB)) {
-                        int spins = 0;
-                        while (*prog_left < e + 3) {
-                            BA_SPIN_PAUSE();
-                            if (++spins > (1 << 24)) {
-                                *P.long_err = 1;
-                                break;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
+                const int pre_row = 8 * (e + 1) + 1 + t;  // my boundary row of the NEXT period
+                const bool pre_on = rd_bnd && t < BA16_PERIOD && pre_row <= nbnd;
+                if (pre_on) pre = BA_LDCG(bnd + pre_row);  // lands at the end of this period
                 if ((e & (BA16_PROF_CHUNK / BA16_PERIOD - 1)) == 0) {
                     // rows 8e+1 .. 8e+CHUNK enter the rings (lanes of the group share the load)
                     __syncwarp();
@@ -391,14 +424,37 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         rH = (KIND == KIND_NW) ? pack16(go + i * er, go + i * er) : 0u;
                     }
                     if (MULTI && pass > 0 && i >= 1 && i <= nbnd) {
-                        rM = BA_LDCG(bnd + 3 * i + 0);
-                        rL = BA_LDCG(bnd + 3 * i + 1);
-                        rH = BA_LDCG(bnd + 3 * i + 2);
+                        const uint4 b = bbuf[grp][j];
+                        rM = b.x;
+                        rL = b.y;
+                        rH = b.z;
                     }
                 }
 
                 // NW/Fitted: a lane whose first row has not come yet keeps its row-0 border state
                 if (KIND == KIND_SW || i >= 1) {
+                if (LIN) {
+                    // one sweep along the row: X = max(diag + sub, up + er), T = max(left + eq, X [, 0])
+                    unsigned Hd = sdiagH, Tl = rH;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        unsigned sub;
+                        if (!GSUB)
+                            sub = ba_prmt(profA, profB, sel[k]);
+                        else
+                            sub = *(const unsigned *)((const char *)subA + profA + sel[k]) |
+                                  *(const unsigned *)((const char *)subB + profB + qb4[k]);
+                        const unsigned old = Hu[k];
+                        const unsigned X = __viaddmax_s16x2(Hd, sub, __vadd2(old, erp));
+                        Tl = (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Tl, eqp, X) : __viaddmax_s16x2(Tl, eqp, X);
+                        Hu[k] = Tl;
+                        Mu[k] = Tl;
+                        Hd = old;
+                        if (k == COLS - 1) mc0 = Tl;
+                    }
+                    sdiagH = rH;
+                    outM = outH = Tl;
+                } else {
                 // Three sweeps, each updating its array in place (no register rotation):
                 //  U from the previous row's (M, U); M from the previous row's H; then L along the
                 //  row and H = max3 for the next row's diagonal.
@@ -437,6 +493,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 outL = Ll;
                 outH = Hu[NC - 1];
                 }
+                }
                 if (KIND == KIND_SW) {
 #pragma unroll
                 for (int k = 0; k + 1 < NC; k += 2) bmax = __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
@@ -445,19 +502,15 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 // column checkpoints (M, clamped L) of my two strips, staged per pair for this period
                 {
                     // SW re-applies the clamp its recurrence deferred; NW/Fitted store raw values
-                    const unsigned l0 = (KIND == KIND_SW) ? __vimax_s16x2_relu(lc0, erp) : lc0;
-                    const unsigned l1 = (KIND == KIND_SW) ? __vimax_s16x2_relu(outL, erp) : outL;
+                    const unsigned l0 = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(lc0, erp) : lc0;
+                    const unsigned l1 = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(outL, erp) : outL;
                     unsigned *w = cst[j >> 2][j & 3];
                     w[0] = ba_prmt(mc0, l0, 0x5410u);
                     w[BA16_STAGE_WORDS] = ba_prmt(mc0, l0, 0x7632u);
                     w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, l1, 0x5410u);
                     w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, l1, 0x7632u);
                 }
-                if (MULTI && t == 15 && i >= 1 && i <= nbnd && pass + 1 < max(npassA, npassB)) {
-                    bnd[3 * i + 0] = outM;
-                    bnd[3 * i + 1] = outL;
-                    bnd[3 * i + 2] = outH;
-                }
+                if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(outM, outL, outH, (unsigned)pass + 1u);
                 }
                 // ---- end of the period: row checkpoint, flush both arrays, best-cell bookkeeping
                 {
@@ -466,7 +519,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     for (int x = 0; x < 16; x++) wa[x] = wb[x] = 0;
 #pragma unroll
                     for (int k = 0; k < NC; k++) {
-                        const unsigned u = (KIND == KIND_SW) ? __vimax_s16x2_relu(Uu[k], erp) : Uu[k];
+                        const unsigned u = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(Uu[k], erp) : Uu[k];
                         const int x = (k >= COLS ? 8 + (k - COLS) : k);  // word inside my 16-word region
                         wa[x] = ba_prmt(Mu[k], u, 0x5410u);
                         wb[x] = ba_prmt(Mu[k], u, 0x7632u);
@@ -484,10 +537,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 if (plA && 8 * e + 7 < nstepsA) ba16_flush_period<false>(rowA, rowckA + (int64_t)e * 64, t);
                 if (plB && 8 * e + 7 < nstepsB) ba16_flush_period<false>(rowB, rowckB + (int64_t)e * 64, t);
                 __syncwarp();
-                if (LONG) {
-                    BA_FENCE();      // boundary rows of this period are visible before the counter moves
+                if (MULTI) {
+                    // lane 0 is done with this period's boundary rows: land the next ones
+                    if (pre_on) BA16_BND_LAND(pre_row);
                     __syncwarp();
-                    if (t == 0) *prog_me = e + 1;
                 }
                 if (KIND == KIND_SW) {
                     // best tracking at period granularity ('>=' keeps the LAST period)
@@ -498,11 +551,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     bmax = 0;
                 }
             }
-            if (LONG) {
-                BA_FENCE();
-                __syncwarp();
-                if (t == 0) *prog_me = 0x3fffffff;  // finished: nobody waits on this pass any more
-            }
+#undef BA16_BND_LAND
             if (KIND == KIND_SW && plA) {
                 int2 *cand = (int2 *)(P.arena + offA + (int64_t)npassA * passbA) + pass * 16 + t;
                 *cand = make_int2(lo16(vbest), per_lo);

@@ -41,9 +41,10 @@ inline int cols_for(int m)
 
 // capacity of the per-pair segment slot buffer of the 16-bit path; pairs that emit more are
 // re-run on the exact two-pass path
-inline int32_t slot_cap_for(int n, int m)
+inline int32_t slot_cap_for(int n, int m, int affine)
 {
-    int64_t c = ((int64_t)n + m) / 12 + 12;
+    // linear gaps scatter: an indel costs the same wherever it opens
+    int64_t c = affine ? ((int64_t)n + m) / 12 + 12 : ((int64_t)n + m) / 5 + 16;
     const int64_t hi = (int64_t)n + m + 2;
     return (int32_t)(c < hi ? c : hi);
 }
@@ -69,7 +70,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             const int c = cols_for(m0);
             int64_t cb = mode16 ? ba16_ck_bytes(c, n0, m0) : ba_code_bytes(affine, c, n0, m0);
             cb = (cb + 255) & ~(int64_t)255;
-            const int32_t cap = slot_cap_for(n0, m0);
+            const int32_t cap = slot_cap_for(n0, m0, affine);
             int64_t per_wave = cb > 0 ? arena_cap / cb : nids;
             if (per_wave < 1) per_wave = 1;
             if (per_wave > nids) per_wave = nids;
@@ -182,7 +183,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
                 memo_m = qry_len[p];
                 memo_cb = mode16 ? ba16_ck_bytes(c, memo_n, memo_m) : ba_code_bytes(affine, c, memo_n, memo_m);
                 memo_cb = (memo_cb + 255) & ~(int64_t)255;
-                memo_cap = slot_cap_for(memo_n, memo_m);
+                memo_cap = slot_cap_for(memo_n, memo_m, affine);
             }
             const int64_t cb = memo_cb;
             if (wave.count > 0 && wave.code_bytes + cb > arena_cap) {

@@ -116,7 +116,7 @@ __device__ __forceinline__ Cell3 border_col0(int i, int go, int er)
 // store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).
 // S is the scoring matrix scaled by BA_SCALE in shared memory (row stride `let`).
 template <int KIND>
-__device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
+__device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                              uint8_t *tile, TileProbe &pb)
 {
@@ -256,7 +256,127 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
     }
 }
 
+// Linear-gap tile (ba_fill16 LIN): one table T; the checkpoints hold it in their M field.  Codes
+// are linear_cell<KIND>'s: 3 diag, 2 up, 1 left, 0 = SW cell clamped to zero (stop).
 template <int KIND>
+__device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S, int let, const uint8_t *rs,
+                                                 const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
+                                                 uint8_t *tile, TileProbe &pb)
+{
+    const int v = CkView::lane_of(g);
+    const int rt = max(BA16_PERIOD * e - v, 0);
+    const int c0 = ck.left_col(g);
+    const int cL = max(c0, 0);
+    const int kfirst = cL - c0;
+    const int klast = jmax - c0 - 1;
+    const int er_u = S[let], eq_u = S[1];
+    const int gl = g - 1;
+
+    int qo[BA_MAX_COLS], eqv[BA_MAX_COLS], Tv[BA_MAX_COLS];
+#pragma unroll
+    for (int k = 0; k < BA_MAX_COLS; k++) {
+        qo[k] = 0;
+        eqv[k] = 0;
+        Tv[k] = 0;
+        if (k >= kfirst && k <= klast) {
+            qo[k] = qs[(c0 + k) * stride];
+            eqv[k] = S[qo[k]];
+            if (rt >= 1) {
+                int mm, uu;
+                ck.row_mu(g, e - 1, k, mm, uu);
+                Tv[k] = mm * BA_SCALE;
+            } else if (KIND != KIND_SW) {
+                Tv[k] = (c0 + k + 1) * eq_u;    // row 0: nw_letters.go:91-93, fitted_letters.go:83-85
+            }
+        }
+    }
+    // T at (row, cL): DP border column (nw_letters.go:94-96; zero for SW and Fitted) or strip gl's
+    // checkpointed last column
+    auto left_at = [&](int r) -> int {
+        if (cL > 0) {
+            if (r == 0) return (KIND == KIND_SW) ? 0 : cL * eq_u;
+            int mm, ll;
+            ck.col_ml(gl, r, mm, ll);
+            return mm * BA_SCALE;
+        }
+        return (KIND == KIND_NW) ? r * er_u : 0;
+    };
+    int dprev = left_at(rt);
+    uint8_t *trow = tile;
+    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * BA_TRACE_THREADS) {
+        const int *Srow = S + (int)rs[(r - 1) * stride] * let;
+        const int er = Srow[0];
+        const int left = left_at(r);
+        int d = dprev, l = left;
+#pragma unroll
+        for (int k = 0; k < BA_MAX_COLS; k++) {
+            if (k >= kfirst && k <= klast) {
+                unsigned code;
+                const int old = Tv[k];
+                const int nw = linear_cell<KIND>(d, old, l, Srow[qo[k]], er, eqv[k], code);
+                trow[k * BA_TRACE_THREADS] = (uint8_t)code;
+                const int col = c0 + k + 1;
+                if (KIND == KIND_SW && pb.want >= 0 && nw == pb.want) {
+                    pb.fi = r;
+                    pb.fj = col;
+                }
+                // fitted_letters.go:128-135: last row with T >= max whose letter scores >= 0
+                // against the last query letter
+                if (KIND == KIND_FIT && col == pb.col && nw >= pb.best && Srow[qo[k]] >= 0) {
+                    pb.best = nw;
+                    pb.besti = r;
+                }
+                Tv[k] = nw;
+                d = old;
+                l = nw;
+            }
+        }
+        dprev = left;
+    }
+}
+
+template <int KIND, bool LIN>
+__device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
+                                             const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
+                                             uint8_t *tile, TileProbe &pb)
+{
+    if (LIN)
+        trace16_tile_lin<KIND>(ck, S, let, rs, qs, stride, g, e, imax, jmax, tile, pb);
+    else
+        trace16_tile_aff<KIND>(ck, S, let, go, rs, qs, stride, g, e, imax, jmax, tile, pb);
+}
+
+// One step of the walk: decode the cell's code for the current layer into (move, next layer,
+// score delta).  Affine: the seven candidates of align/sw_affine_letters.go:171-275 (diag
+// sub-order differs for NW/Fitted, nw_affine_letters.go:255-299).  Linear: diag, up, left
+// (align/sw_letters.go:137-171).  Returns false when no candidate matched.
+template <int KIND, bool LIN>
+__device__ __forceinline__ bool trace16_decode(unsigned code, int layer, int er, int eq, int sub, int go, int &move,
+                                               int &nl, int &delta)
+{
+    nl = 0;
+    if (LIN) {
+        switch (code & 3u) {
+        case 3: move = MV_DIAG; delta = sub; return true;
+        case 2: move = MV_UP;   delta = er;  return true;
+        case 1: move = MV_LEFT; delta = eq;  return true;
+        default: move = MV_DIAG; delta = 0;  return false;
+        }
+    }
+    const unsigned f = (layer == 0) ? (code & 7u) : (layer == 1) ? ((code >> 3) & 3u) : (code >> 5);
+    switch (f) {
+    case 1: move = MV_UP;   nl = 1; delta = er;      return true;
+    case 2: move = MV_LEFT; nl = 2; delta = eq;      return true;
+    case 3: move = MV_UP;   nl = 0; delta = go + er; return true;
+    case 4: move = MV_LEFT; nl = 0; delta = go + eq; return true;
+    case 5: move = MV_DIAG; nl = (KIND == KIND_SW) ? 0 : 1; delta = sub; return true;
+    case 6: move = MV_DIAG; nl = (KIND == KIND_SW) ? 1 : 2; delta = sub; return true;
+    case 7: move = MV_DIAG; nl = (KIND == KIND_SW) ? 2 : 0; delta = sub; return true;
+    default: move = MV_DIAG; delta = 0; return false;
+    }
+}
+
+template <int KIND, bool LIN>
 __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_kernel(Trace16Params P)
 {
     __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
@@ -285,7 +405,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
     const int stride = P.stride;
     const DeviceScoring *sc = P.sc;
     const int let = sc->let;
-    const int go = sc->gap_open;
+    const int go = LIN ? 0 : sc->gap_open;
     const int go8 = go * BA_SCALE;
 
     CkView ck;
@@ -339,7 +459,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
                     if (rlast < i || (rlast == i && clast < j)) continue;  // cannot come later
                     TileProbe pb;
                     pb.want = Smax * BA_SCALE;
-                    trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
                     if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
                         i = pb.fi;
                         j = pb.fj;
@@ -358,7 +478,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         TileProbe pb;
         pb.ci = i;
         pb.cj = j;
-        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
                            tile, pb);
         int best = pb.cM;
         if (pb.cU > best) {
@@ -377,7 +497,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         for (int e = 0; BA16_PERIOD * e - v < n; e++) {
             const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
             if (rlast < 1) continue;
-            trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+            trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         i = pb.besti;
     }
@@ -392,28 +512,20 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         const int rt = max(BA16_PERIOD * e - v, 0);
         const int c0 = max(ck.left_col(g), 0);
         TileProbe pb0;
-        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
+        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
         const int cbase = ck.left_col(g);
         while (i > rt && j > c0) {
             if (KIND == KIND_SW && cur == 0) break;
             const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
             const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
             const bool corner = (i == n && j == m);
-            const unsigned f = (layer == 0) ? (code & 7u) : (layer == 1) ? ((code >> 3) & 3u) : (code >> 5);
             const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
             int move, nl = 0, delta;
-            switch (f) {
-            case 1: move = MV_UP;   nl = 1; delta = er;      break;
-            case 2: move = MV_LEFT; nl = 2; delta = eq;      break;
-            case 3: move = MV_UP;   nl = 0; delta = go + er; break;
-            case 4: move = MV_LEFT; nl = 0; delta = go + eq; break;
-            case 5: move = MV_DIAG; nl = (KIND == KIND_SW) ? 0 : 1; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
-            case 6: move = MV_DIAG; nl = (KIND == KIND_SW) ? 1 : 2; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
-            case 7: move = MV_DIAG; nl = (KIND == KIND_SW) ? 2 : 0; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
-            default: move = MV_DIAG; delta = 0; bad = true; break;
-            }
+            if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl, delta))
+                bad = true;
             if (bad) break;
-            if (last != move && (move == MV_DIAG || !corner)) {
+            // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
+            if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
                 T16_EMIT(i, maxI, j, maxJ, score);
                 maxI = i;
                 maxJ = j;
@@ -456,7 +568,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
 // Lane 0 emits.  A window always contains the tile under the walk, so every round advances.
 #define BA_TW_STRIPS 4
 #define BA_TW_PERIODS 8
-template <int KIND>
+template <int KIND, bool LIN>
 __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_kernel(Trace16Params P)
 {
     __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
@@ -487,7 +599,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     const uint8_t *qs = P.enc + P.qry_off[p];
     const int stride = P.stride;
     const int let = P.sc->let;
-    const int go = P.sc->gap_open;
+    const int go = LIN ? 0 : P.sc->gap_open;
     const int go8 = go * BA_SCALE;
 
     CkView ck;
@@ -540,7 +652,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
                     if (rlast < i || (rlast == i && clast < j)) continue;
                     TileProbe pb;
                     pb.want = Smax * BA_SCALE;
-                    trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
                     if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
                         i = pb.fi;
                         j = pb.fj;
@@ -565,7 +677,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         TileProbe pb;
         pb.ci = i;
         pb.cj = j;
-        trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
                            tile, pb);
         int best = pb.cM;
         if (pb.cU > best) {
@@ -583,7 +695,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         for (int e = lane; BA16_PERIOD * e - v < n; e += 32) {
             const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
             if (rlast < 1) continue;
-            trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+            trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         // last row attaining the maximum: larger value wins, ties go to the larger row
         int best = pb.best, besti = pb.besti;
@@ -615,7 +727,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             const int rtop = max(BA16_PERIOD * e - v, 0);
             if (g >= 0 && e >= 0 && clast >= 1 && rlast > rtop) {
                 TileProbe pb0;
-                trace16_tile<KIND>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
+                trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
             }
         }
         __syncwarp();
@@ -633,21 +745,13 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             const unsigned code =
                 tiles[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS + wbase + ws * 8 + we];
             const bool corner = (i == n && j == m);
-            const unsigned f = (layer == 0) ? (code & 7u) : (layer == 1) ? ((code >> 3) & 3u) : (code >> 5);
             const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
             int move, nl = 0, delta;
-            switch (f) {
-            case 1: move = MV_UP;   nl = 1; delta = er;      break;
-            case 2: move = MV_LEFT; nl = 2; delta = eq;      break;
-            case 3: move = MV_UP;   nl = 0; delta = go + er; break;
-            case 4: move = MV_LEFT; nl = 0; delta = go + eq; break;
-            case 5: move = MV_DIAG; nl = (KIND == KIND_SW) ? 0 : 1; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
-            case 6: move = MV_DIAG; nl = (KIND == KIND_SW) ? 1 : 2; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
-            case 7: move = MV_DIAG; nl = (KIND == KIND_SW) ? 2 : 0; delta = S[R * let + Q] >> BA_SCALE_SHIFT; break;
-            default: move = MV_DIAG; delta = 0; bad = true; break;
-            }
+            if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl, delta))
+                bad = true;
             if (bad) break;
-            if (last != move && (move == MV_DIAG || !corner)) {
+            // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
+            if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
                 T16W_EMIT(i, maxI, j, maxJ, score);
                 maxI = i;
                 maxJ = j;

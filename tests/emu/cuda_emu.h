@@ -228,6 +228,10 @@ struct int2 {
     int x, y;
 };
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct ulonglong2 {
+    unsigned long long x, y;
+};
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 using std::max;

@@ -248,3 +248,60 @@ def test_fast16_warp_per_pair_traceback(emu_ctx, kind):
         emu_ctx.set_option("trace_mode", 1)
     assert res0.stats["warp_trace_launches"] == 0
     helpers.compare(res0, orc, f"thread trace kind {kind}")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SW", "NW", "Fitted"])
+def test_fast16_linear_kinds(emu_ctx, kind):
+    """Linear-gap aligners on the packed path (LIN mode of ba_fill16 + linear tiles of ba_trace16):
+    DNA through PRMT profiles, Protein through the shared-memory tables, several passes, both
+    traceback kernels and the wavefront over passes."""
+    rng = random.Random(4700 + kind)
+    M = gv.match(-1, 2, -1)
+    pairs = randcases.rand_pairs(rng, 36, [1, 2, 5, 17, 40, 90, 150, 260], [1, 3, 4, 16, 33, 64, 100, 257, 300, 520],
+                                 related=0.85, dirty=0.0)
+    pairs += randcases.rand_pairs(rng, 6, [30, 120], [30, 120], related=0.0, dirty=0.0)
+    pk = helpers.pack(pairs)
+    orc = helpers.run_oracle(kind, False, M, 0, DNA_IDX, pk)
+    for mode in (0, 2):
+        emu_ctx.set_option("trace_mode", mode)
+        try:
+            res = helpers.run_lib(emu_ctx, kind, False, M, 0, DNA_IDX, 5, pk)
+        finally:
+            emu_ctx.set_option("trace_mode", 1)
+        assert res.stats["pairs_fast16"] >= len(pairs) // 2   # segment-slot overflow re-runs on the exact path
+        helpers.compare(res, orc, f"fast16 linear kind {kind} trace_mode {mode}")
+    # ties everywhere: match 1 / mismatch -1 / gap -1 makes diag, up and left collide often
+    T = gv.match(-1, 1, -1)
+    tp = randcases.rand_pairs(rng, 30, [3, 20, 64, 130], [3, 20, 64, 130, 300], related=0.6, dirty=0.0, alpha=b"AC")
+    tpk = helpers.pack(tp, 2)
+    res = helpers.run_lib(emu_ctx, kind, False, T, 0, DNA_IDX, 5, tpk, 2)
+    assert res.stats["pairs_fast16"] >= len(tp) // 2
+    helpers.compare(res, helpers.run_oracle(kind, False, T, 0, DNA_IDX, tpk, 2), f"fast16 linear ties kind {kind}")
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    P = matrix.with_gap(matrix.BLOSUM62, -4)
+    ppairs = randcases.rand_pairs(rng, 20, [3, 20, 45, 80, 300], [2, 20, 45, 80, 300], related=0.8, dirty=0.15,
+                                  alpha=aa, dirty_alpha=aa + b"BZX*J-acdu")
+    ppk = helpers.pack(ppairs)
+    res = helpers.run_lib(emu_ctx, kind, False, P, 0, PROT_IDX, 26, ppk)
+    assert res.stats["pairs_fast16"] > 0
+    helpers.compare(res, helpers.run_oracle(kind, False, P, 0, PROT_IDX, ppk), f"fast16 linear protein kind {kind}")
+    long_pairs = randcases.rand_pairs(rng, 5, [9, 60, 200], [800, 1025, 1300], related=0.85, dirty=0.0)
+    lpk = helpers.pack(long_pairs)
+    emu_ctx.set_option("long_mode", 2)
+    try:
+        res = helpers.run_lib(emu_ctx, kind, False, M, 0, DNA_IDX, 5, lpk)
+    finally:
+        emu_ctx.set_option("long_mode", 1)
+    assert res.stats["wavefront_launches"] >= 1
+    helpers.compare(res, helpers.run_oracle(kind, False, M, 0, DNA_IDX, lpk), f"fast16 linear wavefront kind {kind}")
+
+
+def test_linear_sw_with_zero_gap_scores_takes_the_exact_path(emu_ctx):
+    """er = eq = 0 breaks 'the maximum is always reached through the diagonal': not eligible."""
+    rng = random.Random(4800)
+    M = gv.match(0, 1, -1)
+    pairs = randcases.rand_pairs(rng, 12, [5, 30, 70], [5, 30, 70], related=0.7, dirty=0.0)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(emu_ctx, 0, False, M, 0, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] == 0
+    helpers.compare(res, helpers.run_oracle(0, False, M, 0, DNA_IDX, pk), "linear SW gap 0")

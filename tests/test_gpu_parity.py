@@ -332,3 +332,50 @@ def test_warp_per_pair_traceback_matches_thread_per_pair(gpu_ctx, kind):
             gpu_ctx.set_option("trace_mode", 1)
         assert (res.stats["warp_trace_launches"] >= 1) == want
         helpers.compare(res, orc, f"trace_mode {mode} kind {kind}")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SW", "NW", "Fitted"])
+def test_fast16_linear_kinds(gpu_ctx, kind):
+    """Linear-gap aligners on the packed DPX path: DNA, Protein, long queries, both trace kernels."""
+    rng = random.Random(5400 + kind)
+    M = gv.match(-1, 2, -1)
+    pairs = randcases.rand_pairs(rng, 1500, [1, 5, 17, 40, 150, 500, 900], [1, 4, 16, 64, 150, 257, 300, 1100],
+                                 related=0.9, dirty=0.0)
+    pk = helpers.pack(pairs)
+    orc = helpers.run_oracle(kind, False, M, 0, DNA_IDX, pk, 1, 16)
+    for mode in (0, 2):
+        gpu_ctx.set_option("trace_mode", mode)
+        try:
+            res = helpers.run_lib(gpu_ctx, kind, False, M, 0, DNA_IDX, 5, pk)
+        finally:
+            gpu_ctx.set_option("trace_mode", 1)
+        assert res.stats["pairs_fast16"] > 0.7 * len(pairs)
+        helpers.compare(res, orc, f"fast16 linear kind {kind} trace_mode {mode}")
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    P = matrix.with_gap(matrix.BLOSUM62, -4)
+    ppairs = randcases.rand_pairs(rng, 600, [20, 45, 80, 300], [20, 45, 80, 300], related=0.8, dirty=0.1, alpha=aa,
+                                  dirty_alpha=aa + b"BZX*J-acdu")
+    ppk = helpers.pack(ppairs, 2)
+    res = helpers.run_lib(gpu_ctx, kind, False, P, 0, PROT_IDX, 26, ppk, 2)
+    assert res.stats["pairs_fast16"] > 0.4 * len(ppairs)
+    helpers.compare(res, helpers.run_oracle(kind, False, P, 0, PROT_IDX, ppk, 2, 16), f"fast16 linear protein {kind}")
+    lp = randcases.rand_pairs(rng, 9, [700, 2500], [1100, 3000], related=0.9, dirty=0.0)
+    lpk = helpers.pack(lp)
+    res = helpers.run_lib(gpu_ctx, kind, False, M, 0, DNA_IDX, 5, lpk)
+    assert res.stats["wavefront_launches"] >= 1
+    helpers.compare(res, helpers.run_oracle(kind, False, M, 0, DNA_IDX, lpk, 1, 8), f"fast16 linear wavefront {kind}")
+
+
+def test_config1_fast_and_exact_paths_agree(gpu_ctx):
+    w = synth.config(1, 20000)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    idx = w.alpha.LetterIndex()
+    fast = helpers.run_lib(gpu_ctx, w.kind, False, w.matrix, 0, idx, 5, pk)
+    assert fast.stats["pairs_fast16"] > 0.99 * w.n
+    gpu_ctx.set_option("force_path", 1)
+    try:
+        exact = helpers.run_lib(gpu_ctx, w.kind, False, w.matrix, 0, idx, 5, pk)
+    finally:
+        gpu_ctx.set_option("force_path", 0)
+    assert exact.stats["pairs_fast16"] == 0
+    helpers.compare(fast, exact, "cfg1 fast vs exact")
