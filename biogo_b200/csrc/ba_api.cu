@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -107,7 +108,7 @@ struct ba_ctx {
     DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
     DevBuf flags, slot_off, slot_cap, slots, seg_clip, tasks, prog;
-    int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1;
+    int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1, opt_exclusive = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
@@ -172,6 +173,25 @@ void pinned_put(ba_ctx *ctx, void *p)
         if (b.p == p) b.used = false;
 }
 
+// Work lists travel host -> device through a kernel that reads the pinned host buffer directly
+// (zero-copy over PCIe) instead of the copy engine: an H2D copy-engine transfer would queue behind
+// the 100+ MB letters upload another context may have in flight (exclusive_compute pipelining).
+__global__ void ba_upload_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int64_t words)
+{
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < words; x += (int64_t)gridDim.x * blockDim.x)
+        dst[x] = src[x];
+}
+int upload_words(ba_ctx *ctx, void *dst, const void *pinned_src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return BA_OK;
+    const int64_t words = (int64_t)(bytes / 4);  // every work-list element is a multiple of 4 bytes
+    int64_t blocks = (words + 255) / 256;
+    if (blocks > 2 * (int64_t)ctx->sm_count) blocks = 2 * (int64_t)ctx->sm_count;
+    BA_LAUNCH(ba_upload_kernel, (unsigned)blocks, 256, st, (uint32_t *)dst, (const uint32_t *)pinned_src, words);
+    CK(cudaGetLastError());
+    return BA_OK;
+}
+
 // seg_base = exclusive prefix sum of seg_count (int32 -> int64)
 int exclusive_scan(ba_ctx *ctx, void *tmp, size_t &tmp_bytes, const int32_t *in, int64_t *out, int n,
                    cudaStream_t st)
@@ -220,6 +240,10 @@ struct Batch {
 };
 
 static bool g_timing = getenv("BA_TIMING") != nullptr;
+// One batch's kernel phase at a time per device (option "exclusive_compute"): callers driving several
+// contexts from several threads then pipeline -- the H2D copy of one batch runs under the kernels
+// of another instead of all copies and all kernels coinciding.
+static std::mutex g_compute_token[64];
 #define BA_TSEC(name, t0) do { if (g_timing) fprintf(stderr, "[ba timing] %-22s %8.3f ms\n", name, (now_s() - (t0)) * 1e3); } while (0)
 
 static inline double now_s()
@@ -358,12 +382,16 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
 
     for (auto &w : plan.waves) {
         WorkItem *d_items = (WorkItem *)ctx->items.p;
-        CK(cudaMemcpyAsync(d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count,
-                           cudaMemcpyHostToDevice, st));
+        if ((rc = upload_words(ctx, d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count, st)) != BA_OK)
+            return rc;
+        B.launches++;
         int64_t *d_aux_off = (int64_t *)ctx->aux_off.p;
-        if (kind == KIND_FIT)
-            CK(cudaMemcpyAsync(d_aux_off, plan.aux_off + w.first, sizeof(int64_t) * (size_t)w.count,
-                               cudaMemcpyHostToDevice, st));
+        if (kind == KIND_FIT) {
+            if ((rc = upload_words(ctx, d_aux_off, plan.aux_off + w.first, sizeof(int64_t) * (size_t)w.count, st)) !=
+                BA_OK)
+                return rc;
+            B.launches++;
+        }
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
 
         // ---- fill
@@ -635,12 +663,15 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
 
     for (auto &w : plan.waves) {
         WorkItem *d_items = (WorkItem *)ctx->items.p;
-        CK(cudaMemcpyAsync(d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count,
-                           cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->slot_off.p, plan.slot_off + w.first, sizeof(int64_t) * (size_t)w.count,
-                           cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->slot_cap.p, plan.slot_cap + w.first, sizeof(int32_t) * (size_t)w.count,
-                           cudaMemcpyHostToDevice, st));
+        if ((rc = upload_words(ctx, d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count, st)) != BA_OK)
+            return rc;
+        if ((rc = upload_words(ctx, ctx->slot_off.p, plan.slot_off + w.first, sizeof(int64_t) * (size_t)w.count,
+                               st)) != BA_OK)
+            return rc;
+        if ((rc = upload_words(ctx, ctx->slot_cap.p, plan.slot_cap + w.first, sizeof(int32_t) * (size_t)w.count,
+                               st)) != BA_OK)
+            return rc;
+        B.launches += 3;
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
 
         // ---- fill (values + checkpoints)
@@ -709,8 +740,9 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 if ((rc = ensure(ctx, ctx->tasks, sizeof(WorkItem) * (size_t)ntasks)) != BA_OK) return rc;
                 if ((rc = ensure(ctx, ctx->prog, 64)) != BA_OK) return rc;
                 if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * ncp))) != BA_OK) return rc;
-                CK(cudaMemcpyAsync(ctx->tasks.p, h_tasks, sizeof(WorkItem) * (size_t)ntasks, cudaMemcpyHostToDevice,
-                                   st));
+                if ((rc = upload_words(ctx, ctx->tasks.p, h_tasks, sizeof(WorkItem) * (size_t)ntasks, st)) != BA_OK)
+                    return rc;
+                B.launches++;
                 CK(cudaMemsetAsync(ctx->prog.p, 0, 64, st));
                 // row tags start out invalid
                 CK(cudaMemsetAsync(ctx->bnd.p, 0, sizeof(int32_t) * (size_t)(bnd_stride * ncp), st));
@@ -1064,6 +1096,10 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
         ctx->opt_trace_mode = value;
         return BA_OK;
     }
+    if (!strcmp(key, "exclusive_compute")) {
+        ctx->opt_exclusive = value;
+        return BA_OK;
+    }
     if (!strcmp(key, "force_path")) {
         ctx->opt_force_path = value;
         return BA_OK;
@@ -1201,17 +1237,46 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
     if ((rc = ensure(ctx, ctx->ref_len, sizeof(int32_t) * (size_t)(n + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->qry_len, sizeof(int32_t) * (size_t)(n + 1))) != BA_OK) return rc;
     CK(cudaEventRecord(ctx->ev[0], st));
-    if (letters_bytes > 0)
-        CK(cudaMemcpyAsync(ctx->letters.p, letters, (size_t)letters_bytes, cudaMemcpyHostToDevice, st));
+    // The offset/length arrays are the caller's pageable memory: a copy straight from them would
+    // block inside the driver behind the letters copy.  Stage them in pinned memory and send them
+    // first; the letters buffer may be pinned (ba_alloc_host) or not.
+    uint8_t *stage = nullptr;
     if (n > 0) {
-        CK(cudaMemcpyAsync(ctx->ref_off.p, ref_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->qry_off.p, qry_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->ref_len.p, ref_len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->qry_len.p, qry_len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        const size_t b8 = sizeof(int64_t) * (size_t)n, b4 = sizeof(int32_t) * (size_t)n;
+        stage = (uint8_t *)pinned_get(ctx, 2 * b8 + 2 * b4);
+        if (!stage) {
+            ctx->err = "pinned host allocation failed";
+            return BA_ERR_NOMEM;
+        }
+        memcpy(stage, ref_off, b8);
+        memcpy(stage + b8, qry_off, b8);
+        memcpy(stage + 2 * b8, ref_len, b4);
+        memcpy(stage + 2 * b8 + b4, qry_len, b4);
+        CK(cudaMemcpyAsync(ctx->ref_off.p, stage, b8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->qry_off.p, stage + b8, b8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ref_len.p, stage + 2 * b8, b4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->qry_len.p, stage + 2 * b8 + b4, b4, cudaMemcpyHostToDevice, st));
     }
-    rc = run_device(ctx, (const uint8_t *)ctx->letters.p, letters_bytes, stride, (const int64_t *)ctx->ref_off.p,
-                    (const int32_t *)ctx->ref_len.p, (const int64_t *)ctx->qry_off.p,
-                    (const int32_t *)ctx->qry_len.p, ref_len, qry_len, n, st, out);
+    // in pieces: the small H2D copies of another context's kernel phase (work lists) share the copy
+    // engine and must not queue behind one 100+ MB transfer
+    for (int64_t o = 0; o < letters_bytes; o += (4 << 20)) {
+        const size_t len = (size_t)std::min<int64_t>(4 << 20, letters_bytes - o);
+        CK(cudaMemcpyAsync((uint8_t *)ctx->letters.p + o, letters + o, len, cudaMemcpyHostToDevice, st));
+    }
+    {
+        std::unique_lock<std::mutex> token(g_compute_token[ctx->device & 63], std::defer_lock);
+        if (ctx->opt_exclusive) {
+            // inputs on the device first, then wait for the GPU's kernel phase to be free
+            CK(cudaEventRecord(ctx->ev[7], st));
+            CK(cudaEventSynchronize(ctx->ev[7]));
+            token.lock();
+        }
+        rc = run_device(ctx, (const uint8_t *)ctx->letters.p, letters_bytes, stride, (const int64_t *)ctx->ref_off.p,
+                        (const int32_t *)ctx->ref_len.p, (const int64_t *)ctx->qry_off.p,
+                        (const int32_t *)ctx->qry_len.p, ref_len, qry_len, n, st, out);
+    }
+    if (rc != BA_OK) cudaStreamSynchronize(st);  // the staged copies may still be in flight
+    if (stage) pinned_put(ctx, stage);           // on success run_device returned with the stream drained
     if (rc != BA_OK) {
         ba_free_result(ctx, out);
         return rc;
