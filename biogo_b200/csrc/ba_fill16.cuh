@@ -91,24 +91,23 @@ __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); 
 // of the two arrays (about 1 byte per DP cell for 8-column strips).  The fill stages both
 // through shared memory and writes every period as fully coalesced 16-byte stores.
 __host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + BA16_SKEW + BA16_PERIOD - 1) / BA16_PERIOD; }
-__host__ __device__ inline int64_t ba16_colck_bytes(int64_t n) { return ba16_nper(n) * 32 * 32; }
-__host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, int cols)
+// Linear kinds (`lin`) have one table: their slots are int16 {T}, and a sector holds TWO
+// consecutive periods (low halves = even period, high halves = odd period), i.e. half the bytes.
+__host__ __device__ inline int64_t ba16_nsect(int64_t n, bool lin) { return lin ? (ba16_nper(n) + 1) / 2 : ba16_nper(n); }
+__host__ __device__ inline int64_t ba16_colck_bytes(int64_t n, bool lin) { return ba16_nsect(n, lin) * 32 * 32; }
+__host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, bool lin) { return ba16_nsect(n, lin) * 32 * 32; }
+__host__ __device__ inline int64_t ba16_pass_bytes(int64_t n, bool lin)
 {
-    (void)cols;
-    return ba16_nper(n) * 32 * 32;
-}
-__host__ __device__ inline int64_t ba16_pass_bytes(int64_t n, int cols)
-{
-    return ba16_colck_bytes(n) + ba16_rowck_bytes(n, cols);
+    return ba16_colck_bytes(n, lin) + ba16_rowck_bytes(n, lin);
 }
 // After the passes: one candidate record per (pass, lane): {best score of the lane's two
 // strips, last period attaining it} -- the start-cell candidates of ba_trace16.
 __host__ __device__ inline int64_t ba16_npass(int cols, int64_t m) { return (m + 32LL * cols - 1) / (32LL * cols); }
-__host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m)
+__host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m, bool lin)
 {
     if (n <= 0 || m <= 0) return 0;
     const int64_t np = ba16_npass(cols, m);
-    return np * ba16_pass_bytes(n, cols) + np * 16 * 8;
+    return np * ba16_pass_bytes(n, lin) + np * 16 * 8;
 }
 // Columns are RIGHT-aligned: strip g of pass p covers table columns
 //   jshift + p*W + g*COLS + 1 .. + COLS   with W = 32*COLS, jshift = m - npass*W  (<= 0),
@@ -282,7 +281,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
         int nsteps_w = max(nstepsA, nstepsB), npass_w = max(npassA, npassB);
         nsteps_w = max(nsteps_w, __shfl_xor_sync(FULL, nsteps_w, 16));
         npass_w = MULTI ? max(npass_w, __shfl_xor_sync(FULL, npass_w, 16)) : 1;
-        const int64_t passbA = ba16_pass_bytes(nA, COLS), passbB = ba16_pass_bytes(nB, COLS);
+        const int64_t passbA = ba16_pass_bytes(nA, LIN), passbB = ba16_pass_bytes(nB, LIN);
         const int jshiftA = (KIND == KIND_SW) ? mA - npassA * W : 0, jshiftB = (KIND == KIND_SW) ? mB - npassB * W : 0;
         // rows staged between passes: only pairs that really have a next pass (bounds the scratch)
         const int nbnd = max(npassA > 1 ? nA : 0, npassB > 1 ? nB : 0);
@@ -370,9 +369,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             unsigned vbest = pack16(1, 1);
             int per_lo = -1, per_hi = -1;
             uint4 *colckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA);
-            uint4 *rowckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA + ba16_colck_bytes(nA));
+            uint4 *rowckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA + ba16_colck_bytes(nA, LIN));
             uint4 *colckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB);
-            uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB));
+            uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB, LIN));
             unsigned ro = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;  // byte offset of my row in the rings
             unsigned mc0 = 0, lc0 = 0;  // boundary column of my first strip (M, L) at the current row
 
@@ -385,6 +384,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 for (int jj = 0; jj < 4; jj++) cst[c][jj] = colA + ba16_stage_word(t, c) + ((jj + (t >> 3)) & 3);
             const int nper_w = (nsteps_w + BA16_PERIOD - 1) >> BA16_PSHIFT;
             for (int e = 0; e < nper_w; e++) {
+                const int parofs = (e & 1) * BA16_STAGE_PLANE;  // LIN: chunk of this period inside its sector
                 const int pre_row = 8 * (e + 1) + 1 + t;  // my boundary row of the NEXT period
                 const bool pre_on = rd_bnd && t < BA16_PERIOD && pre_row <= nbnd;
                 if (pre_on) pre = BA_LDCG(bnd + pre_row);  // lands at the end of this period
@@ -505,15 +505,46 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     const unsigned l0 = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(lc0, erp) : lc0;
                     const unsigned l1 = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(outL, erp) : outL;
                     unsigned *w = cst[j >> 2][j & 3];
-                    w[0] = ba_prmt(mc0, l0, 0x5410u);
-                    w[BA16_STAGE_WORDS] = ba_prmt(mc0, l0, 0x7632u);
-                    w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, l1, 0x5410u);
-                    w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, l1, 0x7632u);
+                    if (LIN) {
+                        // int16 slots: the even period of a sector fills its first 16-byte chunk, the
+                        // odd period the second; step j is half-word j of the chunk
+                        unsigned short *h = (unsigned short *)(cst[0][j >> 1] + parofs) + (j & 1);
+                        h[0] = (unsigned short)mc0;
+                        h[2 * BA16_STAGE_WORDS] = (unsigned short)(mc0 >> 16);
+                        h[4 * BA16_STAGE_PLANE] = (unsigned short)outM;
+                        h[4 * BA16_STAGE_PLANE + 2 * BA16_STAGE_WORDS] = (unsigned short)(outM >> 16);
+                    } else {
+                        w[0] = ba_prmt(mc0, l0, 0x5410u);
+                        w[BA16_STAGE_WORDS] = ba_prmt(mc0, l0, 0x7632u);
+                        w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, l1, 0x5410u);
+                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, l1, 0x7632u);
+                    }
                 }
                 if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(outM, outL, outH, (unsigned)pass + 1u);
                 }
                 // ---- end of the period: row checkpoint, flush both arrays, best-cell bookkeeping
-                {
+                if (LIN) {
+                    // int16 {T}: eight columns of a strip make one 16-byte chunk (this period's half
+                    // of the sector); two columns per word
+                    unsigned wa[2 * 4], wb[2 * 4];
+#pragma unroll
+                    for (int x = 0; x < 8; x++) wa[x] = wb[x] = 0;
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+                        for (int kk = 0; kk < COLS; kk += 2) {
+                            const unsigned lo = Mu[s2 * COLS + kk];
+                            const unsigned hi = (kk + 1 < COLS) ? Mu[s2 * COLS + kk + 1] : 0u;
+                            wa[4 * s2 + (kk >> 1)] = ba_prmt(lo, hi, 0x5410u);
+                            wb[4 * s2 + (kk >> 1)] = ba_prmt(lo, hi, 0x7632u);
+                        }
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        const int w = ba16_stage_word(t, 2 * s2) + parofs;
+                        *(uint4 *)(rowA + w) = make_uint4(wa[4 * s2], wa[4 * s2 + 1], wa[4 * s2 + 2], wa[4 * s2 + 3]);
+                        *(uint4 *)(rowB + w) = make_uint4(wb[4 * s2], wb[4 * s2 + 1], wb[4 * s2 + 2], wb[4 * s2 + 3]);
+                    }
+                } else {
                     unsigned wa[4 * 4], wb[4 * 4];  // four chunks of four words per pair
 #pragma unroll
                     for (int x = 0; x < 16; x++) wa[x] = wb[x] = 0;
@@ -532,10 +563,26 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     }
                 }
                 __syncwarp();
+                if (LIN) {
+                    // a sector holds two periods: flush after the odd one (or after the very last)
+                    if ((e & 1) || e == nper_w - 1) {
+                        const int e0 = e & ~1;
+                        const int64_t so = (int64_t)(e >> 1) * 64;
+                        if (plA && (e0 << BA16_PSHIFT) < nstepsA) {
+                            ba16_flush_period<true>(colA, colckA + so, t);
+                            ba16_flush_period<false>(rowA, rowckA + so, t);
+                        }
+                        if (plB && (e0 << BA16_PSHIFT) < nstepsB) {
+                            ba16_flush_period<true>(colB, colckB + so, t);
+                            ba16_flush_period<false>(rowB, rowckB + so, t);
+                        }
+                    }
+                } else {
                 if (plA && (e << BA16_PSHIFT) < nstepsA) ba16_flush_period<true>(colA, colckA + (int64_t)e * 64, t);
                 if (plB && (e << BA16_PSHIFT) < nstepsB) ba16_flush_period<true>(colB, colckB + (int64_t)e * 64, t);
                 if (plA && 8 * e + 7 < nstepsA) ba16_flush_period<false>(rowA, rowckA + (int64_t)e * 64, t);
                 if (plB && 8 * e + 7 < nstepsB) ba16_flush_period<false>(rowB, rowckB + (int64_t)e * 64, t);
+                }
                 __syncwarp();
                 if (MULTI) {
                     // lane 0 is done with this period's boundary rows: land the next ones

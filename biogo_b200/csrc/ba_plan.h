@@ -68,7 +68,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         }
         if (same) {
             const int c = cols_for(m0);
-            int64_t cb = mode16 ? ba16_ck_bytes(c, n0, m0) : ba_code_bytes(affine, c, n0, m0);
+            int64_t cb = mode16 ? ba16_ck_bytes(c, n0, m0, !affine) : ba_code_bytes(affine, c, n0, m0);
             cb = (cb + 255) & ~(int64_t)255;
             const int32_t cap = slot_cap_for(n0, m0, affine);
             int64_t per_wave = cb > 0 ? arena_cap / cb : nids;
@@ -181,7 +181,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             if (ref_len[p] != memo_n || qry_len[p] != memo_m) {
                 memo_n = ref_len[p];
                 memo_m = qry_len[p];
-                memo_cb = mode16 ? ba16_ck_bytes(c, memo_n, memo_m) : ba_code_bytes(affine, c, memo_n, memo_m);
+                memo_cb = mode16 ? ba16_ck_bytes(c, memo_n, memo_m, !affine) : ba_code_bytes(affine, c, memo_n, memo_m);
                 memo_cb = (memo_cb + 255) & ~(int64_t)255;
                 memo_cap = slot_cap_for(memo_n, memo_m, affine);
             }

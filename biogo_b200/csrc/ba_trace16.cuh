@@ -45,6 +45,7 @@ struct Trace16Params {
 struct CkView {
     const uint8_t *base;
     int n, m, cols, npass, jshift;
+    bool lin;  // linear kinds: int16 {T} slots, two periods per sector (ba_fill16.cuh)
     int64_t pass_bytes, colck_bytes;
     // Strip g (global index: pass*32 + strip) belongs to lane (g & 31) >> 1 of the fill, which
     // handles row i at step i-1+lane.
@@ -54,9 +55,17 @@ struct CkView {
     {
         const int pass = g >> 5;
         const int st = r - 1 + lane_of(g);
+        const int e = st >> BA16_PSHIFT;
+        if (lin) {
+            const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
+                                             ((int64_t)((e >> 1) * 32 + (g & 31)) * 32 + (e & 1) * 16 +
+                                              (st & (BA16_PERIOD - 1)) * 2));
+            M = p[0];
+            L = 0;
+            return;
+        }
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
-                                         ((int64_t)((st >> BA16_PSHIFT) * 32 + (g & 31)) * 8 +
-                                          (st & (BA16_PERIOD - 1))) * 4);
+                                         ((int64_t)(e * 32 + (g & 31)) * 8 + (st & (BA16_PERIOD - 1))) * 4);
         M = p[0];
         L = p[1];
     }
@@ -64,6 +73,13 @@ struct CkView {
     __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const
     {
         const int pass = g >> 5;
+        if (lin) {
+            const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
+                                             ((int64_t)((e >> 1) * 32 + (g & 31)) * 32 + (e & 1) * 16 + k * 2));
+            M = p[0];
+            U = 0;
+            return;
+        }
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
                                          ((int64_t)(e * 32 + (g & 31)) * 8 + k) * 4);
         M = p[0];
@@ -415,8 +431,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
     ck.cols = item.cols;
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
-    ck.pass_bytes = ba16_pass_bytes(n, item.cols);
-    ck.colck_bytes = ba16_colck_bytes(n);
+    ck.lin = LIN;
+    ck.pass_bytes = ba16_pass_bytes(n, LIN);
+    ck.colck_bytes = ba16_colck_bytes(n, LIN);
 
     int32_t *out = P.slots + 5 * P.slot_off[it];
     const int cap = P.slot_cap[it];
@@ -609,8 +626,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     ck.cols = item.cols;
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
-    ck.pass_bytes = ba16_pass_bytes(n, item.cols);
-    ck.colck_bytes = ba16_colck_bytes(n);
+    ck.lin = LIN;
+    ck.pass_bytes = ba16_pass_bytes(n, LIN);
+    ck.colck_bytes = ba16_colck_bytes(n, LIN);
 
     int32_t *out = P.slots + 5 * P.slot_off[it];
     const int cap = P.slot_cap[it];
