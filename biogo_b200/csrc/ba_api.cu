@@ -108,6 +108,18 @@ struct ba_ctx {
     DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
     DevBuf flags, slot_off, slot_cap, slots, seg_clip, tasks, prog;
+    // Plan cache: batches of the same shape (same length arrays, same scoring) reuse the split, the
+    // work lists and -- for single-wave plans -- their device copies.
+    struct PlanCache {
+        bool valid = false, plan_built = false;
+        int64_t n = 0, cells = 0, arena_cap = 0, slot_cap_opt = 0;
+        uint64_t epoch = 0;
+        std::vector<int32_t> ref_len, qry_len, fast, slow0;
+        Plan plan;
+        const void *dev_items = nullptr, *dev_slot_off = nullptr, *dev_slot_cap = nullptr;  // where the device copy lives
+    } pc;
+    uint64_t scoring_epoch = 1;
+    int64_t opt_plan_cache = 1;
     int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1, opt_exclusive = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
@@ -330,6 +342,20 @@ int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, in
     return BA_OK;
 }
 
+void plan_cache_drop(ba_ctx *ctx)
+{
+    ba_ctx::PlanCache &pc = ctx->pc;
+    if (pc.plan_built) {
+        pinned_put(ctx, pc.plan.items);
+        pinned_put(ctx, pc.plan.slot_off);
+        pinned_put(ctx, pc.plan.slot_cap);
+    }
+    pc.plan = Plan();
+    pc.plan_built = false;
+    pc.valid = false;
+    pc.dev_items = pc.dev_slot_off = pc.dev_slot_cap = nullptr;
+}
+
 // ---- path A: 32-bit exact-code fill + two-pass walk (all kinds, any matrix) ---------------
 int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
 {
@@ -337,6 +363,7 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
     const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
     cudaStream_t st = B.st;
     int rc;
+    ctx->pc.dev_items = nullptr;  // this path reuses the work-list buffers
     int64_t arena_cap = 0;
     if (arena_budget(ctx, arena_cap) != 0) {
         ctx->err = "cudaMemGetInfo failed";
@@ -589,7 +616,8 @@ bool fast16_pair_ok(const DeviceScoring &s, const Fast16 &f, int n, int m)
     return true;
 }
 
-int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsub, std::vector<int32_t> &overflow)
+int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsub, std::vector<int32_t> &overflow,
+               bool use_cache)
 {
     const int kind = ctx->h_sc.kind;
     const bool lin = !ctx->h_sc.affine;
@@ -602,30 +630,48 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         ctx->err = "cudaMemGetInfo failed";
         return BA_ERR_CUDA;
     }
-    Plan plan;
+    Plan local_plan;
+    ba_ctx::PlanCache &pc = ctx->pc;
     const double tp0 = now_s();
-    plan.items = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)nids);
-    plan.slot_off = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)nids);
-    plan.slot_cap = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)nids);
-    if (!plan.items || !plan.slot_off || !plan.slot_cap) {
-        ctx->err = "pinned host allocation failed";
-        return BA_ERR_NOMEM;
+    if (use_cache && pc.plan_built && (pc.arena_cap != arena_cap || pc.slot_cap_opt != ctx->opt_slot_cap)) {
+        pinned_put(ctx, pc.plan.items);
+        pinned_put(ctx, pc.plan.slot_off);
+        pinned_put(ctx, pc.plan.slot_cap);
+        pc.plan = Plan();
+        pc.plan_built = false;
+        pc.dev_items = nullptr;
     }
-    const double tp1 = now_s();
-    build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, lin ? 0 : 1, true, arena_cap, plan);
-    BA_TSEC("plan16 pinned_get", tp0);
-    BA_TSEC("plan16 build", tp1);
-    B.host_s += now_s() - tp0;
-    if (ctx->opt_slot_cap > 0) {  // test hook: force the overflow -> exact-path fallback
-        for (auto &w : plan.waves) {
-            w.slots = 0;
-            for (int64_t k = 0; k < w.count; k++) {
-                plan.slot_off[w.first + k] = w.slots;
-                plan.slot_cap[w.first + k] = (int32_t)ctx->opt_slot_cap;
-                w.slots += ctx->opt_slot_cap;
+    Plan &plan = use_cache ? pc.plan : local_plan;
+    if (!(use_cache && pc.plan_built)) {
+        plan.items = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)nids);
+        plan.slot_off = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)nids);
+        plan.slot_cap = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)nids);
+        if (!plan.items || !plan.slot_off || !plan.slot_cap) {
+            ctx->err = "pinned host allocation failed";
+            return BA_ERR_NOMEM;
+        }
+        const double tp1 = now_s();
+        build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, lin ? 0 : 1, true, arena_cap, plan);
+        BA_TSEC("plan16 pinned_get", tp0);
+        BA_TSEC("plan16 build", tp1);
+        if (ctx->opt_slot_cap > 0) {  // test hook: force the overflow -> exact-path fallback
+            for (auto &w : plan.waves) {
+                w.slots = 0;
+                for (int64_t k = 0; k < w.count; k++) {
+                    plan.slot_off[w.first + k] = w.slots;
+                    plan.slot_cap[w.first + k] = (int32_t)ctx->opt_slot_cap;
+                    w.slots += ctx->opt_slot_cap;
+                }
             }
         }
+        if (use_cache) {
+            pc.plan_built = true;
+            pc.arena_cap = arena_cap;
+            pc.slot_cap_opt = ctx->opt_slot_cap;
+            pc.dev_items = nullptr;
+        }
     }
+    B.host_s += now_s() - tp0;
     int64_t max_items = 0, max_code = 0, max_slots = 0;
     for (auto &w : plan.waves) {
         max_items = std::max(max_items, w.count);
@@ -663,15 +709,27 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
 
     for (auto &w : plan.waves) {
         WorkItem *d_items = (WorkItem *)ctx->items.p;
-        if ((rc = upload_words(ctx, d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count, st)) != BA_OK)
-            return rc;
-        if ((rc = upload_words(ctx, ctx->slot_off.p, plan.slot_off + w.first, sizeof(int64_t) * (size_t)w.count,
-                               st)) != BA_OK)
-            return rc;
-        if ((rc = upload_words(ctx, ctx->slot_cap.p, plan.slot_cap + w.first, sizeof(int32_t) * (size_t)w.count,
-                               st)) != BA_OK)
-            return rc;
-        B.launches += 3;
+        const bool dev_ok = use_cache && plan.waves.size() == 1 && pc.dev_items == ctx->items.p &&
+                            pc.dev_slot_off == ctx->slot_off.p && pc.dev_slot_cap == ctx->slot_cap.p;
+        if (!dev_ok) {
+            if ((rc = upload_words(ctx, d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count, st)) !=
+                BA_OK)
+                return rc;
+            if ((rc = upload_words(ctx, ctx->slot_off.p, plan.slot_off + w.first, sizeof(int64_t) * (size_t)w.count,
+                                   st)) != BA_OK)
+                return rc;
+            if ((rc = upload_words(ctx, ctx->slot_cap.p, plan.slot_cap + w.first, sizeof(int32_t) * (size_t)w.count,
+                                   st)) != BA_OK)
+                return rc;
+            B.launches += 3;
+            if (use_cache && plan.waves.size() == 1) {
+                pc.dev_items = ctx->items.p;
+                pc.dev_slot_off = ctx->slot_off.p;
+                pc.dev_slot_cap = ctx->slot_cap.p;
+            } else {
+                pc.dev_items = nullptr;
+            }
+        }
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
 
         // ---- fill (values + checkpoints)
@@ -859,9 +917,11 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     pinned_put(ctx, h_cnt);
     pinned_put(ctx, h_raw);
     pinned_put(ctx, h_base);
-    pinned_put(ctx, plan.items);
-    pinned_put(ctx, plan.slot_off);
-    pinned_put(ctx, plan.slot_cap);
+    if (!use_cache) {
+        pinned_put(ctx, plan.items);
+        pinned_put(ctx, plan.slot_off);
+        pinned_put(ctx, plan.slot_cap);
+    }
     return BA_OK;
 }
 
@@ -932,32 +992,47 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
     CK(cudaGetLastError());
     BA_TSEC("T result+enc launch", t_call);
 
-    const double th0 = now_s();
-    int64_t cells = 0;
-    for (int64_t p = 0; p < n; p++) cells += (int64_t)h_ref_len[p] * (int64_t)h_qry_len[p];
-    out->cells = cells;
-    BA_TSEC("cells loop", th0);
-    B.host_s += now_s() - th0;
-
-    // ---- split the batch between the two paths
+    // ---- split the batch between the two paths (cached for batches of the same shape)
     std::vector<int32_t> slow;
     if (fast16) {
         // size eligibility is known on the host; letter eligibility (ACGT only) is decided on the
         // device: ineligible pairs come back from the traceback marked for the exact path
         const double ts0 = now_s();
-        std::vector<int32_t> fast;
-        fast.reserve((size_t)n);
-        for (int64_t p = 0; p < n; p++) {
-            const bool ok = fast16_pair_ok(ctx->h_sc, f16, h_ref_len[p], h_qry_len[p]);
-            (ok ? fast : slow).push_back((int32_t)p);
+        ba_ctx::PlanCache &pc = ctx->pc;
+        const bool hit = ctx->opt_plan_cache && pc.valid && pc.n == n && pc.epoch == ctx->scoring_epoch &&
+                         memcmp(pc.ref_len.data(), h_ref_len, sizeof(int32_t) * (size_t)n) == 0 &&
+                         memcmp(pc.qry_len.data(), h_qry_len, sizeof(int32_t) * (size_t)n) == 0;
+        if (!hit) {
+            plan_cache_drop(ctx);
+            pc.n = n;
+            pc.epoch = ctx->scoring_epoch;
+            pc.ref_len.assign(h_ref_len, h_ref_len + n);
+            pc.qry_len.assign(h_qry_len, h_qry_len + n);
+            pc.fast.clear();
+            pc.slow0.clear();
+            pc.fast.reserve((size_t)n);
+            pc.cells = 0;
+            for (int64_t p = 0; p < n; p++) {
+                pc.cells += (int64_t)h_ref_len[p] * (int64_t)h_qry_len[p];
+                const bool ok = fast16_pair_ok(ctx->h_sc, f16, h_ref_len[p], h_qry_len[p]);
+                (ok ? pc.fast : pc.slow0).push_back((int32_t)p);
+            }
+            pc.valid = true;
         }
+        out->cells = pc.cells;
+        slow = pc.slow0;
         BA_TSEC("partition", ts0);
         B.host_s += now_s() - ts0;
         const size_t nslow0 = slow.size();
-        if ((rc = run_path16(ctx, B, fast.data(), (int64_t)fast.size(), f16.gsub, slow)) != BA_OK) return rc;
-        out->pairs_fast16 = (int64_t)fast.size() - (int64_t)(slow.size() - nslow0);
+        if ((rc = run_path16(ctx, B, pc.fast.data(), (int64_t)pc.fast.size(), f16.gsub, slow,
+                             ctx->opt_plan_cache != 0)) != BA_OK)
+            return rc;
+        out->pairs_fast16 = (int64_t)pc.fast.size() - (int64_t)(slow.size() - nslow0);
         if ((rc = run_path32(ctx, B, slow.data(), (int64_t)slow.size())) != BA_OK) return rc;
     } else {
+        int64_t cells = 0;
+        for (int64_t p = 0; p < n; p++) cells += (int64_t)h_ref_len[p] * (int64_t)h_qry_len[p];
+        out->cells = cells;
         if ((rc = run_path32(ctx, B, nullptr, n)) != BA_OK) return rc;
     }
 
@@ -1100,6 +1175,11 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
         ctx->opt_exclusive = value;
         return BA_OK;
     }
+    if (!strcmp(key, "plan_cache")) {
+        ctx->opt_plan_cache = value;
+        plan_cache_drop(ctx);
+        return BA_OK;
+    }
     if (!strcmp(key, "force_path")) {
         ctx->opt_force_path = value;
         return BA_OK;
@@ -1135,7 +1215,7 @@ int ba_set_scoring(ba_ctx *ctx, int kind, int affine, const int64_t *la, int let
         ctx->err = "scoring values exceed the 32-bit device range";
         return BA_ERR_RANGE;
     }
-    DeviceScoring &s = ctx->h_sc;
+    DeviceScoring s;
     memset(&s, 0, sizeof s);
     for (int k = 0; k < let * let; k++) s.la[k] = (int32_t)la[k];
     s.let = let;
@@ -1144,10 +1224,15 @@ int ba_set_scoring(ba_ctx *ctx, int kind, int affine, const int64_t *la, int let
     s.kind = kind;
     s.affine = affine ? 1 : 0;
     for (int k = 0; k < 256; k++) s.index[k] = (index[k] < 0 || index[k] > 253) ? 0xFF : (uint8_t)index[k];
+    // the matrix is re-read every call (callers may mutate it), but an unchanged one
+    // keeps the device copy and the cached plans
+    if (ctx->have_scoring && memcmp(&s, &ctx->h_sc, sizeof s) == 0) return BA_OK;
+    ctx->h_sc = s;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->d_sc, &s, sizeof s, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sc, &ctx->h_sc, sizeof s, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_scoring = true;
+    ctx->scoring_epoch++;  // cached plans depend on the scoring (eligibility, kind)
     return BA_OK;
 }
 

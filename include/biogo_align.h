@@ -143,7 +143,8 @@ void ba_free_host(void *p);
  * "trace_mode" (16-bit path traceback: 0 thread per pair, 1 automatic, 2 warp per pair),
  * "exclusive_compute" (default 1: ba_align_batch calls on the same device run their kernel phases
  * one at a time, so that with several contexts on several threads the upload of one batch overlaps
- * the kernels of another). */
+ * the kernels of another), "plan_cache" (default 1: a batch whose length arrays equal the previous
+ * batch's reuses its work lists). */
 int ba_set_option(ba_ctx *ctx, const char *key, int64_t value);
 
 /* Build/ABI information. */

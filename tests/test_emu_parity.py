@@ -305,3 +305,49 @@ def test_linear_sw_with_zero_gap_scores_takes_the_exact_path(emu_ctx):
     res = helpers.run_lib(emu_ctx, 0, False, M, 0, DNA_IDX, 5, pk)
     assert res.stats["pairs_fast16"] == 0
     helpers.compare(res, helpers.run_oracle(0, False, M, 0, DNA_IDX, pk), "linear SW gap 0")
+
+
+def test_plan_cache_reuses_work_lists_for_same_shaped_batches(emu_ctx):
+    """Same length arrays, different letters: the cached plan must not leak results between
+    calls; a new scoring, new lengths or a changed option drop it."""
+    rng = random.Random(4900)
+    lens_r, lens_q = [40, 90, 150, 33], [30, 64, 100, 257]
+    shape = [(rng.choice(lens_r), rng.choice(lens_q)) for _ in range(24)]
+
+    def batch(seed):
+        r = random.Random(seed)
+        out = []
+        for n, m in shape:
+            ref = bytes(r.choice(b"ACGT") for _ in range(n))
+            qry = bytearray(ref[:m].ljust(m, b"A"))
+            for _ in range(max(1, m // 10)):
+                qry[r.randrange(m)] = r.choice(b"ACGT")
+            out.append((ref, bytes(qry)))
+        return out
+
+    M = gv.match(-1, 2, -1)
+    for kind, affine, go in ((0, True, -4), (1, True, -4), (0, False, 0)):
+        for seed in (1, 2, 2, 3):
+            pk = helpers.pack(batch(seed))
+            res = helpers.run_lib(emu_ctx, kind, affine, M, go, DNA_IDX, 5, pk)
+            helpers.compare(res, helpers.run_oracle(kind, affine, M, go, DNA_IDX, pk), f"cache {kind} {affine} seed {seed}")
+    # an overflowing pair in between (exact path reuses the work-list buffers) and a different shape
+    emu_ctx.set_option("slot_cap", 2)
+    try:
+        pk = helpers.pack(batch(5))
+        res = helpers.run_lib(emu_ctx, 0, True, M, -4, DNA_IDX, 5, pk)
+    finally:
+        emu_ctx.set_option("slot_cap", 0)
+    helpers.compare(res, helpers.run_oracle(0, True, M, -4, DNA_IDX, pk), "cache after overflow")
+    pk = helpers.pack(batch(6))
+    res = helpers.run_lib(emu_ctx, 0, True, M, -4, DNA_IDX, 5, pk)
+    helpers.compare(res, helpers.run_oracle(0, True, M, -4, DNA_IDX, pk), "cache rebuilt")
+    pk = helpers.pack(batch(6)[:11])
+    res = helpers.run_lib(emu_ctx, 0, True, M, -4, DNA_IDX, 5, pk)
+    helpers.compare(res, helpers.run_oracle(0, True, M, -4, DNA_IDX, pk), "cache other n")
+    emu_ctx.set_option("plan_cache", 0)
+    try:
+        res = helpers.run_lib(emu_ctx, 0, True, M, -4, DNA_IDX, 5, pk)
+    finally:
+        emu_ctx.set_option("plan_cache", 1)
+    helpers.compare(res, helpers.run_oracle(0, True, M, -4, DNA_IDX, pk), "cache off")
