@@ -321,8 +321,19 @@ def main():
         hbm_peak, peak_src = load_peaks()
         fill_s = agg["ms_fill"] * 1e-3
         ach = agg["code_bytes"] / fill_s / 1e9 if fill_s > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of the fill kernel, captured once with ncu --set full
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                ent = json.load(f)["entries"].get(w.name)
+            if ent and ent["pairs"] == w.n and agg["pairs_fast16"]:
+                traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
+                traffic_src = "profiles/ncu_traffic.json (" + ent["kernel"] + ", one launch)"
+        except (OSError, KeyError, ValueError):
+            pass
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": agg["code_bytes"] / max(agg["fill_launches"], 1),
+                "peak_source": peak_src,
                 "kernel": ("ba_fill16_kernel (packed s16x2 DPX fill + checkpoint stores)" if agg["pairs_fast16"]
                            else "ba_fill32_kernel (DP fill + traceback-code stores)"),
                 "algorithmic_bytes_per_cell": (1.0 if w.affine else 0.25),
