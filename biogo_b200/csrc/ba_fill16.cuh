@@ -21,7 +21,7 @@
 //       maximum has max3(diag) == diag M, i.e. qualifies for bíogo's best-cell rule
 //       (align/sw_affine_letters.go:126-134), so "last cell in row-major order with the maximum
 //       score" is the reference's start cell; U and L may skip the clamp at 0 inside the
-//       recurrence (it is re-applied when checkpoints are written)
+//       recurrence (it is re-applied when ba_trace16 reads the checkpoints)
 //   C3  letters restricted to alphabet indices 1..4 and |la| < 128: the substitution score of
 //       a packed cell pair is ONE PRMT (byte permute with sign replication) of two 4-byte row
 //       profiles
@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             uint4 *colckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB);
             uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB, LIN));
             unsigned ro = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;  // byte offset of my row in the rings
-            unsigned mc0 = 0, lc0 = 0;  // boundary column of my first strip (M, L) at the current row
+            unsigned mc0 = 0;            // LIN: T of my first strip's last column at the current row
+            unsigned ck0a = 0, ck0b = 0; // affine: packed (M, L) checkpoint words of that column, pairs A and B
 
             // staging addresses of my column-checkpoint words: [half of the period][word], pair A,
             // strip 2t; strip 2t+1 is two chunk planes further, pair B one buffer further
@@ -484,8 +485,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     Ml = Mu[k];
                     Hu[k] = __vimax3_s16x2(Ml, Uu[k], Ll);
                     if (k == COLS - 1) {
-                        mc0 = Ml;
-                        lc0 = Ll;
+                        // checkpoint words of my first strip, taken where (M, L) are live
+                        ck0a = ba_prmt(Ml, Ll, 0x5410u);
+                        ck0b = ba_prmt(Ml, Ll, 0x7632u);
                     }
                 }
                 sdiagH = rH;
@@ -501,9 +503,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 
                 // column checkpoints (M, clamped L) of my two strips, staged per pair for this period
                 {
-                    // SW re-applies the clamp its recurrence deferred; NW/Fitted store raw values
-                    const unsigned l0 = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(lc0, erp) : lc0;
-                    const unsigned l1 = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(outL, erp) : outL;
+                    // raw values: SW's deferred clamp of U and L is re-applied by the reader (ba_trace16 CkView)
                     unsigned *w = cst[j >> 2][j & 3];
                     if (LIN) {
                         // int16 slots: the even period of a sector fills its first 16-byte chunk, the
@@ -514,10 +514,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         h[4 * BA16_STAGE_PLANE] = (unsigned short)outM;
                         h[4 * BA16_STAGE_PLANE + 2 * BA16_STAGE_WORDS] = (unsigned short)(outM >> 16);
                     } else {
-                        w[0] = ba_prmt(mc0, l0, 0x5410u);
-                        w[BA16_STAGE_WORDS] = ba_prmt(mc0, l0, 0x7632u);
-                        w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, l1, 0x5410u);
-                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, l1, 0x7632u);
+                        w[0] = ck0a;
+                        w[BA16_STAGE_WORDS] = ck0b;
+                        w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, outL, 0x5410u);
+                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, outL, 0x7632u);
                     }
                 }
                 if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(outM, outL, outH, (unsigned)pass + 1u);
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     for (int x = 0; x < 16; x++) wa[x] = wb[x] = 0;
 #pragma unroll
                     for (int k = 0; k < NC; k++) {
-                        const unsigned u = LIN ? 0u : (KIND == KIND_SW) ? __vimax_s16x2_relu(Uu[k], erp) : Uu[k];
+                        const unsigned u = LIN ? 0u : Uu[k];
                         const int x = (k >= COLS ? 8 + (k - COLS) : k);  // word inside my 16-word region
                         wa[x] = ba_prmt(Mu[k], u, 0x5410u);
                         wb[x] = ba_prmt(Mu[k], u, 0x7632u);

@@ -46,6 +46,7 @@ struct CkView {
     const uint8_t *base;
     int n, m, cols, npass, jshift;
     bool lin;  // linear kinds: int16 {T} slots, two periods per sector (ba_fill16.cuh)
+    bool clamp;  // affine SW: the fill defers the clamp of U and L at zero and stores them raw
     int64_t pass_bytes, colck_bytes;
     // Strip g (global index: pass*32 + strip) belongs to lane (g & 31) >> 1 of the fill, which
     // handles row i at step i-1+lane.
@@ -67,7 +68,7 @@ struct CkView {
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
                                          ((int64_t)(e * 32 + (g & 31)) * 8 + (st & (BA16_PERIOD - 1))) * 4);
         M = p[0];
-        L = p[1];
+        L = clamp ? max((int)p[1], 0) : (int)p[1];
     }
     // (M, clamped U) of column k of strip g at its checkpoint row of period e
     __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const
@@ -83,7 +84,7 @@ struct CkView {
         const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
                                          ((int64_t)(e * 32 + (g & 31)) * 8 + k) * 4);
         M = p[0];
-        U = p[1];
+        U = clamp ? max((int)p[1], 0) : (int)p[1];
     }
     __device__ __forceinline__ int strip_of(int j) const { return (j - jshift - 1) / cols; }
     __device__ __forceinline__ int left_col(int g) const { return jshift + g * cols; }
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
     ck.lin = LIN;
+    ck.clamp = (KIND == KIND_SW) && !LIN;
     ck.pass_bytes = ba16_pass_bytes(n, LIN);
     ck.colck_bytes = ba16_colck_bytes(n, LIN);
 
@@ -627,6 +629,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
     ck.lin = LIN;
+    ck.clamp = (KIND == KIND_SW) && !LIN;
     ck.pass_bytes = ba16_pass_bytes(n, LIN);
     ck.colck_bytes = ba16_colck_bytes(n, LIN);
 
