@@ -539,16 +539,17 @@ Fill16Fn pick_fill16(int kind, bool lin, int cols, bool multi, bool gsub, bool w
     return ba_pick_fill16_2_0(cols, multi, gsub, wavefront);
 }
 typedef void (*Trace16Fn)(Trace16Params);
-Trace16Fn pick_trace16w(int kind, bool lin)
+template <int NT>
+Trace16Fn pick_trace16t(int kind, bool lin)
 {
     if (lin) {
-        if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, true>;
-        if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, true>;
-        return ba_trace16w_kernel<KIND_FIT, true>;
+        if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, true, NT>;
+        if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, true, NT>;
+        return ba_trace16w_kernel<KIND_FIT, true, NT>;
     }
-    if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, false>;
-    if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, false>;
-    return ba_trace16w_kernel<KIND_FIT, false>;
+    if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, false, NT>;
+    if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, false, NT>;
+    return ba_trace16w_kernel<KIND_FIT, false, NT>;
 }
 Trace16Fn pick_trace16(int kind, bool lin)
 {
@@ -863,12 +864,19 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.slots = (int32_t *)ctx->slots.p;
         // one thread per pair when the batch fills the GPU that way, else one warp per pair
         // (window of speculatively rebuilt tiles, see ba_trace16w_kernel)
+        // (window of speculatively rebuilt tiles, see ba_trace16w_kernel), a whole CTA per pair when
+        // even that leaves SMs idle
+        const bool cta_trace = ctx->opt_trace_mode == 3 ||
+                               (ctx->opt_trace_mode == 1 && w.count <= 2 * (int64_t)ctx->sm_count);
         const bool warp_trace = ctx->opt_trace_mode == 2 ||
                                 (ctx->opt_trace_mode == 1 &&
                                  w.count * 32 <= (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS * 2);
-        if (warp_trace) {
+        if (cta_trace) {
+            BA_LAUNCH(pick_trace16t<BA_TRACE_THREADS>(kind, lin), (unsigned)w.count, BA_TRACE_THREADS, st, tp);
+            B.out->warp_trace_launches++;
+        } else if (warp_trace) {
             const unsigned tb = (unsigned)((w.count + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-            BA_LAUNCH(pick_trace16w(kind, lin), tb, BA_TRACE_THREADS, st, tp);
+            BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, st, tp);
             B.out->warp_trace_launches++;
         } else {
             const unsigned tblocks = (unsigned)((w.count + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
@@ -1167,7 +1175,7 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
         ctx->opt_long_mode = value;
         return BA_OK;
     }
-    if (!strcmp(key, "trace_mode")) {  // 0 = thread per pair, 1 = automatic, 2 = warp per pair
+    if (!strcmp(key, "trace_mode")) {  // 0 = thread per pair, 1 = automatic, 2 = warp per pair, 3 = CTA per pair
         ctx->opt_trace_mode = value;
         return BA_OK;
     }

@@ -578,18 +578,26 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-per-pair variant for batches too small to fill the GPU with one thread per pair
-// (kb-scale pairs, BASELINE config 4).  Same tiles, same walk; the 32 lanes
-//   * split the start-cell search (SW candidates / Fitted last-column periods), and
-//   * rebuild a WINDOW of 4 strips x 8 periods up-left of the walk position concurrently, one
-//     full tile per lane; then every lane walks the identical path through the cached tiles
-//     (all lanes read the same code byte: a shared-memory broadcast) until it leaves the window.
-// Lane 0 emits.  A window always contains the tile under the walk, so every round advances.
+// Team-per-pair variant for batches too small to fill the GPU with one thread per pair
+// (kb-scale pairs, BASELINE config 4).  Same tiles, same walk; a team of NT threads
+//   * splits the start-cell search (SW candidates / Fitted last-column periods), and
+//   * rebuilds a WINDOW of tiles up-left of the walk position concurrently, one full tile per
+//     thread; then every thread walks the identical path through the cached tiles (all read
+//     the same code byte: a shared-memory broadcast) until it leaves the window.
+// NT = 32 (a warp; four pairs per CTA): window = 4 strips x 8 periods.  NT = 128 (the whole CTA,
+// for a handful of very long pairs): a diagonal BAND of 42 strips x 3 periods -- strip s of the
+// window is centred on the period the main diagonal through the anchor reaches there -- so one
+// round covers ~330 columns of a near-diagonal path instead of 32.
+// Thread 0 emits.  A window always contains the tile under the walk, so every round advances.
 #define BA_TW_STRIPS 4
 #define BA_TW_PERIODS 8
-template <int KIND, bool LIN>
+#define BA_TB_PERIODS 3
+#define BA_TB_STRIPS (BA_TRACE_THREADS / BA_TB_PERIODS)
+template <int KIND, bool LIN, int NT>
 __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_kernel(Trace16Params P)
 {
+    static_assert(NT == 32 || NT == BA_TRACE_THREADS, "a team is a warp or the CTA");
+    __shared__ int red[BA_TRACE_THREADS / 32][2];
     __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
     __shared__ int S[BA_MAX_LET * BA_MAX_LET];
     {
@@ -598,10 +606,43 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int wbase = threadIdx.x & ~31;   // first thread of my warp: its 32 tile columns are the window
-    const int it = blockIdx.x * (BA_TRACE_THREADS / 32) + (threadIdx.x >> 5);
-    if (it >= P.n_items) return;           // warp-uniform
+    const int lane = threadIdx.x & (NT - 1);    // my index inside the team
+    const int wbase = threadIdx.x & ~(NT - 1);  // first thread of my team: its NT tile columns are the window
+    const int it = blockIdx.x * (BA_TRACE_THREADS / NT) + threadIdx.x / NT;
+    if (it >= P.n_items) return;                // team-uniform
+#define T16W_SYNC()                  \
+    do {                             \
+        if (NT == 32)                \
+            __syncwarp();            \
+        else                         \
+            __syncthreads();         \
+    } while (0)
+    // lexicographic maximum of (a, b) over the team, result in every thread
+#define T16W_MAX2(a, b)                                                                          \
+    do {                                                                                         \
+        for (int o_ = 16; o_; o_ >>= 1) {                                                        \
+            const int oa_ = __shfl_xor_sync(FULL, (a), o_), ob_ = __shfl_xor_sync(FULL, (b), o_); \
+            if (oa_ > (a) || (oa_ == (a) && ob_ > (b))) {                                        \
+                (a) = oa_;                                                                       \
+                (b) = ob_;                                                                       \
+            }                                                                                    \
+        }                                                                                        \
+        if (NT > 32) {                                                                           \
+            __syncthreads();                                                                     \
+            if ((threadIdx.x & 31) == 0) {                                                       \
+                red[threadIdx.x >> 5][0] = (a);                                                  \
+                red[threadIdx.x >> 5][1] = (b);                                                  \
+            }                                                                                    \
+            __syncthreads();                                                                     \
+            for (int w_ = 0; w_ < BA_TRACE_THREADS / 32; w_++) {                                 \
+                const int oa_ = red[w_][0], ob_ = red[w_][1];                                    \
+                if (oa_ > (a) || (oa_ == (a) && ob_ > (b))) {                                    \
+                    (a) = oa_;                                                                   \
+                    (b) = ob_;                                                                   \
+                }                                                                                \
+            }                                                                                    \
+        }                                                                                        \
+    } while (0)
     uint8_t *tile = tiles + threadIdx.x;
     const WorkItem item = P.items[it];
     const int p = item.pair;
@@ -654,13 +695,16 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     if (KIND == KIND_SW && n > 0 && m > 0) {
         const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
         int Smax = 0;
-        for (int x = lane; x < ck.npass * 16; x += 32) {
+        for (int x = lane; x < ck.npass * 16; x += NT) {
             const int2 c = cand[x];
             if (c.y >= 0) Smax = max(Smax, c.x);
         }
-        for (int o = 16; o; o >>= 1) Smax = max(Smax, __shfl_xor_sync(FULL, Smax, o));
+        {
+            int z = 0;
+            T16W_MAX2(Smax, z);
+        }
         if (Smax > 0) {
-            for (int x = lane; x < ck.npass * 16; x += 32) {
+            for (int x = lane; x < ck.npass * 16; x += NT) {
                 const int2 c = cand[x];
                 if (c.y < 0 || c.x != Smax) continue;
                 const int e = c.y;
@@ -680,14 +724,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
                     }
                 }
             }
-            // last cell in row-major order over the lanes
-            for (int o = 16; o; o >>= 1) {
-                const int oi = __shfl_xor_sync(FULL, i, o), oj = __shfl_xor_sync(FULL, j, o);
-                if (oi > i || (oi == i && oj > j)) {
-                    i = oi;
-                    j = oj;
-                }
-            }
+            // last cell in row-major order over the team
+            T16W_MAX2(i, j);
             cur = Smax;
         }
     }
@@ -713,36 +751,33 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         const int v = CkView::lane_of(g);
         TileProbe pb;
         pb.col = m;
-        for (int e = lane; BA16_PERIOD * e - v < n; e += 32) {
+        for (int e = lane; BA16_PERIOD * e - v < n; e += NT) {
             const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
             if (rlast < 1) continue;
             trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         // last row attaining the maximum: larger value wins, ties go to the larger row
         int best = pb.best, besti = pb.besti;
-        for (int o = 16; o; o >>= 1) {
-            const int ob = __shfl_xor_sync(FULL, best, o), oi = __shfl_xor_sync(FULL, besti, o);
-            if (ob > best || (ob == best && oi > besti)) {
-                best = ob;
-                besti = oi;
-            }
-        }
+        T16W_MAX2(best, besti);
         i = besti;
     }
-    __syncwarp();
+    T16W_SYNC();
 
     int maxI = i, maxJ = j, score = 0, last = MV_DIAG;
     bool bad = false;
     while (i > 0 && j > 0 && !bad) {
         if (KIND == KIND_SW && cur == 0) break;
-        // ---- window anchored at (i, j): my tile is strip g_hi - ws, ws = lane / 8, period
-        // (period of row i in that strip) - lane % 8
+        // ---- window anchored at (i, j).  Warp team: my tile is strip g_hi - lane / 8, period (period
+        // of row i0 there) - lane % 8.  CTA team: strip g_hi - lane / 3, period (period of the
+        // diagonal's row i0 - ws*cols there) + 1 - lane % 3.
         const int g_hi = ck.strip_of(j);
         const int i0 = i;
         {
-            const int g = g_hi - (lane >> 3);
-            const int v = CkView::lane_of(g & 1023);  // (negative g is skipped below)
-            const int e = ((i0 + v - 1) >> BA16_PSHIFT) - (lane & 7);
+            const int ws = (NT == 32) ? (lane >> 3) : (lane / BA_TB_PERIODS);
+            const int g = g_hi - ws;
+            const int v = CkView::lane_of(g);  // (negative g is skipped below)
+            const int e = (NT == 32) ? ((i0 + v - 1) >> BA16_PSHIFT) - (lane & 7)
+                                     : ((max(i0 - ws * ck.cols, 1) + v - 1) >> BA16_PSHIFT) + 1 - (lane % BA_TB_PERIODS);
             const int clast = min(ck.left_col(g) + ck.cols, m);
             const int rlast = min(min(n, BA16_PERIOD * e + BA16_PERIOD - v), i0);
             const int rtop = max(BA16_PERIOD * e - v, 0);
@@ -751,20 +786,28 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
                 trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
             }
         }
-        __syncwarp();
+        T16W_SYNC();
         for (;;) {
             if (i <= 0 || j <= 0) break;
             if (KIND == KIND_SW && cur == 0) break;
             const int g = ck.strip_of(j);
             const int v = CkView::lane_of(g);
             const int ws = g_hi - g;
-            const int we = ((i0 + v - 1) >> BA16_PSHIFT) - ((i + v - 1) >> BA16_PSHIFT);
-            if (ws >= BA_TW_STRIPS || we >= BA_TW_PERIODS) break;  // left the window: rebuild
+            int we, slot;
+            if (NT == 32) {
+                we = ((i0 + v - 1) >> BA16_PSHIFT) - ((i + v - 1) >> BA16_PSHIFT);
+                if (ws >= BA_TW_STRIPS || we >= BA_TW_PERIODS) break;  // left the window: rebuild
+                slot = ws * BA_TW_PERIODS + we;
+            } else {
+                we = ((max(i0 - ws * ck.cols, 1) + v - 1) >> BA16_PSHIFT) + 1 - ((i + v - 1) >> BA16_PSHIFT);
+                if (ws >= BA_TB_STRIPS || we < 0 || we >= BA_TB_PERIODS) break;
+                slot = ws * BA_TB_PERIODS + we;
+            }
             const int rt = max(BA16_PERIOD * ((i + v - 1) >> BA16_PSHIFT) - v, 0);
             const int cbase = ck.left_col(g);
             const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
             const unsigned code =
-                tiles[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS + wbase + ws * 8 + we];
+                tiles[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS + wbase + slot];
             const bool corner = (i == n && j == m);
             const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
             int move, nl = 0, delta;
@@ -785,7 +828,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             layer = nl;
             last = move;
         }
-        __syncwarp();
+        T16W_SYNC();
     }
     T16W_EMIT(i, maxI, j, maxJ, score);
     if (KIND == KIND_NW && i != j) {
@@ -797,6 +840,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         T16W_EMIT(0, i, 0, j, b);
     }
 #undef T16W_EMIT
+#undef T16W_SYNC
+#undef T16W_MAX2
     if (lane == 0) {
         if (bad) {
             P.status[p] = 4;  // BA_PAIR_NO_PATH

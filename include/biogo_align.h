@@ -140,7 +140,8 @@ void ba_free_host(void *p);
  * or 60 % of free HBM), "force_path" (0 auto, 1 = 32-bit exact-code kernels only), "slot_cap"
  * (test hook: segment slots per pair on the 16-bit path, 0 = automatic), "long_mode" (wavefront
  * over the passes of kb-scale pairs: 0 never, 1 automatic, 2 whenever a launch has >= 4 passes),
- * "trace_mode" (16-bit path traceback: 0 thread per pair, 1 automatic, 2 warp per pair),
+ * "trace_mode" (16-bit path traceback: 0 thread per pair, 1 automatic, 2 warp per pair, 3 CTA per
+ * pair),
  * "exclusive_compute" (default 1: ba_align_batch calls on the same device run their kernel phases
  * one at a time, so that with several contexts on several threads the upload of one batch overlaps
  * the kernels of another), "plan_cache" (default 1: a batch whose length arrays equal the previous

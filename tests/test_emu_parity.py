@@ -230,17 +230,18 @@ def test_fast16_warp_per_pair_traceback(emu_ctx, kind):
     pairs += randcases.rand_pairs(rng, 4, [30, 200], [30, 200], related=0.0, dirty=0.0)   # unrelated: gappy paths
     pk = helpers.pack(pairs)
     orc = helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk)
-    emu_ctx.set_option("trace_mode", 2)
-    try:
-        res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
-        assert res.stats["warp_trace_launches"] >= 1
-        helpers.compare(res, orc, f"warp trace kind {kind}")
-        emu_ctx.set_option("slot_cap", 2)
-        res2 = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
-        helpers.compare(res2, orc, f"warp trace overflow kind {kind}")
-    finally:
-        emu_ctx.set_option("slot_cap", 0)
-        emu_ctx.set_option("trace_mode", 1)
+    for mode in (2, 3):   # a warp per pair (4 x 8 tile window), a CTA per pair (diagonal band of tiles)
+        emu_ctx.set_option("trace_mode", mode)
+        try:
+            res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+            assert res.stats["warp_trace_launches"] >= 1
+            helpers.compare(res, orc, f"team trace mode {mode} kind {kind}")
+            emu_ctx.set_option("slot_cap", 2)
+            res2 = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+            helpers.compare(res2, orc, f"team trace overflow mode {mode} kind {kind}")
+        finally:
+            emu_ctx.set_option("slot_cap", 0)
+            emu_ctx.set_option("trace_mode", 1)
     emu_ctx.set_option("trace_mode", 0)
     try:
         res0 = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
@@ -262,7 +263,7 @@ def test_fast16_linear_kinds(emu_ctx, kind):
     pairs += randcases.rand_pairs(rng, 6, [30, 120], [30, 120], related=0.0, dirty=0.0)
     pk = helpers.pack(pairs)
     orc = helpers.run_oracle(kind, False, M, 0, DNA_IDX, pk)
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         emu_ctx.set_option("trace_mode", mode)
         try:
             res = helpers.run_lib(emu_ctx, kind, False, M, 0, DNA_IDX, 5, pk)
