@@ -54,16 +54,68 @@ def load_dpx_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clocks + throttle reasons sampled DURING the timed region: NVML from a thread (a few ms
+    per sample, so even a 100 ms region gets tens of samples); nvidia-smi -lms as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str | None = None):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.h, self.samples, self.run = None, None, [], False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:  # noqa: BLE001
+                    h = None
+            self.h = h or pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        while self.run:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, rs))
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.004)
+
+    def _nvml_stop(self):
+        self.run = False
+        self.t.join(timeout=2)
+        n = self.nvml
+        if not self.samples:
+            return None
+        sm = sorted(x[0] for x in self.samples)
+        reasons = set()
+        names = (("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+        for _, _, rs in self.samples:
+            for name, bit in names:
+                if rs & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(max(x[1] for x in self.samples)),
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": "nvml"}
 
     def start(self):
+        if self.nvml:
+            self.run = True
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -78,6 +130,10 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            r = self._nvml_stop()
+            if r:
+                return r
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -151,7 +207,20 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Write the one JSON line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -166,6 +235,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner, torchrun notices) write
+    # to file descriptor 1 directly, so park the real stdout and point fd 1 at stderr meanwhile.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,7 +291,11 @@ def main():
 
     for _ in range(max(args.warmup, 0)):
         step_device()
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:  # noqa: BLE001
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -374,7 +454,7 @@ def main():
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port",
                                     "sample": f"first {n} pairs of the step ({c} cells), C port of the Go path "
                                               f"(full int64 table per pair), {threads} pthreads, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
