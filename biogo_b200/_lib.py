@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(_HERE, "lib", "libbiogoalign.so")
 ABI_SYMBOLS = (
     "ba_create", "ba_destroy", "ba_last_error", "ba_set_scoring", "ba_align_batch",
     "ba_align_batch_device", "ba_free_result", "ba_alloc_host", "ba_free_host",
-    "ba_set_option", "ba_abi_version", "ba_build_info",
+    "ba_set_option", "ba_abi_version", "ba_build_info", "ba_format_batch", "ba_free_formatted",
 )
 
 
@@ -50,6 +50,19 @@ class BaResult(C.Structure):
         ("pairs_fast16", C.c_int64),
         ("wavefront_launches", C.c_int64),
         ("warp_trace_launches", C.c_int64),
+    ]
+
+
+class BaFormatted(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("off_a", C.POINTER(C.c_int64)),
+        ("off_b", C.POINTER(C.c_int64)),
+        ("row_a", C.POINTER(C.c_uint8)),
+        ("row_b", C.POINTER(C.c_uint8)),
+        ("bytes_a", C.c_int64),
+        ("bytes_b", C.c_int64),
+        ("ms_kernels", C.c_float),
     ]
 
 
@@ -87,6 +100,11 @@ def _bind(lib):
     lib.ba_abi_version.restype = i32
     lib.ba_build_info.argtypes = []
     lib.ba_build_info.restype = C.c_char_p
+    lib.ba_format_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, C.c_uint8,
+                                    C.POINTER(BaFormatted)]
+    lib.ba_format_batch.restype = i32
+    lib.ba_free_formatted.argtypes = [vp, C.POINTER(BaFormatted)]
+    lib.ba_free_formatted.restype = None
     return lib
 
 
@@ -207,6 +225,38 @@ class Context:
         stats = _stats(res)
         self.lib.ba_free_result(self._h, C.byref(res))
         return stats
+
+    def format_packed(self, letters, stride: int, ref_off, ref_len, qry_off, qry_len, result: "BatchResult",
+                      gap: int = ord("-")):
+        """ba_format_batch: align.Format for every pair of a batch.  ``letters=None`` formats the batch
+        of this context's last align_packed call (its letters are still on the device).
+        Returns (off_a, off_b, row_a, row_b): row p of side x is row_x[off_x[p]:off_x[p+1]]."""
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+        qry_off = np.ascontiguousarray(qry_off, dtype=np.int64)
+        ref_len = np.ascontiguousarray(ref_len, dtype=np.int32)
+        qry_len = np.ascontiguousarray(qry_len, dtype=np.int32)
+        seg_start = np.ascontiguousarray(result.seg_start, dtype=np.int64)
+        seg_count = np.ascontiguousarray(result.seg_count, dtype=np.int32)
+        segs = np.ascontiguousarray(result.segs, dtype=np.int32).reshape(-1)
+        n = len(ref_off)
+        lp = None
+        if letters is not None:
+            letters = np.ascontiguousarray(letters, dtype=np.uint8)
+            lp = letters.ctypes.data
+        f = BaFormatted()
+        rc = self.lib.ba_format_batch(self._h, lp, stride, ref_off.ctypes.data, ref_len.ctypes.data,
+                                      qry_off.ctypes.data, qry_len.ctypes.data, n, seg_start.ctypes.data,
+                                      seg_count.ctypes.data, segs.ctypes.data if len(segs) else None, len(segs) // 5,
+                                      int(gap), C.byref(f))
+        self._check(rc)
+        try:
+            off_a = _as_array(f.off_a, n + 1, np.int64)
+            off_b = _as_array(f.off_b, n + 1, np.int64)
+            row_a = _as_array(f.row_a, int(f.bytes_a), np.uint8)
+            row_b = _as_array(f.row_b, int(f.bytes_b), np.uint8)
+        finally:
+            self.lib.ba_free_formatted(self._h, C.byref(f))
+        return off_a, off_b, row_a, row_b
 
     def align_device(self, d_letters: int, letters_bytes: int, stride: int, d_ref_off: int, d_ref_len: int,
                      d_qry_off: int, d_qry_len: int, h_ref_len, h_qry_len, stream: int = 0,

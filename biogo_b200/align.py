@@ -329,3 +329,70 @@ def Format(a, b, f, gap):
             else:
                 out[i] = out[i].Append(src[i].Slice(fc[i].Start(), fc[i].End()))
     return out
+
+
+def FormatBatch(a_list, b_list, alns, gap):
+    """align.Format for many alignments in one device call (ba_format_batch; the reference has only
+    the per-alignment Format, align/align.go:146-170).  ``alns[k]`` is the []feat.Pair of pair k
+    (None or empty -> two empty rows).  Returns a list of [row_a, row_b] like Format; rows carry
+    letters only; the qualities of QLetters rows are re-attached on the host."""
+    if isinstance(gap, str):
+        gap = ord(gap)
+    n = len(a_list)
+    if len(b_list) != n or len(alns) != n:
+        raise ValueError("align: FormatBatch needs equally long lists")
+    if n == 0:
+        return []
+    chunks, ref_off, ref_len, qry_off, qry_len = [], [], [], [], []
+    seg_start, seg_count, segs = [], [], []
+    stride0, off = None, 0
+    for k in range(n):
+        r_raw, stride = _slice_bytes(a_list[k].Slice())
+        q_raw, stride_q = _slice_bytes(b_list[k].Slice())
+        if stride != stride_q or (stride0 is not None and stride != stride0):
+            raise ValueError("align: FormatBatch needs one sequence type per call")
+        stride0 = stride
+        chunks += [r_raw, q_raw]
+        ref_off.append(off)
+        ref_len.append(len(r_raw) // stride)
+        off += len(r_raw)
+        qry_off.append(off)
+        qry_len.append(len(q_raw) // stride)
+        off += len(q_raw)
+        seg_start.append(len(segs))
+        f = alns[k] or []
+        seg_count.append(len(f))
+        for fs in f:
+            fc = fs.Features()
+            segs.append((fc[0].Start(), fc[0].End(), fc[1].Start(), fc[1].End(), fs.Score()))
+
+    class _Res:
+        pass
+    res = _Res()
+    res.seg_start = np.array(seg_start, np.int64)
+    res.seg_count = np.array(seg_count, np.int32)
+    res.segs = np.array(segs, np.int32).reshape(-1, 5)
+    letters = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+    off_a, off_b, row_a, row_b = context().format_packed(letters, stride0, ref_off, ref_len, qry_off, qry_len, res, gap)
+    out = []
+    for k in range(n):
+        rows = []
+        for src, off_x, row_x in ((a_list[k], off_a, row_a), (b_list[k], off_b, row_b)):
+            raw = row_x[off_x[k]:off_x[k + 1]].tobytes()
+            sl = src.Slice()
+            if isinstance(sl, _alphabet.QLetters):
+                # the device rows carry letters; qualities follow the same segments on the host
+                # (gap QLetter has Q = 0, align/align.go:161)
+                side = 0 if src is a_list[k] else 1
+                q = bytearray()
+                for fs in (alns[k] or []):
+                    fc = fs.Features()
+                    if fc[side].Len() == 0:
+                        q += bytes(fc[1 - side].Len())
+                    else:
+                        q += sl.raw[2 * fc[side].Start() + 1:2 * fc[side].End():2]
+                rows.append(_alphabet.QLetters(raw, bytes(q)))
+            else:
+                rows.append(_alphabet.Letters(raw))
+        out.append(rows)
+    return out

@@ -23,6 +23,7 @@
 #include "ba_fill16.cuh"
 #include "ba_trace16.cuh"
 #include "ba_plan.h"
+#include "ba_format.cuh"
 
 // One spelling for kernel launches so the same scheduler source also drives the CPU
 // emulator of the no-GPU test tier (tests/emu).
@@ -119,6 +120,10 @@ struct ba_ctx {
         const void *dev_items = nullptr, *dev_slot_off = nullptr, *dev_slot_cap = nullptr;  // where the device copy lives
     } pc;
     uint64_t scoring_epoch = 1;
+    // the batch whose raw letters and offsets are still on the device (ba_format_batch with letters == NULL)
+    int64_t last_n = -1, last_letters_bytes = 0;
+    int last_stride = 0;
+    DevBuf fmt_len, fmt_off, fmt_rows, fmt_segs, fmt_seg_start, fmt_seg_count;
     int64_t opt_plan_cache = 1;
     int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1, opt_exclusive = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
@@ -1147,7 +1152,8 @@ void ba_destroy(ba_ctx *ctx)
                       &ctx->status,  &ctx->err_pos, &ctx->start,  &ctx->items,    &ctx->aux_off, &ctx->aux,
                       &ctx->bnd,     &ctx->seg_count, &ctx->seg_base, &ctx->segs, &ctx->arena,   &ctx->scan_tmp,
                       &ctx->counters, &ctx->flags,  &ctx->slot_off,  &ctx->slot_cap, &ctx->slots, &ctx->seg_clip,
-                      &ctx->tasks,   &ctx->prog};
+                      &ctx->tasks,   &ctx->prog,     &ctx->fmt_len, &ctx->fmt_off, &ctx->fmt_rows,
+                      &ctx->fmt_segs, &ctx->fmt_seg_start, &ctx->fmt_seg_count};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
@@ -1379,7 +1385,166 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
         out->ms_h2d = ms;
     }
+    ctx->last_n = n;
+    ctx->last_stride = stride;
+    ctx->last_letters_bytes = letters_bytes;
     return BA_OK;
+}
+
+int ba_format_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_t *ref_off,
+                    const int32_t *ref_len, const int64_t *qry_off, const int32_t *qry_len, int64_t n,
+                    const int64_t *seg_start, const int32_t *seg_count, const int32_t *segs, int64_t n_segs,
+                    uint8_t gap, ba_formatted *out)
+{
+    if (!ctx || !out || n < 0 || n_segs < 0 || (stride != 1 && stride != 2)) return BA_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (!ctx->d_sc) {
+        ctx->err = "context has no device (ba_create failed)";
+        return BA_ERR_CUDA;
+    }
+    if (n > 0 && (!seg_start || !seg_count || (n_segs > 0 && !segs))) return BA_ERR_ARG;
+    if (n > 0 && (!ref_len || !qry_len)) return BA_ERR_ARG;
+    if (n > 0x7fffffff) return BA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    // every segment must lie inside its pair (the kernels trust the coordinates)
+    for (int64_t p = 0; p < n; p++) {
+        if (seg_count[p] < 0 || seg_start[p] < 0 || seg_start[p] + seg_count[p] > n_segs) {
+            ctx->err = "segment range outside the segment array";
+            return BA_ERR_ARG;
+        }
+        const int32_t *s = segs + 5 * seg_start[p];
+        for (int k = 0; k < seg_count[p]; k++, s += 5)
+            if (s[0] < 0 || s[1] < s[0] || s[1] > ref_len[p] || s[2] < 0 || s[3] < s[2] || s[3] > qry_len[p]) {
+                ctx->err = "segment outside its sequences";
+                return BA_ERR_ARG;
+            }
+    }
+    const uint8_t *d_letters;
+    const int64_t *d_ref_off, *d_qry_off;
+    if (!letters) {
+        if (ctx->last_n != n || ctx->last_stride != stride) {
+            ctx->err = "letters == NULL needs a preceding ba_align_batch call of the same batch on this context";
+            return BA_ERR_ARG;
+        }
+    } else {
+        if (n > 0 && (!ref_off || !qry_off)) return BA_ERR_ARG;
+        int64_t letters_bytes = 0;
+        for (int64_t p = 0; p < n; p++) {
+            if (ref_off[p] < 0 || qry_off[p] < 0 || ref_len[p] < 0 || qry_len[p] < 0) return BA_ERR_ARG;
+            int64_t e1 = ref_len[p] ? ref_off[p] + ((int64_t)ref_len[p] - 1) * stride + 1 : 0;
+            int64_t e2 = qry_len[p] ? qry_off[p] + ((int64_t)qry_len[p] - 1) * stride + 1 : 0;
+            letters_bytes = std::max(letters_bytes, std::max(e1, e2));
+        }
+        if ((rc = ensure(ctx, ctx->letters, (size_t)letters_bytes + 16)) != BA_OK) return rc;
+        if ((rc = ensure(ctx, ctx->ref_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
+        if ((rc = ensure(ctx, ctx->qry_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
+        ctx->last_n = -1;  // the device copy now belongs to this call
+        if (letters_bytes > 0)
+            CK(cudaMemcpyAsync(ctx->letters.p, letters, (size_t)letters_bytes, cudaMemcpyHostToDevice, st));
+        if (n > 0) {
+            CK(cudaMemcpyAsync(ctx->ref_off.p, ref_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->qry_off.p, qry_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        }
+    }
+    d_letters = (const uint8_t *)ctx->letters.p;
+    d_ref_off = (const int64_t *)ctx->ref_off.p;
+    d_qry_off = (const int64_t *)ctx->qry_off.p;
+
+    out->n = n;
+    out->off_a = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(n + 1));
+    out->off_b = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(n + 1));
+    if (!out->off_a || !out->off_b) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    out->off_a[0] = out->off_b[0] = 0;
+    if (n == 0) return BA_OK;
+
+    if ((rc = ensure(ctx, ctx->fmt_segs, sizeof(int32_t) * 5 * (size_t)(n_segs + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->fmt_seg_start, sizeof(int64_t) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->fmt_seg_count, sizeof(int32_t) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->fmt_len, sizeof(int32_t) * 2 * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->fmt_off, sizeof(int64_t) * 2 * (size_t)(n + 1))) != BA_OK) return rc;
+    if (n_segs > 0)
+        CK(cudaMemcpyAsync(ctx->fmt_segs.p, segs, sizeof(int32_t) * 5 * (size_t)n_segs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->fmt_seg_start.p, seg_start, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->fmt_seg_count.p, seg_count, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+
+    FormatParams fp;
+    fp.letters = d_letters;
+    fp.stride = stride;
+    fp.ref_off = d_ref_off;
+    fp.qry_off = d_qry_off;
+    fp.seg_start = (const int64_t *)ctx->fmt_seg_start.p;
+    fp.seg_count = (const int32_t *)ctx->fmt_seg_count.p;
+    fp.segs = (const int32_t *)ctx->fmt_segs.p;
+    fp.n = n;
+    fp.len_a = (int32_t *)ctx->fmt_len.p;
+    fp.len_b = fp.len_a + n;
+    int64_t *d_off_a = (int64_t *)ctx->fmt_off.p, *d_off_b = d_off_a + (n + 1);
+    fp.off_a = d_off_a;
+    fp.off_b = d_off_b;
+    fp.row_a = fp.row_b = nullptr;
+    fp.gap = gap;
+    BA_LAUNCH(ba_format_size_kernel, (unsigned)((n + 255) / 256), 256, st, fp);
+    size_t scan_bytes = 0;
+    if ((rc = exclusive_scan(ctx, nullptr, scan_bytes, fp.len_a, d_off_a, (int)n, st)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
+    size_t tb = ctx->scan_tmp.cap;
+    if ((rc = exclusive_scan(ctx, ctx->scan_tmp.p, tb, fp.len_a, d_off_a, (int)n, st)) != BA_OK) return rc;
+    tb = ctx->scan_tmp.cap;
+    if ((rc = exclusive_scan(ctx, ctx->scan_tmp.p, tb, fp.len_b, d_off_b, (int)n, st)) != BA_OK) return rc;
+    // row sizes to the host: the last offsets + the last lengths give the totals
+    int32_t *h_len = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 2 * (size_t)n);
+    if (!h_len) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    CK(cudaMemcpyAsync(out->off_a, d_off_a, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->off_b, d_off_b, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_len, fp.len_a, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->bytes_a = out->off_a[n - 1] + h_len[n - 1];
+    out->bytes_b = out->off_b[n - 1] + h_len[2 * n - 1];
+    out->off_a[n] = out->bytes_a;
+    out->off_b[n] = out->bytes_b;
+    pinned_put(ctx, h_len);
+    if ((rc = ensure(ctx, ctx->fmt_rows, (size_t)(out->bytes_a + out->bytes_b) + 32)) != BA_OK) return rc;
+    fp.row_a = (uint8_t *)ctx->fmt_rows.p;
+    fp.row_b = fp.row_a + out->bytes_a;
+    int64_t wblocks = (n + 7) / 8;
+    if (wblocks > (int64_t)ctx->sm_count * 8) wblocks = (int64_t)ctx->sm_count * 8;
+    BA_LAUNCH(ba_format_write_kernel, (unsigned)wblocks, 256, st, fp);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], st));
+    out->row_a = (uint8_t *)pinned_get(ctx, (size_t)out->bytes_a + 1);
+    out->row_b = (uint8_t *)pinned_get(ctx, (size_t)out->bytes_b + 1);
+    if (!out->row_a || !out->row_b) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    if (out->bytes_a > 0)
+        CK(cudaMemcpyAsync(out->row_a, fp.row_a, (size_t)out->bytes_a, cudaMemcpyDeviceToHost, st));
+    if (out->bytes_b > 0)
+        CK(cudaMemcpyAsync(out->row_b, fp.row_b, (size_t)out->bytes_b, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+    out->ms_kernels = ms;
+    return BA_OK;
+}
+
+void ba_free_formatted(ba_ctx *ctx, ba_formatted *f)
+{
+    if (!ctx || !f) return;
+    if (f->off_a) pinned_put(ctx, f->off_a);
+    if (f->off_b) pinned_put(ctx, f->off_b);
+    if (f->row_a) pinned_put(ctx, f->row_a);
+    if (f->row_b) pinned_put(ctx, f->row_b);
+    memset(f, 0, sizeof *f);
 }
 
 void ba_free_result(ba_ctx *ctx, ba_result *res)

@@ -132,6 +132,25 @@ int ba_align_batch_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters
 
 void ba_free_result(ba_ctx *ctx, ba_result *res);
 
+/* align.Format for a batch (reference: align/align.go:146-170): the two gapped rows of every
+ * alignment.  `letters` and the offset/length arrays describe the packed batch exactly as for ba_align_batch;
+ * pass letters == NULL to format the batch of this context's last ba_align_batch call, whose letters
+ * are still on the device.  seg_start/seg_count/segs are a ba_result's arrays.  Rows hold letters
+ * only (for QLetters the L byte; quality bytes are not carried).  Row p of side x is
+ * row_x[off_x[p] .. off_x[p+1]). */
+typedef struct ba_formatted {
+    int64_t n;
+    int64_t *off_a, *off_b; /* n + 1 entries each */
+    uint8_t *row_a, *row_b;
+    int64_t bytes_a, bytes_b;
+    float ms_kernels;
+} ba_formatted;
+int ba_format_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_t *ref_off,
+                    const int32_t *ref_len, const int64_t *qry_off, const int32_t *qry_len, int64_t n,
+                    const int64_t *seg_start, const int32_t *seg_count, const int32_t *segs, int64_t n_segs,
+                    uint8_t gap, ba_formatted *out);
+void ba_free_formatted(ba_ctx *ctx, ba_formatted *f);
+
 /* Pinned host allocation so a caller (cgo, ctypes) can pack straight into DMA-able memory. */
 void *ba_alloc_host(size_t bytes);
 void ba_free_host(void *p);

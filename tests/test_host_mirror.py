@@ -90,6 +90,11 @@ def test_examples_and_format(vec):
         if fmt:
             fa = align.Format(sa, sb, aln, "-")
             assert (str(fa[0]), str(fa[1])) == fmt
+            # the batched device Format agrees with the per-alignment one, qualities included
+            fb = align.FormatBatch([sa, sa], [sb, sb], [aln, None], "-")
+            assert (str(fb[0][0]), str(fb[0][1])) == fmt and (str(fb[1][0]), str(fb[1][1])) == ("", "")
+            assert type(fb[0][0]) is type(fa[0]) and getattr(fb[0][0], "raw", None) == getattr(fa[0], "raw", None)
+            assert getattr(fb[0][1], "raw", None) == getattr(fa[1], "raw", None)
 
 
 def test_align_batch_mixes_errors_and_results():
