@@ -29,8 +29,12 @@
 // emulator of the no-GPU test tier (tests/emu).
 #ifdef BA_EMULATE
 #define BA_LAUNCH(kernel, grid, block, stream, ...) emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#define BA_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+    emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
 #else
 #define BA_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define BA_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
 namespace {
@@ -292,7 +296,7 @@ int64_t arena_budget(ba_ctx *ctx, int64_t &cap)
 }
 
 template <typename Fn>
-int cached_occupancy(ba_ctx *ctx, Fn fn, int threads, int &occ)
+int cached_occupancy(ba_ctx *ctx, Fn fn, int threads, int &occ, size_t dyn_smem = 0)
 {
     for (auto &e : ctx->occ_cache)
         if (e.first == (const void *)fn) {
@@ -300,7 +304,11 @@ int cached_occupancy(ba_ctx *ctx, Fn fn, int threads, int &occ)
             return BA_OK;
         }
     occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0));
+#ifndef BA_EMULATE
+    if (dyn_smem > 0)  // beyond the 48 KB a kernel gets without opting in (static + dynamic)
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+#endif
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, dyn_smem));
     if (occ < 1) occ = 1;
     ctx->occ_cache.push_back({(const void *)fn, occ});
     return BA_OK;
@@ -584,6 +592,7 @@ Fast16 fast16_scoring(const DeviceScoring &s)
     if (s.let < 2 || s.let > BA_MAX_LET) return f;
     const int64_t gap_open = s.affine ? s.gap_open : 0;
     f.gsub = (s.let != 5);
+    if (f.gsub && s.let > BA_MAX_LET - 1) return f;  // row `let` of the score tables is the virtual letter
     const int er = s.la[1 * s.let], eq = s.la[1];
     int maxsub = -1000000, maxabs = 0;
     for (int a = 1; a < s.let; a++) {
@@ -771,15 +780,18 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 }
             }
             Fill16Fn fn = pick_fill16(kind, lin, L.cols, multi, gsub, false);
+            // GSUB kernels keep their score tables in dynamic shared memory (the size depends on the
+            // matrix only, so the per-kernel cache entry stays valid until the scoring changes)
+            const size_t dyn = gsub ? (size_t)BA16_WARPS * ba16_gsub_bytes_per_warp(ctx->h_sc.let) : 0;
             int occ = 1;
-            if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
+            if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ, dyn)) != BA_OK) return rc;
             int64_t maxb = (int64_t)ctx->sm_count * occ;
             const int64_t pair_warps = (L.count + 3) / 4;
             const bool use_long = maxp >= 4 && (ctx->opt_long_mode == 2 || pair_warps < maxb * BA16_WARPS) &&
                                   (int64_t)maxp * (L.count + 4) < (1 << 22);
             if (use_long) {
                 fn = pick_fill16(kind, lin, L.cols, true, gsub, true);
-                if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ)) != BA_OK) return rc;
+                if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ, dyn)) != BA_OK) return rc;
                 maxb = (int64_t)ctx->sm_count * occ;
                 const int64_t ncp = ((L.count + 3) / 4) * 2;         // couples per pass, even
                 const int64_t ntasks = (int64_t)maxp * 2 * ncp;
@@ -818,7 +830,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 fp.long_err = (int *)ctx->prog.p;
                 int64_t blocks = (ntasks + 4 * BA16_WARPS - 1) / (4 * BA16_WARPS);
                 if (blocks > maxb) blocks = maxb;
-                BA_LAUNCH(fn, (unsigned)blocks, BA16_WARPS * 32, st, fp);
+                BA_LAUNCH_SMEM(fn, (unsigned)blocks, BA16_WARPS * 32, dyn, st, fp);
                 CK(cudaMemcpyAsync(h_long_err + (long_tasks.size() & 15), ctx->prog.p, sizeof(int), cudaMemcpyDeviceToHost,
                                    st));
                 long_tasks.push_back(h_tasks);
@@ -839,7 +851,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             fp.n_items = (int)L.count;
             fp.bnd = (int32_t *)ctx->bnd.p;
             fp.bnd_stride = bnd_stride;
-            BA_LAUNCH(fn, (unsigned)blocks, BA16_WARPS * 32, st, fp);
+            BA_LAUNCH_SMEM(fn, (unsigned)blocks, BA16_WARPS * 32, dyn, st, fp);
             B.launches++;
             B.fill_launches++;
         }
@@ -1247,6 +1259,7 @@ int ba_set_scoring(ba_ctx *ctx, int kind, int affine, const int64_t *la, int let
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_scoring = true;
     ctx->scoring_epoch++;  // cached plans depend on the scoring (eligibility, kind)
+    ctx->occ_cache.clear(); // dynamic shared memory of the GSUB kernels depends on the matrix size
     return BA_OK;
 }
 

@@ -144,6 +144,22 @@ __device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gd
 
 // MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
 // inter-pass boundary code is compiled out of the common single-pass instance).
+// Dynamic shared memory (GSUB score tables); the emulator backs it with a static buffer.
+__host__ __device__ inline size_t ba16_gsub_bytes_per_warp(int let) { return (size_t)(let + 1) * 512; }
+#ifdef BA_EMULATE
+static inline uint8_t *ba_dyn_smem()
+{
+    static uint8_t buf[BA16_WARPS * (BA_MAX_LET + 1) * 512];
+    return buf;
+}
+#else
+__device__ __forceinline__ uint8_t *ba_dyn_smem()
+{
+    extern __shared__ __align__(16) uint8_t ba_dyn_smem_[];
+    return ba_dyn_smem_;
+}
+#endif
+
 #ifdef BA_EMULATE
 #define BA_SPIN_PAUSE() emu::yield()
 #define BA_LDCG(p) (*(p))
@@ -193,8 +209,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     // row profiles: ring[group][pair][i & (RING-1)] = 4 substitution bytes of the letter of row i
     __shared__ unsigned ring[BA16_GROUPS][2][BA16_PROF_RING + 8];
     __shared__ unsigned proftab[BA_MAX_LET + 1];  // PRMT: letter -> 4 sub bytes; GSUB: letter -> row byte offset
-    __shared__ unsigned subA[GSUB ? (BA_MAX_LET + 1) * BA_MAX_LET : 1];  // GSUB: sub & 0xffff  (pair A half)
-    __shared__ unsigned subB[GSUB ? (BA_MAX_LET + 1) * BA_MAX_LET : 1];  // GSUB: sub << 16     (pair B half)
+    // GSUB: signed-byte score tables in dynamic shared memory, sixteen replicas per warp (one per
+    // lane couple, each confined to its own two banks so a lookup meets at most one other lane):
+    // byte (R, q) of replica r lives at  ((R*32 + q) >> 3) * 128 + 8 r + (q & 7)  of the warp's slab
+    // of (let + 1) * 512 bytes; row `let` is the virtual letter (-128 against everything).
+    uint8_t *gtab = GSUB ? ba_dyn_smem() + (size_t)(threadIdx.x >> 5) * ba16_gsub_bytes_per_warp(P.sc->let) : nullptr;
     __shared__ __align__(16) unsigned colbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged column checkpoints
     __shared__ __align__(16) unsigned rowbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged row checkpoint
     __shared__ uint4 bbuf[MULTI ? BA16_GROUPS : 1][BA16_PERIOD];  // boundary rows (M, L, H) of the current period
@@ -210,15 +229,14 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             proftab[threadIdx.x] = w;
         }
     } else {
-        // row `let` is the virtual letter: -128 against everything
-        for (int x = threadIdx.x; x < (let + 1) * let; x += blockDim.x) {
-            const int v = (x < let * let) ? P.sc->la[x] : -128;
-            subA[x] = (unsigned)v & 0xffffu;
-            subB[x] = (unsigned)v << 16;
+        for (int x = threadIdx.x & 31; x < (let + 1) * 32 * 16; x += 32) {
+            const int r = x & 15, bo = x >> 4, R = bo >> 5, q = bo & 31;
+            const int v = (R == let) ? -128 : (q < let ? P.sc->la[R * let + q] : 0);
+            gtab[(bo >> 3) * 128 + 8 * r + (bo & 7)] = (uint8_t)v;
         }
-        for (int x = threadIdx.x; x <= BA_MAX_LET; x += blockDim.x) proftab[x] = (unsigned)(min(x, let) * let * 4);
+        for (int x = threadIdx.x; x <= BA_MAX_LET; x += blockDim.x) proftab[x] = (unsigned)(min(x, let) * 512);
     }
-    const unsigned VROW = GSUB ? (unsigned)(let * let * 4) : 0x80808080u;  // ring entry of a virtual row
+    const unsigned VROW = GSUB ? (unsigned)(let * 512) : 0x80808080u;  // ring entry of a virtual row
     __syncthreads();
     const int er = P.sc->la[1 * let];  // C1: identical for letters 1..4
     const int eq = P.sc->la[1];
@@ -337,8 +355,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     }
                     sel[k] = nl | nh;
                 } else {
-                    sel[k] = oka ? 4u * (unsigned)qA[(int64_t)(ja - 1) * stride] : 0u;
-                    qb4[k] = okb ? 4u * (unsigned)qB[(int64_t)(jb - 1) * stride] : 0u;
+                    // byte offset of the query letter inside a table row of my replica (lane couple)
+                    const unsigned la_ = oka ? (unsigned)qA[(int64_t)(ja - 1) * stride] : 0u;
+                    const unsigned lb_ = okb ? (unsigned)qB[(int64_t)(jb - 1) * stride] : 0u;
+                    sel[k] = (la_ >> 3) * 128u + (la_ & 7u) + 8u * (unsigned)(lane >> 1);
+                    qb4[k] = (lb_ >> 3) * 128u + (lb_ & 7u) + 8u * (unsigned)(lane >> 1);
                 }
             }
             // ---- profile rings: rows -15..0 virtual, rows 1.. loaded in chunks inside the step loop
@@ -443,8 +464,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         if (!GSUB)
                             sub = ba_prmt(profA, profB, sel[k]);
                         else
-                            sub = *(const unsigned *)((const char *)subA + profA + sel[k]) |
-                                  *(const unsigned *)((const char *)subB + profB + qb4[k]);
+                            sub = ba_prmt((unsigned)(int)*(const signed char *)(gtab + profA + sel[k]),
+                                          (unsigned)(int)*(const signed char *)(gtab + profB + qb4[k]), 0x5410u);
                         const unsigned old = Hu[k];
                         const unsigned X = __viaddmax_s16x2(Hd, sub, __vadd2(old, erp));
                         Tl = (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Tl, eqp, X) : __viaddmax_s16x2(Tl, eqp, X);
@@ -469,8 +490,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         if (!GSUB)
                             sub = ba_prmt(profA, profB, sel[k]);
                         else
-                            sub = *(const unsigned *)((const char *)subA + profA + sel[k]) |
-                                  *(const unsigned *)((const char *)subB + profB + qb4[k]);
+                            sub = ba_prmt((unsigned)(int)*(const signed char *)(gtab + profA + sel[k]),
+                                          (unsigned)(int)*(const signed char *)(gtab + profB + qb4[k]), 0x5410u);
                         if (KIND == KIND_SW)
                             Mu[k] = __viaddmax_s16x2_relu(Hd, sub, erp);  // erp <= 0: same as max(.,0)
                         else
