@@ -145,7 +145,16 @@ __device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gd
 // MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
 // inter-pass boundary code is compiled out of the common single-pass instance).
 // Dynamic shared memory (GSUB score tables); the emulator backs it with a static buffer.
-__host__ __device__ inline size_t ba16_gsub_bytes_per_warp(int let) { return (size_t)(let + 1) * 512; }
+// A replica serves BA16_GSUB_SHARE lanes and is confined to as many banks: byte (R, q) of replica r
+// lives at ((R*32 + q) / (4*SHARE)) * 128 + 4*SHARE*r + (R*32 + q) % (4*SHARE) of the warp's slab.
+#ifndef BA16_GSUB_SHARE
+#define BA16_GSUB_SHARE 2
+#endif
+#define BA16_GSUB_SPAN (4 * BA16_GSUB_SHARE)            // bytes of a replica per 128-byte bank row
+__host__ __device__ inline size_t ba16_gsub_bytes_per_warp(int let)
+{
+    return (size_t)(let + 1) * 32 / BA16_GSUB_SPAN * 128;
+}
 #ifdef BA_EMULATE
 static inline uint8_t *ba_dyn_smem()
 {
@@ -207,12 +216,13 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 {
     constexpr int NC = 2 * COLS;  // columns per lane
     // row profiles: ring[group][pair][i & (RING-1)] = 4 substitution bytes of the letter of row i
-    __shared__ unsigned ring[BA16_GROUPS][2][BA16_PROF_RING + 8];
+    // GSUB kernels trade ring capacity for their score tables (shared memory bounds their occupancy)
+    constexpr int RING = GSUB ? 128 : BA16_PROF_RING, CHUNK = GSUB ? 64 : BA16_PROF_CHUNK;
+    __shared__ unsigned ring[BA16_GROUPS][2][RING + 8];
     __shared__ unsigned proftab[BA_MAX_LET + 1];  // PRMT: letter -> 4 sub bytes; GSUB: letter -> row byte offset
-    // GSUB: signed-byte score tables in dynamic shared memory, sixteen replicas per warp (one per
-    // lane couple, each confined to its own two banks so a lookup meets at most one other lane):
-    // byte (R, q) of replica r lives at  ((R*32 + q) >> 3) * 128 + 8 r + (q & 7)  of the warp's slab
-    // of (let + 1) * 512 bytes; row `let` is the virtual letter (-128 against everything).
+    // GSUB: signed-byte score tables in dynamic shared memory, replicated per BA16_GSUB_SHARE lanes and
+    // confined to as many banks, so a lookup meets at most SHARE - 1 other lanes instead of 31;
+    // row `let` is the virtual letter (-128 against everything).
     uint8_t *gtab = GSUB ? ba_dyn_smem() + (size_t)(threadIdx.x >> 5) * ba16_gsub_bytes_per_warp(P.sc->let) : nullptr;
     __shared__ __align__(16) unsigned colbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged column checkpoints
     __shared__ __align__(16) unsigned rowbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged row checkpoint
@@ -229,14 +239,16 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             proftab[threadIdx.x] = w;
         }
     } else {
-        for (int x = threadIdx.x & 31; x < (let + 1) * 32 * 16; x += 32) {
-            const int r = x & 15, bo = x >> 4, R = bo >> 5, q = bo & 31;
+        constexpr int NREP = 32 / BA16_GSUB_SHARE;
+        for (int x = threadIdx.x & 31; x < (let + 1) * 32 * NREP; x += 32) {
+            const int r = x % NREP, bo = x / NREP, R = bo >> 5, q = bo & 31;
             const int v = (R == let) ? -128 : (q < let ? P.sc->la[R * let + q] : 0);
-            gtab[(bo >> 3) * 128 + 8 * r + (bo & 7)] = (uint8_t)v;
+            gtab[(bo / BA16_GSUB_SPAN) * 128 + BA16_GSUB_SPAN * r + (bo % BA16_GSUB_SPAN)] = (uint8_t)v;
         }
-        for (int x = threadIdx.x; x <= BA_MAX_LET; x += blockDim.x) proftab[x] = (unsigned)(min(x, let) * 512);
+        for (int x = threadIdx.x; x <= BA_MAX_LET; x += blockDim.x)
+            proftab[x] = (unsigned)(min(x, let) * (32 / BA16_GSUB_SPAN * 128));
     }
-    const unsigned VROW = GSUB ? (unsigned)(let * 512) : 0x80808080u;  // ring entry of a virtual row
+    const unsigned VROW = GSUB ? (unsigned)(let * (32 / BA16_GSUB_SPAN * 128)) : 0x80808080u;  // ring entry of a virtual row
     __syncthreads();
     const int er = P.sc->la[1 * let];  // C1: identical for letters 1..4
     const int eq = P.sc->la[1];
@@ -358,13 +370,14 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     // byte offset of the query letter inside a table row of my replica (lane couple)
                     const unsigned la_ = oka ? (unsigned)qA[(int64_t)(ja - 1) * stride] : 0u;
                     const unsigned lb_ = okb ? (unsigned)qB[(int64_t)(jb - 1) * stride] : 0u;
-                    sel[k] = (la_ >> 3) * 128u + (la_ & 7u) + 8u * (unsigned)(lane >> 1);
-                    qb4[k] = (lb_ >> 3) * 128u + (lb_ & 7u) + 8u * (unsigned)(lane >> 1);
+                    const unsigned rep_ = (unsigned)BA16_GSUB_SPAN * (unsigned)(lane / BA16_GSUB_SHARE);
+                    sel[k] = (la_ / BA16_GSUB_SPAN) * 128u + (la_ % BA16_GSUB_SPAN) + rep_;
+                    qb4[k] = (lb_ / BA16_GSUB_SPAN) * 128u + (lb_ % BA16_GSUB_SPAN) + rep_;
                 }
             }
             // ---- profile rings: rows -15..0 virtual, rows 1.. loaded in chunks inside the step loop
-            ringA[(t - 15) & (BA16_PROF_RING - 1)] = VROW;
-            ringB[(t - 15) & (BA16_PROF_RING - 1)] = VROW;
+            ringA[(t - 15) & (RING - 1)] = VROW;
+            ringB[(t - 15) & (RING - 1)] = VROW;
             __syncwarp();
 
             unsigned Mu[NC], Uu[NC], Hu[NC];
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             uint4 *rowckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA + ba16_colck_bytes(nA, LIN));
             uint4 *colckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB);
             uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB, LIN));
-            unsigned ro = (unsigned)((1 - t) & (BA16_PROF_RING - 1)) * 4u;  // byte offset of my row in the rings
+            unsigned ro = (unsigned)((1 - t) & (RING - 1)) * 4u;  // byte offset of my row in the rings
             unsigned mc0 = 0;            // LIN: T of my first strip's last column at the current row
             unsigned ck0a = 0, ck0b = 0; // affine: packed (M, L) checkpoint words of that column, pairs A and B
 
@@ -410,16 +423,16 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 const int pre_row = 8 * (e + 1) + 1 + t;  // my boundary row of the NEXT period
                 const bool pre_on = rd_bnd && t < BA16_PERIOD && pre_row <= nbnd;
                 if (pre_on) pre = BA_LDCG(bnd + pre_row);  // lands at the end of this period
-                if ((e & (BA16_PROF_CHUNK / BA16_PERIOD - 1)) == 0) {
+                if ((e & (CHUNK / BA16_PERIOD - 1)) == 0) {
                     // rows 8e+1 .. 8e+CHUNK enter the rings (lanes of the group share the load)
                     __syncwarp();
-                    for (int x = t; x < BA16_PROF_CHUNK; x += 16) {
+                    for (int x = t; x < CHUNK; x += 16) {
                         const int i = 8 * e + 1 + x;
                         unsigned wa = VROW, wb = VROW;
                         if (plA && i <= nA) wa = proftab[rA[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
                         if (plB && i <= nB) wb = proftab[rB[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
-                        ringA[i & (BA16_PROF_RING - 1)] = wa;
-                        ringB[i & (BA16_PROF_RING - 1)] = wb;
+                        ringA[i & (RING - 1)] = wa;
+                        ringB[i & (RING - 1)] = wb;
                     }
                     __syncwarp();
                 }
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 const int i = s + 1 - t;
                 const unsigned profA = *(const unsigned *)((const char *)ringA + ro);
                 const unsigned profB = *(const unsigned *)((const char *)ringB + ro);
-                ro = (ro + 4u) & (BA16_PROF_RING * 4u - 1u);
+                ro = (ro + 4u) & (RING * 4u - 1u);
 
                 // boundary column of the left neighbour lane; lane 0: DP column 0 (all zero for SW)
                 // or the staged last column of the previous pass
