@@ -381,3 +381,19 @@ def test_config1_fast_and_exact_paths_agree(gpu_ctx):
     assert np.array_equal(fast.status, exact.status)
     for p in range(w.n):
         assert np.array_equal(fast.pairs(p), exact.pairs(p)), p
+
+
+def test_config4_nuc4_scores_promote_to_the_32bit_path(gpu_ctx):
+    """BASELINE config 4, second run: +5/-4 scores (NUC_4-like, gaps -2, GapOpen -10) on a pair long
+    enough that the best score leaves the int16 range: the pair must be promoted to the 32-bit
+    exact-code kernels and still match the oracle."""
+    rng = random.Random(5600)
+    M = gv.match(-2, 5, -4)
+    pairs = randcases.rand_pairs(rng, 1, [6600], [6100], related=1.0, dirty=0.0)
+    pairs += randcases.rand_pairs(rng, 3, [700, 900], [600], related=1.0, dirty=0.0)   # these stay on the packed path
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(gpu_ctx, 2, True, M, -10, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] == 3
+    best = int(res.pairs(0)[:, 4].sum())
+    assert best > 32767, best
+    helpers.compare(res, helpers.run_oracle(2, True, M, -10, DNA_IDX, pk, 1, 2), "cfg4 NUC_4-like")
