@@ -389,7 +389,11 @@ def test_config4_nuc4_scores_promote_to_the_32bit_path(gpu_ctx):
     exact-code kernels and still match the oracle."""
     rng = random.Random(5600)
     M = gv.match(-2, 5, -4)
-    pairs = randcases.rand_pairs(rng, 1, [6600], [6100], related=1.0, dirty=0.0)
+    ref = bytes(rng.choice(b"ACGT") for _ in range(7600))
+    qry = bytearray(ref[150:7350])
+    for _ in range(len(qry) // 40):                   # 2.5 % substitutions: best score ~ 7200 * 4.8
+        qry[rng.randrange(len(qry))] = rng.choice(b"ACGT")
+    pairs = [(ref, bytes(qry))]
     pairs += randcases.rand_pairs(rng, 3, [700, 900], [600], related=1.0, dirty=0.0)   # these stay on the packed path
     pk = helpers.pack(pairs)
     res = helpers.run_lib(gpu_ctx, 2, True, M, -10, DNA_IDX, 5, pk)
