@@ -880,9 +880,9 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.slot_cap = (const int32_t *)ctx->slot_cap.p;
         tp.slots = (int32_t *)ctx->slots.p;
         // one thread per pair when the batch fills the GPU that way, else one warp per pair
-        // (window of speculatively rebuilt tiles, see ba_trace16w_kernel)
         // (window of speculatively rebuilt tiles, see ba_trace16w_kernel), a whole CTA per pair when
-        // even that leaves SMs idle
+        // even that leaves SMs idle; a mixed batch gives warps to its longest pairs (the head of
+        // the size-sorted work list) as far as thread slots are free
         const bool cta_trace = ctx->opt_trace_mode == 3 ||
                                (ctx->opt_trace_mode == 1 && w.count <= 2 * (int64_t)ctx->sm_count);
         const bool warp_trace = ctx->opt_trace_mode == 2 ||
@@ -896,8 +896,34 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, st, tp);
             B.out->warp_trace_launches++;
         } else {
-            const unsigned tblocks = (unsigned)((w.count + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
-            BA_LAUNCH(pick_trace16(kind, lin), tblocks, BA_TRACE_THREADS, st, tp);
+            const int64_t slots_free = (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS - w.count;
+            int64_t head = (ctx->opt_trace_mode == 1 && slots_free > 0) ? std::min(w.count, slots_free / 31) : 0;
+            if (head > 0 && head < w.count) {
+                // worth it only when the head really is longer than what follows
+                const WorkItem &a = plan.items[w.first], &b = plan.items[w.first + head];
+                const int64_t la = (int64_t)B.h_ref_len[a.pair] + B.h_qry_len[a.pair];
+                const int64_t lb = (int64_t)B.h_ref_len[b.pair] + B.h_qry_len[b.pair];
+                if (la < 2 * lb) head = 0;
+            }
+            if (ctx->opt_trace_mode == 4) head = (w.count + 3) / 4;  // test hook: always split
+            if (head > 0) {
+                Trace16Params th = tp;
+                th.n_items = (int)head;
+                const unsigned tb = (unsigned)((head + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
+                BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, st, th);
+                B.out->warp_trace_launches++;
+                B.launches++;
+            }
+            if (head < w.count) {
+                Trace16Params tt = tp;
+                tt.items = tp.items + head;
+                tt.n_items = (int)(w.count - head);
+                tt.seg_count = tp.seg_count + head;
+                tt.slot_off = tp.slot_off + head;
+                tt.slot_cap = tp.slot_cap + head;
+                const unsigned tblocks = (unsigned)((w.count - head + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
+                BA_LAUNCH(pick_trace16(kind, lin), tblocks, BA_TRACE_THREADS, st, tt);
+            }
         }
         const unsigned cblocks = (unsigned)((w.count + 255) / 256);
         BA_LAUNCH(ba_clip_counts_kernel, cblocks, 256, st, (const int32_t *)ctx->seg_count.p,
@@ -1193,7 +1219,7 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
         ctx->opt_long_mode = value;
         return BA_OK;
     }
-    if (!strcmp(key, "trace_mode")) {  // 0 = thread per pair, 1 = automatic, 2 = warp per pair, 3 = CTA per pair
+    if (!strcmp(key, "trace_mode")) {  // 0 = thread per pair, 1 = automatic, 2 = warp per pair, 3 = CTA per pair, 4 = split (test hook)
         ctx->opt_trace_mode = value;
         return BA_OK;
     }

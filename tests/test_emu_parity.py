@@ -230,7 +230,9 @@ def test_fast16_warp_per_pair_traceback(emu_ctx, kind):
     pairs += randcases.rand_pairs(rng, 4, [30, 200], [30, 200], related=0.0, dirty=0.0)   # unrelated: gappy paths
     pk = helpers.pack(pairs)
     orc = helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk)
-    for mode in (2, 3):   # a warp per pair (4 x 8 tile window), a CTA per pair (diagonal band of tiles)
+    # a warp per pair (4 x 8 tile window), a CTA per pair (diagonal band of tiles), warps for the head of
+    # the work list and threads for the rest
+    for mode in (2, 3, 4):
         emu_ctx.set_option("trace_mode", mode)
         try:
             res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)

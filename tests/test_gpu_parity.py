@@ -401,3 +401,17 @@ def test_config4_nuc4_scores_promote_to_the_32bit_path(gpu_ctx):
     best = int(res.pairs(0)[:, 4].sum())
     assert best > 32767, best
     helpers.compare(res, helpers.run_oracle(2, True, M, -10, DNA_IDX, pk, 1, 2), "cfg4 NUC_4-like")
+
+
+def test_mixed_batch_gives_warps_to_its_longest_pairs(gpu_ctx):
+    """Between ~4.7 k and ~75 k pairs of very different lengths the traceback runs the head of the
+    size-sorted work list with one warp per pair and the rest with one thread per pair."""
+    rng = random.Random(5700)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 300, [2500, 3500], [1300, 2000], related=0.9, dirty=0.0)
+    pairs += randcases.rand_pairs(rng, 6000, [60, 150, 300], [40, 100, 200], related=0.9, dirty=0.0)
+    rng.shuffle(pairs)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(gpu_ctx, 0, True, M, -5, DNA_IDX, 5, pk)
+    assert res.stats["warp_trace_launches"] >= 1 and res.stats["pairs_fast16"] > 0.95 * len(pairs)
+    helpers.compare(res, helpers.run_oracle(0, True, M, -5, DNA_IDX, pk, 1, 16), "mixed trace")
