@@ -897,13 +897,20 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             B.out->warp_trace_launches++;
         } else {
             const int64_t slots_free = (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS - w.count;
-            int64_t head = (ctx->opt_trace_mode == 1 && slots_free > 0) ? std::min(w.count, slots_free / 31) : 0;
-            if (head > 0 && head < w.count) {
-                // worth it only when the head really is longer than what follows
-                const WorkItem &a = plan.items[w.first], &b = plan.items[w.first + head];
-                const int64_t la = (int64_t)B.h_ref_len[a.pair] + B.h_qry_len[a.pair];
-                const int64_t lb = (int64_t)B.h_ref_len[b.pair] + B.h_qry_len[b.pair];
-                if (la < 2 * lb) head = 0;
+            auto path_len = [&](int64_t k) {
+                const WorkItem &x = plan.items[w.first + k];
+                return (int64_t)B.h_ref_len[x.pair] + B.h_qry_len[x.pair];
+            };
+            int64_t head = 0;
+            if (ctx->opt_trace_mode == 1) {
+                if (path_len(0) >= 3 * path_len(w.count / 2)) {
+                    // strongly mixed lengths: with a thread per pair the few longest walks would run
+                    // alone at the end; warps shorten exactly those
+                    head = w.count;
+                } else if (slots_free > 0) {
+                    head = std::min(w.count, slots_free / 31);
+                    if (head < w.count && path_len(0) < 2 * path_len(head)) head = 0;  // the head is not longer
+                }
             }
             if (ctx->opt_trace_mode == 4) head = (w.count + 3) / 4;  // test hook: always split
             if (head > 0) {
