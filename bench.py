@@ -430,6 +430,10 @@ def main():
             roof["dpx"] = {"achieved_lane_results_per_s": achieved_lane, "peak_lane_results_per_s": peak_lane,
                            "frac": achieved_lane / peak_lane, "lane_results_per_cell": lanes_per_cell,
                            "peak_source": "profiles/dpx_peaks.json (ba_microbench on B200)"}
+            if traffic is not None:  # the same ncu capture: how busy the integer/DPX pipe really is
+                roof["dpx"]["ncu_alu_pipe_pct"] = ent.get("alu_pipe_pct")
+                roof["dpx"]["ncu_issue_active_pct"] = ent.get("issue_active_pct")
+                roof["dpx"]["ncu_thread_inst_per_cell"] = ent.get("inst_per_cell")
         line = {
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -438,7 +442,8 @@ def main():
             "config": {"workload": w.name, "pairs_per_gpu_per_step": w.n, "cells_per_gpu_per_step": cells_step,
                        "parallelism": f"independent pairs sharded over {world} GPU(s), no collective",
                        "l2": "inputs + traceback codes per step exceed the 126 MB L2",
-                       "seed": "splitmix64 0xB10600+config (+rank<<20)"},
+                       "seed": "splitmix64 0xB10600+config (+rank<<20)",
+                       "host_plan": "work lists cached across same-shaped batches (lengths only, never results)"},
             "roofline": roof, "clocks": clocks,
             "breakdown_ms_per_step": {"fill": agg["ms_fill"] / args.steps, "trace": agg["ms_trace"] / args.steps,
                                       "d2h": agg["ms_d2h"] / args.steps, "host_plan_scatter": agg["ms_host"] / args.steps,
