@@ -15,6 +15,7 @@ BA_SW, BA_NW, BA_FITTED = 0, 1, 2
 
 BA_OK = 0
 BA_ERR_ARG, BA_ERR_CUDA, BA_ERR_MATRIX_SIZE, BA_ERR_RANGE, BA_ERR_NOMEM, BA_ERR_NO_SCORING = -1, -2, -3, -4, -5, -6
+BA_ERR_FORMAT = -7
 BA_PAIR_OK, BA_PAIR_ILLEGAL_REF, BA_PAIR_ILLEGAL_QRY, BA_PAIR_PANIC, BA_PAIR_NO_PATH = 0, 1, 2, 3, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -25,6 +26,7 @@ ABI_SYMBOLS = (
     "ba_create", "ba_destroy", "ba_last_error", "ba_set_scoring", "ba_align_batch",
     "ba_align_batch_device", "ba_free_result", "ba_alloc_host", "ba_free_host",
     "ba_set_option", "ba_abi_version", "ba_build_info", "ba_format_batch", "ba_free_formatted",
+    "ba_fasta_parse", "ba_fastq_parse", "ba_seqfile_free",
 )
 
 
@@ -63,6 +65,25 @@ class BaFormatted(C.Structure):
         ("bytes_a", C.c_int64),
         ("bytes_b", C.c_int64),
         ("ms_kernels", C.c_float),
+    ]
+
+
+class BaSeqFile(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("stride", C.c_int),
+        ("letters", C.POINTER(C.c_uint8)),
+        ("letters_bytes", C.c_int64),
+        ("seq_off", C.POINTER(C.c_int64)),
+        ("seq_len", C.POINTER(C.c_int32)),
+        ("text", C.POINTER(C.c_char)),
+        ("text_bytes", C.c_int64),
+        ("name_off", C.POINTER(C.c_int64)),
+        ("desc_off", C.POINTER(C.c_int64)),
+        ("name_len", C.POINTER(C.c_int32)),
+        ("desc_len", C.POINTER(C.c_int32)),
+        ("err_line", C.c_int64),
+        ("err", C.c_char * 160),
     ]
 
 
@@ -105,6 +126,12 @@ def _bind(lib):
     lib.ba_format_batch.restype = i32
     lib.ba_free_formatted.argtypes = [vp, C.POINTER(BaFormatted)]
     lib.ba_free_formatted.restype = None
+    lib.ba_fasta_parse.argtypes = [vp, i64, i32, C.POINTER(BaSeqFile)]
+    lib.ba_fasta_parse.restype = i32
+    lib.ba_fastq_parse.argtypes = [vp, i64, i32, C.POINTER(BaSeqFile)]
+    lib.ba_fastq_parse.restype = i32
+    lib.ba_seqfile_free.argtypes = [C.POINTER(BaSeqFile)]
+    lib.ba_seqfile_free.restype = None
     return lib
 
 

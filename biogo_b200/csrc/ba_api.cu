@@ -1620,3 +1620,5 @@ void ba_free_host(void *p)
 }
 
 }  // extern "C"
+
+#include "ba_seqio.inl"

@@ -38,7 +38,8 @@ enum {
     BA_ERR_MATRIX_SIZE = -3,  /* align.ErrMatrixWrongSize{Size,Len} (align/align.go:66-73); SW/NW kinds only */
     BA_ERR_RANGE = -4,        /* score bound does not fit the 32-bit device lanes */
     BA_ERR_NOMEM = -5,        /* host or device allocation failed */
-    BA_ERR_NO_SCORING = -6    /* ba_align_batch before ba_set_scoring */
+    BA_ERR_NO_SCORING = -6,   /* ba_align_batch before ba_set_scoring */
+    BA_ERR_FORMAT = -7        /* ba_fasta_parse / ba_fastq_parse: malformed text (ba_seqfile.err) */
 };
 
 /* Per-pair status (ba_result.status[k]). */
@@ -150,6 +151,32 @@ int ba_format_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64
                     const int64_t *seg_start, const int32_t *seg_count, const int32_t *segs, int64_t n_segs,
                     uint8_t gap, ba_formatted *out);
 void ba_free_formatted(ba_ctx *ctx, ba_formatted *f);
+
+/* FASTA / FASTQ text -> packed batch (reference readers: io/seqio/fasta/fasta.go:60-113,
+ * io/seqio/fastq/fastq.go:62-141).  Host-side: no context, no device.  `letters` is pinned memory
+ * laid out like ba_align_batch's input (stride 1: Letters; stride 2: QLetters {L, Q}), so a pair
+ * (record i, record j) is aligned by passing seq_off[i], seq_len[i], seq_off[j], seq_len[j].
+ * Names and descriptions live in `text` (not NUL-terminated).  On BA_ERR_FORMAT `err` and
+ * `err_line` describe the first bad line, with the reference readers' messages. */
+typedef struct ba_seqfile {
+    int64_t n;
+    int stride;
+    uint8_t *letters;
+    int64_t letters_bytes;
+    int64_t *seq_off;
+    int32_t *seq_len;
+    char *text;
+    int64_t text_bytes;
+    int64_t *name_off, *desc_off;
+    int32_t *name_len, *desc_len;
+    int64_t err_line;
+    char err[160];
+} ba_seqfile;
+int ba_fasta_parse(const uint8_t *data, int64_t len, int stride, ba_seqfile *out);
+/* quality_offset: 33 (Sanger, Illumina 1.8+) or 64 (Illumina 1.3/1.5); Q = byte - offset as in
+ * alphabet/letters.go:66-72 */
+int ba_fastq_parse(const uint8_t *data, int64_t len, int quality_offset, ba_seqfile *out);
+void ba_seqfile_free(ba_seqfile *f);
 
 /* Pinned host allocation so a caller (cgo, ctypes) can pack straight into DMA-able memory. */
 void *ba_alloc_host(size_t bytes);
