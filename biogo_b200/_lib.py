@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "ba_create", "ba_destroy", "ba_last_error", "ba_set_scoring", "ba_align_batch",
     "ba_align_batch_device", "ba_free_result", "ba_alloc_host", "ba_free_host",
     "ba_set_option", "ba_abi_version", "ba_build_info", "ba_format_batch", "ba_free_formatted",
-    "ba_fasta_parse", "ba_fastq_parse", "ba_seqfile_free",
+    "ba_fasta_parse", "ba_fastq_parse", "ba_seqfile_free", "ba_gather_pairs",
 )
 
 
@@ -132,6 +132,8 @@ def _bind(lib):
     lib.ba_fastq_parse.restype = i32
     lib.ba_seqfile_free.argtypes = [C.POINTER(BaSeqFile)]
     lib.ba_seqfile_free.restype = None
+    lib.ba_gather_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
+    lib.ba_gather_pairs.restype = i32
     return lib
 
 

@@ -231,3 +231,28 @@ void ba_seqfile_free(ba_seqfile *f)
 }
 
 }  // extern "C"
+
+// ---- one batch over several devices: the host deals pairs to devices and
+// gathers results by pair index; this helper packs a device's share contiguously so that it
+// uploads only its own letters.
+extern "C" int ba_gather_pairs(const uint8_t *letters, int stride, const int64_t *ref_off, const int32_t *ref_len,
+                               const int64_t *qry_off, const int32_t *qry_len, const int64_t *ids, int64_t k,
+                               uint8_t *dst, int64_t dst_bytes, int64_t *new_ref_off, int64_t *new_qry_off)
+{
+    if (k < 0 || (stride != 1 && stride != 2) || (k > 0 && (!ids || !ref_off || !ref_len || !qry_off || !qry_len ||
+                                                            !new_ref_off || !new_qry_off)))
+        return BA_ERR_ARG;
+    int64_t o = 0;
+    for (int64_t x = 0; x < k; x++) {
+        const int64_t p = ids[x];
+        const int64_t rb = (int64_t)ref_len[p] * stride, qb = (int64_t)qry_len[p] * stride;
+        if (rb < 0 || qb < 0 || o + rb + qb > dst_bytes) return BA_ERR_ARG;
+        if (rb) memcpy(dst + o, letters + ref_off[p], (size_t)rb);
+        new_ref_off[x] = o;
+        o += rb;
+        if (qb) memcpy(dst + o, letters + qry_off[p], (size_t)qb);
+        new_qry_off[x] = o;
+        o += qb;
+    }
+    return BA_OK;
+}

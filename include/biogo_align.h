@@ -178,6 +178,16 @@ int ba_fasta_parse(const uint8_t *data, int64_t len, int stride, ba_seqfile *out
 int ba_fastq_parse(const uint8_t *data, int64_t len, int quality_offset, ba_seqfile *out);
 void ba_seqfile_free(ba_seqfile *f);
 
+/* One batch over several devices (pairs never communicate: no collective).  The host deals pair
+ * ids to devices (largest cells first, so every device gets the same work within ~1 %), calls
+ * this to pack a device's share contiguously -- dst needs stride * sum(ref_len + qry_len) bytes over
+ * the share -- runs ba_align_batch per device from its own host thread and scatters the results
+ * back by pair id (biogo_b200/shard.py is that host logic; go/align would do the same with one
+ * goroutine per device). */
+int ba_gather_pairs(const uint8_t *letters, int stride, const int64_t *ref_off, const int32_t *ref_len,
+                    const int64_t *qry_off, const int32_t *qry_len, const int64_t *ids, int64_t k,
+                    uint8_t *dst, int64_t dst_bytes, int64_t *new_ref_off, int64_t *new_qry_off);
+
 /* Pinned host allocation so a caller (cgo, ctypes) can pack straight into DMA-able memory. */
 void *ba_alloc_host(size_t bytes);
 void ba_free_host(void *p);

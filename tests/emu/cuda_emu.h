@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 namespace emu {
@@ -101,8 +102,16 @@ inline void fiber_entry()
     swapcontext(&f.ctx, &b->sched);
 }
 
+inline std::mutex &launch_mutex()
+{
+    static std::mutex m;
+    return m;
+}
+
 inline void launch(unsigned grid, unsigned block, const std::function<void()> &body)
 {
+    // the emulator keeps its block state and every __shared__ array in statics: one launch at a time
+    std::lock_guard<std::mutex> only_one(launch_mutex());
     const size_t STACK = 256 * 1024;
     Block b;
     b.body = body;
