@@ -72,28 +72,29 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
         const int n = ref_len[p], m = qry_len[p];
         const uint8_t *r = enc + ref_off[p];
         const uint8_t *q = enc + qry_off[p];
+        // Per lane: first illegal position and the letter-class flags of its share; one reduction
+        // per pair at the end (no warp collective inside the scan, so the byte loads pipeline).
         int bad_r = 0x7fffffff, bad_q = 0x7fffffff;  // first illegal position
-        int oob = 0;                                 // any index beyond the matrix
-        int other = 0;                               // any letter outside alphabet indices 1..4
-        int zero = 0;                                // any gap letter (alphabet index 0)
-        for (int base = 0; base < n && bad_r == 0x7fffffff; base += 32) {
-            int x = base + lane;
-            uint8_t v = (x < n) ? r[(int64_t)x * stride] : 1;
-            unsigned b = __ballot_sync(0xffffffffu, v == 0xFF);
-            oob |= __any_sync(0xffffffffu, v == 0xFE);
-            other |= __any_sync(0xffffffffu, v < 1 || v > 4);
-            zero |= __any_sync(0xffffffffu, v == 0);
-            if (b) bad_r = base + __ffs(b) - 1;
+        unsigned flags = 0;                          // 1: index beyond the matrix, 2: outside 1..4, 4: gap letter
+#pragma unroll 4
+        for (int x = lane; x < n; x += 32) {
+            const unsigned v = r[(int64_t)x * stride];
+            if (v == 0xFFu) bad_r = min(bad_r, x);
+            flags |= (v == 0xFEu ? 1u : 0u) | ((v < 1u || v > 4u) ? 2u : 0u) | (v == 0u ? 4u : 0u);
         }
-        for (int base = 0; base < m && bad_q == 0x7fffffff; base += 32) {
-            int x = base + lane;
-            uint8_t v = (x < m) ? q[(int64_t)x * stride] : 1;
-            unsigned b = __ballot_sync(0xffffffffu, v == 0xFF);
-            oob |= __any_sync(0xffffffffu, v == 0xFE);
-            other |= __any_sync(0xffffffffu, v < 1 || v > 4);
-            zero |= __any_sync(0xffffffffu, v == 0);
-            if (b) bad_q = base + __ffs(b) - 1;
+#pragma unroll 4
+        for (int x = lane; x < m; x += 32) {
+            const unsigned v = q[(int64_t)x * stride];
+            if (v == 0xFFu) bad_q = min(bad_q, x);
+            flags |= (v == 0xFEu ? 1u : 0u) | ((v < 1u || v > 4u) ? 2u : 0u) | (v == 0u ? 4u : 0u);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bad_r = min(bad_r, __shfl_xor_sync(0xffffffffu, bad_r, o));
+            bad_q = min(bad_q, __shfl_xor_sync(0xffffffffu, bad_q, o));
+            flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+        }
+        const int oob = (int)(flags & 1u), other = (int)(flags & 2u), zero = (int)(flags & 4u);
         const bool hr = bad_r != 0x7fffffff, hq = bad_q != 0x7fffffff;
         int st = 0;
         int64_t ep = -1;
