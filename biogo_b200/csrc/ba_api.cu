@@ -405,7 +405,7 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
     if ((rc = ensure(ctx, ctx->seg_count, sizeof(int32_t) * (size_t)max_items)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->seg_base, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->arena, (size_t)max_code + 256)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 64)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 128)) != BA_OK) return rc;
     size_t scan_bytes = 0;
     if ((rc = exclusive_scan(ctx, nullptr, scan_bytes, (const int32_t *)ctx->seg_count.p,
                              (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
@@ -432,7 +432,7 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
                 return rc;
             B.launches++;
         }
-        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 128, st));
 
         // ---- fill
         CK(cudaEventRecord(ctx->ev[4], st));
@@ -563,6 +563,17 @@ Trace16Fn pick_trace16t(int kind, bool lin)
     if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, false, NT>;
     if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, false, NT>;
     return ba_trace16w_kernel<KIND_FIT, false, NT>;
+}
+Trace16Fn pick_trace16p(int kind, bool lin)
+{
+    if (lin) {
+        if (kind == KIND_SW) return ba_trace16p_kernel<KIND_SW, true>;
+        if (kind == KIND_NW) return ba_trace16p_kernel<KIND_NW, true>;
+        return ba_trace16p_kernel<KIND_FIT, true>;
+    }
+    if (kind == KIND_SW) return ba_trace16p_kernel<KIND_SW, false>;
+    if (kind == KIND_NW) return ba_trace16p_kernel<KIND_NW, false>;
+    return ba_trace16p_kernel<KIND_FIT, false>;
 }
 Trace16Fn pick_trace16(int kind, bool lin)
 {
@@ -701,7 +712,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     if ((rc = ensure(ctx, ctx->seg_clip, sizeof(int32_t) * (size_t)max_items)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->seg_base, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->arena, (size_t)max_code + 256)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 64)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 128)) != BA_OK) return rc;
     size_t scan_bytes = 0;
     if ((rc = exclusive_scan(ctx, nullptr, scan_bytes, (const int32_t *)ctx->seg_clip.p,
                              (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
@@ -745,7 +756,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 pc.dev_items = nullptr;
             }
         }
-        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 64, st));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 128, st));
 
         // ---- fill (values + checkpoints)
         CK(cudaEventRecord(ctx->ev[4], st));
@@ -879,6 +890,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.slot_off = (const int64_t *)ctx->slot_off.p;
         tp.slot_cap = (const int32_t *)ctx->slot_cap.p;
         tp.slots = (int32_t *)ctx->slots.p;
+        tp.counter = (int *)ctx->counters.p + 64;  // zeroed with the fill counters at the start of the wave
         // one thread per pair when the batch fills the GPU that way, else one warp per pair
         // (window of speculatively rebuilt tiles, see ba_trace16w_kernel), a whole CTA per pair when
         // even that leaves SMs idle; a mixed batch gives warps to its longest pairs (the head of
@@ -928,8 +940,15 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 tt.seg_count = tp.seg_count + head;
                 tt.slot_off = tp.slot_off + head;
                 tt.slot_cap = tp.slot_cap + head;
-                const unsigned tblocks = (unsigned)((w.count - head + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS);
-                BA_LAUNCH(pick_trace16(kind, lin), tblocks, BA_TRACE_THREADS, st, tt);
+                int64_t tblocks = (w.count - head + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS;
+                if (ctx->opt_trace_mode == 0) {
+                    // static assignment: thread k of the grid walks pair k
+                    BA_LAUNCH(pick_trace16(kind, lin), (unsigned)tblocks, BA_TRACE_THREADS, st, tt);
+                } else {
+                    // persistent grid, pairs claimed from a counter (largest first)
+                    tblocks = std::min<int64_t>(tblocks, (int64_t)ctx->sm_count * BA_TRACE_MINB);
+                    BA_LAUNCH(pick_trace16p(kind, lin), (unsigned)tblocks, BA_TRACE_THREADS, st, tt);
+                }
             }
         }
         const unsigned cblocks = (unsigned)((w.count + 255) / 256);
@@ -1226,7 +1245,8 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
         ctx->opt_long_mode = value;
         return BA_OK;
     }
-    if (!strcmp(key, "trace_mode")) {  // 0 = thread per pair, 1 = automatic, 2 = warp per pair, 3 = CTA per pair, 4 = split (test hook)
+    if (!strcmp(key, "trace_mode")) {  // 0 = thread per pair (static), 1 = automatic, 2 = warp per pair, 3 = CTA per pair,
+                                       // 4 = split (test hook), 5 = thread per pair (persistent)
         ctx->opt_trace_mode = value;
         return BA_OK;
     }

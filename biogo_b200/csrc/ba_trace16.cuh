@@ -40,6 +40,7 @@ struct Trace16Params {
     const int64_t *slot_off;   // per item: first slot, in segments
     const int32_t *slot_cap;   // per item
     int32_t *slots;            // 5 ints per segment, in EMISSION order (reverse of final)
+    int *counter;              // ba_trace16p_kernel: next work item
 };
 
 struct CkView {
@@ -575,6 +576,285 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_ke
         nseg = 0;
     }
     P.seg_count[it] = nseg;
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent thread-per-pair variant for large batches.  Every thread claims pairs from a global
+// counter (the work list is sorted largest first), so a lane that finishes early takes the
+// next pair instead of idling until the slowest of its warp is done, and there is no
+// under-filled last round of CTAs.  The pair is processed as a small state machine around ONE
+// tile computation site -- start-cell search tiles (SW candidates, Fitted last column, NW start
+// layer) and walk tiles all go through the same trace16_tile call -- so lanes in different
+// phases of different pairs still execute the expensive code together.
+enum { T16P_NEW = 0, T16P_SW_SEARCH, T16P_FIT_SEARCH, T16P_NW_PROBE, T16P_WALK, T16P_FINISH };
+
+template <int KIND, bool LIN>
+__global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_kernel(Trace16Params P)
+{
+    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    __shared__ int S[BA_MAX_LET * BA_MAX_LET];
+    {
+        const int ll = P.sc->let;
+        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] * BA_SCALE;
+    }
+    __syncthreads();
+    uint8_t *tile = tiles + threadIdx.x;
+    const int stride = P.stride;
+    const int let = P.sc->let;
+    const int go = LIN ? 0 : P.sc->gap_open;
+    const int go8 = go * BA_SCALE;
+
+    // ---- per-pair state
+    int phase = T16P_NEW;
+    int it = 0, p = 0, n = 0, m = 0, cap = 0, nseg = 0;
+    const uint8_t *rs = nullptr, *qs = nullptr;
+    int32_t *out = nullptr;
+    CkView ck;
+    int i = 0, j = 0, cur = 0, layer = 0, maxI = 0, maxJ = 0, score = 0, last = MV_DIAG;
+    bool bad = false;
+    int sx = 0, sh = 0, Smax = 0;   // SW search: candidate index, strip half, table maximum
+    int fe = 0;                     // Fitted search: period
+    TileProbe pb;
+
+    for (;;) {
+        if (phase == T16P_NEW) {
+            it = atomicAdd(P.counter, 1);
+            if (it >= P.n_items) break;
+            const WorkItem item = P.items[it];
+            p = item.pair;
+            if (P.status[p] != 0) {
+                P.seg_count[it] = 0;
+                continue;
+            }
+            if ((P.acgt_only[p] & P.flag_mask) != P.flag_mask) {
+                P.seg_count[it] = -1;  // the host re-runs this pair on the exact path
+                continue;
+            }
+            n = P.ref_len[p];
+            m = P.qry_len[p];
+            rs = P.enc + P.ref_off[p];
+            qs = P.enc + P.qry_off[p];
+            ck.base = P.arena + item.code_off;
+            ck.n = n;
+            ck.m = m;
+            ck.cols = item.cols;
+            ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
+            ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
+            ck.lin = LIN;
+            ck.clamp = (KIND == KIND_SW) && !LIN;
+            ck.pass_bytes = ba16_pass_bytes(n, LIN);
+            ck.colck_bytes = ba16_colck_bytes(n, LIN);
+            out = P.slots + 5 * P.slot_off[it];
+            cap = P.slot_cap[it];
+            nseg = 0;
+            i = j = cur = layer = score = 0;
+            last = MV_DIAG;
+            bad = false;
+            pb = TileProbe();
+            if (KIND == KIND_SW) {
+                Smax = 0;
+                if (n > 0 && m > 0) {
+                    const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
+                    for (int x = 0; x < ck.npass * 16; x++) {
+                        const int2 c = cand[x];
+                        if (c.y >= 0) Smax = max(Smax, c.x);
+                    }
+                }
+                sx = 0;
+                sh = 0;
+                pb.want = Smax * BA_SCALE;
+                phase = Smax > 0 ? T16P_SW_SEARCH : T16P_WALK;
+            } else if (KIND == KIND_NW) {
+                i = n;
+                j = m;
+                pb.ci = i;
+                pb.cj = j;
+                phase = T16P_NW_PROBE;
+            } else {
+                j = m;
+                pb.col = m;
+                fe = 0;
+                phase = T16P_FIT_SEARCH;
+            }
+            if (phase == T16P_WALK) {
+                maxI = i;
+                maxJ = j;
+            }
+        }
+
+        // ---- which tile does this pair need next?
+        int tg = 0, te = 0, ti = 0, tj = 0;
+        bool need = false;
+        if (KIND == KIND_SW && phase == T16P_SW_SEARCH) {
+            // candidates: per (pass, lane) {best score, last period attaining it}; a lane has two strips
+            const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
+            while (sx < ck.npass * 16) {
+                const int2 c = cand[sx];
+                if (c.y >= 0 && c.x == Smax) {
+                    const int g = (sx >> 4) * 32 + 2 * (sx & 15) + sh;
+                    const int v = CkView::lane_of(g);
+                    const int rlast = min(n, BA16_PERIOD * c.y + BA16_PERIOD - v);
+                    const int clast = ck.left_col(g) + ck.cols;
+                    const bool useful = rlast >= 1 && clast >= 1 && !(rlast < i || (rlast == i && clast < j));
+                    if (++sh == 2) {
+                        sh = 0;
+                        sx++;
+                    }
+                    if (useful) {
+                        tg = g;
+                        te = c.y;
+                        ti = rlast;
+                        tj = clast;
+                        need = true;
+                        break;
+                    }
+                } else {
+                    sh = 0;
+                    sx++;
+                }
+            }
+            if (!need) {
+                cur = Smax;
+                maxI = i;
+                maxJ = j;
+                pb.want = -1;
+                phase = T16P_WALK;
+            }
+        }
+        if (KIND == KIND_FIT && phase == T16P_FIT_SEARCH) {
+            // last row maximising the last column (fitted_affine_letters.go:170-181, fitted_letters.go:112-139)
+            const int g = ck.strip_of(j);
+            const int v = CkView::lane_of(g);
+            while (BA16_PERIOD * fe - v < n) {
+                const int rlast = min(n, BA16_PERIOD * fe + BA16_PERIOD - v);
+                const int e = fe++;
+                if (rlast < 1) continue;
+                tg = g;
+                te = e;
+                ti = rlast;
+                tj = j;
+                need = true;
+                break;
+            }
+            if (!need) {
+                i = pb.besti;
+                maxI = i;
+                maxJ = j;
+                pb.col = -1;
+                phase = T16P_WALK;
+            }
+        }
+        if (KIND == KIND_NW && phase == T16P_NW_PROBE) {
+            tg = ck.strip_of(j);
+            te = (i + CkView::lane_of(tg) - 1) >> BA16_PSHIFT;
+            ti = i;
+            tj = j;
+            need = n > 0 && m > 0;
+            if (!need) {
+                maxI = i;
+                maxJ = j;
+                phase = T16P_WALK;
+            }
+        }
+        if (phase == T16P_WALK) {
+            if (i > 0 && j > 0 && !bad && !(KIND == KIND_SW && cur == 0)) {
+                tg = ck.strip_of(j);
+                te = (i + CkView::lane_of(tg) - 1) >> BA16_PSHIFT;
+                ti = i;
+                tj = j;
+                need = true;
+            } else {
+                phase = T16P_FINISH;
+            }
+        }
+        if (phase == T16P_FINISH) {
+#define T16P_EMIT(a0, a1, b0, b1, sc_)    \
+    do {                                  \
+        if (nseg < cap) {                 \
+            int32_t *o_ = out + 5 * nseg; \
+            o_[0] = (a0);                 \
+            o_[1] = (a1);                 \
+            o_[2] = (b0);                 \
+            o_[3] = (b1);                 \
+            o_[4] = (sc_);                \
+        }                                 \
+        nseg++;                           \
+    } while (0)
+            T16P_EMIT(i, maxI, j, maxJ, score);
+            if (KIND == KIND_NW && i != j) {
+                // nw_affine_letters.go:311-325 / nw_letters.go:183-189: leading gap, its score is the border value
+                int b = go;
+                if (i == 0)
+                    for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> BA_SCALE_SHIFT;
+                else
+                    for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> BA_SCALE_SHIFT;
+                T16P_EMIT(0, i, 0, j, b);
+            }
+            if (bad) {
+                P.status[p] = 4;  // BA_PAIR_NO_PATH
+                nseg = 0;
+            }
+            P.seg_count[it] = nseg;
+            phase = T16P_NEW;
+            continue;
+        }
+        if (!need) continue;  // the phase changed: decide again
+
+        // ---- the one tile computation all phases share
+        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, tg, te, ti, tj, tile, pb);
+
+        // ---- what the tile was for
+        if (KIND == KIND_SW && phase == T16P_SW_SEARCH) {
+            if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
+                i = pb.fi;
+                j = pb.fj;
+            }
+        } else if (KIND == KIND_NW && phase == T16P_NW_PROBE) {
+            // start layer: strict '>' scanning M, U, L (nw_affine_letters.go:183-192); linear has one table
+            int best = pb.cM;
+            if (pb.cU > best) {
+                best = pb.cU;
+                layer = 1;
+            }
+            if (pb.cL > best) layer = 2;
+            pb.ci = pb.cj = -1;
+            maxI = i;
+            maxJ = j;
+            phase = T16P_WALK;
+        } else if (phase == T16P_WALK) {
+            const int v = CkView::lane_of(tg);
+            const int rt = max(BA16_PERIOD * te - v, 0);
+            const int c0 = max(ck.left_col(tg), 0);
+            const int cbase = ck.left_col(tg);
+            while (i > rt && j > c0) {
+                if (KIND == KIND_SW && cur == 0) break;
+                const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
+                const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
+                const bool corner = (i == n && j == m);
+                const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
+                int move, nl = 0, delta;
+                if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl,
+                                               delta)) {
+                    bad = true;
+                    break;
+                }
+                // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
+                if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
+                    T16P_EMIT(i, maxI, j, maxJ, score);
+                    maxI = i;
+                    maxJ = j;
+                    score = 0;
+                }
+                score += delta;
+                if (KIND == KIND_SW) cur -= delta;
+                if (move != MV_LEFT) i--;
+                if (move != MV_UP) j--;
+                layer = nl;
+                last = move;
+            }
+        }
+#undef T16P_EMIT
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -232,11 +232,11 @@ def test_fast16_warp_per_pair_traceback(emu_ctx, kind):
     orc = helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk)
     # a warp per pair (4 x 8 tile window), a CTA per pair (diagonal band of tiles), warps for the head of
     # the work list and threads for the rest
-    for mode in (2, 3, 4):
+    for mode in (2, 3, 4, 5):
         emu_ctx.set_option("trace_mode", mode)
         try:
             res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
-            assert res.stats["warp_trace_launches"] >= 1
+            assert (res.stats["warp_trace_launches"] >= 1) == (mode != 5)   # 5: persistent thread-per-pair kernel
             helpers.compare(res, orc, f"team trace mode {mode} kind {kind}")
             emu_ctx.set_option("slot_cap", 2)
             res2 = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
@@ -265,7 +265,7 @@ def test_fast16_linear_kinds(emu_ctx, kind):
     pairs += randcases.rand_pairs(rng, 6, [30, 120], [30, 120], related=0.0, dirty=0.0)
     pk = helpers.pack(pairs)
     orc = helpers.run_oracle(kind, False, M, 0, DNA_IDX, pk)
-    for mode in (0, 2, 3):
+    for mode in (0, 2, 3, 5):
         emu_ctx.set_option("trace_mode", mode)
         try:
             res = helpers.run_lib(emu_ctx, kind, False, M, 0, DNA_IDX, 5, pk)

@@ -324,7 +324,7 @@ def test_warp_per_pair_traceback_matches_thread_per_pair(gpu_ctx, kind):
     pairs += randcases.rand_pairs(rng, 40, [100, 400], [100, 400], related=0.0, dirty=0.0)
     pk = helpers.pack(pairs)
     orc = helpers.run_oracle(kind, True, M, -5, DNA_IDX, pk, 1, 16)
-    for mode, want in ((2, True), (3, True), (0, False)):
+    for mode, want in ((2, True), (3, True), (0, False), (5, False)):
         gpu_ctx.set_option("trace_mode", mode)
         try:
             res = helpers.run_lib(gpu_ctx, kind, True, M, -5, DNA_IDX, 5, pk)
@@ -343,7 +343,7 @@ def test_fast16_linear_kinds(gpu_ctx, kind):
                                  related=0.9, dirty=0.0)
     pk = helpers.pack(pairs)
     orc = helpers.run_oracle(kind, False, M, 0, DNA_IDX, pk, 1, 16)
-    for mode in (0, 2, 3):
+    for mode in (0, 2, 3, 5):
         gpu_ctx.set_option("trace_mode", mode)
         try:
             res = helpers.run_lib(gpu_ctx, kind, False, M, 0, DNA_IDX, 5, pk)
