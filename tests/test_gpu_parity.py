@@ -415,3 +415,22 @@ def test_mixed_batch_gives_warps_to_its_longest_pairs(gpu_ctx):
     res = helpers.run_lib(gpu_ctx, 0, True, M, -5, DNA_IDX, 5, pk)
     assert res.stats["warp_trace_launches"] >= 1 and res.stats["pairs_fast16"] > 0.95 * len(pairs)
     helpers.compare(res, helpers.run_oracle(0, True, M, -5, DNA_IDX, pk, 1, 16), "mixed trace")
+
+
+@pytest.mark.parametrize("num,n", [(3, 20000), (5, 3000), (4, 6)])
+def test_fast16_and_exact_paths_agree_at_config_shapes(gpu_ctx, num, n):
+    """Oracle-free at sizes the CPU oracle cannot reach quickly: the packed DPX path against the
+    32-bit exact-code path (itself pinned to the oracle) on BASELINE configs 3, 5 and 4."""
+    w = synth.config(num, n)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    idx, al = w.alpha.LetterIndex(), w.alpha.Len()
+    fast = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, idx, al, pk, w.stride)
+    assert fast.stats["pairs_fast16"] > 0.9 * w.n
+    gpu_ctx.set_option("force_path", 1)
+    try:
+        exact = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, idx, al, pk, w.stride)
+    finally:
+        gpu_ctx.set_option("force_path", 0)
+    assert exact.stats["pairs_fast16"] == 0
+    assert np.array_equal(fast.status, exact.status) and np.array_equal(fast.seg_count, exact.seg_count)
+    assert np.array_equal(fast.segs, exact.segs)
