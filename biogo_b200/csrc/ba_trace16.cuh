@@ -1083,30 +1083,38 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
                 if (ws >= BA_TB_STRIPS || we < 0 || we >= BA_TB_PERIODS) break;
                 slot = ws * BA_TB_PERIODS + we;
             }
+            // inside this tile the walk only needs tile-local arithmetic
             const int rt = max(BA16_PERIOD * ((i + v - 1) >> BA16_PSHIFT) - v, 0);
             const int cbase = ck.left_col(g);
-            const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
-            const unsigned code =
-                tiles[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS + wbase + slot];
-            const bool corner = (i == n && j == m);
-            const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
-            int move, nl = 0, delta;
-            if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl, delta))
-                bad = true;
-            if (bad) break;
-            // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
-            if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
-                T16W_EMIT(i, maxI, j, maxJ, score);
-                maxI = i;
-                maxJ = j;
-                score = 0;
+            const int c0 = max(cbase, 0);
+            const uint8_t *tcodes = tiles + wbase + slot;
+            while (i > rt && j > c0) {
+                if (KIND == KIND_SW && cur == 0) break;
+                const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
+                const unsigned code = tcodes[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
+                const bool corner = (i == n && j == m);
+                const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
+                int move, nl = 0, delta;
+                if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl,
+                                               delta)) {
+                    bad = true;
+                    break;
+                }
+                // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
+                if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
+                    T16W_EMIT(i, maxI, j, maxJ, score);
+                    maxI = i;
+                    maxJ = j;
+                    score = 0;
+                }
+                score += delta;
+                if (KIND == KIND_SW) cur -= delta;
+                if (move != MV_LEFT) i--;
+                if (move != MV_UP) j--;
+                layer = nl;
+                last = move;
             }
-            score += delta;
-            if (KIND == KIND_SW) cur -= delta;
-            if (move != MV_LEFT) i--;
-            if (move != MV_UP) j--;
-            layer = nl;
-            last = move;
+            if (bad) break;
         }
         T16W_SYNC();
     }
