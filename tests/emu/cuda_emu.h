@@ -277,6 +277,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
     return r;
 }
 static inline int __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline void __syncwarp() { emu::warp_barrier(); }
 static inline void __syncthreads() { emu::block_barrier(); }
 static inline int atomicAdd(int *p, int v)
