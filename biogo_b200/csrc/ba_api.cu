@@ -1363,6 +1363,7 @@ int ba_align_batch_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters
     if (rc != BA_OK) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     CK(cudaEventRecord(ctx->ev[0], st));
+    ctx->last_n = -1;  // the context's own letters buffer no longer mirrors the last batch (ba_format_batch)
     rc = run_device(ctx, d_letters, letters_bytes, stride, d_ref_off, d_ref_len, d_qry_off, d_qry_len,
                     h_ref_len, h_qry_len, n, st, out);
     out->ms_h2d = 0.f;
@@ -1398,6 +1399,7 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
     }
     if (letters_bytes > 0 && !letters) return BA_ERR_ARG;
     cudaStream_t st = ctx->stream;
+    ctx->last_n = -1;
     if ((rc = ensure(ctx, ctx->letters, (size_t)letters_bytes + 16)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->ref_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->qry_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
