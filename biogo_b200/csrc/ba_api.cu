@@ -255,6 +255,10 @@ struct Batch {
     };
     std::vector<WaveOut> wave_out;
     int64_t seg_total = 0;
+    // exclusive_compute: the per-device kernel-phase token this call holds, released as soon as the
+    // last kernel of the batch is enqueued (the result copies then overlap the next batch's kernels)
+    std::unique_lock<std::mutex> *token = nullptr;
+    bool more_kernels_later = false;   // pairs are already queued for the exact path after this one
     float ms_d2h = 0.f, ms_fill = 0.f, ms_trace = 0.f;
     double host_s = 0.0;
     int64_t launches = 0, fill_launches = 0, code_bytes = 0;
@@ -318,7 +322,8 @@ int cached_occupancy(ba_ctx *ctx, Fn fn, int threads, int &occ, size_t dyn_smem 
 // seg_start/seg_count by pair id.  `skip_overflow`: items whose count exceeds their slot
 // capacity are left for the exact path and reported through `overflow`.
 int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, int32_t *h_cnt, int64_t *h_base,
-                int64_t wsegs, const int32_t *d_segs, const int32_t *h_raw_cnt, std::vector<int32_t> *overflow)
+                int64_t wsegs, const int32_t *d_segs, const int32_t *h_raw_cnt, std::vector<int32_t> *overflow,
+                bool release_token = false)
 {
     cudaStream_t st = B.st;
     int32_t *h_segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(wsegs + 1));
@@ -330,6 +335,7 @@ int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, in
     if (wsegs > 0)
         CK(cudaMemcpyAsync(h_segs, d_segs, sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[3], st));
+    if (release_token && B.token && B.token->owns_lock()) B.token->unlock();  // no kernel of this batch follows
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
@@ -987,8 +993,14 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         B.launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[6], st));
+        // last wave, nothing queued for the exact path and no pair overflowed its slots or failed the
+        // letter-class check: the kernel phase of this batch ends here
+        bool last_kernels = B.token && &w == &plan.waves.back() && !B.more_kernels_later && overflow.empty();
+        if (last_kernels)
+            for (int64_t k = 0; k < w.count && last_kernels; k++)
+                last_kernels = h_raw[k] >= 0 && h_raw[k] <= plan.slot_cap[w.first + k];
         if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, h_raw,
-                              &overflow)) != BA_OK)
+                              &overflow, last_kernels)) != BA_OK)
             return rc;
         BA_TSEC("P16 wave gathered", tp0);
     }
@@ -1007,7 +1019,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
 int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int stride,
                const int64_t *d_ref_off, const int32_t *d_ref_len, const int64_t *d_qry_off,
                const int32_t *d_qry_len, const int32_t *h_ref_len, const int32_t *h_qry_len,
-               int64_t n, cudaStream_t st, ba_result *out)
+               int64_t n, cudaStream_t st, ba_result *out, std::unique_lock<std::mutex> *token = nullptr)
 {
     const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
     const double t_call = now_s();
@@ -1039,6 +1051,7 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
     B.n = n;
     B.st = st;
     B.out = out;
+    B.token = token;
 
     // ---- encode + validate
     int rc;
@@ -1103,6 +1116,7 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         BA_TSEC("partition", ts0);
         B.host_s += now_s() - ts0;
         const size_t nslow0 = slow.size();
+        B.more_kernels_later = nslow0 > 0;
         if ((rc = run_path16(ctx, B, pc.fast.data(), (int64_t)pc.fast.size(), f16.gsub, slow,
                              ctx->opt_plan_cache != 0)) != BA_OK)
             return rc;
@@ -1364,8 +1378,14 @@ int ba_align_batch_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     CK(cudaEventRecord(ctx->ev[0], st));
     ctx->last_n = -1;  // the context's own letters buffer no longer mirrors the last batch (ba_format_batch)
-    rc = run_device(ctx, d_letters, letters_bytes, stride, d_ref_off, d_ref_len, d_qry_off, d_qry_len,
-                    h_ref_len, h_qry_len, n, st, out);
+    {
+        // same kernel-phase token as ba_align_batch: with several contexts the result copies and
+        // the host gather of one batch run under the kernels of the next
+        std::unique_lock<std::mutex> token(g_compute_token[ctx->device & 63], std::defer_lock);
+        if (ctx->opt_exclusive) token.lock();
+        rc = run_device(ctx, d_letters, letters_bytes, stride, d_ref_off, d_ref_len, d_qry_off, d_qry_len,
+                        h_ref_len, h_qry_len, n, st, out, ctx->opt_exclusive ? &token : nullptr);
+    }
     out->ms_h2d = 0.f;
     if (rc != BA_OK) ba_free_result(ctx, out);
     return rc;
@@ -1442,7 +1462,8 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
         }
         rc = run_device(ctx, (const uint8_t *)ctx->letters.p, letters_bytes, stride, (const int64_t *)ctx->ref_off.p,
                         (const int32_t *)ctx->ref_len.p, (const int64_t *)ctx->qry_off.p,
-                        (const int32_t *)ctx->qry_len.p, ref_len, qry_len, n, st, out);
+                        (const int32_t *)ctx->qry_len.p, ref_len, qry_len, n, st, out,
+                        ctx->opt_exclusive ? &token : nullptr);
     }
     if (rc != BA_OK) cudaStreamSynchronize(st);  // the staged copies may still be in flight
     if (stage) pinned_put(ctx, stage);           // on success run_device returned with the stream drained
