@@ -225,14 +225,21 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     // ---- rows rt+1 .. imax
     Cell3 dprev = corner;  // (row-1, cL)
     uint8_t *trow = tile;
+    // the next row's letter and left-boundary checkpoint are fetched one row ahead, so their
+    // latency hides under the current row's cells
+    int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0, nM = 0, nL = 0;
+    if (cL > 0 && rt + 1 <= imax) ck.col_ml(gl, rt + 1, nM, nL);
     for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * BA_TRACE_THREADS) {
-        const int *Srow = S + (int)rs[(r - 1) * stride] * let;
+        const int *Srow = S + nR * let;
+        const int mm = nM, ll = nL;
+        if (r + 1 <= imax) {
+            nR = (int)rs[(int64_t)r * stride];
+            if (cL > 0) ck.col_ml(gl, r + 1, nM, nL);
+        }
         const int er = Srow[0];
         const int goer = go + er;
         Cell3 left;
         if (cL > 0) {
-            int mm, ll;
-            ck.col_ml(gl, r, mm, ll);
             // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er [, 0])
             leftU = max(dprev.M + goer, leftU + er);
             if (KIND == KIND_SW) leftU = max(leftU, 0);
@@ -321,10 +328,17 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
     };
     int dprev = left_at(rt);
     uint8_t *trow = tile;
+    // next row's letter and left boundary value, fetched one row ahead
+    int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0;
+    int nLeft = (rt + 1 <= imax) ? left_at(rt + 1) : 0;
     for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * BA_TRACE_THREADS) {
-        const int *Srow = S + (int)rs[(r - 1) * stride] * let;
+        const int *Srow = S + nR * let;
+        const int left = nLeft;
+        if (r + 1 <= imax) {
+            nR = (int)rs[(int64_t)r * stride];
+            nLeft = left_at(r + 1);
+        }
         const int er = Srow[0];
-        const int left = left_at(r);
         int d = dprev, l = left;
 #pragma unroll
         for (int k = 0; k < BA_MAX_COLS; k++) {
