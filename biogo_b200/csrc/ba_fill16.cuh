@@ -381,7 +381,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             __syncwarp();
 
             unsigned Mu[NC], Uu[NC], Hu[NC];
-            unsigned outM = 0, outL = 0, outH = 0, sdiagH = 0;
+            // the right-most column handed to the next lane is (Mu[NC-1], outL, Hu[NC-1]): M and H stay in
+            // their arrays until the next step's shuffles have read them
+            unsigned outL = 0, sdiagH = 0;
 #pragma unroll
             for (int k = 0; k < NC; k++) {
                 if (KIND == KIND_SW) {
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             if (KIND != KIND_SW) {
                 const int j0 = pass * W + t * NC;  // the column left of my first one: H[0][j0]
                 sdiagH = (j0 == 0) ? 0u : pack16(go + j0 * eq, go + j0 * eq);
-                outM = outL = NEGP;
+                outL = NEGP;
             }
             unsigned bmax = 0;  // running max of the current period
             // per lane (both pairs packed): best value of this pass and the LAST period attaining it
@@ -446,9 +448,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 
                 // boundary column of the left neighbour lane; lane 0: DP column 0 (all zero for SW)
                 // or the staged last column of the previous pass
-                unsigned rM = __shfl_up_sync(FULL, outM, 1, 16);
+                unsigned rM = __shfl_up_sync(FULL, Mu[NC - 1], 1, 16);
                 unsigned rL = __shfl_up_sync(FULL, outL, 1, 16);
-                unsigned rH = __shfl_up_sync(FULL, outH, 1, 16);
+                unsigned rH = __shfl_up_sync(FULL, Hu[NC - 1], 1, 16);
                 if (t == 0) {
                     if (KIND == KIND_SW) {
                         rM = rL = rH = 0;
@@ -488,7 +490,6 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         if (k == COLS - 1) mc0 = Tl;
                     }
                     sdiagH = rH;
-                    outM = outH = Tl;
                 } else {
                 // Three sweeps, each updating its array in place (no register rotation):
                 //  U from the previous row's (M, U); M from the previous row's H; then L along the
@@ -525,9 +526,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     }
                 }
                 sdiagH = rH;
-                outM = Mu[NC - 1];
                 outL = Ll;
-                outH = Hu[NC - 1];
                 }
                 }
                 if (KIND == KIND_SW) {
@@ -545,16 +544,16 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         unsigned short *h = (unsigned short *)(cst[0][j >> 1] + parofs) + (j & 1);
                         h[0] = (unsigned short)mc0;
                         h[2 * BA16_STAGE_WORDS] = (unsigned short)(mc0 >> 16);
-                        h[4 * BA16_STAGE_PLANE] = (unsigned short)outM;
-                        h[4 * BA16_STAGE_PLANE + 2 * BA16_STAGE_WORDS] = (unsigned short)(outM >> 16);
+                        h[4 * BA16_STAGE_PLANE] = (unsigned short)Mu[NC - 1];
+                        h[4 * BA16_STAGE_PLANE + 2 * BA16_STAGE_WORDS] = (unsigned short)(Mu[NC - 1] >> 16);
                     } else {
                         w[0] = ck0a;
                         w[BA16_STAGE_WORDS] = ck0b;
-                        w[2 * BA16_STAGE_PLANE] = ba_prmt(outM, outL, 0x5410u);
-                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(outM, outL, 0x7632u);
+                        w[2 * BA16_STAGE_PLANE] = ba_prmt(Mu[NC - 1], outL, 0x5410u);
+                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(Mu[NC - 1], outL, 0x7632u);
                     }
                 }
-                if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(outM, outL, outH, (unsigned)pass + 1u);
+                if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(Mu[NC - 1], outL, Hu[NC - 1], (unsigned)pass + 1u);
                 }
                 // ---- end of the period: row checkpoint, flush both arrays, best-cell bookkeeping
                 if (LIN) {
