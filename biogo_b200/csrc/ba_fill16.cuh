@@ -420,6 +420,17 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) cst[c][jj] = colA + ba16_stage_word(t, c) + ((jj + (t >> 3)) & 3);
             const int nper_w = (nsteps_w + BA16_PERIOD - 1) >> BA16_PSHIFT;
+            // letters of the first ring chunk (prefetching variant, see the refill below)
+            constexpr int PFN = (CHUNK <= 64) ? CHUNK / 16 : 0;
+            unsigned pfA[PFN > 0 ? PFN : 1], pfB[PFN > 0 ? PFN : 1];
+            if (PFN > 0) {
+#pragma unroll
+                for (int y = 0; y < (PFN > 0 ? PFN : 1); y++) {
+                    const int i = 1 + t + 16 * y;
+                    pfA[y] = (plA && i <= nA) ? rA[(int64_t)(i - 1) * stride] : 0;
+                    pfB[y] = (plB && i <= nB) ? rB[(int64_t)(i - 1) * stride] : 0;
+                }
+            }
             for (int e = 0; e < nper_w; e++) {
                 const int parofs = (e & 1) * BA16_STAGE_PLANE;  // LIN: chunk of this period inside its sector
                 const int pre_row = 8 * (e + 1) + 1 + t;  // my boundary row of the NEXT period
@@ -428,13 +439,30 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 if ((e & (CHUNK / BA16_PERIOD - 1)) == 0) {
                     // rows 8e+1 .. 8e+CHUNK enter the rings (lanes of the group share the load)
                     __syncwarp();
-                    for (int x = t; x < CHUNK; x += 16) {
-                        const int i = 8 * e + 1 + x;
-                        unsigned wa = VROW, wb = VROW;
-                        if (plA && i <= nA) wa = proftab[rA[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
-                        if (plB && i <= nB) wb = proftab[rB[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
-                        ringA[i & (RING - 1)] = wa;
-                        ringB[i & (RING - 1)] = wb;
+                    if (PFN > 0) {
+                        // small chunks (GSUB): the letters were fetched at the previous refill, the
+                        // next chunk's are requested now and land while this one is consumed
+#pragma unroll
+                        for (int y = 0; y < (PFN > 0 ? PFN : 1); y++) {
+                            const int i = 8 * e + 1 + t + 16 * y;
+                            unsigned wa = VROW, wb = VROW;
+                            if (plA && i <= nA) wa = proftab[pfA[y] & 31];
+                            if (plB && i <= nB) wb = proftab[pfB[y] & 31];
+                            ringA[i & (RING - 1)] = wa;
+                            ringB[i & (RING - 1)] = wb;
+                            const int i2 = i + CHUNK;
+                            pfA[y] = (plA && i2 <= nA) ? rA[(int64_t)(i2 - 1) * stride] : 0;
+                            pfB[y] = (plB && i2 <= nB) ? rB[(int64_t)(i2 - 1) * stride] : 0;
+                        }
+                    } else {
+                        for (int x = t; x < CHUNK; x += 16) {
+                            const int i = 8 * e + 1 + x;
+                            unsigned wa = VROW, wb = VROW;
+                            if (plA && i <= nA) wa = proftab[rA[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
+                            if (plB && i <= nB) wb = proftab[rB[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
+                            ringA[i & (RING - 1)] = wa;
+                            ringB[i & (RING - 1)] = wb;
+                        }
                     }
                     __syncwarp();
                 }
