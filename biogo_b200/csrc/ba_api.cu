@@ -336,14 +336,7 @@ int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, in
         CK(cudaMemcpyAsync(h_segs, d_segs, sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[3], st));
     if (release_token && B.token && B.token->owns_lock()) B.token->unlock();  // no kernel of this batch follows
-    CK(cudaStreamSynchronize(st));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-    B.ms_d2h += ms;
-    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
-    B.ms_fill += ms;
-    CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
-    B.ms_trace += ms;
+    // the per-pair scatter only needs the counts (already on the host): do it while the segments travel
     const double t0 = now_s();
     for (int64_t k = 0; k < w.count; k++) {
         const int32_t p = plan.items[w.first + k].pair;
@@ -354,10 +347,18 @@ int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, in
         B.out->seg_start[p] = B.seg_total + h_base[k];
         B.out->seg_count[p] = h_cnt[k];
     }
-    B.wave_out.push_back({h_segs, wsegs});
-    B.seg_total += wsegs;
     BA_TSEC("gather scatter", t0);
     B.host_s += now_s() - t0;
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    B.ms_d2h += ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    B.ms_fill += ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+    B.ms_trace += ms;
+    B.wave_out.push_back({h_segs, wsegs});
+    B.seg_total += wsegs;
     return BA_OK;
 }
 
