@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     constexpr int NC = 2 * COLS;  // columns per lane
     // row profiles: ring[group][pair][i & (RING-1)] = 4 substitution bytes of the letter of row i
     // GSUB kernels trade ring capacity for their score tables (shared memory bounds their occupancy)
-    constexpr int RING = GSUB ? 128 : BA16_PROF_RING, CHUNK = GSUB ? 64 : BA16_PROF_CHUNK;
+    // (so do the linear kernels, whose small register footprint leaves shared memory as the limit)
+    constexpr int RING = GSUB ? 128 : LIN ? 256 : BA16_PROF_RING, CHUNK = GSUB ? 64 : LIN ? 128 : BA16_PROF_CHUNK;
     __shared__ unsigned ring[BA16_GROUPS][2][RING + 8];
     __shared__ unsigned proftab[BA_MAX_LET + 1];  // PRMT: letter -> 4 sub bytes; GSUB: letter -> row byte offset
     // GSUB: signed-byte score tables in dynamic shared memory, replicated per BA16_GSUB_SHARE lanes and

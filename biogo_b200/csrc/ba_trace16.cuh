@@ -408,8 +408,9 @@ __device__ __forceinline__ bool trace16_decode(unsigned code, int layer, int er,
     }
 }
 
+// (linear tiles are cheap, the walk is bound by checkpoint-load latency: more resident CTAs)
 template <int KIND, bool LIN>
-__global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16_kernel(Trace16Params P)
+__global__ void __launch_bounds__(BA_TRACE_THREADS, LIN ? 6 : BA_TRACE_MINB) ba_trace16_kernel(Trace16Params P)
 {
     __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
     __shared__ int S[BA_MAX_LET * BA_MAX_LET];
