@@ -410,7 +410,6 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             uint4 *colckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB);
             uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB, LIN));
             unsigned ro = (unsigned)((1 - t) & (RING - 1)) * 4u;  // byte offset of my row in the rings
-            unsigned mc0 = 0;            // LIN: T of my first strip's last column at the current row
             unsigned ck0a = 0, ck0b = 0; // affine: packed (M, L) checkpoint words of that column, pairs A and B
 
             // staging addresses of my column-checkpoint words: [half of the period][word], pair A,
@@ -514,9 +513,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         const unsigned X = __viaddmax_s16x2(Hd, sub, __vadd2(old, erp));
                         Tl = (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Tl, eqp, X) : __viaddmax_s16x2(Tl, eqp, X);
                         Hu[k] = Tl;
-                        Mu[k] = Tl;
                         Hd = old;
-                        if (k == COLS - 1) mc0 = Tl;
                     }
                     sdiagH = rH;
                 } else {
@@ -560,7 +557,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 }
                 if (KIND == KIND_SW) {
 #pragma unroll
-                for (int k = 0; k + 1 < NC; k += 2) bmax = __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
+                for (int k = 0; k + 1 < NC; k += 2)
+                    bmax = LIN ? __vimax3_s16x2(bmax, Hu[k], Hu[k + 1]) : __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
                 }
 
                 // column checkpoints (M, clamped L) of my two strips, staged per pair for this period
@@ -571,10 +569,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         // int16 slots: the even period of a sector fills its first 16-byte chunk, the
                         // odd period the second; step j is half-word j of the chunk
                         unsigned short *h = (unsigned short *)(cst[0][j >> 1] + parofs) + (j & 1);
-                        h[0] = (unsigned short)mc0;
-                        h[2 * BA16_STAGE_WORDS] = (unsigned short)(mc0 >> 16);
-                        h[4 * BA16_STAGE_PLANE] = (unsigned short)Mu[NC - 1];
-                        h[4 * BA16_STAGE_PLANE + 2 * BA16_STAGE_WORDS] = (unsigned short)(Mu[NC - 1] >> 16);
+                        h[0] = (unsigned short)Hu[COLS - 1];
+                        h[2 * BA16_STAGE_WORDS] = (unsigned short)(Hu[COLS - 1] >> 16);
+                        h[4 * BA16_STAGE_PLANE] = (unsigned short)Hu[NC - 1];
+                        h[4 * BA16_STAGE_PLANE + 2 * BA16_STAGE_WORDS] = (unsigned short)(Hu[NC - 1] >> 16);
                     } else {
                         w[0] = ck0a;
                         w[BA16_STAGE_WORDS] = ck0b;
@@ -582,7 +580,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(Mu[NC - 1], outL, 0x7632u);
                     }
                 }
-                if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(Mu[NC - 1], outL, Hu[NC - 1], (unsigned)pass + 1u);
+                if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(LIN ? 0u : Mu[NC - 1], outL, Hu[NC - 1], (unsigned)pass + 1u);
                 }
                 // ---- end of the period: row checkpoint, flush both arrays, best-cell bookkeeping
                 if (LIN) {
@@ -595,8 +593,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     for (int s2 = 0; s2 < 2; s2++)
 #pragma unroll
                         for (int kk = 0; kk < COLS; kk += 2) {
-                            const unsigned lo = Mu[s2 * COLS + kk];
-                            const unsigned hi = (kk + 1 < COLS) ? Mu[s2 * COLS + kk + 1] : 0u;
+                            const unsigned lo = Hu[s2 * COLS + kk];  // LIN: the one table lives in Hu
+                            const unsigned hi = (kk + 1 < COLS) ? Hu[s2 * COLS + kk + 1] : 0u;
                             wa[4 * s2 + (kk >> 1)] = ba_prmt(lo, hi, 0x5410u);
                             wb[4 * s2 + (kk >> 1)] = ba_prmt(lo, hi, 0x7632u);
                         }
