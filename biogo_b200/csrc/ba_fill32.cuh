@@ -308,10 +308,13 @@ __global__ void __launch_bounds__(BA_FILL_WARPS * 32) ba_fill32_kernel(FillParam
                         // sw_affine_letters.go:126-134, row-major order inside my strip
 #pragma unroll
                         for (int k = 0; k < COLS; k++) {
-                            if (dmv[k] && Pv[k].M >= best && j0 + 1 + k <= m) {
-                                best = Pv[k].M;
+                            // "last in row-major order": rows only grow inside a pass, but a later pass
+                            // revisits small rows, so ties are settled on (i, j), not on arrival order
+                            const int v = Pv[k].M, jj = j0 + 1 + k;
+                            if (dmv[k] && jj <= m && (v > best || (v == best && (i > bi || (i == bi && jj > bj))))) {
+                                best = v;
                                 bi = i;
-                                bj = j0 + 1 + k;
+                                bj = jj;
                             }
                         }
                     }
@@ -377,10 +380,11 @@ __global__ void __launch_bounds__(BA_FILL_WARPS * 32) ba_fill32_kernel(FillParam
                         // sw_letters.go:110-114: score >= maxS && score == diagScore
 #pragma unroll
                         for (int k = 0; k < COLS; k++) {
-                            if (cdv[k] == 3u && Tv[k] >= best && j0 + 1 + k <= m) {
-                                best = Tv[k];
+                            const int v = Tv[k], jj = j0 + 1 + k;  // ties: see the affine branch
+                            if (cdv[k] == 3u && jj <= m && (v > best || (v == best && (i > bi || (i == bi && jj > bj))))) {
+                                best = v;
                                 bi = i;
-                                bj = j0 + 1 + k;
+                                bj = jj;
                             }
                         }
                     }

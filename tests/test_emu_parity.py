@@ -354,3 +354,23 @@ def test_plan_cache_reuses_work_lists_for_same_shaped_batches(emu_ctx):
     finally:
         emu_ctx.set_option("plan_cache", 1)
     helpers.compare(res, helpers.run_oracle(0, True, M, -4, DNA_IDX, pk), "cache off")
+
+
+@pytest.mark.parametrize("affine", [True, False], ids=["SWAffine", "SW"])
+def test_sw_best_cell_ties_across_passes(emu_ctx, affine):
+    """Unrelated sequences with a harsh mismatch score: the table maximum is small and attained in
+    many cells, often in different 256-column passes.  The reference keeps the LAST one in row-major
+    order (align/sw_affine_letters.go:126-134, sw_letters.go:110-114) whatever pass it lies in."""
+    rng = random.Random(5900 + affine)
+    M = gv.match(-2, 1, -4)
+    pairs = randcases.rand_pairs(rng, 10, [150, 330], [520, 700], related=0.0, dirty=0.0)
+    pk = helpers.pack(pairs)
+    go = -2 if affine else 0
+    orc = helpers.run_oracle(0, affine, M, go, DNA_IDX, pk)
+    for force in (1, 0):
+        emu_ctx.set_option("force_path", force)
+        try:
+            res = helpers.run_lib(emu_ctx, 0, affine, M, go, DNA_IDX, 5, pk)
+        finally:
+            emu_ctx.set_option("force_path", 0)
+        helpers.compare(res, orc, f"ties across passes, force_path {force}")

@@ -434,3 +434,22 @@ def test_fast16_and_exact_paths_agree_at_config_shapes(gpu_ctx, num, n):
     assert exact.stats["pairs_fast16"] == 0
     assert np.array_equal(fast.status, exact.status) and np.array_equal(fast.seg_count, exact.seg_count)
     assert np.array_equal(fast.segs, exact.segs)
+
+
+@pytest.mark.parametrize("affine", [True, False], ids=["SWAffine", "SW"])
+def test_sw_best_cell_ties_across_passes(gpu_ctx, affine):
+    """Many cells share the (small) table maximum of unrelated sequences, in different 256-column
+    passes; the reference keeps the last one in row-major order.  Both device paths vs the oracle."""
+    rng = random.Random(5950 + affine)
+    M = gv.match(-2, 1, -4)
+    pairs = randcases.rand_pairs(rng, 60, [300, 900], [520, 1030, 1500], related=0.0, dirty=0.0)
+    pk = helpers.pack(pairs)
+    go = -2 if affine else 0
+    orc = helpers.run_oracle(0, affine, M, go, DNA_IDX, pk, 1, 16)
+    for force in (1, 0):
+        gpu_ctx.set_option("force_path", force)
+        try:
+            res = helpers.run_lib(gpu_ctx, 0, affine, M, go, DNA_IDX, 5, pk)
+        finally:
+            gpu_ctx.set_option("force_path", 0)
+        helpers.compare(res, orc, f"ties across passes, force_path {force}")
