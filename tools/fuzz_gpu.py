@@ -35,16 +35,21 @@ while time.time() < t_end:
         M = [[0] + [gap] * 4] + [[gap] + [ma if a == b else mi for b in range(4)] for a in range(4)]
         idx, al, alpha = DNA_IDX, 5, b"ACGT"
     go = rng.choice([-2, -5, -8, -12]) if affine else 0
-    shape = rng.choice(["short", "mid", "long", "mixed"])
-    lens_r = {"short": [1, 7, 33, 90], "mid": [150, 300, 700], "long": [900, 2200, 4000], "mixed": [5, 120, 900, 3000]}[shape]
-    lens_q = {"short": [1, 9, 40, 100], "mid": [100, 257, 520], "long": [1030, 1800, 3100], "mixed": [3, 250, 1100, 2600]}[shape]
-    count = {"short": 400, "mid": 200, "long": 14, "mixed": 60}[shape]
+    shape = rng.choice(["short", "mid", "long", "mixed", "edge", "edge"])
+    lens_r = {"short": [1, 7, 33, 90], "mid": [150, 300, 700], "long": [900, 2200, 4000], "mixed": [5, 120, 900, 3000],
+              "edge": [1, 2, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 513]}[shape]
+    lens_q = {"short": [1, 9, 40, 100], "mid": [100, 257, 520], "long": [1030, 1800, 3100], "mixed": [3, 250, 1100, 2600],
+              "edge": [1, 2, 15, 16, 17, 31, 32, 33, 64, 65, 159, 160, 161, 255, 256, 257, 319, 320, 321, 511, 512, 513,
+                       767, 768, 769, 1024, 1025]}[shape]
+    count = {"short": 400, "mid": 200, "long": 14, "mixed": 60, "edge": 120}[shape]
     pairs = randcases.rand_pairs(rng, count, lens_r, lens_q, related=rng.choice([0.0, 0.7, 0.95]),
                                  dirty=rng.choice([0.0, 0.05]), alpha=alpha)
     stride = rng.choice([1, 2])
     pk = helpers.pack(pairs, stride)
     opts = {"trace_mode": rng.choice([0, 1, 2, 3, 4, 5]), "long_mode": rng.choice([0, 1, 2]),
             "plan_cache": rng.choice([0, 1])}
+    if rng.random() < 0.1:
+        opts["slot_cap"] = rng.choice([1, 3])
     if rng.random() < 0.15:
         opts["arena_bytes"] = rng.choice([200_000, 5_000_000])
     for k, v in opts.items():
@@ -56,6 +61,7 @@ while time.time() < t_end:
     finally:
         ctx.set_option("force_path", 0)
         ctx.set_option("arena_bytes", 0)
+        ctx.set_option("slot_cap", 0)
         ctx.set_option("trace_mode", 1)
         ctx.set_option("long_mode", 1)
         ctx.set_option("plan_cache", 1)
