@@ -125,6 +125,58 @@ void run(int sms, unsigned *d_out, long long *d_cyc, int clock_khz)
     (void)clock_khz;
 }
 
+// ---- HBM write-only / read-only / copy bandwidth (the fill kernels are pure writers)
+__global__ void bw_write_kernel(uint4 *dst, size_t n16, unsigned v)
+{
+    const uint4 val = make_uint4(v, v + 1, v + 2, v + 3);
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < n16; x += (size_t)gridDim.x * blockDim.x) dst[x] = val;
+}
+__global__ void bw_read_kernel(const uint4 *src, size_t n16, unsigned *out)
+{
+    unsigned acc = 0;
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < n16; x += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[x];
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+__global__ void bw_copy_kernel(uint4 *dst, const uint4 *src, size_t n16)
+{
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < n16; x += (size_t)gridDim.x * blockDim.x) dst[x] = src[x];
+}
+static void run_bandwidth(int sms, unsigned *d_out)
+{
+    const size_t bytes = (size_t)8 << 30, n16 = bytes / 16;
+    uint4 *a = nullptr, *b = nullptr;
+    if (cudaMalloc(&a, bytes) != cudaSuccess || cudaMalloc(&b, bytes) != cudaSuccess) {
+        fprintf(stderr, "bandwidth test: allocation failed\n");
+        return;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 16, threads = 512;
+    const char *names[3] = {"hbm_write_only", "hbm_read_only", "hbm_copy"};
+    for (int k = 0; k < 3; k++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; rep++) {
+            cudaEventRecord(e0);
+            if (k == 0) bw_write_kernel<<<blocks, threads>>>(a, n16, (unsigned)rep);
+            if (k == 1) bw_read_kernel<<<blocks, threads>>>(a, n16, d_out);
+            if (k == 2) bw_copy_kernel<<<blocks, threads>>>(b, a, n16);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double moved = (k == 2) ? 2.0 * bytes : (double)bytes;
+        printf("{\"op\": \"%s\", \"GBps\": %.1f, \"ms\": %.3f, \"bytes_moved\": %.0f}\n", names[k], moved / best * 1e-6, best, moved);
+    }
+    cudaFree(a);
+    cudaFree(b);
+}
+
 int main()
 {
     cudaDeviceProp prop;
@@ -154,6 +206,7 @@ int main()
     run<OP_MIX_DPX_LOP>(sms, d_out, d_cyc, prop.clockRate);
     run<OP_SHFL>(sms, d_out, d_cyc, prop.clockRate);
     run<OP_LDS>(sms, d_out, d_cyc, prop.clockRate);
+    run_bandwidth(sms, d_out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e));
