@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BA_ABI_VERSION 1
+#define BA_ABI_VERSION 2 /* 2: ba_result grew (wavefront/warp-trace counters); format, seqio and gather entry points */
 
 /* Aligner kind: align/sw.go:18, align/nw.go:16, align/fitted.go:16 (and *_affine.go:16). */
 enum { BA_SW = 0, BA_NW = 1, BA_FITTED = 2 };
