@@ -26,6 +26,7 @@ import (
 
 	"github.com/biogo/biogo/alphabet"
 	"github.com/biogo/biogo/feat"
+	"github.com/biogo/biogo/seq"
 )
 
 const (
@@ -255,4 +256,97 @@ func alignBatch(kind int, affine bool, m Linear, gapOpen int, checkSize bool,
 		alns[k], errs[k] = a[p], e[p]
 	}
 	return alns, errs
+}
+
+// FormatBatch is align.Format (align/align.go:146-170) for many alignments in one device call
+// (ba_format_batch).  The rows come back as letters; for QLetters the qualities are re-attached
+// here along the same segments (the gap QLetter has Q = 0, align/align.go:161).
+func FormatBatch(as, bs []seq.Slicer, alns [][]feat.Pair, gap alphabet.Letter) [][2]alphabet.Slice {
+	n := len(as)
+	out := make([][2]alphabet.Slice, n)
+	var (
+		buf              []byte
+		refOff, qryOff   []int64
+		refLen, qryLen   []int32
+		segStart         = make([]int64, n)
+		segCount         = make([]int32, n)
+		segs             []int32
+		stride           = 1
+	)
+	pack := func(s alphabet.Slice) (off int64, ln int32) {
+		off = int64(len(buf))
+		switch v := s.(type) {
+		case alphabet.Letters:
+			buf = append(buf, alphabet.LettersToBytes(v)...)
+			ln = int32(len(v))
+		case alphabet.QLetters:
+			stride = 2
+			for _, l := range v {
+				buf = append(buf, byte(l.L), byte(l.Q))
+			}
+			ln = int32(len(v))
+		}
+		return
+	}
+	for k := 0; k < n; k++ {
+		o, l := pack(as[k].Slice())
+		refOff, refLen = append(refOff, o), append(refLen, l)
+		o, l = pack(bs[k].Slice())
+		qryOff, qryLen = append(qryOff, o), append(qryLen, l)
+		segStart[k], segCount[k] = int64(len(segs)/5), int32(len(alns[k]))
+		for _, fp := range alns[k] {
+			f := fp.Features()
+			segs = append(segs, int32(f[0].Start()), int32(f[0].End()), int32(f[1].Start()), int32(f[1].End()),
+				int32(fp.Score()))
+		}
+	}
+	if n == 0 {
+		return out
+	}
+	ctx := ctxPool.Get().(*C.ba_ctx)
+	defer ctxPool.Put(ctx)
+	var res C.ba_formatted
+	var segp *C.int32_t
+	if len(segs) > 0 {
+		segp = (*C.int32_t)(unsafe.Pointer(&segs[0]))
+	}
+	rc := C.ba_format_batch(ctx, (*C.uint8_t)(unsafe.Pointer(&buf[0])), C.int(stride),
+		(*C.int64_t)(unsafe.Pointer(&refOff[0])), (*C.int32_t)(unsafe.Pointer(&refLen[0])),
+		(*C.int64_t)(unsafe.Pointer(&qryOff[0])), (*C.int32_t)(unsafe.Pointer(&qryLen[0])), C.int64_t(n),
+		(*C.int64_t)(unsafe.Pointer(&segStart[0])), (*C.int32_t)(unsafe.Pointer(&segCount[0])), segp,
+		C.int64_t(len(segs)/5), C.uint8_t(gap), &res)
+	if rc != C.BA_OK {
+		panic("align: " + C.GoString(C.ba_last_error(ctx))) // no CPU fallback
+	}
+	defer C.ba_free_formatted(ctx, &res)
+	offA := unsafe.Slice((*int64)(unsafe.Pointer(res.off_a)), n+1)
+	offB := unsafe.Slice((*int64)(unsafe.Pointer(res.off_b)), n+1)
+	rowA := unsafe.Slice((*byte)(unsafe.Pointer(res.row_a)), int(res.bytes_a))
+	rowB := unsafe.Slice((*byte)(unsafe.Pointer(res.row_b)), int(res.bytes_b))
+	for k := 0; k < n; k++ {
+		rows := [2][]byte{rowA[offA[k]:offA[k+1]], rowB[offB[k]:offB[k+1]]}
+		for side, src := range [2]alphabet.Slice{as[k].Slice(), bs[k].Slice()} {
+			switch v := src.(type) {
+			case alphabet.Letters:
+				out[k][side] = alphabet.BytesToLetters(append([]byte(nil), rows[side]...))
+			case alphabet.QLetters:
+				ql := make(alphabet.QLetters, 0, len(rows[side]))
+				x := 0
+				for _, fp := range alns[k] {
+					f := fp.Features()
+					if f[side].Len() == 0 {
+						for i := 0; i < f[1-side].Len(); i, x = i+1, x+1 {
+							ql = append(ql, alphabet.QLetter{L: alphabet.Letter(rows[side][x])})
+						}
+					} else {
+						for i := f[side].Start(); i < f[side].End(); i, x = i+1, x+1 {
+							ql = append(ql, alphabet.QLetter{L: alphabet.Letter(rows[side][x]), Q: v[i].Q})
+						}
+					}
+				}
+				out[k][side] = ql
+			}
+		}
+	}
+	return out
 }
