@@ -5,7 +5,7 @@ CSRC      := biogo_b200/csrc
 OBJDIR    := biogo_b200/lib/obj
 LIB       := biogo_b200/lib/libbiogoalign.so
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h $(CSRC)/*.inl) include/biogo_align.h
-FAMILIES  := 0_0 1_0 2_0 0_1 1_1 2_1
+FAMILIES  := 0_0 1_0 2_0 0_1 1_1 2_1 0_2 1_2 2_2
 OBJS      := $(OBJDIR)/ba_api.o $(foreach f,$(FAMILIES),$(OBJDIR)/ba_fill16_$(f).o)
 
 all: $(LIB) biogo_b200/lib/ba_microbench

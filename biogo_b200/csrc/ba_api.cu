@@ -129,7 +129,7 @@ struct ba_ctx {
     int last_stride = 0;
     DevBuf fmt_len, fmt_off, fmt_rows, fmt_segs, fmt_seg_start, fmt_seg_count;
     int64_t opt_plan_cache = 1;
-    int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1, opt_exclusive = 1;
+    int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1, opt_exclusive = 1, opt_sym = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
@@ -546,9 +546,23 @@ Fill16Fn ba_pick_fill16_2_0(int cols, bool multi, bool gsub, bool wavefront);
 Fill16Fn ba_pick_fill16_0_1(int cols, bool multi, bool gsub, bool wavefront);
 Fill16Fn ba_pick_fill16_1_1(int cols, bool multi, bool gsub, bool wavefront);
 Fill16Fn ba_pick_fill16_2_1(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_0_2(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_1_2(int cols, bool multi, bool gsub, bool wavefront);
+Fill16Fn ba_pick_fill16_2_2(int cols, bool multi, bool gsub, bool wavefront);
 namespace {
-Fill16Fn pick_fill16(int kind, bool lin, int cols, bool multi, bool gsub, bool wavefront)
+bool g_sym_scoring(const DeviceScoring &s)
 {
+    // affine with one gap-extension value for both sequences and go + e <= 0: the SYM kernels apply
+    const int er = s.la[1 * s.let], eq = s.la[1];
+    return s.affine && er == eq && s.gap_open + er <= 0;
+}
+Fill16Fn pick_fill16(int kind, bool lin, int cols, bool multi, bool gsub, bool wavefront, bool sym = false)
+{
+    if (!lin && sym) {
+        if (kind == KIND_SW) return ba_pick_fill16_0_2(cols, multi, gsub, wavefront);
+        if (kind == KIND_NW) return ba_pick_fill16_1_2(cols, multi, gsub, wavefront);
+        return ba_pick_fill16_2_2(cols, multi, gsub, wavefront);
+    }
     if (lin) {
         if (kind == KIND_SW) return ba_pick_fill16_0_1(cols, multi, gsub, wavefront);
         if (kind == KIND_NW) return ba_pick_fill16_1_1(cols, multi, gsub, wavefront);
@@ -797,7 +811,8 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                     max_n = std::max(max_n, B.h_ref_len[p]);
                 }
             }
-            Fill16Fn fn = pick_fill16(kind, lin, L.cols, multi, gsub, false);
+            const bool sym = !lin && ctx->opt_sym != 0 && g_sym_scoring(ctx->h_sc);
+            Fill16Fn fn = pick_fill16(kind, lin, L.cols, multi, gsub, false, sym);
             // GSUB kernels keep their score tables in dynamic shared memory (the size depends on the
             // matrix only, so the per-kernel cache entry stays valid until the scoring changes)
             const size_t dyn = gsub ? (size_t)BA16_WARPS * ba16_gsub_bytes_per_warp(ctx->h_sc.let) : 0;
@@ -808,7 +823,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             const bool use_long = maxp >= 4 && (ctx->opt_long_mode == 2 || pair_warps < maxb * BA16_WARPS) &&
                                   (int64_t)maxp * (L.count + 4) < (1 << 22);
             if (use_long) {
-                fn = pick_fill16(kind, lin, L.cols, true, gsub, true);
+                fn = pick_fill16(kind, lin, L.cols, true, gsub, true, sym);
                 if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ, dyn)) != BA_OK) return rc;
                 maxb = (int64_t)ctx->sm_count * occ;
                 const int64_t ncp = ((L.count + 3) / 4) * 2;         // couples per pass, even
@@ -1269,6 +1284,10 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     }
     if (!strcmp(key, "exclusive_compute")) {
         ctx->opt_exclusive = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "sym_kernels")) {  // 0: never use the symmetric-gap fill variant (test hook)
+        ctx->opt_sym = value;
         return BA_OK;
     }
     if (!strcmp(key, "plan_cache")) {

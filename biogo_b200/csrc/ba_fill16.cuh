@@ -211,7 +211,13 @@ __device__ __forceinline__ uint4 ba16_bnd_unpack(const ulonglong2 &w)
 // checkpoints carry it in their M field (the second field is zero).  SW needs er < 0 and eq < 0
 // so that every cell holding the table maximum came through the diagonal (best-cell rule,
 // align/sw_letters.go:110-114).
-template <int KIND, int COLS, bool MULTI, bool GSUB, bool LONG, bool LIN>
+// SYM (affine, er == eq, go + er <= 0 -- every BASELINE scoring): the M array holds G = M + go + e
+// instead of M, because both gap recurrences want exactly that sum:
+//   U' = max(U + e, G_prev_row)     L = max(L_left + e, G_left)     one add-max each,
+// so a packed cell costs PRMT, add-max (M), add (G), add-max (U), add-max (L), max3 (H) = 6
+// instructions (+ half a max3 of best tracking) instead of 7.5.  M itself is transient inside
+// the step; checkpoints recover it as G - (go + e).
+template <int KIND, int COLS, bool MULTI, bool GSUB, bool LONG, bool LIN, bool SYM = false>
 __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params P)
 {
     constexpr int NC = 2 * COLS;  // columns per lane
@@ -384,15 +390,17 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             unsigned Mu[NC], Uu[NC], Hu[NC];
             // the right-most column handed to the next lane is (Mu[NC-1], outL, Hu[NC-1]): M and H stay in
             // their arrays until the next step's shuffles have read them
-            unsigned outL = 0, sdiagH = 0;
+            unsigned outL = 0, sdiagH = 0, mlast = 0;  // mlast (SYM): M of my last column at the current row
 #pragma unroll
             for (int k = 0; k < NC; k++) {
                 if (KIND == KIND_SW) {
-                    Mu[k] = Uu[k] = Hu[k] = 0;
+                    Mu[k] = SYM ? goerp : 0u;   // SYM: Mu holds M + go + e
+                    Uu[k] = Hu[k] = 0;
                 } else {
                     // row 0: M = U = -inf, L = go + j*eq (nw_affine_letters.go:119-131); H = L
                     const int j = pass * W + t * NC + k + 1;
-                    Mu[k] = Uu[k] = NEGP;
+                    Mu[k] = SYM ? __vadd2(NEGP, goerp) : NEGP;
+                    Uu[k] = NEGP;
                     Hu[k] = pack16(go + j * eq, go + j * eq);
                 }
             }
@@ -481,11 +489,13 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 unsigned rH = __shfl_up_sync(FULL, Hu[NC - 1], 1, 16);
                 if (t == 0) {
                     if (KIND == KIND_SW) {
-                        rM = rL = rH = 0;
+                        rM = SYM ? goerp : 0u;
+                        rL = rH = 0;
                     } else {
                         // DP column 0: M = L = -inf; U = go + i*er (NW, nw_affine_letters.go:132-142)
                         // or 0 (Fitted, fitted_affine_letters.go:123-132); H = U
-                        rM = rL = NEGP;
+                        rM = SYM ? __vadd2(NEGP, goerp) : NEGP;
+                        rL = NEGP;
                         rH = (KIND == KIND_NW) ? pack16(go + i * er, go + i * er) : 0u;
                     }
                     if (MULTI && pass > 0 && i >= 1 && i <= nbnd) {
@@ -516,6 +526,39 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         Hd = old;
                     }
                     sdiagH = rH;
+                } else if (SYM) {
+                    // U of this row from the previous row's (G, U)
+#pragma unroll
+                    for (int k = 0; k < NC; k++) Uu[k] = __viaddmax_s16x2(Uu[k], erp, Mu[k]);
+                    unsigned Hd = sdiagH, Gl = rM, Ll = rL, Mprev = 0;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        unsigned sub;
+                        if (!GSUB)
+                            sub = ba_prmt(profA, profB, sel[k]);
+                        else
+                            sub = ba_prmt((unsigned)(int)*(const signed char *)(gtab + profA + sel[k]),
+                                          (unsigned)(int)*(const signed char *)(gtab + profB + qb4[k]), 0x5410u);
+                        const unsigned M = (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Hd, sub, erp) : __vadd2(Hd, sub);
+                        Hd = Hu[k];
+                        Ll = __viaddmax_s16x2(Ll, eqp, Gl);
+                        Hu[k] = __vimax3_s16x2(M, Uu[k], Ll);
+                        Gl = __vadd2(M, goerp);
+                        Mu[k] = Gl;
+                        if (KIND == KIND_SW) {
+                            if (k & 1)
+                                bmax = __vimax3_s16x2(bmax, Mprev, M);
+                            else
+                                Mprev = M;
+                        }
+                        if (k == COLS - 1) {
+                            ck0a = ba_prmt(M, Ll, 0x5410u);
+                            ck0b = ba_prmt(M, Ll, 0x7632u);
+                        }
+                        if (k == NC - 1) mlast = M;
+                    }
+                    sdiagH = rH;
+                    outL = Ll;
                 } else {
                 // Three sweeps, each updating its array in place (no register rotation):
                 //  U from the previous row's (M, U); M from the previous row's H; then L along the
@@ -555,7 +598,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 outL = Ll;
                 }
                 }
-                if (KIND == KIND_SW) {
+                if (KIND == KIND_SW && !SYM) {
 #pragma unroll
                 for (int k = 0; k + 1 < NC; k += 2)
                     bmax = LIN ? __vimax3_s16x2(bmax, Hu[k], Hu[k + 1]) : __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
@@ -576,8 +619,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     } else {
                         w[0] = ck0a;
                         w[BA16_STAGE_WORDS] = ck0b;
-                        w[2 * BA16_STAGE_PLANE] = ba_prmt(Mu[NC - 1], outL, 0x5410u);
-                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(Mu[NC - 1], outL, 0x7632u);
+                        const unsigned ml = SYM ? mlast : Mu[NC - 1];
+                        w[2 * BA16_STAGE_PLANE] = ba_prmt(ml, outL, 0x5410u);
+                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(ml, outL, 0x7632u);
                     }
                 }
                 if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(LIN ? 0u : Mu[NC - 1], outL, Hu[NC - 1], (unsigned)pass + 1u);
@@ -612,8 +656,9 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     for (int k = 0; k < NC; k++) {
                         const unsigned u = LIN ? 0u : Uu[k];
                         const int x = (k >= COLS ? 8 + (k - COLS) : k);  // word inside my 16-word region
-                        wa[x] = ba_prmt(Mu[k], u, 0x5410u);
-                        wb[x] = ba_prmt(Mu[k], u, 0x7632u);
+                        const unsigned mk = SYM ? __vsub2(Mu[k], goerp) : Mu[k];
+                        wa[x] = ba_prmt(mk, u, 0x5410u);
+                        wb[x] = ba_prmt(mk, u, 0x7632u);
                     }
 #pragma unroll
                     for (int c = 0; c < 4; c++) {

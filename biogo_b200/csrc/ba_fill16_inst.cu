@@ -1,6 +1,7 @@
 // ba_fill16_inst.cu -- one translation unit per (kind, linear/affine) family of the packed fill
 // kernel, so that the ~45 template instances of a family compile in parallel with the others.
-// Built six times with -DBA_INST_KIND={0,1,2} -DBA_INST_LIN={0,1}; ba_api.cu picks kernels through
+// Built nine times with -DBA_INST_KIND={0,1,2} -DBA_INST_LIN={0: affine, 1: linear, 2: affine with
+// symmetric gap scores}; ba_api.cu picks kernels through
 // the ba_pick_fill16_<kind>_<lin>() functions defined here.
 #include "ba_fill16.cuh"
 
@@ -15,16 +16,16 @@ template <bool MULTI, bool GSUB>
 Fill16Fn pick_c(int cols)
 {
     constexpr int K = BA_INST_KIND;
-    constexpr bool LIN = BA_INST_LIN != 0;
+    constexpr bool LIN = BA_INST_LIN == 1, SYM = BA_INST_LIN == 2;
     switch (cols) {
-    case 1: return ba_fill16_kernel<K, 1, MULTI, GSUB, false, LIN>;
-    case 2: return ba_fill16_kernel<K, 2, MULTI, GSUB, false, LIN>;
-    case 3: return ba_fill16_kernel<K, 3, MULTI, GSUB, false, LIN>;
-    case 4: return ba_fill16_kernel<K, 4, MULTI, GSUB, false, LIN>;
-    case 5: return ba_fill16_kernel<K, 5, MULTI, GSUB, false, LIN>;
-    case 6: return ba_fill16_kernel<K, 6, MULTI, GSUB, false, LIN>;
-    case 7: return ba_fill16_kernel<K, 7, MULTI, GSUB, false, LIN>;
-    default: return ba_fill16_kernel<K, 8, MULTI, GSUB, false, LIN>;
+    case 1: return ba_fill16_kernel<K, 1, MULTI, GSUB, false, LIN, SYM>;
+    case 2: return ba_fill16_kernel<K, 2, MULTI, GSUB, false, LIN, SYM>;
+    case 3: return ba_fill16_kernel<K, 3, MULTI, GSUB, false, LIN, SYM>;
+    case 4: return ba_fill16_kernel<K, 4, MULTI, GSUB, false, LIN, SYM>;
+    case 5: return ba_fill16_kernel<K, 5, MULTI, GSUB, false, LIN, SYM>;
+    case 6: return ba_fill16_kernel<K, 6, MULTI, GSUB, false, LIN, SYM>;
+    case 7: return ba_fill16_kernel<K, 7, MULTI, GSUB, false, LIN, SYM>;
+    default: return ba_fill16_kernel<K, 8, MULTI, GSUB, false, LIN, SYM>;
     }
 }
 // LONG (inter-pass wavefront) instances exist for the two widest column classes only: pairs with
@@ -33,9 +34,9 @@ template <bool GSUB>
 Fill16Fn pick_long(int cols)
 {
     constexpr int K = BA_INST_KIND;
-    constexpr bool LIN = BA_INST_LIN != 0;
-    if (cols == 7) return ba_fill16_kernel<K, 7, true, GSUB, true, LIN>;
-    return ba_fill16_kernel<K, 8, true, GSUB, true, LIN>;
+    constexpr bool LIN = BA_INST_LIN == 1, SYM = BA_INST_LIN == 2;
+    if (cols == 7) return ba_fill16_kernel<K, 7, true, GSUB, true, LIN, SYM>;
+    return ba_fill16_kernel<K, 8, true, GSUB, true, LIN, SYM>;
 }
 }  // namespace
 

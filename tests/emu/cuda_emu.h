@@ -381,6 +381,7 @@ static inline short emu_lo(unsigned v) { return (short)(v & 0xffffu); }
 static inline short emu_hi(unsigned v) { return (short)(v >> 16); }
 static inline unsigned emu_pk(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 static inline unsigned __vadd2(unsigned a, unsigned b) { return emu_pk(emu_lo(a) + emu_lo(b), emu_hi(a) + emu_hi(b)); }
+static inline unsigned __vsub2(unsigned a, unsigned b) { return emu_pk(emu_lo(a) - emu_lo(b), emu_hi(a) - emu_hi(b)); }
 static inline unsigned __vmaxs2(unsigned a, unsigned b)
 {
     return emu_pk(std::max(emu_lo(a), emu_lo(b)), std::max(emu_hi(a), emu_hi(b)));

@@ -374,3 +374,30 @@ def test_sw_best_cell_ties_across_passes(emu_ctx, affine):
         finally:
             emu_ctx.set_option("force_path", 0)
         helpers.compare(res, orc, f"ties across passes, force_path {force}")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["SWAffine", "NWAffine", "FittedAffine"])
+def test_fast16_general_and_symmetric_gap_kernels(emu_ctx, kind):
+    """The SYM fill variant (er == eq: M is kept as M + go + e) and the general one must agree with
+    the oracle: symmetric scores with the variant switched off, and asymmetric gap scores (which
+    can only take the general kernels)."""
+    rng = random.Random(6100 + kind)
+    pairs = randcases.rand_pairs(rng, 26, [1, 9, 40, 130, 260], [1, 16, 64, 100, 257, 300, 600], related=0.85, dirty=0.0)
+    pk = helpers.pack(pairs)
+    M = gv.match(-1, 2, -1)
+    orc = helpers.run_oracle(kind, True, M, -4, DNA_IDX, pk)
+    for sym in (1, 0):
+        emu_ctx.set_option("sym_kernels", sym)
+        try:
+            res = helpers.run_lib(emu_ctx, kind, True, M, -4, DNA_IDX, 5, pk)
+        finally:
+            emu_ctx.set_option("sym_kernels", 1)
+        assert res.stats["pairs_fast16"] >= len(pairs) - 3
+        helpers.compare(res, orc, f"sym_kernels {sym} kind {kind}")
+    A = [row[:] for row in M]
+    for a in range(1, 5):
+        A[a][0] = -1      # reference letter against a gap
+        A[0][a] = -2      # gap against a query letter
+    res = helpers.run_lib(emu_ctx, kind, True, A, -4, DNA_IDX, 5, pk)
+    assert res.stats["pairs_fast16"] >= len(pairs) - 3
+    helpers.compare(res, helpers.run_oracle(kind, True, A, -4, DNA_IDX, pk), f"asymmetric gaps kind {kind}")

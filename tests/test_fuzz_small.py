@@ -34,7 +34,7 @@ def test_fuzz_slice(emu_ctx, seed):
         pk = helpers.pack(pairs, stride)
         orc = helpers.run_oracle(kind, affine, M, go, idx, pk, stride)
         opts = {"trace_mode": rng.choice([0, 1, 2, 3, 4, 5]), "long_mode": rng.choice([0, 1, 2]),
-                "plan_cache": rng.choice([0, 1]), "slot_cap": rng.choice([0, 0, 0, 2])}
+                "plan_cache": rng.choice([0, 1]), "slot_cap": rng.choice([0, 0, 0, 2]), "sym_kernels": rng.choice([0, 1])}
         try:
             for k, v in opts.items():
                 emu_ctx.set_option(k, v)
@@ -43,5 +43,5 @@ def test_fuzz_slice(emu_ctx, seed):
                 res = helpers.run_lib(emu_ctx, kind, affine, M, go, idx, al, pk, stride)
                 helpers.compare(res, orc, f"seed {seed} kind {kind} affine {affine} protein {protein} opts {opts} force {force}")
         finally:
-            for k, v in (("force_path", 0), ("trace_mode", 1), ("long_mode", 1), ("plan_cache", 1), ("slot_cap", 0)):
+            for k, v in (("force_path", 0), ("trace_mode", 1), ("long_mode", 1), ("plan_cache", 1), ("slot_cap", 0), ("sym_kernels", 1)):
                 emu_ctx.set_option(k, v)

@@ -32,7 +32,8 @@ while time.time() < t_end:
         idx, al, alpha = PROT_IDX, 26, b"ACDEFGHIKLMNPQRSTVWY"
     else:
         gap, ma, mi = rng.choice([-1, -2, -3]), rng.choice([1, 2, 5]), rng.choice([-1, -3, -4])
-        M = [[0] + [gap] * 4] + [[gap] + [ma if a == b else mi for b in range(4)] for a in range(4)]
+        gap2 = gap if rng.random() < 0.7 else rng.choice([-1, -2, -3])   # sometimes er != eq
+        M = [[0] + [gap2] * 4] + [[gap] + [ma if a == b else mi for b in range(4)] for a in range(4)]
         idx, al, alpha = DNA_IDX, 5, b"ACGT"
     go = rng.choice([-2, -5, -8, -12]) if affine else 0
     shape = rng.choice(["short", "mid", "long", "mixed", "edge", "edge"])
@@ -47,7 +48,7 @@ while time.time() < t_end:
     stride = rng.choice([1, 2])
     pk = helpers.pack(pairs, stride)
     opts = {"trace_mode": rng.choice([0, 1, 2, 3, 4, 5]), "long_mode": rng.choice([0, 1, 2]),
-            "plan_cache": rng.choice([0, 1])}
+            "plan_cache": rng.choice([0, 1]), "sym_kernels": rng.choice([0, 1])}
     if rng.random() < 0.1:
         opts["slot_cap"] = rng.choice([1, 3])
     if rng.random() < 0.15:
@@ -65,6 +66,7 @@ while time.time() < t_end:
         ctx.set_option("trace_mode", 1)
         ctx.set_option("long_mode", 1)
         ctx.set_option("plan_cache", 1)
+        ctx.set_option("sym_kernels", 1)
     # segment arrays may be laid out in a different order by the two paths: compare pair by pair
     ok = np.array_equal(fast.status, exact.status) and np.array_equal(fast.seg_count, exact.seg_count)
     if ok:
