@@ -7,7 +7,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=${TMPDIR:-/tmp}/ba_asan
 mkdir -p "$OUT"
 FLAGS="-O1 -g -fsanitize=address -fno-omit-frame-pointer -std=c++17 -DBA_EMULATE -I$ROOT/tests/emu -I$ROOT/biogo_b200/csrc -fPIC -x c++"
-for k in 0 1 2; do for l in 0 1; do
+for k in 0 1 2; do for l in 0 1 2; do
   g++ $FLAGS -DBA_INST_KIND=$k -DBA_INST_LIN=$l -c "$ROOT/biogo_b200/csrc/ba_fill16_inst.cu" -o "$OUT/f_${k}_${l}.o" &
 done; done
 g++ $FLAGS -c "$ROOT/biogo_b200/csrc/ba_api.cu" -o "$OUT/api.o" &
