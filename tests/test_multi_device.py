@@ -68,3 +68,38 @@ def _uniform():
     pairs = randcases.rand_pairs(rng, 64, [200], [100], related=1.0, dirty=0.0)
     pk = helpers.pack(pairs)
     return pk[0], 1, pk[1], pk[2], pk[3], pk[4]
+
+
+def test_two_host_threads_two_contexts(built):
+    """bíogo's aligners are called from many goroutines (concurrent/processor.go:48-74): two host
+    threads, one context each, interleaved batches -- the per-device compute token serialises the
+    kernel phases, results stay per context."""
+    import threading
+
+    from biogo_b200 import _lib
+
+    rng = random.Random(77)
+    M = gv.match(-1, 1, -1)
+    jobs = []
+    for kind, affine, go in ((0, True, -5), (1, False, 0)):
+        pairs = randcases.rand_pairs(rng, 25, [10, 90, 200], [10, 64, 257], related=0.8, dirty=0.1)
+        pk = helpers.pack(pairs)
+        jobs.append((kind, affine, go, pk, helpers.run_oracle(kind, affine, M, go, DNA_IDX, pk)))
+    errs = []
+
+    def worker(job):
+        try:
+            kind, affine, go, pk, orc = job
+            ctx = _lib.Context(0, helpers.EMU_LIB)
+            for _ in range(4):
+                res = helpers.run_lib(ctx, kind, affine, M, go, DNA_IDX, 5, pk)
+                helpers.compare(res, orc, f"thread kind {kind}")
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    th = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs[0]
