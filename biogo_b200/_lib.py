@@ -52,6 +52,7 @@ class BaResult(C.Structure):
         ("pairs_fast16", C.c_int64),
         ("wavefront_launches", C.c_int64),
         ("warp_trace_launches", C.c_int64),
+        ("waves", C.c_int64),
     ]
 
 
@@ -166,7 +167,7 @@ class BatchResult:
 def _stats(res: BaResult) -> dict:
     return {k: (float(getattr(res, k)) if k.startswith("ms_") else int(getattr(res, k)))
             for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_fill", "ms_trace", "ms_host", "cells", "gpu_launches", "fill_launches",
-                      "code_bytes", "pairs_fast16", "wavefront_launches", "warp_trace_launches", "n_segs")}
+                      "code_bytes", "pairs_fast16", "wavefront_launches", "warp_trace_launches", "waves", "n_segs")}
 
 
 def _as_array(ptr, n, dtype):

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -48,11 +49,14 @@ struct PinnedBlock {
     void *p;
     size_t cap;
     bool used;
+    uint64_t stamp;   // last release (pool trimming frees the least recently used blocks first)
 };
 
 struct ToInt64 {
     __host__ __device__ int64_t operator()(int32_t v) const { return (int64_t)v; }
 };
+
+#define BA_ERR_LONG_TIMEOUT (-100)   // internal: a wavefront pass gave up waiting; the batch is re-run without LONG
 
 typedef void (*FillFn)(FillParams);
 typedef void (*WalkFn)(WalkParams);
@@ -102,8 +106,15 @@ WalkFn pick_walk(int kind, int affine)
 struct ba_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // main stream: encode, validate, fills of the even waves, exact path
+    cudaStream_t s_fill2 = nullptr;  // fills of the odd waves (the tail of one fill overlaps the head of the next)
+    cudaStream_t s_trace = nullptr;  // traceback + compaction of wave w beside the fill of wave w+1 (high priority)
+    cudaStream_t s_h2d = nullptr;    // input upload, in groups the first waves do not have to wait for
+    cudaStream_t s_d2h = nullptr;    // result copies
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // pooled events of one call (timing / no timing), handed out in order and reused by the next call
+    std::vector<cudaEvent_t> ev_timed, ev_plain, ev_upload;
+    size_t ev_timed_next = 0, ev_plain_next = 0;
     std::string err;
     bool have_scoring = false;
     DeviceScoring h_sc;
@@ -113,11 +124,12 @@ struct ba_ctx {
     DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
     DevBuf flags, slot_off, slot_cap, slots, seg_clip, tasks, prog;
+    DevBuf pair_seg_start, pair_seg_count, meta, ovf;
     // Plan cache: batches of the same shape (same length arrays, same scoring) reuse the split, the
-    // work lists and -- for single-wave plans -- their device copies.
+    // work lists and their device copies.
     struct PlanCache {
         bool valid = false, plan_built = false;
-        int64_t n = 0, cells = 0, arena_cap = 0, slot_cap_opt = 0;
+        int64_t n = 0, cells = 0, arena_cap = 0, slot_cap_opt = 0, waves_opt = 0;
         uint64_t epoch = 0;
         std::vector<int32_t> ref_len, qry_len, fast, slow0;
         Plan plan;
@@ -130,9 +142,16 @@ struct ba_ctx {
     DevBuf fmt_len, fmt_off, fmt_rows, fmt_segs, fmt_seg_start, fmt_seg_count;
     int64_t opt_plan_cache = 1;
     int64_t opt_force_path = 0, opt_slot_cap = 0, opt_long_mode = 1, opt_trace_mode = 1, opt_exclusive = 1, opt_sym = 1;
+    // overlap scheduling (see run_path16): waves per batch (0 = automatic), fill streams (1 or 2), claims a
+    // fill warp takes before its CTA retires (0 = persistent grid), resident fill CTAs per SM (0 = all that
+    // fit), threads per thread-per-pair traceback CTA (0 = automatic), upload groups (0 = automatic)
+    int64_t opt_waves = 0, opt_fill_streams = 2, opt_fill_claims = 1, opt_fill_cap = 0, opt_trace_cta = 0;
+    int64_t opt_upload_groups = 0, opt_taper = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
+    std::mutex pinned_mu;                            // ba_free_result may run on another thread (GC finalizers)
+    int64_t pinned_budget = 0;                       // bytes of unused pinned blocks kept for reuse (0 = default)
 };
 
 namespace {
@@ -166,9 +185,13 @@ int ensure(ba_ctx *ctx, DevBuf &b, size_t bytes)
     return BA_OK;
 }
 
+// Pinned host memory pool of a context.  Blocks are reused best-fit; unused blocks beyond a budget
+// (default 1 GiB, option "pinned_budget") are returned to the driver, least recently used first, so a
+// long-lived context fed batches of varying size does not accumulate page-locked memory.
 void *pinned_get(ba_ctx *ctx, size_t bytes)
 {
     if (bytes == 0) bytes = 8;
+    std::lock_guard<std::mutex> lk(ctx->pinned_mu);
     int bestk = -1;
     for (size_t k = 0; k < ctx->pinned.size(); k++) {
         PinnedBlock &b = ctx->pinned[k];
@@ -184,14 +207,78 @@ void *pinned_get(ba_ctx *ctx, size_t bytes)
         (void)cudaGetLastError();
         return nullptr;
     }
-    ctx->pinned.push_back({p, cap, true});
+    ctx->pinned.push_back({p, cap, true, 0});
     return p;
 }
 
 void pinned_put(ba_ctx *ctx, void *p)
 {
-    for (auto &b : ctx->pinned)
-        if (b.p == p) b.used = false;
+    if (!p) return;
+    static std::atomic<uint64_t> clock_{1};
+    std::lock_guard<std::mutex> lk(ctx->pinned_mu);
+    size_t idle = 0;
+    for (auto &b : ctx->pinned) {
+        if (b.p == p) {
+            b.used = false;
+            b.stamp = clock_++;
+        }
+        if (!b.used) idle += b.cap;
+    }
+    const size_t budget = ctx->pinned_budget > 0 ? (size_t)ctx->pinned_budget : ((size_t)1 << 30);
+    while (idle > budget) {
+        int old = -1;
+        for (size_t k = 0; k < ctx->pinned.size(); k++)
+            if (!ctx->pinned[k].used && (old < 0 || ctx->pinned[k].stamp < ctx->pinned[old].stamp)) old = (int)k;
+        if (old < 0) break;
+        idle -= ctx->pinned[old].cap;
+        cudaFreeHost(ctx->pinned[old].p);
+        ctx->pinned.erase(ctx->pinned.begin() + old);
+    }
+}
+
+// Pinned blocks a call holds: released on every exit path unless handed to the caller (ba_result).
+struct Lease {
+    ba_ctx *ctx;
+    std::vector<void *> held;
+    explicit Lease(ba_ctx *c) : ctx(c) {}
+    ~Lease()
+    {
+        for (void *p : held) pinned_put(ctx, p);
+    }
+    void *get(size_t bytes)
+    {
+        void *p = pinned_get(ctx, bytes);
+        if (p) held.push_back(p);
+        return p;
+    }
+    void keep(void *p)   // ownership moves to the caller's result
+    {
+        for (size_t k = 0; k < held.size(); k++)
+            if (held[k] == p) {
+                held.erase(held.begin() + k);
+                return;
+            }
+    }
+    void drop(void *p)
+    {
+        keep(p);
+        pinned_put(ctx, p);
+    }
+};
+
+cudaEvent_t ev_new(ba_ctx *ctx, bool timed)
+{
+    std::vector<cudaEvent_t> &pool = timed ? ctx->ev_timed : ctx->ev_plain;
+    size_t &next = timed ? ctx->ev_timed_next : ctx->ev_plain_next;
+    if (next == pool.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, timed ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        pool.push_back(e);
+    }
+    return pool[next++];
 }
 
 // Work lists travel host -> device through a kernel that reads the pinned host buffer directly
@@ -238,37 +325,55 @@ int exclusive_scan(ba_ctx *ctx, void *tmp, size_t &tmp_bytes, const int32_t *in,
 }
 
 // ---- everything the two execution paths share for one ba_align_batch call
+// Input upload groups: pairs [p_lo, p_hi) reference only letters below byte b_hi, and the group's own
+// upload (and encode) covers bytes [b_lo, b_hi).  A wave may start as soon as the groups up to its
+// largest pair id are on the device, encoded and validated -- the rest of the batch uploads under its
+// kernels (ba_align_batch); device-resident callers have one group that is ready from the start.
+struct UploadGroup {
+    int64_t p_lo, p_hi, b_lo, b_hi;
+    cudaEvent_t ready = nullptr;    // recorded on the upload stream after this group's copy (nullptr: resident)
+    cudaEvent_t checked = nullptr;  // recorded on the main stream after encode + validate of the group
+};
+
 struct Batch {
-    const uint8_t *d_enc;
-    int stride;
-    const int64_t *d_ref_off, *d_qry_off;
-    const int32_t *d_ref_len, *d_qry_len;
-    const int32_t *h_ref_len, *h_qry_len;
-    int64_t n;
-    cudaStream_t st;
-    int32_t *d_status;
-    PairStart *d_start;
-    ba_result *out;
-    struct WaveOut {
-        int32_t *segs;
-        int64_t nsegs;
-    };
-    std::vector<WaveOut> wave_out;
-    int64_t seg_total = 0;
-    // exclusive_compute: the per-device kernel-phase token this call holds, released as soon as the
-    // last kernel of the batch is enqueued (the result copies then overlap the next batch's kernels)
-    std::unique_lock<std::mutex> *token = nullptr;
-    bool more_kernels_later = false;   // pairs are already queued for the exact path after this one
-    float ms_d2h = 0.f, ms_fill = 0.f, ms_trace = 0.f;
+    const uint8_t *d_letters = nullptr;
+    uint8_t *d_enc = nullptr;
+    int stride = 1;
+    const int64_t *d_ref_off = nullptr, *d_qry_off = nullptr;
+    const int32_t *d_ref_len = nullptr, *d_qry_len = nullptr;
+    const int32_t *h_ref_len = nullptr, *h_qry_len = nullptr;
+    int64_t n = 0;
+    cudaStream_t st = nullptr;  // main stream (the caller's for ba_align_batch_device)
+    int32_t *d_status = nullptr;
+    int64_t *d_err_pos = nullptr;
+    uint8_t *d_flags = nullptr;   // letter-class flags per pair (16-bit path eligibility), or nullptr
+    PairStart *d_start = nullptr;
+    ba_result *out = nullptr;
+    Lease *lease = nullptr;
+    std::vector<UploadGroup> groups;
+    size_t next_group = 0;
+    // all segments of the batch in ONE pinned block (grown in the rare case the estimate was short)
+    int32_t *h_segs = nullptr;
+    int64_t h_segs_cap = 0;     // in segments
+    int64_t seg_total = 0;      // segments produced so far == next free position
+    cudaEvent_t ev_d2h0 = nullptr;  // first result copy of the call (ms_d2h)
+    float ms_fill = 0.f, ms_trace = 0.f;
     double host_s = 0.0;
-    int64_t launches = 0, fill_launches = 0, code_bytes = 0;
+    int64_t launches = 0, fill_launches = 0, code_bytes = 0, waves = 0;
 };
 
 static bool g_timing = getenv("BA_TIMING") != nullptr;
-// One batch's kernel phase at a time per device (option "exclusive_compute"): callers driving several
-// contexts from several threads then pipeline -- the H2D copy of one batch runs under the kernels
-// of another instead of all copies and all kernels coinciding.
-static std::mutex g_compute_token[64];
+// exclusive_compute: ba_align_batch calls on one device run their FILL phases one after the other
+// even when they come from several contexts on several threads -- as a DEVICE-side dependency (the
+// first fill of a batch waits for the event the previous batch recorded after its last fill), so no
+// host thread ever blocks for it.  Uploads, encode/validate, the tail traceback and the result
+// copies of neighbouring batches overlap freely.
+struct DeviceGate {
+    std::mutex mu;
+    cudaEvent_t last_fill = nullptr;
+    bool armed = false;
+};
+static DeviceGate g_gate[64];
 #define BA_TSEC(name, t0) do { if (g_timing) fprintf(stderr, "[ba timing] %-22s %8.3f ms\n", name, (now_s() - (t0)) * 1e3); } while (0)
 
 static inline double now_s()
@@ -318,32 +423,81 @@ int cached_occupancy(ba_ctx *ctx, Fn fn, int threads, int &occ, size_t dyn_smem 
     return BA_OK;
 }
 
-// D2H of one wave's compact segments + per-item (count, base), then the host-side scatter of
-// seg_start/seg_count by pair id.  `skip_overflow`: items whose count exceeds their slot
-// capacity are left for the exact path and reported through `overflow`.
-int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, int32_t *h_cnt, int64_t *h_base,
-                int64_t wsegs, const int32_t *d_segs, const int32_t *h_raw_cnt, std::vector<int32_t> *overflow,
-                bool release_token = false)
+// Encode + validate every upload group up to the one holding pair `pmax` (main stream, in order).
+int prep_pairs(ba_ctx *ctx, Batch &B, int64_t pmax)
 {
-    cudaStream_t st = B.st;
-    int32_t *h_segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(wsegs + 1));
-    if (!h_segs) {
+    const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+    while (B.next_group < B.groups.size() && B.groups[B.next_group].p_lo <= pmax) {
+        UploadGroup &g = B.groups[B.next_group++];
+        if (g.ready) CK(cudaStreamWaitEvent(B.st, g.ready, 0));
+        const int64_t nb = g.b_hi - g.b_lo, np = g.p_hi - g.p_lo;
+        if (nb > 0) {
+            int64_t blocks = (nb / 16 + 255) / 256;
+            if (blocks < 1) blocks = 1;
+            if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+            BA_LAUNCH(ba_encode_kernel, (unsigned)blocks, 256, B.st, B.d_letters + g.b_lo, B.d_enc + g.b_lo, nb,
+                      ctx->d_sc);
+            B.launches++;
+        }
+        if (np > 0) {
+            int64_t blocks = (np + 7) / 8;
+            if (blocks > ctx->sm_count * 32) blocks = ctx->sm_count * 32;
+            BA_LAUNCH(ba_validate_kernel, (unsigned)blocks, 256, B.st, B.d_enc, B.stride, B.d_ref_off + g.p_lo,
+                      B.d_ref_len + g.p_lo, B.d_qry_off + g.p_lo, B.d_qry_len + g.p_lo, np, kind, affine,
+                      B.d_status + g.p_lo, B.d_err_pos + g.p_lo, B.d_flags ? B.d_flags + g.p_lo : nullptr);
+            B.launches++;
+        }
+        CK(cudaGetLastError());
+        g.checked = ev_new(ctx, false);
+        if (!g.checked) {
+            ctx->err = "cudaEventCreate failed";
+            return BA_ERR_CUDA;
+        }
+        CK(cudaEventRecord(g.checked, B.st));
+    }
+    return BA_OK;
+}
+
+// Room for `need` segments in the batch's pinned segment block; copies already enqueued on the
+// result stream land first when the block has to move.
+int segs_reserve(ba_ctx *ctx, Batch &B, int64_t need, int64_t valid)
+{
+    if (need <= B.h_segs_cap) return BA_OK;
+    const int64_t cap = need + need / 8 + 1024;
+    int32_t *nb = (int32_t *)B.lease->get(sizeof(int32_t) * 5 * (size_t)cap);
+    if (!nb) {
         ctx->err = "pinned host allocation failed";
         return BA_ERR_NOMEM;
     }
-    CK(cudaEventRecord(ctx->ev[2], st));
+    if (B.h_segs) {
+        CK(cudaStreamSynchronize(ctx->s_d2h));
+        if (valid > 0) memcpy(nb, B.h_segs, sizeof(int32_t) * 5 * (size_t)valid);
+        B.lease->drop(B.h_segs);
+    }
+    B.h_segs = nb;
+    B.h_segs_cap = cap;
+    return BA_OK;
+}
+
+// Exact path: D2H of one wave's compact segments behind the segments the batch already has, and the
+// host-side scatter of seg_start/seg_count by pair id.
+int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, const int32_t *h_cnt,
+                const int64_t *h_base, int64_t wsegs, const int32_t *d_segs)
+{
+    cudaStream_t st = B.st;
+    int rc;
+    if ((rc = segs_reserve(ctx, B, B.seg_total + wsegs, B.seg_total)) != BA_OK) return rc;
+    if (!B.ev_d2h0) {
+        B.ev_d2h0 = ev_new(ctx, true);
+        if (B.ev_d2h0) CK(cudaEventRecord(B.ev_d2h0, st));
+    }
     if (wsegs > 0)
-        CK(cudaMemcpyAsync(h_segs, d_segs, sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev[3], st));
-    if (release_token && B.token && B.token->owns_lock()) B.token->unlock();  // no kernel of this batch follows
+        CK(cudaMemcpyAsync(B.h_segs + 5 * B.seg_total, d_segs, sizeof(int32_t) * 5 * (size_t)wsegs,
+                           cudaMemcpyDeviceToHost, st));
     // the per-pair scatter only needs the counts (already on the host): do it while the segments travel
     const double t0 = now_s();
     for (int64_t k = 0; k < w.count; k++) {
         const int32_t p = plan.items[w.first + k].pair;
-        if (overflow && (h_raw_cnt[k] < 0 || h_raw_cnt[k] > plan.slot_cap[w.first + k])) {
-            overflow->push_back(p);
-            continue;
-        }
         B.out->seg_start[p] = B.seg_total + h_base[k];
         B.out->seg_count[p] = h_cnt[k];
     }
@@ -351,13 +505,10 @@ int gather_wave(ba_ctx *ctx, Batch &B, const Plan &plan, const Plan::Wave &w, in
     B.host_s += now_s() - t0;
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-    B.ms_d2h += ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
     B.ms_fill += ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
     B.ms_trace += ms;
-    B.wave_out.push_back({h_segs, wsegs});
     B.seg_total += wsegs;
     return BA_OK;
 }
@@ -383,6 +534,7 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
     const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
     cudaStream_t st = B.st;
     int rc;
+    if ((rc = prep_pairs(ctx, B, B.n - 1)) != BA_OK) return rc;
     ctx->pc.dev_items = nullptr;  // this path reuses the work-list buffers
     int64_t arena_cap = 0;
     if (arena_budget(ctx, arena_cap) != 0) {
@@ -391,8 +543,8 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
     }
     Plan plan;
     const double tp0 = now_s();
-    plan.items = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)nids);
-    plan.aux_off = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)nids);
+    plan.items = (WorkItem *)B.lease->get(sizeof(WorkItem) * (size_t)nids);
+    plan.aux_off = (int64_t *)B.lease->get(sizeof(int64_t) * (size_t)nids);
     if (!plan.items || !plan.aux_off) {
         ctx->err = "pinned host allocation failed";
         return BA_ERR_NOMEM;
@@ -418,8 +570,8 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
                              (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
         return rc;
     if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
-    int32_t *h_cnt = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
-    int64_t *h_base = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(max_items + 1));
+    int32_t *h_cnt = (int32_t *)B.lease->get(sizeof(int32_t) * (size_t)max_items);
+    int64_t *h_base = (int64_t *)B.lease->get(sizeof(int64_t) * (size_t)(max_items + 1));
     if (!h_cnt || !h_base) {
         ctx->err = "pinned host allocation failed";
         return BA_ERR_NOMEM;
@@ -428,6 +580,7 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
     WalkFn walk_write = pick_walk<true>(kind, affine);
 
     for (auto &w : plan.waves) {
+        B.waves++;
         WorkItem *d_items = (WorkItem *)ctx->items.p;
         if ((rc = upload_words(ctx, d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count, st)) != BA_OK)
             return rc;
@@ -525,14 +678,13 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
         B.launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[6], st));
-        if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, nullptr,
-                              nullptr)) != BA_OK)
+        if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p)) != BA_OK)
             return rc;
     }
-    pinned_put(ctx, h_cnt);
-    pinned_put(ctx, h_base);
-    pinned_put(ctx, plan.items);
-    pinned_put(ctx, plan.aux_off);
+    B.lease->drop(h_cnt);
+    B.lease->drop(h_base);
+    B.lease->drop(plan.items);
+    B.lease->drop(plan.aux_off);
     return BA_OK;
 }
 
@@ -596,16 +748,22 @@ Trace16Fn pick_trace16p(int kind, bool lin)
     if (kind == KIND_NW) return ba_trace16p_kernel<KIND_NW, false>;
     return ba_trace16p_kernel<KIND_FIT, false>;
 }
-Trace16Fn pick_trace16(int kind, bool lin)
+template <int TS>
+Trace16Fn pick_trace16ts(int kind, bool lin)
 {
     if (lin) {
-        if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, true>;
-        if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, true>;
-        return ba_trace16_kernel<KIND_FIT, true>;
+        if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, true, TS>;
+        if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, true, TS>;
+        return ba_trace16_kernel<KIND_FIT, true, TS>;
     }
-    if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, false>;
-    if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, false>;
-    return ba_trace16_kernel<KIND_FIT, false>;
+    if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, false, TS>;
+    if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, false, TS>;
+    return ba_trace16_kernel<KIND_FIT, false, TS>;
+}
+// thread-per-pair traceback with CTAs of `ts` threads (64: fits the SM slot a retiring fill CTA frees)
+Trace16Fn pick_trace16(int kind, bool lin, int ts)
+{
+    return ts == 64 ? pick_trace16ts<64>(kind, lin) : pick_trace16ts<BA_TRACE_THREADS>(kind, lin);
 }
 
 // Scoring-level eligibility of the packed 16-bit path (ba_fill16.cuh):
@@ -663,24 +821,47 @@ bool fast16_pair_ok(const DeviceScoring &s, const Fast16 &f, int n, int m)
     return true;
 }
 
+// How one fill launch of a wave runs (decided for every launch before anything is enqueued, so all
+// buffers are sized once and no allocation happens between overlapping kernels).
+struct FillCfg {
+    Fill16Fn fn = nullptr;
+    size_t dyn = 0;
+    int64_t blocks = 0;
+    int max_claims = 0;
+    bool use_long = false;
+    int maxp = 0, max_n = 0;
+    int64_t ncp = 0, ntasks = 0, bnd_stride = 0, bnd_ints = 0;
+};
+
 int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsub, std::vector<int32_t> &overflow,
-               bool use_cache)
+               bool use_cache, int64_t cells)
 {
     const int kind = ctx->h_sc.kind;
     const bool lin = !ctx->h_sc.affine;
     const int flag_mask = gsub ? 2 : 1;
     if (nids == 0) return BA_OK;
     cudaStream_t st = B.st;
+    Lease &lease = *B.lease;
     int rc;
     int64_t arena_cap = 0;
     if (arena_budget(ctx, arena_cap) != 0) {
         ctx->err = "cudaMemGetInfo failed";
         return BA_ERR_CUDA;
     }
+    // ---- waves: the traceback of wave w runs beside the fill of wave w+1 (different pipes bind them:
+    // the fill saturates the integer pipe, the walk waits on checkpoint loads), so a batch that is
+    // large enough is cut into several waves even when its checkpoints would fit the arena at once.
+    int64_t tw = ctx->opt_waves;
+    if (tw <= 0) {
+        tw = std::min<int64_t>(8, std::min<int64_t>(cells / 2000000000LL, nids / 4096));
+        if (tw < 1) tw = 1;
+    }
+    const int64_t wave_cap = tw > 1 ? std::max<int64_t>(arena_cap / 3, 1) : arena_cap;
     Plan local_plan;
     ba_ctx::PlanCache &pc = ctx->pc;
     const double tp0 = now_s();
-    if (use_cache && pc.plan_built && (pc.arena_cap != arena_cap || pc.slot_cap_opt != ctx->opt_slot_cap)) {
+    if (use_cache && pc.plan_built &&
+        (pc.arena_cap != arena_cap || pc.slot_cap_opt != ctx->opt_slot_cap || pc.waves_opt != tw)) {
         pinned_put(ctx, pc.plan.items);
         pinned_put(ctx, pc.plan.slot_off);
         pinned_put(ctx, pc.plan.slot_cap);
@@ -690,15 +871,27 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     }
     Plan &plan = use_cache ? pc.plan : local_plan;
     if (!(use_cache && pc.plan_built)) {
-        plan.items = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)nids);
-        plan.slot_off = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)nids);
-        plan.slot_cap = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)nids);
+        if (use_cache) {
+            plan.items = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)nids);
+            plan.slot_off = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)nids);
+            plan.slot_cap = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)nids);
+        } else {
+            plan.items = (WorkItem *)lease.get(sizeof(WorkItem) * (size_t)nids);
+            plan.slot_off = (int64_t *)lease.get(sizeof(int64_t) * (size_t)nids);
+            plan.slot_cap = (int32_t *)lease.get(sizeof(int32_t) * (size_t)nids);
+        }
         if (!plan.items || !plan.slot_off || !plan.slot_cap) {
+            if (use_cache) {
+                pinned_put(ctx, plan.items);
+                pinned_put(ctx, plan.slot_off);
+                pinned_put(ctx, plan.slot_cap);
+                plan = Plan();
+            }
             ctx->err = "pinned host allocation failed";
             return BA_ERR_NOMEM;
         }
         const double tp1 = now_s();
-        build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, lin ? 0 : 1, true, arena_cap, plan);
+        build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, lin ? 0 : 1, true, wave_cap, plan, (int)tw);
         BA_TSEC("plan16 pinned_get", tp0);
         BA_TSEC("plan16 build", tp1);
         if (ctx->opt_slot_cap > 0) {  // test hook: force the overflow -> exact-path fallback
@@ -715,75 +908,186 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             pc.plan_built = true;
             pc.arena_cap = arena_cap;
             pc.slot_cap_opt = ctx->opt_slot_cap;
+            pc.waves_opt = tw;
             pc.dev_items = nullptr;
         }
     }
     B.host_s += now_s() - tp0;
-    int64_t max_items = 0, max_code = 0, max_slots = 0;
+    const int64_t nw = (int64_t)plan.waves.size();
+    const bool overlap = nw > 1;
+    int64_t region_bytes = 0, region_slots = 0, total_slots = 0;
     for (auto &w : plan.waves) {
-        max_items = std::max(max_items, w.count);
-        max_code = std::max(max_code, w.code_bytes);
-        max_slots = std::max(max_slots, w.slots);
+        region_bytes = std::max(region_bytes, w.code_bytes);
+        region_slots = std::max(region_slots, w.slots);
+        total_slots += w.slots;
     }
-    if ((rc = ensure(ctx, ctx->items, sizeof(WorkItem) * (size_t)max_items)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->slot_off, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->slot_cap, sizeof(int32_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->slots, sizeof(int32_t) * 5 * (size_t)(max_slots + 1))) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->seg_count, sizeof(int32_t) * (size_t)max_items)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->seg_clip, sizeof(int32_t) * (size_t)max_items)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->seg_base, sizeof(int64_t) * (size_t)(max_items + 1))) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->arena, (size_t)max_code + 256)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 128)) != BA_OK) return rc;
-    size_t scan_bytes = 0;
-    if ((rc = exclusive_scan(ctx, nullptr, scan_bytes, (const int32_t *)ctx->seg_clip.p,
-                             (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
-        return rc;
-    if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
-    int32_t *h_long_err = (int32_t *)pinned_get(ctx, 64);
-    if (!h_long_err) {
-        ctx->err = "pinned host allocation failed";
-        return BA_ERR_NOMEM;
-    }
-    memset(h_long_err, 0, 64);
-    std::vector<WorkItem *> long_tasks;
-    int32_t *h_cnt = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
-    int32_t *h_raw = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)max_items);
-    int64_t *h_base = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)(max_items + 1));
-    if (!h_cnt || !h_raw || !h_base) {
-        ctx->err = "pinned host allocation failed";
-        return BA_ERR_NOMEM;
+    region_bytes = (region_bytes + 255) & ~(int64_t)255;
+    // checkpoint regions: wave w uses region w % R; with R >= 3 a fill never waits for a traceback
+    int64_t R = region_bytes > 0 ? arena_cap / region_bytes : nw;
+    R = std::max<int64_t>(1, std::min<int64_t>(R, nw));
+    const bool two_streams = overlap && ctx->opt_fill_streams >= 2 && R >= 2;
+
+    // ---- launch configurations
+    const bool sym = !lin && ctx->opt_sym != 0 && g_sym_scoring(ctx->h_sc);
+    const size_t dyn = gsub ? (size_t)BA16_WARPS * ba16_gsub_bytes_per_warp(ctx->h_sc.let) : 0;
+    std::vector<std::vector<FillCfg>> cfgs((size_t)nw);
+    int64_t max_bnd_ints = 0, max_tasks = 0;
+    for (int64_t wi = 0; wi < nw; wi++) {
+        const Plan::Wave &w = plan.waves[(size_t)wi];
+        const bool multi = w.max_n_multipass > 0;
+        int64_t wave_bnd = 0, wave_tasks = 0;
+        for (auto &L : w.launches) {
+            FillCfg c;
+            c.dyn = dyn;
+            // ---- LONG: too few pairs to fill the GPU pair by pair, and many passes each: spread the
+            // passes of every pair over warps (wavefront).  Items of a launch are sorted by cells.
+            const int W16 = 32 * L.cols;
+            if (multi && L.cols >= 7 && ctx->opt_long_mode != 0) {
+                for (int64_t k = 0; k < L.count; k++) {
+                    const int32_t p = plan.items[L.first + k].pair;
+                    c.maxp = std::max(c.maxp, (B.h_qry_len[p] + W16 - 1) / W16);
+                    c.max_n = std::max(c.max_n, B.h_ref_len[p]);
+                }
+            }
+            c.fn = pick_fill16(kind, lin, L.cols, multi, gsub, false, sym);
+            // GSUB kernels keep their score tables in dynamic shared memory (the size depends on the
+            // matrix only, so the per-kernel cache entry stays valid until the scoring changes)
+            int occ = 1;
+            if ((rc = cached_occupancy(ctx, c.fn, BA16_WARPS * 32, occ, dyn)) != BA_OK) return rc;
+            if (overlap && ctx->opt_fill_cap > 0) occ = (int)std::min<int64_t>(occ, ctx->opt_fill_cap);
+            int64_t maxb = (int64_t)ctx->sm_count * occ;
+            const int64_t pair_warps = (L.count + 3) / 4;
+            c.use_long = c.maxp >= 4 && (ctx->opt_long_mode == 2 || pair_warps < maxb * BA16_WARPS) &&
+                         (int64_t)c.maxp * (L.count + 4) < (1 << 22);
+            if (c.use_long) {
+                c.fn = pick_fill16(kind, lin, L.cols, true, gsub, true, sym);
+                if ((rc = cached_occupancy(ctx, c.fn, BA16_WARPS * 32, occ, dyn)) != BA_OK) return rc;
+                maxb = (int64_t)ctx->sm_count * occ;
+                c.ncp = ((L.count + 3) / 4) * 2;         // couples per pass, even
+                c.ntasks = (int64_t)c.maxp * 2 * c.ncp;
+                c.bnd_stride = 4 * ((int64_t)c.max_n + 2);
+                c.bnd_ints = c.bnd_stride * c.ncp;
+                c.blocks = std::min(maxb, (c.ntasks + 4 * BA16_WARPS - 1) / (4 * BA16_WARPS));
+                wave_tasks += c.ntasks;
+            } else {
+                const int64_t need = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
+                // single-pass launches of an overlapped batch retire their CTAs after `fill_claims` claims,
+                // so the high-priority traceback CTAs of the previous wave find SM slots all along
+                if (overlap && !multi && ctx->opt_fill_claims > 0) {
+                    c.max_claims = (int)ctx->opt_fill_claims;
+                    c.blocks = (need + c.max_claims - 1) / c.max_claims;
+                } else {
+                    c.blocks = std::min(need, maxb);
+                }
+                if (multi) {
+                    c.bnd_stride = 4 * ((int64_t)w.max_n_multipass + 2);
+                    c.bnd_ints = c.bnd_stride * c.blocks * BA16_GROUPS;
+                }
+            }
+            wave_bnd += c.bnd_ints;
+            cfgs[(size_t)wi].push_back(c);
+        }
+        max_bnd_ints = std::max(max_bnd_ints, wave_bnd);
+        max_tasks = std::max(max_tasks, wave_tasks);
     }
 
-    for (auto &w : plan.waves) {
-        WorkItem *d_items = (WorkItem *)ctx->items.p;
-        const bool dev_ok = use_cache && plan.waves.size() == 1 && pc.dev_items == ctx->items.p &&
-                            pc.dev_slot_off == ctx->slot_off.p && pc.dev_slot_cap == ctx->slot_cap.p;
-        if (!dev_ok) {
-            if ((rc = upload_words(ctx, d_items, plan.items + w.first, sizeof(WorkItem) * (size_t)w.count, st)) !=
-                BA_OK)
-                return rc;
-            if ((rc = upload_words(ctx, ctx->slot_off.p, plan.slot_off + w.first, sizeof(int64_t) * (size_t)w.count,
-                                   st)) != BA_OK)
-                return rc;
-            if ((rc = upload_words(ctx, ctx->slot_cap.p, plan.slot_cap + w.first, sizeof(int32_t) * (size_t)w.count,
-                                   st)) != BA_OK)
-                return rc;
-            B.launches += 3;
-            if (use_cache && plan.waves.size() == 1) {
-                pc.dev_items = ctx->items.p;
-                pc.dev_slot_off = ctx->slot_off.p;
-                pc.dev_slot_cap = ctx->slot_cap.p;
-            } else {
-                pc.dev_items = nullptr;
-            }
+    // ---- device buffers (sized for the whole batch; nothing is allocated once kernels overlap)
+    if ((rc = ensure(ctx, ctx->items, sizeof(WorkItem) * (size_t)nids)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->slot_off, sizeof(int64_t) * (size_t)(nids + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->slot_cap, sizeof(int32_t) * (size_t)(nids + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->slots, sizeof(int32_t) * 5 * (size_t)(R * region_slots + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_count, sizeof(int32_t) * (size_t)nids)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_clip, sizeof(int32_t) * (size_t)nids)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seg_base, sizeof(int64_t) * (size_t)(nids + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->arena, (size_t)(R * region_bytes) + 256)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 128 * (size_t)nw)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(total_slots + 1))) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->ovf, sizeof(int32_t) * (size_t)(nids + 1))) != BA_OK) return rc;
+    const size_t meta_words = BA_META_HEAD + BA_META_WAVE * (size_t)nw;
+    if ((rc = ensure(ctx, ctx->meta, sizeof(long long) * meta_words)) != BA_OK) return rc;
+    // two fills may be in flight (alternating streams): their boundary rows / task lists alternate too
+    if (max_bnd_ints > 0 && (rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(2 * max_bnd_ints))) != BA_OK) return rc;
+    if (max_tasks > 0) {
+        if ((rc = ensure(ctx, ctx->tasks, sizeof(WorkItem) * (size_t)(2 * max_tasks))) != BA_OK) return rc;
+        if ((rc = ensure(ctx, ctx->prog, 64 * (size_t)nw)) != BA_OK) return rc;
+    }
+    size_t scan_bytes = 0;
+    {
+        int64_t max_items = 0;
+        for (auto &w : plan.waves) max_items = std::max(max_items, w.count);
+        if ((rc = exclusive_scan(ctx, nullptr, scan_bytes, (const int32_t *)ctx->seg_clip.p,
+                                 (int64_t *)ctx->seg_base.p, (int)max_items, st)) != BA_OK)
+            return rc;
+    }
+    if ((rc = ensure(ctx, ctx->scan_tmp, scan_bytes + 16)) != BA_OK) return rc;
+    long long *h_meta = (long long *)lease.get(sizeof(long long) * meta_words);
+    int32_t *h_long_err = (int32_t *)lease.get(sizeof(int32_t) * (size_t)(nw + 1));
+    if (!h_meta || !h_long_err) {
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    memset(h_long_err, 0, sizeof(int32_t) * (size_t)(nw + 1));
+    std::vector<WorkItem *> long_tasks;
+
+    // ---- one-time set-up on the main stream: inputs of the first wave, work lists, counters
+    if ((rc = prep_pairs(ctx, B, plan.waves[0].max_pair)) != BA_OK) return rc;
+    WorkItem *d_items = (WorkItem *)ctx->items.p;
+    const bool dev_ok = use_cache && pc.dev_items == ctx->items.p && pc.dev_slot_off == ctx->slot_off.p &&
+                        pc.dev_slot_cap == ctx->slot_cap.p;
+    if (!dev_ok) {
+        if ((rc = upload_words(ctx, d_items, plan.items, sizeof(WorkItem) * (size_t)nids, st)) != BA_OK) return rc;
+        if ((rc = upload_words(ctx, ctx->slot_off.p, plan.slot_off, sizeof(int64_t) * (size_t)nids, st)) != BA_OK)
+            return rc;
+        if ((rc = upload_words(ctx, ctx->slot_cap.p, plan.slot_cap, sizeof(int32_t) * (size_t)nids, st)) != BA_OK)
+            return rc;
+        B.launches += 3;
+        if (use_cache) {
+            pc.dev_items = ctx->items.p;
+            pc.dev_slot_off = ctx->slot_off.p;
+            pc.dev_slot_cap = ctx->slot_cap.p;
         }
-        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 128, st));
+    }
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 128 * (size_t)nw, st));
+    CK(cudaMemsetAsync(ctx->meta.p, 0, sizeof(long long) * meta_words, st));
+    if (max_tasks > 0) CK(cudaMemsetAsync(ctx->prog.p, 0, 64 * (size_t)nw, st));
+    CK(cudaMemsetAsync(ctx->pair_seg_start.p, 0, sizeof(int64_t) * (size_t)B.n, st));
+    CK(cudaMemsetAsync(ctx->pair_seg_count.p, 0, sizeof(int32_t) * (size_t)B.n, st));
+    // the fills of this batch follow the fills of the previous batch on this device
+    DeviceGate &gate = g_gate[ctx->device & 63];
+    std::unique_lock<std::mutex> gate_lock(gate.mu, std::defer_lock);
+    if (ctx->opt_exclusive) {
+        gate_lock.lock();
+        if (gate.armed) CK(cudaStreamWaitEvent(st, gate.last_fill, 0));
+    }
+    cudaEvent_t ev_setup = ev_new(ctx, true);   // also the start of the fill span
+    if (!ev_setup) {
+        ctx->err = "cudaEventCreate failed";
+        return BA_ERR_CUDA;
+    }
+    CK(cudaEventRecord(ev_setup, st));
+    CK(cudaStreamWaitEvent(ctx->s_trace, ev_setup, 0));
+    if (two_streams) CK(cudaStreamWaitEvent(ctx->s_fill2, ev_setup, 0));
+    std::vector<cudaEvent_t> ev_fill_end((size_t)nw), ev_trace_end((size_t)nw);
+    cudaEvent_t ev_trace_start = nullptr;
+
+    for (int64_t wi = 0; wi < nw; wi++) {
+        const Plan::Wave &w = plan.waves[(size_t)wi];
+        B.waves++;
+        cudaStream_t F = (two_streams && (wi & 1)) ? ctx->s_fill2 : st;
+        if ((rc = prep_pairs(ctx, B, w.max_pair)) != BA_OK) return rc;
+        if (F != st && B.next_group > 0) CK(cudaStreamWaitEvent(F, B.groups[B.next_group - 1].checked, 0));
+        if (wi >= R) CK(cudaStreamWaitEvent(F, ev_trace_end[(size_t)(wi - R)], 0));  // its region is free again
+        const int64_t reg = wi % R;
+        uint8_t *arena_w = (uint8_t *)ctx->arena.p + reg * region_bytes;
+        int32_t *slots_w = (int32_t *)ctx->slots.p + 5 * reg * region_slots;
+        const int par = (int)(wi & 1);
 
         // ---- fill (values + checkpoints)
-        CK(cudaEventRecord(ctx->ev[4], st));
         int li = 0;
-        for (auto &L : w.launches) {
-            const bool multi = w.max_n_multipass > 0;
+        int64_t bnd_used = 0, tasks_used = 0;
+        for (size_t lx = 0; lx < w.launches.size(); lx++) {
+            const Plan::Launch &L = w.launches[lx];
+            const FillCfg &c = cfgs[(size_t)wi][lx];
             Fill16Params fp;
             fp.enc = B.d_enc;
             fp.stride = B.stride;
@@ -792,49 +1096,25 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             fp.qry_off = B.d_qry_off;
             fp.qry_len = B.d_qry_len;
             fp.status = B.d_status;
-            fp.acgt_only = (const uint8_t *)ctx->flags.p;
+            fp.acgt_only = B.d_flags;
             fp.flag_mask = flag_mask;
-            fp.counter = (int *)ctx->counters.p + (li++ % 64);
-            fp.arena = (uint8_t *)ctx->arena.p;
+            fp.counter = (int *)ctx->counters.p + 128 * wi + (li++ % 64);
+            fp.arena = arena_w;
             fp.sc = ctx->d_sc;
             fp.long_couples = 0;
             fp.long_err = nullptr;
-
-            // ---- LONG: too few pairs to fill the GPU pair by pair, and many passes each: spread the
-            // passes of every pair over warps (wavefront).  Items of a launch are sorted by cells.
-            const int W16 = 32 * L.cols;
-            int maxp = 0, max_n = 0;
-            if (multi && L.cols >= 7 && ctx->opt_long_mode != 0) {
-                for (int64_t k = 0; k < L.count; k++) {
-                    const int32_t p = plan.items[L.first + k].pair;
-                    maxp = std::max(maxp, (B.h_qry_len[p] + W16 - 1) / W16);
-                    max_n = std::max(max_n, B.h_ref_len[p]);
-                }
-            }
-            const bool sym = !lin && ctx->opt_sym != 0 && g_sym_scoring(ctx->h_sc);
-            Fill16Fn fn = pick_fill16(kind, lin, L.cols, multi, gsub, false, sym);
-            // GSUB kernels keep their score tables in dynamic shared memory (the size depends on the
-            // matrix only, so the per-kernel cache entry stays valid until the scoring changes)
-            const size_t dyn = gsub ? (size_t)BA16_WARPS * ba16_gsub_bytes_per_warp(ctx->h_sc.let) : 0;
-            int occ = 1;
-            if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ, dyn)) != BA_OK) return rc;
-            int64_t maxb = (int64_t)ctx->sm_count * occ;
-            const int64_t pair_warps = (L.count + 3) / 4;
-            const bool use_long = maxp >= 4 && (ctx->opt_long_mode == 2 || pair_warps < maxb * BA16_WARPS) &&
-                                  (int64_t)maxp * (L.count + 4) < (1 << 22);
-            if (use_long) {
-                fn = pick_fill16(kind, lin, L.cols, true, gsub, true, sym);
-                if ((rc = cached_occupancy(ctx, fn, BA16_WARPS * 32, occ, dyn)) != BA_OK) return rc;
-                maxb = (int64_t)ctx->sm_count * occ;
-                const int64_t ncp = ((L.count + 3) / 4) * 2;         // couples per pass, even
-                const int64_t ntasks = (int64_t)maxp * 2 * ncp;
-                WorkItem *h_tasks = (WorkItem *)pinned_get(ctx, sizeof(WorkItem) * (size_t)ntasks);
+            fp.max_claims = c.max_claims;
+            int32_t *bnd_w = (int32_t *)ctx->bnd.p + par * max_bnd_ints + bnd_used;
+            bnd_used += c.bnd_ints;
+            if (c.use_long) {
+                WorkItem *h_tasks = (WorkItem *)lease.get(sizeof(WorkItem) * (size_t)c.ntasks);
                 if (!h_tasks) {
                     ctx->err = "pinned host allocation failed";
                     return BA_ERR_NOMEM;
                 }
-                for (int ps = 0; ps < maxp; ps++)
-                    for (int64_t k = 0; k < 2 * ncp; k++) {
+                const int W16 = 32 * L.cols;
+                for (int ps = 0; ps < c.maxp; ps++)
+                    for (int64_t k = 0; k < 2 * c.ncp; k++) {
                         WorkItem t;
                         t.pair = -1;
                         t.cols = L.cols;
@@ -843,57 +1123,53 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                             const WorkItem &it = plan.items[L.first + k];
                             if (ps < (B.h_qry_len[it.pair] + W16 - 1) / W16) t = it;
                         }
-                        h_tasks[(int64_t)ps * 2 * ncp + k] = t;
+                        h_tasks[(int64_t)ps * 2 * c.ncp + k] = t;
                     }
-                const int64_t bnd_stride = 4 * ((int64_t)max_n + 2);
-                if ((rc = ensure(ctx, ctx->tasks, sizeof(WorkItem) * (size_t)ntasks)) != BA_OK) return rc;
-                if ((rc = ensure(ctx, ctx->prog, 64)) != BA_OK) return rc;
-                if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * ncp))) != BA_OK) return rc;
-                if ((rc = upload_words(ctx, ctx->tasks.p, h_tasks, sizeof(WorkItem) * (size_t)ntasks, st)) != BA_OK)
+                WorkItem *d_tasks = (WorkItem *)ctx->tasks.p + par * max_tasks + tasks_used;
+                tasks_used += c.ntasks;
+                if ((rc = upload_words(ctx, d_tasks, h_tasks, sizeof(WorkItem) * (size_t)c.ntasks, F)) != BA_OK)
                     return rc;
                 B.launches++;
-                CK(cudaMemsetAsync(ctx->prog.p, 0, 64, st));
                 // row tags start out invalid
-                CK(cudaMemsetAsync(ctx->bnd.p, 0, sizeof(int32_t) * (size_t)(bnd_stride * ncp), st));
-                fp.items = (const WorkItem *)ctx->tasks.p;
-                fp.n_items = (int)ntasks;
-                fp.bnd = (int32_t *)ctx->bnd.p;
-                fp.bnd_stride = bnd_stride;
-                fp.long_couples = (int)ncp;
-                fp.long_err = (int *)ctx->prog.p;
-                int64_t blocks = (ntasks + 4 * BA16_WARPS - 1) / (4 * BA16_WARPS);
-                if (blocks > maxb) blocks = maxb;
-                BA_LAUNCH_SMEM(fn, (unsigned)blocks, BA16_WARPS * 32, dyn, st, fp);
-                CK(cudaMemcpyAsync(h_long_err + (long_tasks.size() & 15), ctx->prog.p, sizeof(int), cudaMemcpyDeviceToHost,
-                                   st));
+                CK(cudaMemsetAsync(bnd_w, 0, sizeof(int32_t) * (size_t)c.bnd_ints, F));
+                fp.items = d_tasks;
+                fp.n_items = (int)c.ntasks;
+                fp.bnd = bnd_w;
+                fp.bnd_stride = c.bnd_stride;
+                fp.long_couples = (int)c.ncp;
+                fp.long_err = (int *)((char *)ctx->prog.p + 64 * wi);
+                BA_LAUNCH_SMEM(c.fn, (unsigned)c.blocks, BA16_WARPS * 32, c.dyn, F, fp);
+                CK(cudaMemcpyAsync(h_long_err + wi, fp.long_err, sizeof(int), cudaMemcpyDeviceToHost, F));
                 long_tasks.push_back(h_tasks);
                 B.out->wavefront_launches++;
                 B.launches++;
                 B.fill_launches++;
                 continue;
             }
-            int64_t blocks = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
-            if (blocks > maxb) blocks = maxb;
-            int64_t bnd_stride = 0;
-            if (multi) {
-                bnd_stride = 4 * ((int64_t)w.max_n_multipass + 2);
-                if ((rc = ensure(ctx, ctx->bnd, sizeof(int32_t) * (size_t)(bnd_stride * blocks * BA16_GROUPS))) != BA_OK)
-                    return rc;
-            }
-            fp.items = d_items + (L.first - w.first);
+            fp.items = d_items + L.first;
             fp.n_items = (int)L.count;
-            fp.bnd = (int32_t *)ctx->bnd.p;
-            fp.bnd_stride = bnd_stride;
-            BA_LAUNCH_SMEM(fn, (unsigned)blocks, BA16_WARPS * 32, dyn, st, fp);
+            fp.bnd = bnd_w;
+            fp.bnd_stride = c.bnd_stride;
+            BA_LAUNCH_SMEM(c.fn, (unsigned)c.blocks, BA16_WARPS * 32, c.dyn, F, fp);
             B.launches++;
             B.fill_launches++;
         }
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[5], st));
+        ev_fill_end[(size_t)wi] = ev_new(ctx, true);
+        if (!ev_fill_end[(size_t)wi]) {
+            ctx->err = "cudaEventCreate failed";
+            return BA_ERR_CUDA;
+        }
+        CK(cudaEventRecord(ev_fill_end[(size_t)wi], F));
         B.code_bytes += w.code_bytes;
-        BA_TSEC("P16 fill launched", tp0);
 
-        // ---- tile traceback into slots, clip, scan, compact
+        // ---- tile traceback into slots, then clip, scan, compact (trace stream)
+        cudaStream_t T = ctx->s_trace;
+        CK(cudaStreamWaitEvent(T, ev_fill_end[(size_t)wi], 0));
+        if (wi == 0) {
+            ev_trace_start = ev_new(ctx, true);
+            if (ev_trace_start) CK(cudaEventRecord(ev_trace_start, T));
+        }
         Trace16Params tp;
         tp.enc = B.d_enc;
         tp.stride = B.stride;
@@ -902,32 +1178,35 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.qry_off = B.d_qry_off;
         tp.qry_len = B.d_qry_len;
         tp.status = B.d_status;
-        tp.acgt_only = (const uint8_t *)ctx->flags.p;
+        tp.acgt_only = B.d_flags;
         tp.flag_mask = flag_mask;
-        tp.items = d_items;
+        tp.items = d_items + w.first;
         tp.n_items = (int)w.count;
-        tp.arena = (const uint8_t *)ctx->arena.p;
+        tp.arena = arena_w;
         tp.sc = ctx->d_sc;
-        tp.seg_count = (int32_t *)ctx->seg_count.p;
-        tp.slot_off = (const int64_t *)ctx->slot_off.p;
-        tp.slot_cap = (const int32_t *)ctx->slot_cap.p;
-        tp.slots = (int32_t *)ctx->slots.p;
-        tp.counter = (int *)ctx->counters.p + 64;  // zeroed with the fill counters at the start of the wave
-        // one thread per pair when the batch fills the GPU that way, else one warp per pair
+        tp.seg_count = (int32_t *)ctx->seg_count.p + w.first;
+        tp.slot_off = (const int64_t *)ctx->slot_off.p + w.first;
+        tp.slot_cap = (const int32_t *)ctx->slot_cap.p + w.first;
+        tp.slots = slots_w;
+        tp.counter = (int *)ctx->counters.p + 128 * wi + 64;
+        // one thread per pair when the wave fills the GPU that way, else one warp per pair
         // (window of speculatively rebuilt tiles, see ba_trace16w_kernel), a whole CTA per pair when
-        // even that leaves SMs idle; a mixed batch gives warps to its longest pairs (the head of
+        // even that leaves SMs idle; a mixed wave gives warps to its longest pairs (the head of
         // the size-sorted work list) as far as thread slots are free
         const bool cta_trace = ctx->opt_trace_mode == 3 ||
                                (ctx->opt_trace_mode == 1 && w.count <= 2 * (int64_t)ctx->sm_count);
         const bool warp_trace = ctx->opt_trace_mode == 2 ||
                                 (ctx->opt_trace_mode == 1 &&
                                  w.count * 32 <= (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS * 2);
+        // thread-per-pair CTAs: 64 threads beside a running fill (they fit the slot of one fill CTA)
+        const int tcta = ctx->opt_trace_cta == 64 || (ctx->opt_trace_cta == 0 && overlap && wi + 1 < nw) ? 64
+                                                                                                          : BA_TRACE_THREADS;
         if (cta_trace) {
-            BA_LAUNCH(pick_trace16t<BA_TRACE_THREADS>(kind, lin), (unsigned)w.count, BA_TRACE_THREADS, st, tp);
+            BA_LAUNCH(pick_trace16t<BA_TRACE_THREADS>(kind, lin), (unsigned)w.count, BA_TRACE_THREADS, T, tp);
             B.out->warp_trace_launches++;
         } else if (warp_trace) {
             const unsigned tb = (unsigned)((w.count + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-            BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, st, tp);
+            BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, T, tp);
             B.out->warp_trace_launches++;
         } else {
             const int64_t slots_free = (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS - w.count;
@@ -951,7 +1230,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 Trace16Params th = tp;
                 th.n_items = (int)head;
                 const unsigned tb = (unsigned)((head + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-                BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, st, th);
+                BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, T, th);
                 B.out->warp_trace_launches++;
                 B.launches++;
             }
@@ -962,146 +1241,169 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 tt.seg_count = tp.seg_count + head;
                 tt.slot_off = tp.slot_off + head;
                 tt.slot_cap = tp.slot_cap + head;
-                int64_t tblocks = (w.count - head + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS;
                 if (ctx->opt_trace_mode != 5) {
                     // static assignment: thread k of the grid walks pair k
-                    BA_LAUNCH(pick_trace16(kind, lin), (unsigned)tblocks, BA_TRACE_THREADS, st, tt);
+                    const int64_t tblocks = (w.count - head + tcta - 1) / tcta;
+                    BA_LAUNCH(pick_trace16(kind, lin, tcta), (unsigned)tblocks, tcta, T, tt);
                 } else {
                     // persistent grid, pairs claimed from a counter (largest first).  Measured on B200:
                     // +5 % on configs 1 and 3, -9 % on config 2 against the static kernel, so it is
                     // opt-in (trace_mode 5) until the state machine's overhead is trimmed
+                    int64_t tblocks = (w.count - head + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS;
                     tblocks = std::min<int64_t>(tblocks, (int64_t)ctx->sm_count * BA_TRACE_MINB);
-                    BA_LAUNCH(pick_trace16p(kind, lin), (unsigned)tblocks, BA_TRACE_THREADS, st, tt);
+                    BA_LAUNCH(pick_trace16p(kind, lin), (unsigned)tblocks, BA_TRACE_THREADS, T, tt);
                 }
             }
         }
         const unsigned cblocks = (unsigned)((w.count + 255) / 256);
-        BA_LAUNCH(ba_clip_counts_kernel, cblocks, 256, st, (const int32_t *)ctx->seg_count.p,
-                  (const int32_t *)ctx->slot_cap.p, (int32_t *)ctx->seg_clip.p, (int)w.count);
-        B.launches += 2;
+        long long *d_meta = (long long *)ctx->meta.p;
+        BA_LAUNCH(ba_clip_counts_kernel, cblocks, 256, T, (const int32_t *)ctx->seg_count.p + w.first,
+                  (const int32_t *)ctx->slot_cap.p + w.first, (const WorkItem *)d_items + w.first,
+                  (int32_t *)ctx->seg_clip.p + w.first, d_meta, (int32_t *)ctx->ovf.p, (int)w.count);
         {
             size_t tb = ctx->scan_tmp.cap;
-            if ((rc = exclusive_scan(ctx, ctx->scan_tmp.p, tb, (const int32_t *)ctx->seg_clip.p,
-                                     (int64_t *)ctx->seg_base.p, (int)w.count, st)) != BA_OK)
+            if ((rc = exclusive_scan(ctx, ctx->scan_tmp.p, tb, (const int32_t *)ctx->seg_clip.p + w.first,
+                                     (int64_t *)ctx->seg_base.p + w.first, (int)w.count, T)) != BA_OK)
                 return rc;
-            B.launches += 2;
         }
-        CK(cudaMemcpyAsync(h_cnt, ctx->seg_clip.p, sizeof(int32_t) * (size_t)w.count, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h_raw, ctx->seg_count.p, sizeof(int32_t) * (size_t)w.count, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h_base, ctx->seg_base.p, sizeof(int64_t) * (size_t)w.count, cudaMemcpyDeviceToHost,
-                           st));
-        BA_TSEC("P16 trace launched", tp0);
-        CK(cudaStreamSynchronize(st));
-        BA_TSEC("P16 counts synced", tp0);
-        for (WorkItem *t : long_tasks) pinned_put(ctx, t);
-        long_tasks.clear();
-        for (int k = 0; k < 16; k++)
-            if (h_long_err[k] != 0) {
-                ctx->err = "fill16 wavefront: a pass waited too long for its left neighbour";
-                return BA_ERR_CUDA;
-            }
-        const int64_t wsegs = h_base[w.count - 1] + h_cnt[w.count - 1];
-        if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
-        BA_LAUNCH(ba_compact_kernel, cblocks, 256, st, (const int32_t *)ctx->slots.p,
-                  (const int64_t *)ctx->slot_off.p, (const int32_t *)ctx->slot_cap.p,
-                  (const int32_t *)ctx->seg_count.p, (const int64_t *)ctx->seg_base.p, (int32_t *)ctx->segs.p,
-                  (int)w.count);
-        B.launches++;
+        BA_LAUNCH(ba_compact_kernel, cblocks, 256, T, (const int32_t *)slots_w, (const int64_t *)ctx->slot_off.p + w.first,
+                  (const int32_t *)ctx->slot_cap.p + w.first, (const int32_t *)ctx->seg_count.p + w.first,
+                  (const int64_t *)ctx->seg_base.p + w.first, (const WorkItem *)d_items + w.first,
+                  (const long long *)d_meta, (int32_t *)ctx->segs.p, (int64_t *)ctx->pair_seg_start.p,
+                  (int32_t *)ctx->pair_seg_count.p, (int)w.count);
+        BA_LAUNCH(ba_wave_total_kernel, 1, 32, T, (const int64_t *)ctx->seg_base.p + w.first,
+                  (const int32_t *)ctx->seg_clip.p + w.first, (int)w.count, d_meta, (int)wi);
+        B.launches += 6;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[6], st));
-        // last wave, nothing queued for the exact path and no pair overflowed its slots or failed the
-        // letter-class check: the kernel phase of this batch ends here
-        bool last_kernels = B.token && &w == &plan.waves.back() && !B.more_kernels_later && overflow.empty();
-        if (last_kernels)
-            for (int64_t k = 0; k < w.count && last_kernels; k++)
-                last_kernels = h_raw[k] >= 0 && h_raw[k] <= plan.slot_cap[w.first + k];
-        if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p, h_raw,
-                              &overflow, last_kernels)) != BA_OK)
-            return rc;
-        BA_TSEC("P16 wave gathered", tp0);
+        CK(cudaMemcpyAsync(h_meta + BA_META_HEAD + BA_META_WAVE * wi, d_meta + BA_META_HEAD + BA_META_WAVE * wi,
+                           sizeof(long long) * BA_META_WAVE, cudaMemcpyDeviceToHost, T));
+        ev_trace_end[(size_t)wi] = ev_new(ctx, true);
+        if (!ev_trace_end[(size_t)wi]) {
+            ctx->err = "cudaEventCreate failed";
+            return BA_ERR_CUDA;
+        }
+        CK(cudaEventRecord(ev_trace_end[(size_t)wi], T));
     }
-    pinned_put(ctx, h_long_err);
-    pinned_put(ctx, h_cnt);
-    pinned_put(ctx, h_raw);
-    pinned_put(ctx, h_base);
+    // every fill of this batch is enqueued: the next batch on this device may queue its fills behind them
+    if (ctx->opt_exclusive) {
+        if (!gate.last_fill) CK(cudaEventCreateWithFlags(&gate.last_fill, cudaEventDisableTiming));
+        if (two_streams && nw >= 2)   // the last fill on the second stream (largest odd wave)
+            CK(cudaStreamWaitEvent(st, ev_fill_end[(size_t)(((nw - 1) & 1) ? nw - 1 : nw - 2)], 0));
+        CK(cudaEventRecord(gate.last_fill, st));
+        gate.armed = true;
+        gate_lock.unlock();
+    }
+    BA_TSEC("P16 all waves enqueued", tp0);
+
+    // ---- follow the waves on the host: as soon as a wave is compacted its segments travel
+    for (int64_t wi = 0; wi < nw; wi++) {
+        CK(cudaEventSynchronize(ev_trace_end[(size_t)wi]));
+        const long long *rec = h_meta + BA_META_HEAD + BA_META_WAVE * wi;
+        const int64_t base = rec[0], wsegs = rec[1];
+        int64_t want = base + wsegs;
+        if (wi == 0 && nw > 1) {
+            // size the block for the whole batch from the first wave's segments per pair
+            const double per = (double)wsegs / (double)std::max<int64_t>(plan.waves[0].count, 1);
+            want = std::max<int64_t>(want, (int64_t)(per * 1.1 * (double)nids) + 4096);
+            want = std::min<int64_t>(want, total_slots);
+        }
+        if ((rc = segs_reserve(ctx, B, want, base)) != BA_OK) return rc;
+        if (!B.ev_d2h0) {
+            B.ev_d2h0 = ev_new(ctx, true);
+            if (B.ev_d2h0) CK(cudaEventRecord(B.ev_d2h0, ctx->s_d2h));
+        }
+        if (wsegs > 0)
+            CK(cudaMemcpyAsync(B.h_segs + 5 * base, (const int32_t *)ctx->segs.p + 5 * base,
+                               sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        B.seg_total = base + wsegs;
+    }
+    BA_TSEC("P16 waves done", tp0);
+    for (WorkItem *t : long_tasks) lease.drop(t);
+    // spans on the device (the kernels of different waves overlap)
+    {
+        float ms = 0.f, ms2 = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev_setup, ev_fill_end[(size_t)(nw - 1)]));
+        if (nw >= 2) CK(cudaEventElapsedTime(&ms2, ev_setup, ev_fill_end[(size_t)(nw - 2)]));
+        B.ms_fill += std::max(ms, ms2);
+        if (ev_trace_start) {
+            CK(cudaEventElapsedTime(&ms, ev_trace_start, ev_trace_end[(size_t)(nw - 1)]));
+            B.ms_trace += ms;
+        }
+    }
+    for (int64_t wi = 0; wi < nw; wi++)
+        if (h_long_err[wi] != 0) {
+            ctx->err = "fill16 wavefront: a pass waited too long for its left neighbour";
+            return BA_ERR_LONG_TIMEOUT;
+        }
+    // pairs for the exact path (slot overflow, letters outside the kernel's alphabet class)
+    const int64_t novf = h_meta[BA_META_HEAD + BA_META_WAVE * (nw - 1) + 2];
+    // per-pair results in pair order straight from the device
+    CK(cudaMemcpyAsync(B.out->seg_start, ctx->pair_seg_start.p, sizeof(int64_t) * (size_t)B.n, cudaMemcpyDeviceToHost,
+                       ctx->s_d2h));
+    CK(cudaMemcpyAsync(B.out->seg_count, ctx->pair_seg_count.p, sizeof(int32_t) * (size_t)B.n, cudaMemcpyDeviceToHost,
+                       ctx->s_d2h));
+    int32_t *h_ovf = nullptr;
+    if (novf > 0) {
+        h_ovf = (int32_t *)lease.get(sizeof(int32_t) * (size_t)novf);
+        if (!h_ovf) {
+            ctx->err = "pinned host allocation failed";
+            return BA_ERR_NOMEM;
+        }
+        CK(cudaMemcpyAsync(h_ovf, ctx->ovf.p, sizeof(int32_t) * (size_t)novf, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    if (novf > 0) {
+        std::sort(h_ovf, h_ovf + novf);
+        overflow.insert(overflow.end(), h_ovf, h_ovf + novf);
+        lease.drop(h_ovf);
+    }
+    lease.drop(h_meta);
+    lease.drop(h_long_err);
     if (!use_cache) {
-        pinned_put(ctx, plan.items);
-        pinned_put(ctx, plan.slot_off);
-        pinned_put(ctx, plan.slot_cap);
+        lease.drop(plan.items);
+        lease.drop(plan.slot_off);
+        lease.drop(plan.slot_cap);
     }
+    BA_TSEC("P16 done", tp0);
     return BA_OK;
 }
 
-int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int stride,
-               const int64_t *d_ref_off, const int32_t *d_ref_len, const int64_t *d_qry_off,
-               const int32_t *d_qry_len, const int32_t *h_ref_len, const int32_t *h_qry_len,
-               int64_t n, cudaStream_t st, ba_result *out, std::unique_lock<std::mutex> *token = nullptr)
+int run_device_once(ba_ctx *ctx, Batch &B, int64_t letters_bytes)
 {
     const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+    (void)kind;
+    (void)affine;
     const double t_call = now_s();
-
-    // ---- result arrays (pinned, pooled)
-    out->n = n;
-    out->status = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
-    out->err_pos = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
-    out->seg_start = (int64_t *)pinned_get(ctx, sizeof(int64_t) * (size_t)n);
-    out->seg_count = (int32_t *)pinned_get(ctx, sizeof(int32_t) * (size_t)n);
-    out->segs = nullptr;
-    out->n_segs = 0;
-    if (!out->status || !out->err_pos || !out->seg_start || !out->seg_count) {
-        ctx->err = "pinned host allocation failed";
-        return BA_ERR_NOMEM;
-    }
-    if (n == 0) return BA_OK;
-
-    CK(cudaEventRecord(ctx->ev[1], st));
-
-    Batch B;
-    B.stride = stride;
-    B.d_ref_off = d_ref_off;
-    B.d_qry_off = d_qry_off;
-    B.d_ref_len = d_ref_len;
-    B.d_qry_len = d_qry_len;
-    B.h_ref_len = h_ref_len;
-    B.h_qry_len = h_qry_len;
-    B.n = n;
-    B.st = st;
-    B.out = out;
-    B.token = token;
-
-    // ---- encode + validate
+    ba_result *out = B.out;
+    const int64_t n = B.n;
+    cudaStream_t st = B.st;
     int rc;
+    ctx->ev_timed_next = ctx->ev_plain_next = 0;
+    B.next_group = 0;
+    B.seg_total = 0;
+    B.waves = 0;
+    B.ev_d2h0 = nullptr;
+
     if ((rc = ensure(ctx, ctx->enc, (size_t)letters_bytes + 16)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->status, sizeof(int32_t) * (size_t)n)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->err_pos, sizeof(int64_t) * (size_t)n)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->start, sizeof(PairStart) * (size_t)n)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->flags, (size_t)n + 16)) != BA_OK) return rc;
-    uint8_t *d_enc = (uint8_t *)ctx->enc.p;
-    B.d_enc = d_enc;
+    if ((rc = ensure(ctx, ctx->pair_seg_start, sizeof(int64_t) * (size_t)n)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pair_seg_count, sizeof(int32_t) * (size_t)n)) != BA_OK) return rc;
+    B.d_enc = (uint8_t *)ctx->enc.p;
     B.d_status = (int32_t *)ctx->status.p;
     B.d_start = (PairStart *)ctx->start.p;
-    int64_t *d_err_pos = (int64_t *)ctx->err_pos.p;
+    B.d_err_pos = (int64_t *)ctx->err_pos.p;
     const Fast16 f16 = fast16_scoring(ctx->h_sc);
     const bool fast16 = ctx->opt_force_path != 1 && f16.ok;
-    if (letters_bytes > 0) {
-        int64_t blocks = (letters_bytes / 16 + 255) / 256;
-        if (blocks < 1) blocks = 1;
-        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-        BA_LAUNCH(ba_encode_kernel, (unsigned)blocks, 256, st, d_letters, d_enc, letters_bytes, ctx->d_sc);
-        B.launches++;
-    }
-    {
-        int64_t blocks = (n + 7) / 8;
-        if (blocks > ctx->sm_count * 32) blocks = ctx->sm_count * 32;
-        BA_LAUNCH(ba_validate_kernel, (unsigned)blocks, 256, st, d_enc, stride, d_ref_off, d_ref_len, d_qry_off,
-                  d_qry_len, n, kind, affine, B.d_status, d_err_pos, fast16 ? (uint8_t *)ctx->flags.p : nullptr);
-        B.launches++;
-    }
-    CK(cudaGetLastError());
-    BA_TSEC("T result+enc launch", t_call);
+    B.d_flags = fast16 ? (uint8_t *)ctx->flags.p : nullptr;
+    CK(cudaEventRecord(ctx->ev[1], st));
 
     // ---- split the batch between the two paths (cached for batches of the same shape)
     std::vector<int32_t> slow;
+    const int32_t *h_ref_len = B.h_ref_len, *h_qry_len = B.h_qry_len;
+    bool host_arrays_final = false;   // out->seg_start / seg_count already hold the device's pair-order results
     if (fast16) {
         // size eligibility is known on the host; letter eligibility (ACGT only) is decided on the
         // device: ineligible pairs come back from the traceback marked for the exact path
@@ -1132,10 +1434,12 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         BA_TSEC("partition", ts0);
         B.host_s += now_s() - ts0;
         const size_t nslow0 = slow.size();
-        B.more_kernels_later = nslow0 > 0;
-        if ((rc = run_path16(ctx, B, pc.fast.data(), (int64_t)pc.fast.size(), f16.gsub, slow,
-                             ctx->opt_plan_cache != 0)) != BA_OK)
-            return rc;
+        if (!pc.fast.empty()) {
+            if ((rc = run_path16(ctx, B, pc.fast.data(), (int64_t)pc.fast.size(), f16.gsub, slow,
+                                 ctx->opt_plan_cache != 0, pc.cells)) != BA_OK)
+                return rc;
+            host_arrays_final = true;
+        }
         out->pairs_fast16 = (int64_t)pc.fast.size() - (int64_t)(slow.size() - nslow0);
         if ((rc = run_path32(ctx, B, slow.data(), (int64_t)slow.size())) != BA_OK) return rc;
     } else {
@@ -1144,50 +1448,116 @@ int run_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters_bytes, int
         out->cells = cells;
         if ((rc = run_path32(ctx, B, nullptr, n)) != BA_OK) return rc;
     }
+    (void)host_arrays_final;
+    if ((rc = prep_pairs(ctx, B, n - 1)) != BA_OK) return rc;   // groups no wave asked for (nothing to align)
 
     BA_TSEC("T paths done", t_call);
-    // ---- gather
-    CK(cudaEventRecord(ctx->ev[2], st));
+    // ---- per-pair status (the traceback may have changed it) and error positions
+    if (!B.ev_d2h0) {
+        B.ev_d2h0 = ev_new(ctx, true);
+        if (B.ev_d2h0) CK(cudaEventRecord(B.ev_d2h0, st));
+    }
     CK(cudaMemcpyAsync(out->status, B.d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->err_pos, d_err_pos, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->err_pos, B.d_err_pos, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[3], st));
     CK(cudaStreamSynchronize(st));
     {
         float ms = 0.f, all = 0.f;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-        B.ms_d2h += ms;
+        if (B.ev_d2h0) CK(cudaEventElapsedTime(&ms, B.ev_d2h0, ctx->ev[3]));
         CK(cudaEventElapsedTime(&all, ctx->ev[1], ctx->ev[3]));
-        out->ms_d2h = B.ms_d2h;
-        out->ms_kernels = all - B.ms_d2h;
-    }
-    if (B.wave_out.size() == 1) {
-        out->segs = B.wave_out[0].segs;
-    } else {
-        out->segs = (int32_t *)pinned_get(ctx, sizeof(int32_t) * 5 * (size_t)(B.seg_total + 1));
-        if (!out->segs) {
-            ctx->err = "pinned host allocation failed";
-            return BA_ERR_NOMEM;
-        }
-        int64_t o = 0;
-        for (auto &wo : B.wave_out) {
-            memcpy(out->segs + 5 * o, wo.segs, sizeof(int32_t) * 5 * (size_t)wo.nsegs);
-            o += wo.nsegs;
-            pinned_put(ctx, wo.segs);
-        }
+        out->ms_d2h = ms;          // span from the first result copy to the last (overlaps the kernels of later waves)
+        out->ms_kernels = all;     // whole device span of the call
     }
     for (int64_t p = 0; p < n; p++)
         if (out->status[p] != 0) {
             out->seg_start[p] = 0;
             out->seg_count[p] = 0;
         }
+    out->segs = B.h_segs;
+    if (B.h_segs) B.lease->keep(B.h_segs);
+    B.h_segs = nullptr;
     out->n_segs = B.seg_total;
     out->gpu_launches = B.launches;
     out->fill_launches = B.fill_launches;
     out->code_bytes = B.code_bytes;
+    out->waves = B.waves;
     out->ms_fill = B.ms_fill;
     out->ms_trace = B.ms_trace;
     out->ms_host = (float)(B.host_s * 1e3);
     BA_TSEC("T call total", t_call);
+    return BA_OK;
+}
+
+// Drain every stream of the context (error paths: nothing may still be writing into pooled memory).
+void drain(ba_ctx *ctx, cudaStream_t extra)
+{
+    cudaStream_t all[] = {ctx->stream, ctx->s_fill2, ctx->s_trace, ctx->s_h2d, ctx->s_d2h, extra};
+    for (cudaStream_t s : all)
+        if (s) cudaStreamSynchronize(s);
+    (void)cudaGetLastError();
+}
+
+int run_device(ba_ctx *ctx, Batch &B, int64_t letters_bytes)
+{
+    ba_result *out = B.out;
+    const int64_t n = B.n;
+    Lease lease(ctx);
+    B.lease = &lease;
+    // ---- result arrays (pinned, pooled)
+    out->n = n;
+    out->status = (int32_t *)lease.get(sizeof(int32_t) * (size_t)n);
+    out->err_pos = (int64_t *)lease.get(sizeof(int64_t) * (size_t)n);
+    out->seg_start = (int64_t *)lease.get(sizeof(int64_t) * (size_t)n);
+    out->seg_count = (int32_t *)lease.get(sizeof(int32_t) * (size_t)n);
+    out->segs = nullptr;
+    out->n_segs = 0;
+    if (!out->status || !out->err_pos || !out->seg_start || !out->seg_count) {
+        out->status = nullptr;
+        out->err_pos = nullptr;
+        out->seg_start = nullptr;
+        out->seg_count = nullptr;
+        ctx->err = "pinned host allocation failed";
+        return BA_ERR_NOMEM;
+    }
+    int rc = BA_OK;
+    if (n > 0) {
+        memset(out->seg_start, 0, sizeof(int64_t) * (size_t)n);
+        memset(out->seg_count, 0, sizeof(int32_t) * (size_t)n);
+        rc = run_device_once(ctx, B, letters_bytes);
+        if (rc == BA_ERR_LONG_TIMEOUT) {
+            // a wavefront pass gave up waiting (never observed; the spin is bounded so that a scheduling
+            // anomaly cannot hang the GPU): run the batch again with the pass-by-pass kernels
+            drain(ctx, B.st);
+            const int64_t keep = ctx->opt_long_mode;
+            ctx->opt_long_mode = 0;
+            plan_cache_drop(ctx);
+            const int64_t wl = out->wavefront_launches;
+            B.launches = B.fill_launches = B.code_bytes = 0;
+            B.ms_fill = B.ms_trace = 0.f;
+            if (B.h_segs) lease.drop(B.h_segs);
+            B.h_segs = nullptr;
+            B.h_segs_cap = 0;
+            rc = run_device_once(ctx, B, letters_bytes);
+            out->wavefront_launches = wl;
+            ctx->opt_long_mode = keep;
+            plan_cache_drop(ctx);
+            if (rc == BA_ERR_LONG_TIMEOUT) rc = BA_ERR_CUDA;
+        }
+    }
+    if (rc != BA_OK) {
+        drain(ctx, B.st);
+        plan_cache_drop(ctx);   // its device copy / waves may be half-built
+        out->status = nullptr;
+        out->err_pos = nullptr;
+        out->seg_start = nullptr;
+        out->seg_count = nullptr;
+        out->segs = nullptr;
+        return rc;              // the lease returns every pinned block
+    }
+    lease.keep(out->status);
+    lease.keep(out->err_pos);
+    lease.keep(out->seg_start);
+    lease.keep(out->seg_count);
     return BA_OK;
 }
 
@@ -1228,7 +1598,18 @@ int ba_create(int device, ba_ctx **out)
         return BA_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e != cudaSuccess) return fail(e, "cudaDeviceGetStreamPriorityRange");
+    e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo);
+    if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
+    e = cudaStreamCreateWithPriority(&ctx->s_fill2, cudaStreamNonBlocking, prio_lo);
+    if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
+    e = cudaStreamCreateWithPriority(&ctx->s_trace, cudaStreamNonBlocking, prio_hi);  // CTAs of the traceback go first
+    if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
+    e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
+    e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
     if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
     for (int k = 0; k < 8; k++) {
         e = cudaEventCreate(&ctx->ev[k]);
@@ -1244,19 +1625,28 @@ void ba_destroy(ba_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStream_t streams[] = {ctx->stream, ctx->s_fill2, ctx->s_trace, ctx->s_h2d, ctx->s_d2h};
+    for (cudaStream_t s : streams)
+        if (s) cudaStreamSynchronize(s);
+    plan_cache_drop(ctx);
     DevBuf *bufs[] = {&ctx->letters, &ctx->enc,  &ctx->ref_off,   &ctx->ref_len,  &ctx->qry_off, &ctx->qry_len,
                       &ctx->status,  &ctx->err_pos, &ctx->start,  &ctx->items,    &ctx->aux_off, &ctx->aux,
                       &ctx->bnd,     &ctx->seg_count, &ctx->seg_base, &ctx->segs, &ctx->arena,   &ctx->scan_tmp,
                       &ctx->counters, &ctx->flags,  &ctx->slot_off,  &ctx->slot_cap, &ctx->slots, &ctx->seg_clip,
                       &ctx->tasks,   &ctx->prog,     &ctx->fmt_len, &ctx->fmt_off, &ctx->fmt_rows,
-                      &ctx->fmt_segs, &ctx->fmt_seg_start, &ctx->fmt_seg_count};
+                      &ctx->fmt_segs, &ctx->fmt_seg_start, &ctx->fmt_seg_count, &ctx->pair_seg_start,
+                      &ctx->pair_seg_count, &ctx->meta, &ctx->ovf};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
     if (ctx->d_sc) cudaFree(ctx->d_sc);
     for (int k = 0; k < 8; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (cudaEvent_t e : ctx->ev_timed) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_plain) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_upload) cudaEventDestroy(e);
+    for (cudaStream_t s : streams)
+        if (s) cudaStreamDestroy(s);
     delete ctx;
 }
 
@@ -1297,6 +1687,35 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     }
     if (!strcmp(key, "force_path")) {
         ctx->opt_force_path = value;
+        return BA_OK;
+    }
+    // overlap scheduling of the 16-bit path (run_path16)
+    if (!strcmp(key, "waves")) {           // waves per batch: 0 = automatic, 1 = no overlap, k = about k waves
+        ctx->opt_waves = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "fill_streams")) {    // 1: all fills on one stream; 2 (default): alternate two
+        ctx->opt_fill_streams = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "fill_claims")) {     // claims per fill warp before its CTA retires; 0 = persistent grid
+        ctx->opt_fill_claims = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "fill_cap")) {        // resident fill CTAs per SM while waves overlap; 0 = all that fit
+        ctx->opt_fill_cap = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "trace_cta")) {       // threads per thread-per-pair traceback CTA: 0 automatic, 64, 128
+        ctx->opt_trace_cta = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "upload_groups")) {   // pieces the letters upload is cut into: 0 automatic, 1 = one piece
+        ctx->opt_upload_groups = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "pinned_budget")) {   // bytes of idle pinned host memory a context keeps for reuse
+        ctx->pinned_budget = value;
         return BA_OK;
     }
     ctx->err = std::string("unknown option: ") + key;
@@ -1396,18 +1815,28 @@ int ba_align_batch_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters
     int rc = check_range(ctx, h_ref_len, h_qry_len, n);
     if (rc != BA_OK) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    CK(cudaEventRecord(ctx->ev[0], st));
     ctx->last_n = -1;  // the context's own letters buffer no longer mirrors the last batch (ba_format_batch)
-    {
-        // same kernel-phase token as ba_align_batch: with several contexts the result copies and
-        // the host gather of one batch run under the kernels of the next
-        std::unique_lock<std::mutex> token(g_compute_token[ctx->device & 63], std::defer_lock);
-        if (ctx->opt_exclusive) token.lock();
-        rc = run_device(ctx, d_letters, letters_bytes, stride, d_ref_off, d_ref_len, d_qry_off, d_qry_len,
-                        h_ref_len, h_qry_len, n, st, out, ctx->opt_exclusive ? &token : nullptr);
-    }
+    Batch B;
+    B.d_letters = d_letters;
+    B.stride = stride;
+    B.d_ref_off = d_ref_off;
+    B.d_qry_off = d_qry_off;
+    B.d_ref_len = d_ref_len;
+    B.d_qry_len = d_qry_len;
+    B.h_ref_len = h_ref_len;
+    B.h_qry_len = h_qry_len;
+    B.n = n;
+    B.st = st;
+    B.out = out;
+    UploadGroup g;   // everything is resident already
+    g.p_lo = 0;
+    g.p_hi = n;
+    g.b_lo = 0;
+    g.b_hi = letters_bytes;
+    B.groups.push_back(g);
+    rc = run_device(ctx, B, letters_bytes);
     out->ms_h2d = 0.f;
-    if (rc != BA_OK) ba_free_result(ctx, out);
+    if (rc != BA_OK) memset(out, 0, sizeof *out);
     return rc;
 }
 
@@ -1426,6 +1855,9 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
     CK(cudaSetDevice(ctx->device));
     int rc = check_range(ctx, ref_len, qry_len, n);
     if (rc != BA_OK) return rc;
+    // ---- upload groups: pairs [p_lo, p_hi) need only letters below b_hi (a running maximum of the
+    // sequence ends, so any layout is legal; batches packed in pair order split evenly).  The first
+    // waves start on the first groups while the rest of the letters are still on their way.
     int64_t letters_bytes = 0;
     for (int64_t p = 0; p < n; p++) {
         if (ref_off[p] < 0 || qry_off[p] < 0) {
@@ -1438,21 +1870,47 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
         if (e2 > letters_bytes) letters_bytes = e2;
     }
     if (letters_bytes > 0 && !letters) return BA_ERR_ARG;
-    cudaStream_t st = ctx->stream;
+    Batch B;
+    {
+        int64_t ng = ctx->opt_upload_groups;
+        if (ng <= 0) ng = std::min<int64_t>(16, letters_bytes / (8 << 20));  // pieces of >= 8 MB
+        if (ng < 1) ng = 1;
+        const int64_t piece = (letters_bytes + ng - 1) / ng;
+        int64_t hi = 0, p_lo = 0, b_lo = 0;
+        for (int64_t p = 0; p < n; p++) {
+            int64_t e1 = ref_len[p] ? ref_off[p] + ((int64_t)ref_len[p] - 1) * stride + 1 : 0;
+            int64_t e2 = qry_len[p] ? qry_off[p] + ((int64_t)qry_len[p] - 1) * stride + 1 : 0;
+            hi = std::max(hi, std::max(e1, e2));
+            const bool last = (p + 1 == n);
+            if (last || hi - b_lo >= piece) {
+                UploadGroup g;
+                g.p_lo = p_lo;
+                g.p_hi = p + 1;
+                g.b_lo = b_lo;
+                // groups meet on 16-byte boundaries (vectorised encode); the last one ends the buffer
+                g.b_hi = last ? letters_bytes : std::min(letters_bytes, (hi + 15) & ~(int64_t)15);
+                B.groups.push_back(g);
+                p_lo = p + 1;
+                b_lo = g.b_hi;
+            }
+        }
+    }
+    cudaStream_t st = ctx->stream, up = ctx->s_h2d;
     ctx->last_n = -1;
     if ((rc = ensure(ctx, ctx->letters, (size_t)letters_bytes + 16)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->ref_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->qry_off, sizeof(int64_t) * (size_t)(n + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->ref_len, sizeof(int32_t) * (size_t)(n + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->qry_len, sizeof(int32_t) * (size_t)(n + 1))) != BA_OK) return rc;
-    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaEventRecord(ctx->ev[0], up));
     // The offset/length arrays are the caller's pageable memory: a copy straight from them would
     // block inside the driver behind the letters copy.  Stage them in pinned memory and send them
     // first; the letters buffer may be pinned (ba_alloc_host) or not.
-    uint8_t *stage = nullptr;
+    Lease stage_lease(ctx);
+    ctx->ev_timed_next = ctx->ev_plain_next = 0;
     if (n > 0) {
         const size_t b8 = sizeof(int64_t) * (size_t)n, b4 = sizeof(int32_t) * (size_t)n;
-        stage = (uint8_t *)pinned_get(ctx, 2 * b8 + 2 * b4);
+        uint8_t *stage = (uint8_t *)stage_lease.get(2 * b8 + 2 * b4);
         if (!stage) {
             ctx->err = "pinned host allocation failed";
             return BA_ERR_NOMEM;
@@ -1461,40 +1919,55 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
         memcpy(stage + b8, qry_off, b8);
         memcpy(stage + 2 * b8, ref_len, b4);
         memcpy(stage + 2 * b8 + b4, qry_len, b4);
-        CK(cudaMemcpyAsync(ctx->ref_off.p, stage, b8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->qry_off.p, stage + b8, b8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->ref_len.p, stage + 2 * b8, b4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->qry_len.p, stage + 2 * b8 + b4, b4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ref_off.p, stage, b8, cudaMemcpyHostToDevice, up));
+        CK(cudaMemcpyAsync(ctx->qry_off.p, stage + b8, b8, cudaMemcpyHostToDevice, up));
+        CK(cudaMemcpyAsync(ctx->ref_len.p, stage + 2 * b8, b4, cudaMemcpyHostToDevice, up));
+        CK(cudaMemcpyAsync(ctx->qry_len.p, stage + 2 * b8 + b4, b4, cudaMemcpyHostToDevice, up));
     }
-    // in pieces: the small H2D copies of another context's kernel phase (work lists) share the copy
-    // engine and must not queue behind one 100+ MB transfer
-    for (int64_t o = 0; o < letters_bytes; o += (4 << 20)) {
-        const size_t len = (size_t)std::min<int64_t>(4 << 20, letters_bytes - o);
-        CK(cudaMemcpyAsync((uint8_t *)ctx->letters.p + o, letters + o, len, cudaMemcpyHostToDevice, st));
-    }
-    {
-        std::unique_lock<std::mutex> token(g_compute_token[ctx->device & 63], std::defer_lock);
-        if (ctx->opt_exclusive) {
-            // inputs on the device first, then wait for the GPU's kernel phase to be free
-            CK(cudaEventRecord(ctx->ev[7], st));
-            CK(cudaEventSynchronize(ctx->ev[7]));
-            token.lock();
+    // the letters, group by group, each in pieces of 4 MB (small copies of other contexts -- work lists,
+    // per-wave records -- share the copy engines and must not queue behind one 100+ MB transfer)
+    std::vector<cudaEvent_t> ready(B.groups.size(), nullptr);
+    for (size_t gi = 0; gi < B.groups.size(); gi++) {
+        const UploadGroup &g = B.groups[gi];
+        for (int64_t o = g.b_lo; o < g.b_hi; o += (4 << 20)) {
+            const size_t len = (size_t)std::min<int64_t>(4 << 20, g.b_hi - o);
+            CK(cudaMemcpyAsync((uint8_t *)ctx->letters.p + o, letters + o, len, cudaMemcpyHostToDevice, up));
         }
-        rc = run_device(ctx, (const uint8_t *)ctx->letters.p, letters_bytes, stride, (const int64_t *)ctx->ref_off.p,
-                        (const int32_t *)ctx->ref_len.p, (const int64_t *)ctx->qry_off.p,
-                        (const int32_t *)ctx->qry_len.p, ref_len, qry_len, n, st, out,
-                        ctx->opt_exclusive ? &token : nullptr);
+        // pooled events: run_device resets the pool cursor, so these come from a pool of their own
+        cudaEvent_t e = nullptr;
+        if (gi < ctx->ev_upload.size())
+            e = ctx->ev_upload[gi];
+        else {
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->ev_upload.push_back(e);
+        }
+        CK(cudaEventRecord(e, up));
+        ready[gi] = e;
     }
-    if (rc != BA_OK) cudaStreamSynchronize(st);  // the staged copies may still be in flight
-    if (stage) pinned_put(ctx, stage);           // on success run_device returned with the stream drained
+    CK(cudaEventRecord(ctx->ev[7], up));
+    for (size_t gi = 0; gi < B.groups.size(); gi++) B.groups[gi].ready = ready[gi];
+    B.d_letters = (const uint8_t *)ctx->letters.p;
+    B.stride = stride;
+    B.d_ref_off = (const int64_t *)ctx->ref_off.p;
+    B.d_qry_off = (const int64_t *)ctx->qry_off.p;
+    B.d_ref_len = (const int32_t *)ctx->ref_len.p;
+    B.d_qry_len = (const int32_t *)ctx->qry_len.p;
+    B.h_ref_len = ref_len;
+    B.h_qry_len = qry_len;
+    B.n = n;
+    B.st = st;
+    B.out = out;
+    rc = run_device(ctx, B, letters_bytes);
     if (rc != BA_OK) {
-        ba_free_result(ctx, out);
+        drain(ctx, nullptr);   // the staged copies may still be in flight
+        memset(out, 0, sizeof *out);
         return rc;
     }
+    CK(cudaStreamSynchronize(up));  // (already drained: every group was waited for)
     if (n > 0) {
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-        out->ms_h2d = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[7]));
+        out->ms_h2d = ms;   // span of the upload stream; it runs beside the kernels of the first waves
     }
     ctx->last_n = n;
     ctx->last_stride = stride;

@@ -60,6 +60,10 @@ struct Fill16Params {
     // reader needs neither flags nor fences (bnd is zeroed before the launch)
     int long_couples;
     int *long_err;           // set when a wait timed out (never expected)
+    // 0: persistent CTAs (loop until the work counter runs out).  k > 0: a warp takes at most k
+    // claims and exits, so that the grid is larger than what is resident and CTAs of other,
+    // higher-priority kernels (the traceback of the previous wave) get SM slots as these retire.
+    int max_claims;
     const DeviceScoring *sc;
 };
 
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     constexpr int W = 32 * COLS;
     const unsigned FULL = 0xffffffffu;
 
-    for (;;) {
+    for (int claim = 0; P.max_claims == 0 || claim < P.max_claims; claim++) {
         // each warp takes four consecutive items: two (pairs A and B) per 16-lane group
         int it0 = 0;
         if (lane == 0) it0 = atomicAdd(P.counter, 4);

@@ -25,6 +25,7 @@ struct Plan {
         int64_t code_bytes, aux_ints, slots;
         std::vector<Launch> launches;
         int max_n_multipass;            // largest n among pairs needing >1 pass (0 = none)
+        int32_t max_pair;               // largest pair id of the wave (which upload groups it needs)
     };
     std::vector<Wave> waves;
 };
@@ -53,10 +54,13 @@ inline int32_t slot_cap_for(int n, int m, int affine)
 // owns (the template instance they need), largest-first inside a group so the dynamic work
 // counter balances the tail, then cut into waves whose traceback data fits the arena.
 // mode16: checkpoint bytes of ba_fill16 instead of the code bytes of ba_fill32.
+// target_waves > 1 (16-bit path): additionally cut the batch into about that many waves of equal
+// traceback bytes, so that the traceback of wave w overlaps the fill of wave w+1 (ba_api.cu).
 inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len, const int32_t *qry_len, int kind,
-                       int affine, bool mode16, int64_t arena_cap, Plan &plan)
+                       int affine, bool mode16, int64_t arena_cap, Plan &plan, int target_waves = 1)
 {
     const bool need_aux = (kind == KIND_FIT) && !mode16;
+    if (target_waves < 1) target_waves = 1;
     // fast path: every pair has the same shape (the common batch): closed-form plan
     if (nids > 0) {
         const int32_t p0 = ids ? ids[0] : 0;
@@ -72,6 +76,12 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             cb = (cb + 255) & ~(int64_t)255;
             const int32_t cap = slot_cap_for(n0, m0, affine);
             int64_t per_wave = cb > 0 ? arena_cap / cb : nids;
+            if (target_waves > 1) {
+                // equal waves, whole warp claims (4 items) each
+                int64_t even = (nids + target_waves - 1) / target_waves;
+                even = (even + 7) & ~(int64_t)7;
+                if (even < per_wave) per_wave = even;
+            }
             if (per_wave < 1) per_wave = 1;
             if (per_wave > nids) per_wave = nids;
             for (int64_t first = 0; first < nids; first += per_wave) {
@@ -83,6 +93,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
                 w.aux_ints = need_aux ? count * ((int64_t)n0 + 1) : 0;
                 w.slots = mode16 ? count * (int64_t)cap : 0;
                 w.max_n_multipass = (m0 > 32 * c) ? n0 : 0;
+                w.max_pair = 0;
                 Plan::Launch L;
                 L.cols = c;
                 L.first = first;
@@ -94,6 +105,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
                     it.cols = c;
                     it.code_off = k * cb;
                     plan.items[first + k] = it;
+                    if (it.pair > w.max_pair) w.max_pair = it.pair;
                 }
                 if (need_aux)
                     for (int64_t k = 0; k < count; k++) plan.aux_off[first + k] = k * ((int64_t)n0 + 1);
@@ -116,10 +128,22 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         uniform[c] = true;
     }
     std::vector<uint8_t> cls((size_t)nids);
+    int64_t total_cb = 0;
+    int tmemo_n = -1, tmemo_m = -1;
+    int64_t tmemo_cb = 0;
     for (int64_t x = 0; x < nids; x++) {
         const int32_t p = ids ? ids[x] : (int32_t)x;
         const int c = cols_for(qry_len[p]);
         cls[(size_t)x] = (uint8_t)c;
+        if (target_waves > 1) {
+            if (ref_len[p] != tmemo_n || qry_len[p] != tmemo_m) {
+                tmemo_n = ref_len[p];
+                tmemo_m = qry_len[p];
+                tmemo_cb = mode16 ? ba16_ck_bytes(c, tmemo_n, tmemo_m, !affine) : ba_code_bytes(affine, c, tmemo_n, tmemo_m);
+                tmemo_cb = (tmemo_cb + 255) & ~(int64_t)255;
+            }
+            total_cb += tmemo_cb;
+        }
         const int64_t cells = (int64_t)ref_len[p] * (int64_t)qry_len[p];
         if (first_cells[c] < 0)
             first_cells[c] = cells;
@@ -143,6 +167,9 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             order[(size_t)fill[cls[(size_t)x]]++] = p;
         }
     }
+    // soft cap for the overlap waves (cuts fall on whole warp claims of four items)
+    int64_t soft_cap = arena_cap;
+    if (target_waves > 1) soft_cap = std::min(arena_cap, total_cb / target_waves + 1);
     Plan::Wave wave;
     wave.first = 0;
     wave.count = 0;
@@ -150,6 +177,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
     wave.aux_ints = 0;
     wave.slots = 0;
     wave.max_n_multipass = 0;
+    wave.max_pair = 0;
     auto flush = [&]() {
         if (wave.count > 0) plan.waves.push_back(wave);
         wave.first += wave.count;
@@ -158,6 +186,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         wave.aux_ints = 0;
         wave.slots = 0;
         wave.max_n_multipass = 0;
+        wave.max_pair = 0;
         wave.launches.clear();
     };
     int64_t w = 0;  // next item slot
@@ -186,7 +215,8 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
                 memo_cap = slot_cap_for(memo_n, memo_m, affine);
             }
             const int64_t cb = memo_cb;
-            if (wave.count > 0 && wave.code_bytes + cb > arena_cap) {
+            if (wave.count > 0 && (wave.code_bytes + cb > arena_cap ||
+                                   (wave.code_bytes + cb > soft_cap && (L.count & 3) == 0))) {
                 if (L.count > 0) wave.launches.push_back(L);
                 flush();
                 L.first = wave.first;
@@ -197,6 +227,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             it.cols = c;
             it.code_off = wave.code_bytes;
             plan.items[w] = it;
+            if (p > wave.max_pair) wave.max_pair = p;
             if (need_aux) {
                 plan.aux_off[w] = wave.aux_ints;
                 wave.aux_ints += (int64_t)ref_len[p] + 1;

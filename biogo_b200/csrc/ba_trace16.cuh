@@ -133,7 +133,7 @@ __device__ __forceinline__ Cell3 border_col0(int i, int go, int er)
 // Recompute the tile of strip g, period e, for rows rt+1 .. imax and columns up to jmax, and
 // store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).
 // S is the scoring matrix scaled by BA_SCALE in shared memory (row stride `let`).
-template <int KIND>
+template <int KIND, int TS>
 __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                              uint8_t *tile, TileProbe &pb)
@@ -229,7 +229,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     // latency hides under the current row's cells
     int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0, nM = 0, nL = 0;
     if (cL > 0 && rt + 1 <= imax) ck.col_ml(gl, rt + 1, nM, nL);
-    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * BA_TRACE_THREADS) {
+    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * TS) {
         const int *Srow = S + nR * let;
         const int mm = nM, ll = nL;
         if (r + 1 <= imax) {
@@ -257,7 +257,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
                 int dm;
                 const Cell3 old = Pv[k];
                 const Cell3 nw = affine_cell<KIND>(d, old, l, Srow[qo[k]], er, goer, eqv[k], go + eqv[k], code, dm);
-                trow[k * BA_TRACE_THREADS] = (uint8_t)code;
+                trow[k * TS] = (uint8_t)code;
                 const int col = c0 + k + 1;
                 if (KIND == KIND_SW && pb.want >= 0 && nw.M == pb.want) {
                     pb.fi = r;
@@ -283,7 +283,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
 
 // Linear-gap tile (ba_fill16 LIN): one table T; the checkpoints hold it in their M field.  Codes
 // are linear_cell<KIND>'s: 3 diag, 2 up, 1 left, 0 = SW cell clamped to zero (stop).
-template <int KIND>
+template <int KIND, int TS>
 __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S, int let, const uint8_t *rs,
                                                  const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                                  uint8_t *tile, TileProbe &pb)
@@ -331,7 +331,7 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
     // next row's letter and left boundary value, fetched one row ahead
     int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0;
     int nLeft = (rt + 1 <= imax) ? left_at(rt + 1) : 0;
-    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * BA_TRACE_THREADS) {
+    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * TS) {
         const int *Srow = S + nR * let;
         const int left = nLeft;
         if (r + 1 <= imax) {
@@ -346,7 +346,7 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
                 unsigned code;
                 const int old = Tv[k];
                 const int nw = linear_cell<KIND>(d, old, l, Srow[qo[k]], er, eqv[k], code);
-                trow[k * BA_TRACE_THREADS] = (uint8_t)code;
+                trow[k * TS] = (uint8_t)code;
                 const int col = c0 + k + 1;
                 if (KIND == KIND_SW && pb.want >= 0 && nw == pb.want) {
                     pb.fi = r;
@@ -367,15 +367,15 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
     }
 }
 
-template <int KIND, bool LIN>
+template <int KIND, bool LIN, int TS = BA_TRACE_THREADS>
 __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                              uint8_t *tile, TileProbe &pb)
 {
     if (LIN)
-        trace16_tile_lin<KIND>(ck, S, let, rs, qs, stride, g, e, imax, jmax, tile, pb);
+        trace16_tile_lin<KIND, TS>(ck, S, let, rs, qs, stride, g, e, imax, jmax, tile, pb);
     else
-        trace16_tile_aff<KIND>(ck, S, let, go, rs, qs, stride, g, e, imax, jmax, tile, pb);
+        trace16_tile_aff<KIND, TS>(ck, S, let, go, rs, qs, stride, g, e, imax, jmax, tile, pb);
 }
 
 // One step of the walk: decode the cell's code for the current layer into (move, next layer,
@@ -409,10 +409,13 @@ __device__ __forceinline__ bool trace16_decode(unsigned code, int layer, int er,
 }
 
 // (linear tiles are cheap, the walk is bound by checkpoint-load latency: more resident CTAs)
-template <int KIND, bool LIN>
-__global__ void __launch_bounds__(BA_TRACE_THREADS, LIN ? 6 : BA_TRACE_MINB) ba_trace16_kernel(Trace16Params P)
+// TS = threads per CTA: 128, or 64 -- a CTA that fits into the SM slot one ba_fill16 CTA frees
+// (registers and shared memory), so a traceback running on a high-priority stream beside the next
+// wave's fill is scheduled as fill CTAs retire.
+template <int KIND, bool LIN, int TS = BA_TRACE_THREADS>
+__global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THREADS / TS)) ba_trace16_kernel(Trace16Params P)
 {
-    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * TS];
     __shared__ int S[BA_MAX_LET * BA_MAX_LET];
     {
         const int ll = P.sc->let;
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, LIN ? 6 : BA_TRACE_MINB) ba_
                     if (rlast < i || (rlast == i && clast < j)) continue;  // cannot come later
                     TileProbe pb;
                     pb.want = Smax * BA_SCALE;
-                    trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
                     if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
                         i = pb.fi;
                         j = pb.fj;
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, LIN ? 6 : BA_TRACE_MINB) ba_
         TileProbe pb;
         pb.ci = i;
         pb.cj = j;
-        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+        trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
                            tile, pb);
         int best = pb.cM;
         if (pb.cU > best) {
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, LIN ? 6 : BA_TRACE_MINB) ba_
         for (int e = 0; BA16_PERIOD * e - v < n; e++) {
             const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
             if (rlast < 1) continue;
-            trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+            trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         i = pb.besti;
     }
@@ -547,12 +550,12 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, LIN ? 6 : BA_TRACE_MINB) ba_
         const int rt = max(BA16_PERIOD * e - v, 0);
         const int c0 = max(ck.left_col(g), 0);
         TileProbe pb0;
-        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
+        trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
         const int cbase = ck.left_col(g);
         while (i > rt && j > c0) {
             if (KIND == KIND_SW && cur == 0) break;
             const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
-            const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
+            const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * TS];
             const bool corner = (i == n && j == m);
             const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
             int move, nl = 0, delta;
@@ -1154,17 +1157,54 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     }
 }
 
-// Reverse the emission-order slots of every item into its final, compact place.
+// ---- per-wave finish: clip + overflow list, scan (cub), compact + pair-order scatter, totals ----
+// Device-side bookkeeping of one batch: `total` = segments compacted so far (the next wave's base),
+// `n_overflow` = pairs handed to the exact path, then three int64 per wave {base, segments, overflow so far}
+// that travel to the host after every wave.
+struct WaveMeta {
+    long long total;
+    long long n_overflow;
+};
+#define BA_META_HEAD 2   // int64 words before the per-wave records
+#define BA_META_WAVE 3   // int64 words per wave
+
+// seg_count clipped to what actually gets compacted (overflowed / ineligible items contribute 0
+// and are appended to the overflow list: the host re-runs them on the exact two-pass path)
+__global__ void ba_clip_counts_kernel(const int32_t *__restrict__ seg_count, const int32_t *__restrict__ slot_cap,
+                                      const WorkItem *__restrict__ items, int32_t *__restrict__ clipped,
+                                      long long *__restrict__ meta, int32_t *__restrict__ overflow, int n_items)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int c = seg_count[it];
+    const bool ovf = (c < 0 || c > slot_cap[it]);
+    clipped[it] = ovf ? 0 : c;
+    if (ovf) {
+        const long long k = (long long)atomicAdd((unsigned long long *)(meta + 1), 1ull);
+        overflow[k] = items[it].pair;
+    }
+}
+
+// Reverse the emission-order slots of every item into its final, compact place (after the segments
+// of the earlier waves) and publish the pair's (seg_start, seg_count) in PAIR order, so the host
+// neither scans nor scatters.
 __global__ void ba_compact_kernel(const int32_t *__restrict__ slots, const int64_t *__restrict__ slot_off,
                                   const int32_t *__restrict__ slot_cap, const int32_t *__restrict__ seg_count,
-                                  const int64_t *__restrict__ seg_base, int32_t *__restrict__ segs, int n_items)
+                                  const int64_t *__restrict__ seg_base, const WorkItem *__restrict__ items,
+                                  const long long *__restrict__ meta, int32_t *__restrict__ segs,
+                                  int64_t *__restrict__ pair_seg_start, int32_t *__restrict__ pair_seg_count,
+                                  int n_items)
 {
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
     const int cnt = seg_count[it];
     if (cnt < 0 || cnt > slot_cap[it]) return;  // not eligible / overflow: re-run on the exact two-pass path
+    const int64_t base = (int64_t)meta[0] + seg_base[it];
+    const int32_t p = items[it].pair;
+    pair_seg_start[p] = base;
+    pair_seg_count[p] = cnt;
     const int32_t *src = slots + 5 * slot_off[it];
-    int32_t *dst = segs + 5 * seg_base[it];
+    int32_t *dst = segs + 5 * base;
     for (int k = 0; k < cnt; k++) {
         const int32_t *s = src + 5 * (cnt - 1 - k);
 #pragma unroll
@@ -1172,12 +1212,15 @@ __global__ void ba_compact_kernel(const int32_t *__restrict__ slots, const int64
     }
 }
 
-// seg_count clipped to what actually gets compacted (overflowed items contribute 0)
-__global__ void ba_clip_counts_kernel(const int32_t *__restrict__ seg_count, const int32_t *__restrict__ slot_cap,
-                                      int32_t *__restrict__ clipped, int n_items)
+// after the compaction of wave `w`: record {base, segments, overflow so far} and advance the total
+__global__ void ba_wave_total_kernel(const int64_t *__restrict__ seg_base, const int32_t *__restrict__ clipped,
+                                     int n_items, long long *__restrict__ meta, int w)
 {
-    const int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= n_items) return;
-    const int c = seg_count[it];
-    clipped[it] = (c < 0 || c > slot_cap[it]) ? 0 : c;
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const long long wsegs = n_items > 0 ? (long long)seg_base[n_items - 1] + clipped[n_items - 1] : 0;
+    long long *rec = meta + BA_META_HEAD + (long long)BA_META_WAVE * w;
+    rec[0] = meta[0];
+    rec[1] = wsegs;
+    rec[2] = meta[1];
+    meta[0] += wsegs;
 }

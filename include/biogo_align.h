@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BA_ABI_VERSION 2 /* 2: ba_result grew (wavefront/warp-trace counters); format, seqio and gather entry points */
+#define BA_ABI_VERSION 3 /* 3: ba_result.waves, overlap options, ba_create_multi; 2: wavefront/warp-trace counters, format, seqio, gather */
 
 /* Aligner kind: align/sw.go:18, align/nw.go:16, align/fitted.go:16 (and *_affine.go:16). */
 enum { BA_SW = 0, BA_NW = 1, BA_FITTED = 2 };
@@ -82,6 +82,7 @@ typedef struct {
     int64_t pairs_fast16; /* pairs served by the packed 16-bit DPX path (the rest: 32-bit exact-code path) */
     int64_t wavefront_launches; /* fill launches that spread the passes of long pairs over warps */
     int64_t warp_trace_launches; /* traceback launches that used one warp per pair */
+    int64_t waves;        /* waves the batch was cut into (the traceback of one overlaps the fill of the next) */
 } ba_result;
 
 /* Context: one per (host thread, device).  Thread-compatible: calls on ONE ctx must be

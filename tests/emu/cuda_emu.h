@@ -286,6 +286,12 @@ static inline int atomicAdd(int *p, int v)
     *p = o + v;
     return o;
 }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long o = *p;
+    *p = o + v;
+    return o;
+}
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 
 // DPX / SIMD-in-a-word intrinsics used by the kernels (scalar restatements)
@@ -319,6 +325,18 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)
     *s = (void *)1;
     return cudaSuccess;
 }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int)
+{
+    *s = (void *)1;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi)
+{
+    *lo = 0;
+    *hi = -1;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e)
@@ -326,7 +344,19 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t *e)
     *e = (void *)1;
     return cudaSuccess;
 }
+enum { cudaEventDefault = 0, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned)
+{
+    *e = (void *)1;
+    return cudaSuccess;
+}
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n)
+{
+    *n = 2;  // the emulator pretends to be a two-device box (multi-device scheduler tests)
+    return cudaSuccess;
+}
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t)

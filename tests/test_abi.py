@@ -25,7 +25,7 @@ def test_cuda_library_exports_every_declared_symbol(built):
     for sym in _declared_symbols():
         assert hasattr(lib, sym), sym
     l = _lib.load()
-    assert l.ba_abi_version() == 2
+    assert l.ba_abi_version() == 3
     assert b"sm_100a" in l.ba_build_info()
 
 

@@ -401,3 +401,50 @@ def test_fast16_general_and_symmetric_gap_kernels(emu_ctx, kind):
     res = helpers.run_lib(emu_ctx, kind, True, A, -4, DNA_IDX, 5, pk)
     assert res.stats["pairs_fast16"] >= len(pairs) - 3
     helpers.compare(res, helpers.run_oracle(kind, True, A, -4, DNA_IDX, pk), f"asymmetric gaps kind {kind}")
+
+
+@pytest.mark.parametrize("kind,affine", helpers.KINDS, ids=[helpers.KIND_NAMES[k] for k in helpers.KINDS])
+@pytest.mark.parametrize("setup", [
+    dict(waves=3),
+    dict(waves=5, fill_streams=1, fill_claims=0),
+    dict(waves=4, arena_bytes=40000, fill_claims=2, trace_cta=64),      # fewer checkpoint regions than waves
+    dict(waves=3, upload_groups=4, trace_cta=128, fill_cap=1),
+], ids=["w3", "w5-one-stream-persistent", "w4-region-reuse", "w3-upload-groups"])
+def test_overlapped_waves_do_not_change_results(emu_ctx, kind, affine, setup):
+    """Batches cut into several waves (traceback of wave w beside the fill of wave w+1), with the
+    per-wave device bookkeeping, region reuse and the grouped upload: same results as one wave."""
+    rng = random.Random(4100 + kind + 10 * affine)
+    M = gv.match(-1, 2, -1) if not affine else gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 70, [1, 20, 45, 80, 130], [3, 17, 40, 64, 100, 300], related=0.7, dirty=0.05)
+    pk = helpers.pack(pairs)
+    for k, v in setup.items():
+        emu_ctx.set_option(k, v)
+    try:
+        res = helpers.run_lib(emu_ctx, kind, affine, M, -3, DNA_IDX, 5, pk)
+        assert res.stats["waves"] >= min(setup["waves"], 2)
+    finally:
+        for k in setup:
+            emu_ctx.set_option(k, {"fill_streams": 2, "fill_claims": 1}.get(k, 0))
+    helpers.compare(res, helpers.run_oracle(kind, affine, M, -3, DNA_IDX, pk),
+                    f"{helpers.KIND_NAMES[(kind, affine)]} {setup}")
+
+
+def test_overlapped_waves_with_slot_overflow_and_mixed_alphabet(emu_ctx):
+    """Pairs that overflow their segment slots or leave the 4-letter class are collected on the device
+    across all waves and re-run on the exact path; the rest keep their fast-path results."""
+    rng = random.Random(77)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 60, [30, 60, 90], [20, 50, 90], related=0.6, dirty=0.0)
+    pairs += [(b"ACGTNNACGT", b"ACGTACGT"), (b"ACG-TACGT", b"ACGTACGT")]   # illegal letter; gap letter: exact path
+    rng.shuffle(pairs)
+    pk = helpers.pack(pairs, 2)
+    emu_ctx.set_option("waves", 4)
+    emu_ctx.set_option("slot_cap", 3)
+    try:
+        res = helpers.run_lib(emu_ctx, 0, True, M, -2, DNA_IDX, 5, pk, 2)
+        assert res.stats["waves"] >= 4
+        assert 0 < res.stats["pairs_fast16"] < len(pairs)
+    finally:
+        emu_ctx.set_option("waves", 0)
+        emu_ctx.set_option("slot_cap", 0)
+    helpers.compare(res, helpers.run_oracle(0, True, M, -2, DNA_IDX, pk, 2), "overflow across waves")
