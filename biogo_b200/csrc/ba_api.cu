@@ -146,7 +146,7 @@ struct ba_ctx {
     // fill warp takes before its CTA retires (0 = persistent grid), resident fill CTAs per SM (0 = all that
     // fit), threads per thread-per-pair traceback CTA (0 = automatic), upload groups (0 = automatic)
     int64_t opt_waves = 0, opt_fill_streams = 2, opt_fill_claims = 1, opt_fill_cap = 0, opt_trace_cta = 0;
-    int64_t opt_upload_groups = 0, opt_taper = 1;
+    int64_t opt_upload_groups = 0, opt_chunk_pairs = 8192;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
@@ -831,6 +831,7 @@ struct FillCfg {
     bool use_long = false;
     int maxp = 0, max_n = 0;
     int64_t ncp = 0, ntasks = 0, bnd_stride = 0, bnd_ints = 0;
+    int64_t maxb = 0;   // resident CTAs of this kernel on the whole GPU
 };
 
 int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsub, std::vector<int32_t> &overflow,
@@ -851,11 +852,13 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     // ---- waves: the traceback of wave w runs beside the fill of wave w+1 (different pipes bind them:
     // the fill saturates the integer pipe, the walk waits on checkpoint loads), so a batch that is
     // large enough is cut into several waves even when its checkpoints would fit the arena at once.
+    // Measured on B200 (profiles/r02_overlap_sweep.md): with the present traceback kernel, whose
+    // latency per launch is ~1.4 ms whatever the wave size, cutting config 2 into waves LOSES
+    // (10.3 ms -> 10.9 / 12.2 / 13.7 ms for 2 / 4 / 8 waves), so the automatic setting keeps one wave
+    // per arena-load; "waves" > 1 remains for experiments and is covered by the parity tests.
+    (void)cells;
     int64_t tw = ctx->opt_waves;
-    if (tw <= 0) {
-        tw = std::min<int64_t>(8, std::min<int64_t>(cells / 2000000000LL, nids / 4096));
-        if (tw < 1) tw = 1;
-    }
+    if (tw <= 0) tw = 1;
     const int64_t wave_cap = tw > 1 ? std::max<int64_t>(arena_cap / 3, 1) : arena_cap;
     Plan local_plan;
     ba_ctx::PlanCache &pc = ctx->pc;
@@ -971,6 +974,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 wave_tasks += c.ntasks;
             } else {
                 const int64_t need = (L.count + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);  // two pairs per group
+                c.maxb = maxb;
                 // single-pass launches of an overlapped batch retire their CTAs after `fill_claims` claims,
                 // so the high-priority traceback CTAs of the previous wave find SM slots all along
                 if (overlap && !multi && ctx->opt_fill_claims > 0) {
@@ -1000,7 +1004,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     if ((rc = ensure(ctx, ctx->seg_clip, sizeof(int32_t) * (size_t)nids)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->seg_base, sizeof(int64_t) * (size_t)(nids + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->arena, (size_t)(R * region_bytes) + 256)) != BA_OK) return rc;
-    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 128 * (size_t)nw)) != BA_OK) return rc;
+    if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 256 * (size_t)nw)) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(total_slots + 1))) != BA_OK) return rc;
     if ((rc = ensure(ctx, ctx->ovf, sizeof(int32_t) * (size_t)(nids + 1))) != BA_OK) return rc;
     const size_t meta_words = BA_META_HEAD + BA_META_WAVE * (size_t)nw;
@@ -1047,7 +1051,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             pc.dev_slot_cap = ctx->slot_cap.p;
         }
     }
-    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 128 * (size_t)nw, st));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 256 * (size_t)nw, st));
     CK(cudaMemsetAsync(ctx->meta.p, 0, sizeof(long long) * meta_words, st));
     if (max_tasks > 0) CK(cudaMemsetAsync(ctx->prog.p, 0, 64 * (size_t)nw, st));
     CK(cudaMemsetAsync(ctx->pair_seg_start.p, 0, sizeof(int64_t) * (size_t)B.n, st));
@@ -1066,7 +1070,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     }
     CK(cudaEventRecord(ev_setup, st));
     CK(cudaStreamWaitEvent(ctx->s_trace, ev_setup, 0));
-    if (two_streams) CK(cudaStreamWaitEvent(ctx->s_fill2, ev_setup, 0));
+    if (two_streams || B.groups.size() > 1) CK(cudaStreamWaitEvent(ctx->s_fill2, ev_setup, 0));
     std::vector<cudaEvent_t> ev_fill_end((size_t)nw), ev_trace_end((size_t)nw);
     cudaEvent_t ev_trace_start = nullptr;
 
@@ -1074,8 +1078,16 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         const Plan::Wave &w = plan.waves[(size_t)wi];
         B.waves++;
         cudaStream_t F = (two_streams && (wi & 1)) ? ctx->s_fill2 : st;
-        if ((rc = prep_pairs(ctx, B, w.max_pair)) != BA_OK) return rc;
-        if (F != st && B.next_group > 0) CK(cudaStreamWaitEvent(F, B.groups[B.next_group - 1].checked, 0));
+        // Chunked fill: while parts of the input are still on their way (ba_align_batch uploads in
+        // groups), the fill starts on the pairs that are already here -- one launch per chunk of the
+        // work list, alternating between the two fill streams so the tail of one overlaps the head of
+        // the next; the traceback follows once, after the last chunk.
+        const bool chunked = !overlap && B.groups.size() > 1 && B.next_group < B.groups.size();
+        bool used_alt = false;
+        if (!chunked) {
+            if ((rc = prep_pairs(ctx, B, w.max_pair)) != BA_OK) return rc;
+            if (F != st && B.next_group > 0) CK(cudaStreamWaitEvent(F, B.groups[B.next_group - 1].checked, 0));
+        }
         if (wi >= R) CK(cudaStreamWaitEvent(F, ev_trace_end[(size_t)(wi - R)], 0));  // its region is free again
         const int64_t reg = wi % R;
         uint8_t *arena_w = (uint8_t *)ctx->arena.p + reg * region_bytes;
@@ -1098,7 +1110,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             fp.status = B.d_status;
             fp.acgt_only = B.d_flags;
             fp.flag_mask = flag_mask;
-            fp.counter = (int *)ctx->counters.p + 128 * wi + (li++ % 64);
+            fp.counter = (int *)ctx->counters.p + 256 * wi + (li % 192);
             fp.arena = arena_w;
             fp.sc = ctx->d_sc;
             fp.long_couples = 0;
@@ -1107,6 +1119,11 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             int32_t *bnd_w = (int32_t *)ctx->bnd.p + par * max_bnd_ints + bnd_used;
             bnd_used += c.bnd_ints;
             if (c.use_long) {
+                if (chunked) {   // a wavefront launch needs all its pairs
+                    int32_t mp = 0;
+                    for (int64_t k = 0; k < L.count; k++) mp = std::max(mp, plan.items[L.first + k].pair);
+                    if ((rc = prep_pairs(ctx, B, mp)) != BA_OK) return rc;
+                }
                 WorkItem *h_tasks = (WorkItem *)lease.get(sizeof(WorkItem) * (size_t)c.ntasks);
                 if (!h_tasks) {
                     ctx->err = "pinned host allocation failed";
@@ -1144,17 +1161,53 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 B.out->wavefront_launches++;
                 B.launches++;
                 B.fill_launches++;
+                li++;
                 continue;
             }
-            fp.items = d_items + L.first;
-            fp.n_items = (int)L.count;
             fp.bnd = bnd_w;
             fp.bnd_stride = c.bnd_stride;
-            BA_LAUNCH_SMEM(c.fn, (unsigned)c.blocks, BA16_WARPS * 32, c.dyn, F, fp);
-            B.launches++;
-            B.fill_launches++;
+            int64_t nchunk = 1;
+            if (chunked && li + 32 < 192)
+                nchunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)(B.groups.size() - B.next_group) + 1, 8),
+                                                                L.count / std::max<int64_t>(ctx->opt_chunk_pairs, 8)));
+            int64_t per = (L.count + nchunk - 1) / nchunk;
+            per = (per + 7) & ~(int64_t)7;   // whole CTAs of two warps x four pairs
+            for (int64_t c0 = 0; c0 < L.count; c0 += per) {
+                const int64_t cnt = std::min(per, L.count - c0);
+                cudaStream_t FS = F;
+                if (chunked) {
+                    int32_t mp = 0;
+                    for (int64_t k = 0; k < cnt; k++) mp = std::max(mp, plan.items[L.first + c0 + k].pair);
+                    if ((rc = prep_pairs(ctx, B, mp)) != BA_OK) return rc;
+                    // boundary rows of multi-pass launches are per launch: those stay on one stream
+                    if (ctx->opt_fill_streams >= 2 && c.bnd_ints == 0 && ((c0 / per) & 1)) {
+                        FS = ctx->s_fill2;
+                        used_alt = true;
+                        if (B.next_group > 0) CK(cudaStreamWaitEvent(FS, B.groups[B.next_group - 1].checked, 0));
+                    }
+                }
+                const int64_t need = (cnt + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);
+                const int64_t blocks = c.max_claims > 0 ? (need + c.max_claims - 1) / c.max_claims
+                                                        : std::min(need, std::max<int64_t>(c.maxb, 1));
+                fp.items = d_items + L.first + c0;
+                fp.n_items = (int)cnt;
+                fp.counter = (int *)ctx->counters.p + 256 * wi + (li % 192);
+                li++;
+                BA_LAUNCH_SMEM(c.fn, (unsigned)blocks, BA16_WARPS * 32, c.dyn, FS, fp);
+                B.launches++;
+                B.fill_launches++;
+            }
         }
         CK(cudaGetLastError());
+        if (used_alt) {   // join the second fill stream before the wave's end-of-fill event
+            cudaEvent_t ej = ev_new(ctx, false);
+            if (!ej) {
+                ctx->err = "cudaEventCreate failed";
+                return BA_ERR_CUDA;
+            }
+            CK(cudaEventRecord(ej, ctx->s_fill2));
+            CK(cudaStreamWaitEvent(F, ej, 0));
+        }
         ev_fill_end[(size_t)wi] = ev_new(ctx, true);
         if (!ev_fill_end[(size_t)wi]) {
             ctx->err = "cudaEventCreate failed";
@@ -1188,7 +1241,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.slot_off = (const int64_t *)ctx->slot_off.p + w.first;
         tp.slot_cap = (const int32_t *)ctx->slot_cap.p + w.first;
         tp.slots = slots_w;
-        tp.counter = (int *)ctx->counters.p + 128 * wi + 64;
+        tp.counter = (int *)ctx->counters.p + 256 * wi + 255;
         // one thread per pair when the wave fills the GPU that way, else one warp per pair
         // (window of speculatively rebuilt tiles, see ba_trace16w_kernel), a whole CTA per pair when
         // even that leaves SMs idle; a mixed wave gives warps to its longest pairs (the head of
@@ -1712,6 +1765,10 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     }
     if (!strcmp(key, "upload_groups")) {   // pieces the letters upload is cut into: 0 automatic, 1 = one piece
         ctx->opt_upload_groups = value;
+        return BA_OK;
+    }
+    if (!strcmp(key, "chunk_pairs")) {     // fewest pairs a fill chunk of a still-uploading batch gets (0 = default)
+        ctx->opt_chunk_pairs = value > 0 ? value : 8192;
         return BA_OK;
     }
     if (!strcmp(key, "pinned_budget")) {   // bytes of idle pinned host memory a context keeps for reuse

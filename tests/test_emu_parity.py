@@ -409,7 +409,9 @@ def test_fast16_general_and_symmetric_gap_kernels(emu_ctx, kind):
     dict(waves=5, fill_streams=1, fill_claims=0),
     dict(waves=4, arena_bytes=40000, fill_claims=2, trace_cta=64),      # fewer checkpoint regions than waves
     dict(waves=3, upload_groups=4, trace_cta=128, fill_cap=1),
-], ids=["w3", "w5-one-stream-persistent", "w4-region-reuse", "w3-upload-groups"])
+    dict(waves=1, upload_groups=5, chunk_pairs=8),                       # one wave, fill in chunks as the upload arrives
+    dict(waves=1, upload_groups=3, chunk_pairs=8, fill_streams=1),
+], ids=["w3", "w5-one-stream-persistent", "w4-region-reuse", "w3-upload-groups", "chunked", "chunked-one-stream"])
 def test_overlapped_waves_do_not_change_results(emu_ctx, kind, affine, setup):
     """Batches cut into several waves (traceback of wave w beside the fill of wave w+1), with the
     per-wave device bookkeeping, region reuse and the grouped upload: same results as one wave."""
@@ -422,6 +424,8 @@ def test_overlapped_waves_do_not_change_results(emu_ctx, kind, affine, setup):
     try:
         res = helpers.run_lib(emu_ctx, kind, affine, M, -3, DNA_IDX, 5, pk)
         assert res.stats["waves"] >= min(setup["waves"], 2)
+        if "chunk_pairs" in setup:
+            assert res.stats["fill_launches"] > res.stats["waves"] + 1
     finally:
         for k in setup:
             emu_ctx.set_option(k, {"fill_streams": 2, "fill_claims": 1}.get(k, 0))

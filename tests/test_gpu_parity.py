@@ -453,3 +453,65 @@ def test_sw_best_cell_ties_across_passes(gpu_ctx, affine):
         finally:
             gpu_ctx.set_option("force_path", 0)
         helpers.compare(res, orc, f"ties across passes, force_path {force}")
+
+
+OVERLAP_SETUPS = [
+    dict(waves=3),
+    dict(waves=6, fill_streams=1, fill_claims=0),
+    dict(waves=5, arena_bytes=96 << 20, fill_claims=2, trace_cta=64),   # fewer checkpoint regions than waves
+    dict(waves=4, upload_groups=5, trace_cta=128, fill_cap=4),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("num,n", [(1, 3000), (2, 2000), (3, 3000), (5, 300)])
+@pytest.mark.parametrize("setup", OVERLAP_SETUPS, ids=["w3", "w6-one-stream-persistent", "w5-region-reuse",
+                                                       "w4-upload-groups"])
+def test_overlapped_waves_against_oracle(gpu_ctx, num, n, setup):
+    """Traceback of wave w beside the fill of wave w+1 (separate streams, non-persistent fill
+    grids, per-wave device bookkeeping, grouped upload): bit-exact against the oracle."""
+    w = synth.config(num, n)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    go = w.gap_open if w.affine else 0
+    for k, v in setup.items():
+        gpu_ctx.set_option(k, v)
+    try:
+        res = helpers.run_lib(gpu_ctx, w.kind, w.affine, w.matrix, go, w.alpha.LetterIndex(), w.alpha.Len(), pk,
+                              w.stride)
+        assert res.stats["waves"] >= 2
+    finally:
+        for k in setup:
+            gpu_ctx.set_option(k, {"fill_streams": 2, "fill_claims": 1}.get(k, 0))
+    helpers.compare(res, helpers.run_oracle(w.kind, w.affine, w.matrix, go, w.alpha.LetterIndex(), pk, w.stride, 16),
+                    f"{w.name} {setup}")
+
+
+@pytest.mark.gpu
+def test_waves_and_chunked_upload_equal_one_wave_on_a_large_batch(gpu_ctx):
+    """40 000 pairs of config 2 (10 G cells, 51 MB of letters): the batch uploads in groups and the fill
+    starts chunk by chunk on what has arrived; forced waves overlap traceback and fill.  Every pair's
+    segments equal those of the plain single-piece, single-wave run."""
+    w = synth.config(2, 40_000)
+    pk = (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    gpu_ctx.set_option("upload_groups", 1)
+    try:
+        one = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    finally:
+        gpu_ctx.set_option("upload_groups", 0)
+    assert one.stats["waves"] == 1 and one.stats["fill_launches"] == 1
+    chunked = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    assert chunked.stats["waves"] == 1 and chunked.stats["fill_launches"] >= 3
+    gpu_ctx.set_option("waves", 4)
+    try:
+        waves = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    finally:
+        gpu_ctx.set_option("waves", 0)
+    assert waves.stats["waves"] >= 4
+    for other in (chunked, waves):
+        assert np.array_equal(one.status, other.status) and np.array_equal(one.seg_count, other.seg_count)
+        for p in range(0, w.n, 7):
+            assert np.array_equal(one.pairs(p), other.pairs(p)), p
+    # twice in a row through the cached plan
+    again = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
+    for p in range(0, w.n, 11):
+        assert np.array_equal(one.pairs(p), again.pairs(p)), p
