@@ -27,6 +27,8 @@ ABI_SYMBOLS = (
     "ba_align_batch_device", "ba_free_result", "ba_alloc_host", "ba_free_host",
     "ba_set_option", "ba_abi_version", "ba_build_info", "ba_format_batch", "ba_free_formatted",
     "ba_fasta_parse", "ba_fastq_parse", "ba_seqfile_free", "ba_gather_pairs",
+    "ba_create_multi", "ba_destroy_multi", "ba_multi_devices", "ba_multi_last_error", "ba_multi_set_scoring",
+    "ba_multi_set_option", "ba_align_batch_multi", "ba_multi_free_result",
 )
 
 
@@ -135,6 +137,22 @@ def _bind(lib):
     lib.ba_seqfile_free.restype = None
     lib.ba_gather_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
     lib.ba_gather_pairs.restype = i32
+    lib.ba_create_multi.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.ba_create_multi.restype = i32
+    lib.ba_destroy_multi.argtypes = [vp]
+    lib.ba_destroy_multi.restype = None
+    lib.ba_multi_devices.argtypes = [vp]
+    lib.ba_multi_devices.restype = i32
+    lib.ba_multi_last_error.argtypes = [vp]
+    lib.ba_multi_last_error.restype = C.c_char_p
+    lib.ba_multi_set_scoring.argtypes = [vp, i32, i32, vp, i32, i32, i64, vp]
+    lib.ba_multi_set_scoring.restype = i32
+    lib.ba_multi_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.ba_multi_set_option.restype = i32
+    lib.ba_align_batch_multi.argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, C.POINTER(BaResult)]
+    lib.ba_align_batch_multi.restype = i32
+    lib.ba_multi_free_result.argtypes = [vp, C.POINTER(BaResult)]
+    lib.ba_multi_free_result.restype = None
     return lib
 
 
@@ -304,4 +322,76 @@ class Context:
             return self._collect(res)
         stats = _stats(res)
         self.lib.ba_free_result(self._h, C.byref(res))
+        return stats
+
+
+class MultiContext:
+    """A ba_multi: one batch over several GPUs of one box (ba_align_batch_multi)."""
+
+    def __init__(self, devices=None, lib_path: str | None = None):
+        self.lib = load(lib_path)
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.ba_create_multi(None, 0, C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.ba_create_multi(arr, len(devices), C.byref(h))
+        self._h = h
+        if rc != BA_OK:
+            msg = self.lib.ba_multi_last_error(h).decode() if h else "ba_create_multi failed"
+            if h:
+                self.lib.ba_destroy_multi(h)
+                self._h = None
+            raise AlignError(rc, msg)
+        self.n_devices = int(self.lib.ba_multi_devices(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ba_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != BA_OK:
+            raise AlignError(rc, self.lib.ba_multi_last_error(self._h).decode())
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.ba_multi_set_option(self._h, key.encode(), int(value)))
+
+    def set_scoring(self, kind: int, affine: bool, la, let: int, alpha_len: int, gap_open: int, index):
+        la = np.ascontiguousarray(la, dtype=np.int64).reshape(-1)
+        index = np.ascontiguousarray(index, dtype=np.int32)
+        self._check(self.lib.ba_multi_set_scoring(self._h, kind, int(bool(affine)), la.ctypes.data, let, alpha_len,
+                                                  int(gap_open), index.ctypes.data))
+
+    def align_packed(self, letters, stride: int, ref_off, ref_len, qry_off, qry_len, collect: bool = True):
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+        qry_off = np.ascontiguousarray(qry_off, dtype=np.int64)
+        ref_len = np.ascontiguousarray(ref_len, dtype=np.int32)
+        qry_len = np.ascontiguousarray(qry_len, dtype=np.int32)
+        n = len(ref_off)
+        res = BaResult()
+        self._check(self.lib.ba_align_batch_multi(self._h, letters.ctypes.data, stride, ref_off.ctypes.data,
+                                                  ref_len.ctypes.data, qry_off.ctypes.data, qry_len.ctypes.data, n,
+                                                  C.byref(res)))
+        if collect:
+            out = BatchResult()
+            out.n = n
+            out.status = _as_array(res.status, n, np.int32)
+            out.err_pos = _as_array(res.err_pos, n, np.int64)
+            out.seg_start = _as_array(res.seg_start, n, np.int64)
+            out.seg_count = _as_array(res.seg_count, n, np.int32)
+            ns = int(res.n_segs)
+            out.segs = _as_array(res.segs, 5 * ns, np.int32).reshape(ns, 5)
+            out.stats = _stats(res)
+            self.lib.ba_multi_free_result(self._h, C.byref(res))
+            return out
+        stats = _stats(res)
+        self.lib.ba_multi_free_result(self._h, C.byref(res))
         return stats

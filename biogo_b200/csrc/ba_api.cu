@@ -125,6 +125,7 @@ struct ba_ctx {
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
     DevBuf flags, slot_off, slot_cap, slots, seg_clip, tasks, prog;
     DevBuf pair_seg_start, pair_seg_count, meta, ovf;
+    DevBuf segs32;   // exact path's per-wave segments (ctx->segs keeps the 16-bit path's until they are fetched)
     // Plan cache: batches of the same shape (same length arrays, same scoring) reuse the split, the
     // work lists and their device copies.
     struct PlanCache {
@@ -150,6 +151,7 @@ struct ba_ctx {
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
+    int64_t deferred_dev_segs = 0;                   // multi-device: segments of the last batch still only in ctx->segs
     std::mutex pinned_mu;                            // ba_free_result may run on another thread (GC finalizers)
     int64_t pinned_budget = 0;                       // bytes of unused pinned blocks kept for reuse (0 = default)
 };
@@ -356,6 +358,10 @@ struct Batch {
     int32_t *h_segs = nullptr;
     int64_t h_segs_cap = 0;     // in segments
     int64_t seg_total = 0;      // segments produced so far == next free position
+    // multi-device batches: the compacted segments stay on the device until every device knows where its
+    // share starts in the common result block; then they travel straight to their final place
+    bool defer_segs = false;
+    int64_t dev_segs = 0;       // segments compacted on the device by the 16-bit path (prefix of the batch's segments)
     cudaEvent_t ev_d2h0 = nullptr;  // first result copy of the call (ms_d2h)
     float ms_fill = 0.f, ms_trace = 0.f;
     double host_s = 0.0;
@@ -672,13 +678,13 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
                            st));
         CK(cudaStreamSynchronize(st));
         const int64_t wsegs = h_base[w.count - 1] + h_cnt[w.count - 1];
-        if ((rc = ensure(ctx, ctx->segs, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
-        wp.segs = (int32_t *)ctx->segs.p;
+        if ((rc = ensure(ctx, ctx->segs32, sizeof(int32_t) * 5 * (size_t)(wsegs + 1))) != BA_OK) return rc;
+        wp.segs = (int32_t *)ctx->segs32.p;
         BA_LAUNCH(walk_write, wblocks, 128, st, wp);
         B.launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[6], st));
-        if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs.p)) != BA_OK)
+        if ((rc = gather_wave(ctx, B, plan, w, h_cnt, h_base, wsegs, (const int32_t *)ctx->segs32.p)) != BA_OK)
             return rc;
     }
     B.lease->drop(h_cnt);
@@ -1360,15 +1366,18 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             want = std::max<int64_t>(want, (int64_t)(per * 1.1 * (double)nids) + 4096);
             want = std::min<int64_t>(want, total_slots);
         }
-        if ((rc = segs_reserve(ctx, B, want, base)) != BA_OK) return rc;
-        if (!B.ev_d2h0) {
-            B.ev_d2h0 = ev_new(ctx, true);
-            if (B.ev_d2h0) CK(cudaEventRecord(B.ev_d2h0, ctx->s_d2h));
+        if (!B.defer_segs) {
+            if ((rc = segs_reserve(ctx, B, want, base)) != BA_OK) return rc;
+            if (!B.ev_d2h0) {
+                B.ev_d2h0 = ev_new(ctx, true);
+                if (B.ev_d2h0) CK(cudaEventRecord(B.ev_d2h0, ctx->s_d2h));
+            }
+            if (wsegs > 0)
+                CK(cudaMemcpyAsync(B.h_segs + 5 * base, (const int32_t *)ctx->segs.p + 5 * base,
+                                   sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
-        if (wsegs > 0)
-            CK(cudaMemcpyAsync(B.h_segs + 5 * base, (const int32_t *)ctx->segs.p + 5 * base,
-                               sizeof(int32_t) * 5 * (size_t)wsegs, cudaMemcpyDeviceToHost, ctx->s_d2h));
         B.seg_total = base + wsegs;
+        B.dev_segs = B.seg_total;
     }
     BA_TSEC("P16 waves done", tp0);
     for (WorkItem *t : long_tasks) lease.drop(t);
@@ -1434,6 +1443,7 @@ int run_device_once(ba_ctx *ctx, Batch &B, int64_t letters_bytes)
     ctx->ev_timed_next = ctx->ev_plain_next = 0;
     B.next_group = 0;
     B.seg_total = 0;
+    B.dev_segs = 0;
     B.waves = 0;
     B.ev_d2h0 = nullptr;
 
@@ -1530,6 +1540,7 @@ int run_device_once(ba_ctx *ctx, Batch &B, int64_t letters_bytes)
     if (B.h_segs) B.lease->keep(B.h_segs);
     B.h_segs = nullptr;
     out->n_segs = B.seg_total;
+    ctx->deferred_dev_segs = B.defer_segs ? B.dev_segs : 0;
     out->gpu_launches = B.launches;
     out->fill_launches = B.fill_launches;
     out->code_bytes = B.code_bytes;
@@ -1688,7 +1699,7 @@ void ba_destroy(ba_ctx *ctx)
                       &ctx->counters, &ctx->flags,  &ctx->slot_off,  &ctx->slot_cap, &ctx->slots, &ctx->seg_clip,
                       &ctx->tasks,   &ctx->prog,     &ctx->fmt_len, &ctx->fmt_off, &ctx->fmt_rows,
                       &ctx->fmt_segs, &ctx->fmt_seg_start, &ctx->fmt_seg_count, &ctx->pair_seg_start,
-                      &ctx->pair_seg_count, &ctx->meta, &ctx->ovf};
+                      &ctx->pair_seg_count, &ctx->meta, &ctx->ovf, &ctx->segs32};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
@@ -1897,10 +1908,33 @@ int ba_align_batch_device(ba_ctx *ctx, const uint8_t *d_letters, int64_t letters
     return rc;
 }
 
+// A share of a larger batch whose letters are scattered over the caller's buffer (multi-device
+// batches): pair k of the call is pair ids[k] of the caller.  The call's own layout is "reference then
+// query of every pair, in call order"; each upload group is gathered into the pinned staging buffer
+// right before its copy is enqueued, so the gather of group g+1 runs under the DMA of group g.
+struct GatherSrc {
+    const uint8_t *letters;
+    const int64_t *ref_off, *qry_off;   // the caller's arrays (indexed by ids[k])
+    const int64_t *ids;
+    uint8_t *stage;                     // pinned, the call's letters_bytes long
+};
+
+static int align_host(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_t *ref_off,
+                      const int32_t *ref_len, const int64_t *qry_off, const int32_t *qry_len, int64_t n,
+                      ba_result *out, const GatherSrc *gs, bool defer_segs);
+
 int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_t *ref_off,
                    const int32_t *ref_len, const int64_t *qry_off, const int32_t *qry_len, int64_t n,
                    ba_result *out)
 {
+    return align_host(ctx, letters, stride, ref_off, ref_len, qry_off, qry_len, n, out, nullptr, false);
+}
+
+static int align_host(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_t *ref_off,
+                      const int32_t *ref_len, const int64_t *qry_off, const int32_t *qry_len, int64_t n,
+                      ba_result *out, const GatherSrc *gs, bool defer_segs)
+{
+    if (gs) letters = gs->stage;
     if (!ctx || !out || n < 0 || (stride != 1 && stride != 2)) return BA_ERR_ARG;
     memset(out, 0, sizeof *out);
     if (!ctx->have_scoring) {
@@ -1984,8 +2018,19 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
     // the letters, group by group, each in pieces of 4 MB (small copies of other contexts -- work lists,
     // per-wave records -- share the copy engines and must not queue behind one 100+ MB transfer)
     std::vector<cudaEvent_t> ready(B.groups.size(), nullptr);
+    int64_t gathered = 0;   // pairs whose letters are in the staging buffer (gs)
     for (size_t gi = 0; gi < B.groups.size(); gi++) {
         const UploadGroup &g = B.groups[gi];
+        if (gs) {
+            // every pair that starts below the end of this piece
+            while (gathered < n && ref_off[gathered] < g.b_hi) {
+                const int64_t p = gs->ids[gathered];
+                const size_t rb = (size_t)ref_len[gathered] * stride, qb = (size_t)qry_len[gathered] * stride;
+                if (rb) memcpy(gs->stage + ref_off[gathered], gs->letters + gs->ref_off[p], rb);
+                if (qb) memcpy(gs->stage + qry_off[gathered], gs->letters + gs->qry_off[p], qb);
+                gathered++;
+            }
+        }
         for (int64_t o = g.b_lo; o < g.b_hi; o += (4 << 20)) {
             const size_t len = (size_t)std::min<int64_t>(4 << 20, g.b_hi - o);
             CK(cudaMemcpyAsync((uint8_t *)ctx->letters.p + o, letters + o, len, cudaMemcpyHostToDevice, up));
@@ -2014,6 +2059,7 @@ int ba_align_batch(ba_ctx *ctx, const uint8_t *letters, int stride, const int64_
     B.n = n;
     B.st = st;
     B.out = out;
+    B.defer_segs = defer_segs;
     rc = run_device(ctx, B, letters_bytes);
     if (rc != BA_OK) {
         drain(ctx, nullptr);   // the staged copies may still be in flight
@@ -2217,3 +2263,4 @@ void ba_free_host(void *p)
 }  // extern "C"
 
 #include "ba_seqio.inl"
+#include "ba_multi.inl"

@@ -189,6 +189,33 @@ int ba_gather_pairs(const uint8_t *letters, int stride, const int64_t *ref_off, 
                     const int64_t *qry_off, const int32_t *qry_len, const int64_t *ids, int64_t k,
                     uint8_t *dst, int64_t dst_bytes, int64_t *new_ref_off, int64_t *new_qry_off);
 
+/*
+ * ONE batch over several GPUs of one box (north_star: "batches of independent pairs shard across the 8 GPUs
+ * of one box by length-bucketed work lists, with a host-side gather and no NCCL").  A ba_multi owns one
+ * ba_ctx and one host thread per device.  ba_align_batch_multi deals the pairs to the devices (cells bucketed
+ * in quarter-octave classes, largest first, snake order: equal cells and equal length mix per device; batches
+ * of equal-shaped pairs are cut into contiguous ranges), gathers each share's letters into that device's
+ * pinned staging buffer piece by piece under the upload, runs the shares concurrently and gathers the results
+ * by pair id into ONE ba_result with exactly the layout ba_align_batch produces.  The Go side's
+ * AlignBatch calls this for large batches (go/align/cuda_bridge.go); there is no reference counterpart.
+ *   devices / n_devices   CUDA device ordinals; n_devices <= 0 (or devices == NULL) = every visible device
+ * Thread-compatible like ba_ctx: calls on one ba_multi must be serialised by the caller.
+ * ba_multi_set_option forwards to every device context; its own key: "contiguous_shares" (default 1).
+ */
+typedef struct ba_multi ba_multi;
+int ba_create_multi(const int *devices, int n_devices, ba_multi **out);
+void ba_destroy_multi(ba_multi *m);
+int ba_multi_devices(const ba_multi *m);
+const char *ba_multi_last_error(const ba_multi *m);
+int ba_multi_set_scoring(ba_multi *m, int kind, int affine, const int64_t *la, int let,
+                         int alpha_len, int64_t gap_open, const int32_t *index);
+int ba_multi_set_option(ba_multi *m, const char *key, int64_t value);
+int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride,
+                         const int64_t *ref_off, const int32_t *ref_len,
+                         const int64_t *qry_off, const int32_t *qry_len,
+                         int64_t n, ba_result *out);
+void ba_multi_free_result(ba_multi *m, ba_result *res);
+
 /* Pinned host allocation so a caller (cgo, ctypes) can pack straight into DMA-able memory. */
 void *ba_alloc_host(size_t bytes);
 void ba_free_host(void *p);

@@ -51,16 +51,116 @@ def test_two_emulated_devices(built):
     _check(md1, 9, 3)
 
 
-@pytest.mark.gpu
-def test_all_visible_gpus():
+def _gpu_devices():
+    """Every visible GPU.  BA_TEST_GPUS=N demands at least N physical devices and FAILS otherwise (a
+    multi-GPU run must not silently degrade); without it a one-GPU box stands in with two contexts on
+    device 0, which exercises the host logic but not two physical devices."""
+    import os
+
     import torch
 
     n = torch.cuda.device_count()
-    devices = tuple(range(n)) if n >= 2 else (0, 0)
-    md = shard.MultiDevice(devices)
+    want = int(os.environ.get("BA_TEST_GPUS", "0"))
+    assert n >= want, f"BA_TEST_GPUS={want} but only {n} GPU(s) are visible"
+    return tuple(range(n)) if n >= 2 else (0, 0)
+
+
+@pytest.mark.gpu
+def test_all_visible_gpus():
+    md = shard.MultiDevice(_gpu_devices())
     _check(md, 4000, 4)
     cells = md.align_packed(*_uniform()).stats["cells_per_device"]
     assert max(cells) == min(cells)
+
+
+# ---- the same split UNDER the C ABI: ba_create_multi / ba_align_batch_multi ----------------------
+
+def _check_multi(mc, npairs, seed, stride=1, kinds=((0, True, -4), (1, True, -4), (2, False, 0))):
+    rng = random.Random(seed)
+    pairs = randcases.rand_pairs(rng, npairs, [0, 1, 20, 90, 150, 300], [0, 1, 16, 64, 100, 257, 300], related=0.8,
+                                 dirty=0.15)
+    pk = helpers.pack(pairs, stride)
+    M = gv.match(-1, 2, -1)
+    for kind, affine, go in kinds:
+        mc.set_scoring(kind, affine, np.array(M, np.int64).reshape(-1), 5, 5, go, DNA_IDX)
+        res = mc.align_packed(pk[0], stride, pk[1], pk[2], pk[3], pk[4])
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, go, DNA_IDX, pk, stride), f"abi multi {kind} {affine}")
+        assert res.stats["gpu_launches"] > 0 and res.stats["cells"] == sum(len(r) * len(q) for r, q in pairs)
+
+
+def test_c_abi_multi_device_on_two_emulated_devices(built):
+    from biogo_b200 import _lib
+
+    mc = _lib.MultiContext((0, 1), helpers.EMU_LIB)
+    assert mc.n_devices == 2
+    _check_multi(mc, 41, 11, kinds=[(k, a, -3 if a else 0) for k, a in helpers.KINDS])
+    _check_multi(mc, 23, 12, stride=2)
+    # equal-shaped pairs: contiguous ranges, no gather; then the same batch dealt by buckets
+    rng = random.Random(13)
+    pairs = randcases.rand_pairs(rng, 33, [120], [60], related=0.9, dirty=0.0)
+    pk = helpers.pack(pairs)
+    M = gv.match(-1, 1, -1)
+    mc.set_scoring(0, True, np.array(M, np.int64).reshape(-1), 5, 5, -5, DNA_IDX)
+    orc = helpers.run_oracle(0, True, M, -5, DNA_IDX, pk)
+    helpers.compare(mc.align_packed(pk[0], 1, pk[1], pk[2], pk[3], pk[4]), orc, "ranges")
+    mc.set_option("contiguous_shares", 0)
+    helpers.compare(mc.align_packed(pk[0], 1, pk[1], pk[2], pk[3], pk[4]), orc, "dealt")
+    mc.set_option("contiguous_shares", 1)
+    # pairs that overflow their slots go through the exact path on their device: host-resident segments
+    # of a share are merged behind its device-resident ones
+    mc.set_option("slot_cap", 2)
+    try:
+        _check_multi(mc, 30, 14, kinds=((0, True, -2),))
+    finally:
+        mc.set_option("slot_cap", 0)
+    # one device, and an empty batch
+    m1 = _lib.MultiContext((0,), helpers.EMU_LIB)
+    _check_multi(m1, 9, 15)
+    e = m1.align_packed(np.zeros(0, np.uint8), 1, np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int64),
+                        np.zeros(0, np.int32))
+    assert e.n == 0 and len(e.segs) == 0
+
+
+def test_c_abi_multi_device_dealing_balances_cells(built):
+    """The dealing itself, observed through the per-device cells of a batch of mixed lengths."""
+    from biogo_b200 import _lib
+
+    mc = _lib.MultiContext((0, 1, 0, 1), helpers.EMU_LIB)
+    rng = random.Random(21)
+    pairs = randcases.rand_pairs(rng, 400, [5, 10, 20, 40, 80], [5, 10, 20, 40, 80], related=0.5, dirty=0.0)
+    pk = helpers.pack(pairs)
+    M = gv.match(-1, 1, -1)
+    mc.set_scoring(0, False, np.array(M, np.int64).reshape(-1), 5, 5, 0, DNA_IDX)
+    res = mc.align_packed(pk[0], 1, pk[1], pk[2], pk[3], pk[4])
+    helpers.compare(res, helpers.run_oracle(0, False, M, 0, DNA_IDX, pk), "four shares")
+
+
+@pytest.mark.gpu
+def test_c_abi_multi_device_on_all_visible_gpus():
+    from biogo_b200 import _lib, synth
+
+    mc = _lib.MultiContext(_gpu_devices())
+    _check_multi(mc, 4000, 31)
+    _check_multi(mc, 600, 32, stride=2, kinds=[(k, a, -3 if a else 0) for k, a in helpers.KINDS])
+    # config 2 shape: contiguous shares; every pair equals the single-device result
+    w = synth.config(2, 6000)
+    la = np.array(w.matrix, np.int64).reshape(-1)
+    mc.set_scoring(w.kind, True, la, 5, 5, w.gap_open, w.alpha.LetterIndex())
+    multi = mc.align_packed(w.letters, 1, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    one = _lib.Context(0)
+    one.set_scoring(w.kind, True, la, 5, 5, w.gap_open, w.alpha.LetterIndex())
+    single = one.align_packed(w.letters, 1, w.ref_off, w.ref_len, w.qry_off, w.qry_len)
+    assert np.array_equal(multi.status, single.status) and np.array_equal(multi.seg_count, single.seg_count)
+    for p in range(w.n):
+        assert np.array_equal(multi.pairs(p), single.pairs(p)), p
+    # config 5 shape (mixed lengths, QLetters): dealt by length buckets
+    w5 = synth.config(5, 600)
+    la5 = np.array(w5.matrix, np.int64).reshape(-1)
+    mc.set_scoring(w5.kind, True, la5, 5, 5, w5.gap_open, w5.alpha.LetterIndex())
+    pk5 = (w5.letters, w5.ref_off, w5.ref_len, w5.qry_off, w5.qry_len)
+    res5 = mc.align_packed(w5.letters, w5.stride, *pk5[1:])
+    helpers.compare(res5, helpers.run_oracle(w5.kind, True, w5.matrix, w5.gap_open, w5.alpha.LetterIndex(), pk5,
+                                             w5.stride, 16), "cfg5 multi")
 
 
 def _uniform():
