@@ -29,6 +29,7 @@ ABI_SYMBOLS = (
     "ba_fasta_parse", "ba_fastq_parse", "ba_seqfile_free", "ba_gather_pairs",
     "ba_create_multi", "ba_destroy_multi", "ba_multi_devices", "ba_multi_last_error", "ba_multi_set_scoring",
     "ba_multi_set_option", "ba_align_batch_multi", "ba_multi_free_result",
+    "ba_matrix_count", "ba_matrix_name", "ba_matrix_get", "ba_set_scoring_named",
 )
 
 
@@ -137,6 +138,14 @@ def _bind(lib):
     lib.ba_seqfile_free.restype = None
     lib.ba_gather_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
     lib.ba_gather_pairs.restype = i32
+    lib.ba_matrix_count.argtypes = []
+    lib.ba_matrix_count.restype = i32
+    lib.ba_matrix_name.argtypes = [i32]
+    lib.ba_matrix_name.restype = C.c_char_p
+    lib.ba_matrix_get.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_int16))]
+    lib.ba_matrix_get.restype = i32
+    lib.ba_set_scoring_named.argtypes = [vp, i32, i32, C.c_char_p, i64, i32, i64, vp]
+    lib.ba_set_scoring_named.restype = i32
     lib.ba_create_multi.argtypes = [vp, i32, C.POINTER(vp)]
     lib.ba_create_multi.restype = i32
     lib.ba_destroy_multi.argtypes = [vp]
@@ -240,6 +249,13 @@ class Context:
         self._scoring_key = None
         self._check(rc)
         self._scoring_key = key
+
+    def set_scoring_named(self, kind: int, affine: bool, name: str, gap: int, alpha_len: int, gap_open: int, index):
+        """ba_set_scoring_named: one of the 78 align/matrix tables by name, `gap` in the gap row/column."""
+        index = np.ascontiguousarray(index, dtype=np.int32)
+        self._scoring_key = None
+        self._check(self.lib.ba_set_scoring_named(self._h, kind, int(bool(affine)), name.encode(), int(gap), alpha_len,
+                                                  int(gap_open), index.ctypes.data))
 
     def _collect(self, res: BaResult) -> BatchResult:
         out = BatchResult()
@@ -395,3 +411,20 @@ class MultiContext:
         stats = _stats(res)
         self.lib.ba_multi_free_result(self._h, C.byref(res))
         return stats
+
+
+def matrix_names(lib_path: str | None = None):
+    """Names of the scoring tables compiled into the library (align/matrix/matrices.go)."""
+    lib = load(lib_path)
+    return [lib.ba_matrix_name(k).decode() for k in range(lib.ba_matrix_count())]
+
+
+def matrix_table(name: str, lib_path: str | None = None):
+    """(letters in index order, table as a list of rows) of a named scoring table."""
+    lib = load(lib_path)
+    let, letters, tab = C.c_int(), C.c_char_p(), C.POINTER(C.c_int16)()
+    if lib.ba_matrix_get(name.encode(), C.byref(let), C.byref(letters), C.byref(tab)) != BA_OK:
+        raise KeyError(name)
+    n = let.value
+    flat = [int(tab[k]) for k in range(n * n)]
+    return (letters.value or b"").decode(), [flat[r * n:(r + 1) * n] for r in range(n)]

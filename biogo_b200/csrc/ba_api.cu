@@ -25,6 +25,7 @@
 #include "ba_trace16.cuh"
 #include "ba_plan.h"
 #include "ba_format.cuh"
+#include "ba_matrices.inl"
 
 // One spelling for kernel launches so the same scheduler source also drives the CPU
 // emulator of the no-GPU test tier (tests/emu).
@@ -118,7 +119,15 @@ struct ba_ctx {
     std::string err;
     bool have_scoring = false;
     DeviceScoring h_sc;
-    DeviceScoring *d_sc = nullptr;
+    DeviceScoring *d_sc = nullptr;        // the current scoring's device copy (one of sc_cache)
+    DeviceScoring *d_sc_first = nullptr;  // allocated by ba_create (a context without it has no device)
+    struct ScoringSlot {
+        DeviceScoring h;
+        DeviceScoring *d;
+        uint64_t stamp = 0;
+    };
+    std::vector<ScoringSlot> sc_cache;
+    int64_t scoring_uploads = 0;
     int64_t opt_arena_bytes = 0;
     // grow-only device buffers
     DevBuf letters, enc, ref_off, ref_len, qry_off, qry_len, status, err_pos, start;
@@ -1679,8 +1688,9 @@ int ba_create(int device, ba_ctx **out)
         e = cudaEventCreate(&ctx->ev[k]);
         if (e != cudaSuccess) return fail(e, "cudaEventCreate");
     }
-    e = cudaMalloc((void **)&ctx->d_sc, sizeof(DeviceScoring));
+    e = cudaMalloc((void **)&ctx->d_sc_first, sizeof(DeviceScoring));
     if (e != cudaSuccess) return fail(e, "cudaMalloc");
+    ctx->d_sc = ctx->d_sc_first;
     *out = ctx;
     return BA_OK;
 }
@@ -1703,7 +1713,9 @@ void ba_destroy(ba_ctx *ctx)
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
-    if (ctx->d_sc) cudaFree(ctx->d_sc);
+    for (size_t k = 1; k < ctx->sc_cache.size(); k++)
+        if (ctx->sc_cache[k].d) cudaFree(ctx->sc_cache[k].d);
+    if (ctx->d_sc_first) cudaFree(ctx->d_sc_first);
     for (int k = 0; k < 8; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (cudaEvent_t e : ctx->ev_timed) cudaEventDestroy(e);
@@ -1829,14 +1841,80 @@ int ba_set_scoring(ba_ctx *ctx, int kind, int affine, const int64_t *la, int let
     // the matrix is re-read every call (callers may mutate it), but an unchanged one
     // keeps the device copy and the cached plans
     if (ctx->have_scoring && memcmp(&s, &ctx->h_sc, sizeof s) == 0) return BA_OK;
-    ctx->h_sc = s;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->d_sc, &ctx->h_sc, sizeof s, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // device copies of the last few scorings stay resident (callers that alternate between aligners or
+    // named tables -- ba_set_scoring_named -- switch by pointer instead of uploading again)
+    static std::atomic<uint64_t> clock_{1};
+    ba_ctx::ScoringSlot *slot = nullptr;
+    for (auto &e : ctx->sc_cache)
+        if (memcmp(&s, &e.h, sizeof s) == 0) slot = &e;
+    if (!slot) {
+        if (ctx->sc_cache.size() < 8) {
+            ba_ctx::ScoringSlot e;
+            e.d = nullptr;
+            if (ctx->sc_cache.empty())
+                e.d = ctx->d_sc_first;   // the buffer ba_create allocated
+            else
+                CK(cudaMalloc((void **)&e.d, sizeof(DeviceScoring)));
+            ctx->sc_cache.push_back(e);
+            slot = &ctx->sc_cache.back();
+        } else {
+            slot = &ctx->sc_cache[0];
+            for (auto &e : ctx->sc_cache)
+                if (e.stamp < slot->stamp) slot = &e;
+        }
+        slot->h = s;
+        // no kernel of this context is in flight between calls, so the least recently used copy may be rewritten
+        CK(cudaMemcpyAsync(slot->d, &slot->h, sizeof s, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->scoring_uploads++;
+    }
+    slot->stamp = clock_++;
+    ctx->d_sc = slot->d;
+    ctx->h_sc = s;
     ctx->have_scoring = true;
     ctx->scoring_epoch++;  // cached plans depend on the scoring (eligibility, kind)
     ctx->occ_cache.clear(); // dynamic shared memory of the GSUB kernels depends on the matrix size
     return BA_OK;
+}
+
+// ---- align/matrix as a library: the 78 tables of align/matrix/matrices.go by name
+int ba_matrix_count(void) { return ba_matrix_table_n; }
+
+const char *ba_matrix_name(int k) { return (k >= 0 && k < ba_matrix_table_n) ? ba_matrix_table[k].name : nullptr; }
+
+int ba_matrix_get(const char *name, int *let, const char **letters, const int16_t **table)
+{
+    if (!name) return BA_ERR_ARG;
+    for (int k = 0; k < ba_matrix_table_n; k++)
+        if (!strcmp(ba_matrix_table[k].name, name)) {
+            if (let) *let = ba_matrix_table[k].let;
+            if (letters) *letters = ba_matrix_table[k].letters;
+            if (table) *table = (const int16_t *)ba_matrix_table[k].data;
+            return BA_OK;
+        }
+    return BA_ERR_ARG;
+}
+
+int ba_set_scoring_named(ba_ctx *ctx, int kind, int affine, const char *name, int64_t gap, int alpha_len,
+                         int64_t gap_open, const int32_t *index)
+{
+    if (!ctx) return BA_ERR_ARG;
+    int let = 0;
+    const int16_t *t = nullptr;
+    if (ba_matrix_get(name, &let, nullptr, &t) != BA_OK) {
+        ctx->err = std::string("unknown scoring matrix: ") + (name ? name : "(null)");
+        return BA_ERR_ARG;
+    }
+    std::vector<int64_t> la((size_t)let * let);
+    for (int k = 0; k < let * let; k++) la[(size_t)k] = t[k];
+    // the published tables carry no gap penalty (matrices.go:10-13): write `gap` into the gap letter's
+    // row and column, [0][0] stays
+    for (int k = 1; k < let; k++) {
+        la[(size_t)k] = gap;
+        la[(size_t)k * let] = gap;
+    }
+    return ba_set_scoring(ctx, kind, affine, la.data(), let, alpha_len, gap_open, index);
 }
 
 static int check_range(ba_ctx *ctx, const int32_t *ref_len, const int32_t *qry_len, int64_t n)

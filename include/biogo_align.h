@@ -102,9 +102,36 @@ const char *ba_last_error(const ba_ctx *ctx);
  *             (absent in Fitted/FittedAffine: align/fitted_letters.go:71-78)
  *   index     alphabet.Index, 256 entries, negative = letter not in the alphabet
  * The matrix is copied; callers may mutate theirs afterwards.
+ *
+ * LIMITS that the reference does not have (each is reported, never silently wrong):
+ *   - let > 32                                  -> BA_ERR_RANGE ("scoring matrix larger than 32x32")
+ *   - |entry| > 2^20 or |gap_open| > 2^20        -> BA_ERR_RANGE
+ *   - ba_align_batch: |gap_open| + (len_r + len_q + 2) * max|entry| >= 2^23 for some pair
+ *     (about 1.6 Mbp combined with NUC_4)       -> BA_ERR_RANGE; there is no 64-bit path
+ *   - Fitted / FittedAffine with a matrix SMALLER than the alphabet (legal in the reference, which
+ *     has no size check there) and letters beyond the matrix -> BA_PAIR_PANIC for that pair, where Go
+ *     may silently read a neighbouring matrix row.
+ * The host mirrors surface these as errors (Go: ErrDevice wrapping the text; Python: AlignError).
  */
 int ba_set_scoring(ba_ctx *ctx, int kind, int affine, const int64_t *la, int let,
                    int alpha_len, int64_t gap_open, const int32_t *index);
+
+/*
+ * align/matrix as a library: the 78 scoring tables of align/matrix/matrices.go:14-2400
+ * (NUC_4, NUC_4_4, DAYHOFF, GONNET, IDENTITY, MATCH, BLOSUM30..100, BLOSUMN, PAM10..500 and the *_cdi
+ * variants) are compiled into the library, laid out for biogo's alphabets (gap letter at index 0, gap
+ * row/column zero).  ba_matrix_get returns the dimension, the letters in index order and the row-major
+ * table.  ba_set_scoring_named = ba_set_scoring on a named table with `gap` written into the gap letter's
+ * row and column ([0][0] keeps the table's value), the usual way these tables are used with bíogo's
+ * aligners (align/sw_example_test.go builds its matrix the same way by hand).
+ * Every context keeps the device copies of its last eight scorings: switching back to one of them
+ * (named or not) is a pointer swap, not an upload.
+ */
+int ba_matrix_count(void);
+const char *ba_matrix_name(int k);
+int ba_matrix_get(const char *name, int *let, const char **letters, const int16_t **table);
+int ba_set_scoring_named(ba_ctx *ctx, int kind, int affine, const char *name, int64_t gap,
+                         int alpha_len, int64_t gap_open, const int32_t *index);
 
 /*
  * Modules (2)+(3): DP fill + traceback for n independent pairs.

@@ -1,9 +1,12 @@
-"""FASTA / FASTQ ingest (ba_fasta_parse / ba_fastq_parse) against a pure-Python
-restatement of the reference readers (io/seqio/fasta/fasta.go:60-113, io/seqio/fastq/fastq.go:62-141).
-The reference's own tests hold no small golden vectors for these readers (its fixtures are two large
-alignments), so parity here is restatement against restatement on hand-written and random texts.
-CPU tier: the parsers are host code inside the library (emulator build); the GPU tier feeds parsed
-records straight into ba_align_batch."""
+"""FASTA / FASTQ ingest (ba_fasta_parse / ba_fastq_parse).
+
+PINNED on the reference's own reader fixtures, restated under tests/golden/seqio_fixtures.json by
+tests/golden/make_seqio_fixtures.py: io/seqio/fasta/fasta_test.go:30-93 (testaln0/testaln1 ->
+expectN/expectS) and the nine fqTests of io/seqio/fastq/fastq_test.go:92-399 (ids, letters and Phred
+values, including the '@'/'+' quality-start and the truncated-record cases).  Beyond those, a
+pure-Python restatement of the readers (io/seqio/fasta/fasta.go:60-113, io/seqio/fastq/fastq.go:62-141)
+checks hand-written and random texts.  CPU tier: the parsers are host code inside the library
+(emulator build); the GPU tier feeds parsed records straight into ba_align_batch."""
 import random
 
 import numpy as np
@@ -180,3 +183,46 @@ def test_fasta_records_feed_the_aligner(gpu_ctx):
     helpers.compare(res, helpers.run_oracle(0, True, M, -5, idx, pk), "fasta -> align")
     seqobjs = f.sequences(alphabet.DNAgapped)
     assert seqobjs[3].ID == "s3" and seqobjs[3].Desc == "test" and bytes(seqobjs[3].Slice()) == seqs[3]
+
+
+# ---- the reference's own fixtures ---------------------------------------------------------------
+
+def _fixtures():
+    import json
+    import os
+
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seqio_fixtures.json")))
+
+
+def test_fasta_reader_fixtures_of_the_reference(built):
+    """io/seqio/fasta/fasta_test.go:95-126 TestReadFasta: both layouts of the alignment give expectN / expectS."""
+    fx = _fixtures()["fasta"]
+    assert len(fx["headers"]) == 11
+    for text in fx["inputs"]:
+        for stride in (1, 2):
+            f = seqio.parse_fasta(text.encode(), qletters=(stride == 2), lib_path=helpers.EMU_LIB)
+            assert len(f) == 11
+            for k in range(11):
+                header = f.names[k] + ((" " + f.descs[k]) if f.descs[k] else "")
+                assert header == fx["headers"][k]
+                assert f.raw(k)[::stride] == fx["sequences"][k].encode()
+                assert int(f.seq_len[k]) == len(fx["sequences"][k])
+        assert ref_fasta(text.encode()) == [(n, d, bytes(f.raw(k)[::2])) for k, (n, d) in enumerate(zip(f.names, f.descs))]
+
+
+def test_fastq_reader_fixtures_of_the_reference(built):
+    """io/seqio/fastq/fastq_test.go:401-424 TestReadFastq over all nine fqTests (Sanger)."""
+    fx = _fixtures()["fastq"]
+    assert len(fx["tests"]) == 9
+    for t in fx["tests"]:
+        f = seqio.parse_fastq(t["text"].encode(), seqio.SANGER, lib_path=helpers.EMU_LIB)
+        assert len(f) == len(fx["ids"]) == 5
+        for k, want in enumerate(t["seqs"]):
+            header = f.names[k] + ((" " + f.descs[k]) if f.descs[k] else "")
+            assert header == fx["ids"][k]
+            raw = f.raw(k)
+            if want is None:                       # the reference's nil QLetters: an empty record
+                assert int(f.seq_len[k]) == 0 and raw == b""
+                continue
+            assert raw[0::2] == want["letters"].encode()
+            assert list(raw[1::2]) == want["quals"]
