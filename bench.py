@@ -177,6 +177,16 @@ def cpu_port_gcups(w, sample_pairs: int, threads: int, reps: int = 1):
     return sub.cells / best / 1e9, n, sub.cells, best
 
 
+def workload_config(name: str, config_num: int, pairs_per_gpu: int, world: int) -> dict:
+    """The `config` object of the JSON line -- the SAME for the GPU arm and the reference arm: it names the
+    workload (BASELINE.json config, shape, per-GPU batch of the weak-scaling job), not what a particular
+    arm sampled from it (that is in `cpu_baseline.sample` / `config_sample`)."""
+    return {"workload": name, "baseline_config": config_num, "pairs_per_gpu_per_step": pairs_per_gpu,
+            "parallelism": f"independent pairs sharded over {world} GPU(s), no collective",
+            "l2": "inputs + traceback checkpoints per step exceed the 126 MB L2",
+            "seed": "splitmix64 0xB10600+config (+rank<<20)"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  Go cannot run in
     this image, so it is the oracle port (oracle/align_oracle.c), all host threads."""
@@ -196,12 +206,16 @@ def run_reference(args, rank, world):
         cells += c
     dt = time.perf_counter() - t0
     val = cells / dt / 1e9
+    pairs = args.pairs_per_gpu or DEFAULT_PAIRS[args.config]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": w.name, "pairs_per_step": w.n, "cells_per_step": w.cells},
+        "config": workload_config(w.name, args.config, pairs, world),
+        "config_sample": {"pairs_per_step": w.n, "cells_per_step": w.cells,
+                          "note": "bounded sample of the same workload (same generator, same seed): the first "
+                                  f"{w.n} pairs of the step, so the run ends within minutes"},
         "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": threads, "kind": "port",
                          "sample": f"{w.n} pairs of {w.name} per step, {threads} pthreads"},
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,6 +237,53 @@ def emit(line: dict) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+ALG_BYTES_PER_CELL = {True: 1.0, False: 0.25}   # affine 1 byte/cell, linear 2 bits/cell
+AGG_KEYS = ("ms_fill", "ms_trace", "ms_host", "ms_kernels", "ms_d2h", "gpu_launches", "fill_launches", "code_bytes",
+            "n_segs", "pairs_fast16", "waves")
+
+
+class DeviceBatch:
+    """A workload resident in HBM + a context with its scoring set: one `step()` = one pass of the hot path."""
+
+    def __init__(self, torch, _lib, w, dev, local_rank):
+        self.w, self.torch = w, torch
+        self.ctx = _lib.Context(local_rank, os.environ.get("BA_LIB_PATH") or None)
+        self.ctx.set_scoring(w.kind, w.affine, np.array(w.matrix, np.int64).reshape(-1), len(w.matrix), w.alpha.Len(),
+                             w.gap_open if w.affine else 0, w.alpha.LetterIndex())
+        self.t = [torch.from_numpy(a).to(dev) for a in (w.letters, w.ref_off, w.ref_len, w.qry_off, w.qry_len)]
+
+    def step(self, stream=0):
+        t, w = self.t, self.w
+        return self.ctx.align_device(t[0].data_ptr(), t[0].numel(), w.stride, t[1].data_ptr(), t[2].data_ptr(),
+                                     t[3].data_ptr(), t[4].data_ptr(), w.ref_len, w.qry_len, stream=stream,
+                                     collect=False)
+
+
+def timed_steps(torch, dev, batch, steps, warmup, stream):
+    """W untimed + K timed steps, CUDA events on the launching stream; returns (ms, aggregated stats)."""
+    for _ in range(max(warmup, 0)):
+        batch.step(stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {k: 0.0 for k in AGG_KEYS}
+    e0.record(stream)
+    for _ in range(steps):
+        s = batch.step(stream.cuda_stream)
+        for k in agg:
+            agg[k] += s[k]
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1), agg
+
+
+def roofline_of(w, cells, steps, agg, hbm_peak):
+    """Algorithmic-byte roofline of the fill kernels: bytes/cell x cells / fill time vs measured HBM."""
+    fill_s = agg["ms_fill"] * 1e-3
+    alg = ALG_BYTES_PER_CELL[bool(w.affine)]
+    ach = alg * cells * steps / fill_s / 1e9 if fill_s > 0 else 0.0
+    return ach, alg, fill_s
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +295,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--no-onebatch", action="store_true", help="skip the one-process multi-GPU batch (ba_align_batch_multi)")
     args = ap.parse_args()
 
     # Only the JSON line may reach stdout: libraries (NCCL's version banner, torchrun notices) write
@@ -260,29 +323,18 @@ def main():
         raise SystemExit("bench.py needs a B200: biogo_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits that must not occupy the GPUs
 
     pairs = args.pairs_per_gpu or DEFAULT_PAIRS[args.config]
     w = synth.config(args.config, pairs, shard=rank)
-    ctx = _lib.Context(local_rank, os.environ.get("BA_LIB_PATH") or None)  # override: kernel-variant experiments
-    ctx.set_scoring(w.kind, w.affine, np.array(w.matrix, np.int64).reshape(-1), len(w.matrix), w.alpha.Len(),
-                    w.gap_open if w.affine else 0, w.alpha.LetterIndex())
-
-    # ---- inputs resident in HBM (for `value`)
-    d_letters = torch.from_numpy(w.letters).to(dev)
-    d_ro = torch.from_numpy(w.ref_off).to(dev)
-    d_rl = torch.from_numpy(w.ref_len).to(dev)
-    d_qo = torch.from_numpy(w.qry_off).to(dev)
-    d_ql = torch.from_numpy(w.qry_len).to(dev)
+    batch = DeviceBatch(torch, _lib, w, dev, local_rank)
+    ctx = batch.ctx
     stream = torch.cuda.current_stream(dev)
-
-    def step_device():
-        return ctx.align_device(d_letters.data_ptr(), d_letters.numel(), w.stride, d_ro.data_ptr(),
-                                d_rl.data_ptr(), d_qo.data_ptr(), d_ql.data_ptr(), w.ref_len, w.qry_len,
-                                stream=stream.cuda_stream, collect=False)
 
     def barrier():
         if world > 1:
@@ -290,7 +342,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     for _ in range(max(args.warmup, 0)):
-        step_device()
+        batch.step(stream.cuda_stream)
     try:
         gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:  # noqa: BLE001
@@ -300,10 +352,9 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    agg = {"ms_fill": 0.0, "ms_trace": 0.0, "ms_host": 0.0, "ms_kernels": 0.0, "ms_d2h": 0.0, "gpu_launches": 0,
-           "fill_launches": 0, "code_bytes": 0, "n_segs": 0, "pairs_fast16": 0}
+    agg = {k: 0.0 for k in AGG_KEYS}
     for _ in range(args.steps):
-        s = step_device()
+        s = batch.step(stream.cuda_stream)
         for k in agg:
             agg[k] += s[k]
     e1.record(stream)
@@ -317,6 +368,21 @@ def main():
     cells_step = w.cells
     value = world * cells_step * args.steps / (ms_max * 1e-3) / 1e9
 
+    # ---- the same steps with the plan cache off (every call plans, sorts and uploads its work lists: what a
+    # stream of batches with varying read lengths pays)
+    plan_miss = None
+    try:
+        ctx.set_option("plan_cache", 0)
+        k = max(2, min(args.steps, 5))
+        ms_miss, agg_miss = timed_steps(torch, dev, batch, k, 1, stream)
+        plan_miss = {"ms_per_step": ms_miss / k, "value": cells_step / (ms_miss / k * 1e-3) / 1e9,
+                     "host_plan_ms_per_step": agg_miss["ms_host"] / k, "steps": k}
+    except Exception as ex:  # noqa: BLE001
+        plan_miss = {"error": str(ex)[:200]}
+    finally:
+        ctx.set_option("plan_cache", 1)
+        batch.step(stream.cuda_stream)
+
     # ---- end to end from pinned host buffers (for `e2e`)
     e2e = None
     if not args.no_e2e:
@@ -328,6 +394,7 @@ def main():
             raise SystemExit("ba_alloc_host failed")
         h_letters = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(max(nb, 1),))[:nb]
         h_letters[:] = w.letters
+
         def e2e_step(cx):
             return cx.align_packed(h_letters, w.stride, w.ref_off, w.ref_len, w.qry_off, w.qry_len, collect=False)
 
@@ -341,7 +408,8 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt.item())
 
-        # (1) one call at a time: H2D, kernels and D2H of a batch run back to back
+        # (1) one call at a time: the upload travels in groups and the fill starts on the first of them
+        e2e_step(ctx)
         e2e_step(ctx)
         segs = [0]
 
@@ -351,14 +419,12 @@ def main():
         dt_serial = wall(serial)
 
         # (2) the way bíogo's aligners are driven (many goroutines, concurrent/processor.go:48-74):
-        # two host threads, each with its own ba_ctx, take alternate batches, so the H2D copy of
-        # one batch overlaps the kernels of the other.  Every step still pays its own copies.
+        # two host threads, each with its own ba_ctx, take alternate batches, so the copies and the tail of
+        # one batch overlap the kernels of the other.  Every step still pays its own copies.
         dt = dt_serial
         value_two = None
         mode = "one call at a time (the overlapped run failed: %s)"
         try:
-            import threading
-
             ctx2 = _lib.Context(local_rank, os.environ.get("BA_LIB_PATH") or None)
             ctx2.set_scoring(w.kind, w.affine, np.array(w.matrix, np.int64).reshape(-1), len(w.matrix), w.alpha.Len(),
                              w.gap_open if w.affine else 0, w.alpha.LetterIndex())
@@ -384,12 +450,13 @@ def main():
                 raise errs[0]
 
             # the same two-context scheme on the HBM-resident inputs (each context on its own stream)
+            t_ = batch.t
+
             def dev_worker(cx, k):
                 try:
                     for _ in range(k):
-                        cx.align_device(d_letters.data_ptr(), d_letters.numel(), w.stride, d_ro.data_ptr(),
-                                        d_rl.data_ptr(), d_qo.data_ptr(), d_ql.data_ptr(), w.ref_len, w.qry_len,
-                                        stream=0, collect=False)
+                        cx.align_device(t_[0].data_ptr(), t_[0].numel(), w.stride, t_[1].data_ptr(), t_[2].data_ptr(),
+                                        t_[3].data_ptr(), t_[4].data_ptr(), w.ref_len, w.qry_len, stream=0, collect=False)
                 except Exception as ex:  # noqa: BLE001
                     errs.append(ex)
 
@@ -405,6 +472,7 @@ def main():
             if errs:
                 raise errs[0]
             value_two = world * cells_step * args.steps / dt_dev2 / 1e9
+            ctx2.close()
             del ctx2
             mode = None
         except Exception as ex:  # noqa: BLE001 -- keep the single-call number rather than lose the line
@@ -417,19 +485,60 @@ def main():
                "single_call_value": world * cells_step * args.steps / dt_serial / 1e9,
                "device_resident_two_contexts_value": value_two,
                "timing": "host wall clock around ba_align_batch calls on pinned host buffers, max over ranks; "
-                         "value: " + (mode or "2 host threads with one ba_ctx each take alternate batches (copies of "
-                                              "one overlap kernels of the other)") +
-                         "; single_call_value: one call at a time; device_resident_two_contexts_value: the "
+                         "value: " + (mode or "2 host threads with one ba_ctx each take alternate batches (copies and "
+                                              "tail of one overlap kernels of the other)") +
+                         "; single_call_value: one blocking call at a time (its upload travels in groups, the fill "
+                         "starts chunk by chunk on what has arrived); device_resident_two_contexts_value: the "
                          "two-thread scheme on HBM-resident inputs.  The overlapped numbers can exceed the top-level "
                          "`value`, which runs one context step after step (CUDA-event timed): there the result "
-                         "copy and host gather of a step are not hidden under the next step's kernels"}
+                         "copy and host work of a step are not hidden under the next step's kernels"}
         ctx.lib.ba_free_host(hp)
 
+    # ---- the other BASELINE configs, a few steps each on this rank's GPU (rank 0 reports them)
+    other = {}
+    hbm_peak, peak_src = load_peaks()
+    if not args.no_other_configs and rank == 0:
+        for num, n_pairs in ((1, DEFAULT_PAIRS[1]), (3, DEFAULT_PAIRS[3]), (4, 128), (5, DEFAULT_PAIRS[5])):
+            if num == args.config:
+                continue
+            try:
+                wo = synth.config(num, n_pairs)
+                bo = DeviceBatch(torch, _lib, wo, dev, local_rank)
+                k = 4
+                ms_o, agg_o = timed_steps(torch, dev, bo, k, 3, stream)
+                ach, alg, fill_s = roofline_of(wo, wo.cells, k, agg_o, hbm_peak)
+                other[f"cfg{num}"] = {
+                    "workload": wo.name, "pairs": wo.n, "steps": k, "warmup": 3,
+                    "value": wo.cells * k / (ms_o * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms_o / k,
+                    "fill_ms_per_step": agg_o["ms_fill"] / k, "trace_ms_per_step": agg_o["ms_trace"] / k,
+                    "roofline_frac_algorithmic": ach / hbm_peak, "algorithmic_bytes_per_cell": alg,
+                    "stored_bytes_per_cell": agg_o["code_bytes"] / (wo.cells * k),
+                    "dtype": "int16" if agg_o["pairs_fast16"] else "int32",
+                    "pairs_on_dpx16_path": int(agg_o["pairs_fast16"] // k)}
+                bo.ctx.close()
+                del bo, wo
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001
+                other[f"cfg{num}"] = {"error": str(ex)[:200]}
+
+    # ---- ONE batch over all N GPUs from ONE process (ba_create_multi / ba_align_batch_multi): rank 0 drives
+    # GPUs 0..N-1 while the other ranks wait on the host (gloo), strong scaling of a fixed batch
+    onebatch = None
+    if not args.no_onebatch:
+        if world > 1:
+            ctx.close()                       # the per-rank contexts give their arenas back first
+            batch.t = None
+            torch.cuda.empty_cache()
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            onebatch = run_onebatch(_lib, synth, w, args, world)
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     if rank == 0:
-        hbm_peak, peak_src = load_peaks()
         fill_s = agg["ms_fill"] * 1e-3
-        ach = agg["code_bytes"] / fill_s / 1e9 if fill_s > 0 else 0.0
-        traffic, traffic_src = None, None
+        ach, alg, _ = roofline_of(w, cells_step, args.steps, agg, hbm_peak)
+        traffic, traffic_src, ent = None, None, None
         try:  # DRAM bytes per launch of the fill kernel, captured once with ncu --set full
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 ent = json.load(f)["entries"].get(w.name)
@@ -438,17 +547,23 @@ def main():
                 traffic_src = "profiles/ncu_traffic.json (" + ent["kernel"] + ", one launch)"
         except (OSError, KeyError, ValueError):
             pass
+        launches = max(agg["fill_launches"], 1)
+        alg_per_launch = alg * cells_step * args.steps / launches
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": agg["code_bytes"] / max(agg["fill_launches"], 1),
+                "traffic_ratio": (traffic / alg_per_launch) if traffic else None,
+                "algorithmic_bytes_per_launch": alg_per_launch,
                 "peak_source": peak_src,
                 "kernel": ("ba_fill16_kernel (packed s16x2 DPX fill + checkpoint stores)" if agg["pairs_fast16"]
                            else "ba_fill32_kernel (DP fill + traceback-code stores)"),
-                "algorithmic_bytes_per_cell": (1.0 if w.affine else 0.25),
+                "algorithmic_bytes_per_cell": alg,
                 "stored_bytes_per_cell": agg["code_bytes"] / (cells_step * args.steps),
+                "stored_bytes_per_launch": agg["code_bytes"] / launches,
                 "fill_ms_per_step": agg["ms_fill"] / args.steps,
                 "fill_share_of_step": agg["ms_fill"] / ms if ms > 0 else None,
-                "fill_gcups": cells_step * args.steps / fill_s / 1e9 if fill_s > 0 else None}
+                "fill_gcups": cells_step * args.steps / fill_s / 1e9 if fill_s > 0 else None,
+                "note": "achieved = SURVEY 8(d) algorithmic bytes per cell x cells / fill-kernel time (CUDA events "
+                        "inside the step); the checkpoints actually stored are stored_bytes_per_cell"}
         dpx = load_dpx_peak()
         if dpx and fill_s > 0:
             lanes_per_cell = 3 if w.affine else 1
@@ -458,39 +573,109 @@ def main():
             roof["dpx"] = {"achieved_lane_results_per_s": achieved_lane, "peak_lane_results_per_s": peak_lane,
                            "frac": achieved_lane / peak_lane, "lane_results_per_cell": lanes_per_cell,
                            "peak_source": "profiles/dpx_peaks.json (ba_microbench on B200)"}
-            if traffic is not None:  # the same ncu capture: how busy the integer/DPX pipe really is
+            if traffic is not None and ent:  # the same ncu capture: how busy the integer/DPX pipe really is
                 roof["dpx"]["ncu_alu_pipe_pct"] = ent.get("alu_pipe_pct")
                 roof["dpx"]["ncu_issue_active_pct"] = ent.get("issue_active_pct")
                 roof["dpx"]["ncu_thread_inst_per_cell"] = ent.get("inst_per_cell")
+        cfg = workload_config(w.name, args.config, w.n, world)   # identical in the reference arm's line
+        cfg_detail = {"cells_per_gpu_per_step": cells_step,
+                      "host_plan": "work lists cached across same-shaped batches (lengths only, never results); "
+                                   "the uncached cost is plan_cache_miss"}
         line = {
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int16" if agg["pairs_fast16"] else "int32",
-            "data": "synthetic",
-            "config": {"workload": w.name, "pairs_per_gpu_per_step": w.n, "cells_per_gpu_per_step": cells_step,
-                       "parallelism": f"independent pairs sharded over {world} GPU(s), no collective",
-                       "l2": "inputs + traceback codes per step exceed the 126 MB L2",
-                       "seed": "splitmix64 0xB10600+config (+rank<<20)",
-                       "host_plan": "work lists cached across same-shaped batches (lengths only, never results)"},
+            "data": "synthetic", "config": cfg, "config_detail": cfg_detail,
             "roofline": roof, "clocks": clocks,
             "breakdown_ms_per_step": {"fill": agg["ms_fill"] / args.steps, "trace": agg["ms_trace"] / args.steps,
                                       "d2h": agg["ms_d2h"] / args.steps, "host_plan_scatter": agg["ms_host"] / args.steps,
-                                      "pairs_on_dpx16_path": agg["pairs_fast16"] // args.steps},
+                                      "kernels_span": agg["ms_kernels"] / args.steps,
+                                      "waves": agg["waves"] / args.steps,
+                                      "pairs_on_dpx16_path": int(agg["pairs_fast16"] // args.steps),
+                                      "note": "CUDA-event spans inside the library; per-pair results are gathered in "
+                                              "pair order on the device, the host neither scans nor scatters"},
+            "plan_cache_miss": plan_miss,
             "gpu_launches": int(agg["gpu_launches"]),
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline and world == 1:
+        if other:
+            line["other_configs"] = other
+        if onebatch:
+            line["onebatch"] = onebatch
+        if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or max(64, 2000 * threads)
-            g, n, c, dt = cpu_port_gcups(w, sample, threads)
+            g, n, c, dtc = cpu_port_gcups(w, sample, threads)
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port",
                                     "sample": f"first {n} pairs of the step ({c} cells), C port of the Go path "
-                                              f"(full int64 table per pair), {threads} pthreads, {dt:.1f} s"}
+                                              f"(full int64 table per pair), {threads} pthreads, {dtc:.1f} s"}
         emit(line)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
+
+
+def run_onebatch(_lib, synth, w, args, world):
+    """north_star's multi-GPU path: ONE batch, ONE process, N GPUs, host buffers in, gathered results out
+    (ba_align_batch_multi: dealing + per-device gather/upload + kernels + result gather, all inside the timed
+    region).  Strong scaling: the batch is the same for every N (8 x the per-GPU shard of the headline config,
+    i.e. 1 M pairs of config 2) and, second, 8 x the 25 000-pair shard of config 5 (mixed lengths, QLetters:
+    dealt by length buckets and gathered)."""
+    import ctypes as C
+
+    out = {"n_gpus": world, "process": "one process, one host thread per device, no collective",
+           "timing": "host wall clock around blocking ba_align_batch_multi calls on pinned host buffers",
+           "batches": {}}
+    try:
+        mc = _lib.MultiContext(tuple(range(world)), os.environ.get("BA_LIB_PATH") or None)
+    except Exception as ex:  # noqa: BLE001
+        return {"error": str(ex)[:200]}
+    todo = [("cfg%d" % args.config, w, 8)]
+    if args.config != 5:
+        try:
+            todo.append(("cfg5", synth.config(5, DEFAULT_PAIRS[5]), 8))
+        except Exception as ex:  # noqa: BLE001
+            out["batches"]["cfg5"] = {"error": str(ex)[:200]}
+    for name, ww, reps in todo:
+        hp = None
+        try:
+            nb = ww.letters.nbytes
+            hp = mc.lib.ba_alloc_host(nb * reps)
+            if not hp:
+                raise RuntimeError("ba_alloc_host failed")
+            hl = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(nb * reps,))
+            ro, qo = [], []
+            for r in range(reps):
+                hl[r * nb:(r + 1) * nb] = ww.letters
+                ro.append(ww.ref_off + r * nb)
+                qo.append(ww.qry_off + r * nb)
+            ro, qo = np.concatenate(ro), np.concatenate(qo)
+            rl, ql = np.tile(ww.ref_len, reps), np.tile(ww.qry_len, reps)
+            cells = ww.cells * reps
+            mc.set_scoring(ww.kind, ww.affine, np.array(ww.matrix, np.int64).reshape(-1), len(ww.matrix),
+                           ww.alpha.Len(), ww.gap_open if ww.affine else 0, ww.alpha.LetterIndex())
+            st = None
+            for _ in range(2):
+                st = mc.align_packed(hl, ww.stride, ro, rl, qo, ql, collect=False)
+            k = 3
+            t0 = time.perf_counter()
+            for _ in range(k):
+                st = mc.align_packed(hl, ww.stride, ro, rl, qo, ql, collect=False)
+            dt = (time.perf_counter() - t0) / k
+            out["batches"][name] = {
+                "workload": ww.name, "pairs": int(len(rl)), "cells": int(cells), "steps": k, "warmup": 2,
+                "batch": f"{reps} x the {ww.n}-pair synthetic shard (pairs repeat; lengths and letters as generated)",
+                "ms_per_batch": dt * 1e3, "value": cells / dt / 1e9, "unit": "GCUPS",
+                "h2d_bytes": int(nb * reps + len(rl) * 24), "d2h_bytes": int(st["n_segs"] * 20 + len(rl) * 24),
+                "slowest_device_kernels_span_ms": st["ms_kernels"], "host_deal_ms": st["ms_host"]}
+        except Exception as ex:  # noqa: BLE001
+            out["batches"][name] = {"error": str(ex)[:200]}
+        finally:
+            if hp:
+                mc.lib.ba_free_host(hp)
+    mc.close()
+    return out
 
 
 if __name__ == "__main__":
