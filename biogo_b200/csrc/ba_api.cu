@@ -1049,7 +1049,10 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     std::vector<WorkItem *> long_tasks;
 
     // ---- one-time set-up on the main stream: inputs of the first wave, work lists, counters
-    if ((rc = prep_pairs(ctx, B, plan.waves[0].max_pair)) != BA_OK) return rc;
+    // (ahead of the device gate: encode + validate run beside the previous batch's fills.  A batch whose
+    // upload is still in flight only takes its first group here; the chunked fill asks for the rest.)
+    if ((rc = prep_pairs(ctx, B, (!overlap && B.groups.size() > 1) ? B.groups[0].p_lo : plan.waves[0].max_pair)) != BA_OK)
+        return rc;
     WorkItem *d_items = (WorkItem *)ctx->items.p;
     const bool dev_ok = use_cache && pc.dev_items == ctx->items.p && pc.dev_slot_off == ctx->slot_off.p &&
                         pc.dev_slot_cap == ctx->slot_cap.p;
@@ -1269,12 +1272,23 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         // thread-per-pair CTAs: 64 threads beside a running fill (they fit the slot of one fill CTA)
         const int tcta = ctx->opt_trace_cta == 64 || (ctx->opt_trace_cta == 0 && overlap && wi + 1 < nw) ? 64
                                                                                                           : BA_TRACE_THREADS;
+        // affine kinds keep value tiles in dynamic shared memory (ba_trace16.cuh TileSmem)
+        const size_t tsm128 = lin ? 0 : (size_t)TileSmem<false, BA_TRACE_THREADS>::BYTES;
+        const size_t tsm = lin ? 0 : (tcta == 64 ? (size_t)TileSmem<false, 64>::BYTES : tsm128);
+        auto trace_launch = [&](Trace16Fn fn, unsigned grid, int threads, size_t smem, const Trace16Params &prm) -> int {
+            int occ_unused = 0;
+            int r = cached_occupancy(ctx, fn, threads, occ_unused, smem);   // opts the kernel in to > 48 KB once
+            if (r != BA_OK) return r;
+            BA_LAUNCH_SMEM(fn, grid, threads, smem, T, prm);
+            return BA_OK;
+        };
         if (cta_trace) {
-            BA_LAUNCH(pick_trace16t<BA_TRACE_THREADS>(kind, lin), (unsigned)w.count, BA_TRACE_THREADS, T, tp);
+            if ((rc = trace_launch(pick_trace16t<BA_TRACE_THREADS>(kind, lin), (unsigned)w.count, BA_TRACE_THREADS, tsm128, tp)) != BA_OK)
+                return rc;
             B.out->warp_trace_launches++;
         } else if (warp_trace) {
             const unsigned tb = (unsigned)((w.count + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-            BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, T, tp);
+            if ((rc = trace_launch(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, tsm128, tp)) != BA_OK) return rc;
             B.out->warp_trace_launches++;
         } else {
             const int64_t slots_free = (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS - w.count;
@@ -1298,7 +1312,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 Trace16Params th = tp;
                 th.n_items = (int)head;
                 const unsigned tb = (unsigned)((head + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-                BA_LAUNCH(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, T, th);
+                if ((rc = trace_launch(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, tsm128, th)) != BA_OK) return rc;
                 B.out->warp_trace_launches++;
                 B.launches++;
             }
@@ -1312,14 +1326,15 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 if (ctx->opt_trace_mode != 5) {
                     // static assignment: thread k of the grid walks pair k
                     const int64_t tblocks = (w.count - head + tcta - 1) / tcta;
-                    BA_LAUNCH(pick_trace16(kind, lin, tcta), (unsigned)tblocks, tcta, T, tt);
+                    if ((rc = trace_launch(pick_trace16(kind, lin, tcta), (unsigned)tblocks, tcta, tsm, tt)) != BA_OK) return rc;
                 } else {
                     // persistent grid, pairs claimed from a counter (largest first).  Measured on B200:
                     // +5 % on configs 1 and 3, -9 % on config 2 against the static kernel, so it is
                     // opt-in (trace_mode 5) until the state machine's overhead is trimmed
                     int64_t tblocks = (w.count - head + BA_TRACE_THREADS - 1) / BA_TRACE_THREADS;
                     tblocks = std::min<int64_t>(tblocks, (int64_t)ctx->sm_count * BA_TRACE_MINB);
-                    BA_LAUNCH(pick_trace16p(kind, lin), (unsigned)tblocks, BA_TRACE_THREADS, T, tt);
+                    if ((rc = trace_launch(pick_trace16p(kind, lin), (unsigned)tblocks, BA_TRACE_THREADS, tsm128, tt)) != BA_OK)
+                        return rc;
                 }
             }
         }

@@ -162,7 +162,7 @@ __host__ __device__ inline size_t ba16_gsub_bytes_per_warp(int let)
 #ifdef BA_EMULATE
 static inline uint8_t *ba_dyn_smem()
 {
-    static uint8_t buf[BA16_WARPS * (BA_MAX_LET + 1) * 512];
+    static uint8_t buf[80 * 1024];   // GSUB score tables of the fill, value tiles of the affine traceback
     return buf;
 }
 #else
