@@ -163,6 +163,7 @@ struct ba_ctx {
     int64_t deferred_dev_segs = 0;                   // multi-device: segments of the last batch still only in ctx->segs
     std::mutex pinned_mu;                            // ba_free_result may run on another thread (GC finalizers)
     int64_t pinned_budget = 0;                       // bytes of unused pinned blocks kept for reuse (0 = default)
+    size_t pinned_peak = 0;                          // most pinned bytes in use at once so far
 };
 
 namespace {
@@ -235,7 +236,14 @@ void pinned_put(ba_ctx *ctx, void *p)
         }
         if (!b.used) idle += b.cap;
     }
-    const size_t budget = ctx->pinned_budget > 0 ? (size_t)ctx->pinned_budget : ((size_t)1 << 30);
+    // default budget: what the largest batch so far had in use at once (its blocks come back on the next
+    // call of the same size), at least 1 GiB
+    size_t in_use = 0;
+    for (auto &b : ctx->pinned)
+        if (b.used || b.p == p) in_use += b.cap;
+    ctx->pinned_peak = std::max(ctx->pinned_peak, in_use);
+    const size_t budget = ctx->pinned_budget > 0 ? (size_t)ctx->pinned_budget
+                                                 : std::max((size_t)1 << 30, ctx->pinned_peak + ctx->pinned_peak / 2);
     while (idle > budget) {
         int old = -1;
         for (size_t k = 0; k < ctx->pinned.size(); k++)
@@ -1272,9 +1280,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         // thread-per-pair CTAs: 64 threads beside a running fill (they fit the slot of one fill CTA)
         const int tcta = ctx->opt_trace_cta == 64 || (ctx->opt_trace_cta == 0 && overlap && wi + 1 < nw) ? 64
                                                                                                           : BA_TRACE_THREADS;
-        // affine kinds keep value tiles in dynamic shared memory (ba_trace16.cuh TileSmem)
-        const size_t tsm128 = lin ? 0 : (size_t)TileSmem<false, BA_TRACE_THREADS>::BYTES;
-        const size_t tsm = lin ? 0 : (tcta == 64 ? (size_t)TileSmem<false, 64>::BYTES : tsm128);
+        const size_t tsm128 = 0, tsm = 0;   // the traceback kernels use static shared memory only
         auto trace_launch = [&](Trace16Fn fn, unsigned grid, int threads, size_t smem, const Trace16Params &prm) -> int {
             int occ_unused = 0;
             int r = cached_occupancy(ctx, fn, threads, occ_unused, smem);   // opts the kernel in to > 48 KB once

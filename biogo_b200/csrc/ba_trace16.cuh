@@ -130,89 +130,13 @@ __device__ __forceinline__ Cell3 border_col0(int i, int go, int er)
     return c;
 }
 
-// ---- tile storage in shared memory ------------------------------------------------------------
-// Linear kinds: one code byte per cell (8 x 8).  Affine kinds: the VALUES of the three layers of every cell
-// plus a one-cell halo (the tile's top boundary row and left boundary column), (8+1) x (8+1) cells of
-// {M | U packed in a word, L in a halfword} -- the walk derives the candidate order of
-// align/sw_affine_letters.go:171-275 only at the ~10 cells of a tile it actually visits, instead of the
-// fill-style exact codes for all 64 (which cost ~45 instructions per cell; values alone cost ~13).
-// Everything is interleaved over the threads of the CTA (stride TS) so that the lanes of a warp working
-// on the same cell of their tiles hit distinct banks.
-#define BA_TILE_W (BA_MAX_COLS + 1)
-#define BA_TILE_CELLS ((BA_TILE_ROWS + 1) * BA_TILE_W)
-struct TilePtr {
-    uint8_t *code;    // LIN
-    uint32_t *mu;     // affine: M (low half) | U (high half), int16 each, unscaled
-    uint16_t *l;      // affine: L
-};
-template <bool LIN, int TS>
-struct TileSmem {
-    static constexpr int BYTES = LIN ? BA_TILE_ROWS * BA_MAX_COLS * TS : BA_TILE_CELLS * TS * 6;
-};
-template <bool LIN, int TS>
-__device__ __forceinline__ TilePtr tile_ptr(uint8_t *raw, int column)
-{
-    TilePtr t;
-    t.code = raw + column;
-    t.mu = (uint32_t *)raw + column;
-    t.l = (uint16_t *)(raw + BA_TILE_CELLS * TS * 4) + column;
-    return t;
-}
-template <int TS>
-__device__ __forceinline__ void tile_put(const TilePtr &t, int row, int col, int M, int U, int L)
-{
-    const int x = (row * BA_TILE_W + col) * TS;
-    t.mu[x] = ((unsigned)M & 0xffffu) | ((unsigned)U << 16);
-    t.l[x] = (uint16_t)L;
-}
-template <int TS>
-__device__ __forceinline__ void tile_get(const TilePtr &t, int row, int col, int &M, int &U, int &L)
-{
-    const int x = (row * BA_TILE_W + col) * TS;
-    const unsigned w = t.mu[x];
-    M = (int)(short)(w & 0xffffu);
-    U = (int)(short)(w >> 16);
-    L = (int)(short)t.l[x];
-}
-
-// DP border values, unscaled, with the fill kernel's 16-bit "minus infinity" (ba_fill16.cuh BA16_NEG: finite
-// values stay above -14000, so a candidate derived from it never equals a finite value).
-template <int KIND>
-__device__ __forceinline__ Cell3 border16_row0(int j, int go, int eq)
-{
-    Cell3 c;
-    if (KIND == KIND_SW) {
-        c.M = c.U = c.L = 0;
-    } else if (j == 0) {
-        c.M = 0;                // table[0] = {0, minInt, minInt}
-        c.U = c.L = BA16_NEG;
-    } else {
-        c.M = c.U = BA16_NEG;   // nw_affine_letters.go:119-131
-        c.L = go + j * eq;
-    }
-    return c;
-}
-template <int KIND>
-__device__ __forceinline__ Cell3 border16_col0(int i, int go, int er)
-{
-    Cell3 c;
-    if (KIND == KIND_SW) {
-        c.M = c.U = c.L = 0;
-    } else {
-        c.M = c.L = BA16_NEG;   // nw_affine_letters.go:132-142 / fitted_affine_letters.go:123-132
-        c.U = (KIND == KIND_NW) ? go + i * er : 0;
-    }
-    return c;
-}
-
-// Recompute the VALUES of the tile of strip g, period e, for rows rt+1 .. imax and columns up to jmax, and
-// store them with their halo: cell (r, table column c0+k+1) at tile (r - rt, k + 1); the top boundary row is
-// tile row 0, the left boundary column (table column cL = c0 + kfirst) is tile column kfirst.
-// S is the UNSCALED scoring matrix in shared memory (row stride `let`).
+// Recompute the tile of strip g, period e, for rows rt+1 .. imax and columns up to jmax, and
+// store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).
+// S is the scoring matrix scaled by BA_SCALE in shared memory (row stride `let`).
 template <int KIND, int TS>
 __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
-                                                 const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
-                                                 const TilePtr &tile, TileProbe &pb)
+                                             const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
+                                             uint8_t *tile, TileProbe &pb)
 {
     const int v = CkView::lane_of(g);
     const int rt = max(BA16_PERIOD * e - v, 0); // top boundary row (0 = DP border)
@@ -235,7 +159,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     }
 
     // ---- corner (rt, cL) and the U layer of the left boundary column
-    Cell3 corner = (rt == 0) ? border16_row0<KIND>(cL, go, eq_u) : border16_col0<KIND>(rt, go, er_u);
+    Cell3 corner = (rt == 0) ? border_row0<KIND>(cL, go, eq_u) : border_col0<KIND>(rt, go, er_u);
     int leftU = corner.U;                       // U at (row, cL), advanced row by row
     const int gl = g - 1;                       // strip whose last column is cL
     if (cL > 0) {
@@ -247,16 +171,19 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
         if (r0 >= 1) {
             int mm;
             ck.row_mu(gl, (r0 + vl) / BA16_PERIOD - 1, ck.cols - 1, mm, u);
+            u *= BA_SCALE;
         } else {
             r0 = 0;                             // DP border row
-            u = border16_row0<KIND>(cL, go, eq_u).U;
+            u = border_row0<KIND>(cL, go, eq_u).U;
         }
         for (int r = r0 + 1; r <= rt; r++) {
             int mp, lp;
-            if (r - 1 >= 1)
+            if (r - 1 >= 1) {
                 ck.col_ml(gl, r - 1, mp, lp);
-            else
-                mp = border16_row0<KIND>(cL, go, eq_u).M;
+                mp *= BA_SCALE;
+            } else {
+                mp = border_row0<KIND>(cL, go, eq_u).M;
+            }
             const int er = S[(int)rs[(r - 1) * stride] * let];
             u = max(mp + go + er, u + er);
             if (KIND == KIND_SW) u = max(u, 0);
@@ -265,12 +192,11 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
         if (rt >= 1) {
             int mm, ll;
             ck.col_ml(gl, rt, mm, ll);
-            corner.M = mm;
-            corner.L = ll;
+            corner.M = mm * BA_SCALE;
+            corner.L = ll * BA_SCALE;
             corner.U = u;
         }
     }
-    tile_put<TS>(tile, 0, kfirst, corner.M, corner.U, corner.L);
 
     // ---- top boundary row rt for my columns
     Cell3 Pv[BA_MAX_COLS];
@@ -283,27 +209,27 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
                 if (rt >= 1) {
                     int mm, uu;
                     ck.row_mu(g, e - 1, k, mm, uu);
-                    Pv[k].M = mm;
-                    Pv[k].U = uu;
+                    Pv[k].M = mm * BA_SCALE;
+                    Pv[k].U = uu * BA_SCALE;
                     Pv[k].L = max(lM + go + eqv[k], lL + eqv[k]);
                     if (KIND == KIND_SW) Pv[k].L = max(Pv[k].L, 0);
                     lM = Pv[k].M;
                     lL = Pv[k].L;
                 } else {
-                    Pv[k] = border16_row0<KIND>(c0 + k + 1, go, eq_u);
+                    Pv[k] = border_row0<KIND>(c0 + k + 1, go, eq_u);
                 }
-                tile_put<TS>(tile, 0, k + 1, Pv[k].M, Pv[k].U, Pv[k].L);
             }
         }
     }
 
     // ---- rows rt+1 .. imax
     Cell3 dprev = corner;  // (row-1, cL)
+    uint8_t *trow = tile;
     // the next row's letter and left-boundary checkpoint are fetched one row ahead, so their
     // latency hides under the current row's cells
     int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0, nM = 0, nL = 0;
     if (cL > 0 && rt + 1 <= imax) ck.col_ml(gl, rt + 1, nM, nL);
-    for (int r = rt + 1; r <= imax; r++) {
+    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * TS) {
         const int *Srow = S + nR * let;
         const int mm = nM, ll = nL;
         if (r + 1 <= imax) {
@@ -317,31 +243,21 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
             // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er [, 0])
             leftU = max(dprev.M + goer, leftU + er);
             if (KIND == KIND_SW) leftU = max(leftU, 0);
-            left.M = mm;
-            left.L = ll;
+            left.M = mm * BA_SCALE;
+            left.L = ll * BA_SCALE;
             left.U = leftU;
         } else {
-            left = border16_col0<KIND>(r, go, er_u);
+            left = border_col0<KIND>(r, go, er_u);
         }
-        const int trow = r - rt;
-        tile_put<TS>(tile, trow, kfirst, left.M, left.U, left.L);
         Cell3 d = dprev, l = left;
 #pragma unroll
         for (int k = 0; k < BA_MAX_COLS; k++) {
             if (k >= kfirst && k <= klast) {
+                unsigned code;
+                int dm;
                 const Cell3 old = Pv[k];
-                Cell3 nw;
-                const int dm = __vimax3_s32(d.M, d.U, d.L);
-                if (KIND == KIND_SW) {
-                    nw.M = __viaddmax_s32_relu(dm, Srow[qo[k]], 0);
-                    nw.U = __vimax3_s32_relu(old.U + er, old.M + goer, 0);
-                    nw.L = __vimax3_s32_relu(l.L + eqv[k], l.M + go + eqv[k], 0);
-                } else {
-                    nw.M = dm + Srow[qo[k]];
-                    nw.U = max(old.U + er, old.M + goer);
-                    nw.L = max(l.L + eqv[k], l.M + go + eqv[k]);
-                }
-                tile_put<TS>(tile, trow, k + 1, nw.M, nw.U, nw.L);
+                const Cell3 nw = affine_cell<KIND>(d, old, l, Srow[qo[k]], er, goer, eqv[k], go + eqv[k], code, dm);
+                trow[k * TS] = (uint8_t)code;
                 const int col = c0 + k + 1;
                 if (KIND == KIND_SW && pb.want >= 0 && nw.M == pb.want) {
                     pb.fi = r;
@@ -370,9 +286,8 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
 template <int KIND, int TS>
 __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S, int let, const uint8_t *rs,
                                                  const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
-                                                 const TilePtr &tp_, TileProbe &pb)
+                                                 uint8_t *tile, TileProbe &pb)
 {
-    uint8_t *tile = tp_.code;
     const int v = CkView::lane_of(g);
     const int rt = max(BA16_PERIOD * e - v, 0);
     const int c0 = ck.left_col(g);
@@ -455,7 +370,7 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
 template <int KIND, bool LIN, int TS = BA_TRACE_THREADS>
 __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
-                                             const TilePtr &tile, TileProbe &pb)
+                                             uint8_t *tile, TileProbe &pb)
 {
     if (LIN)
         trace16_tile_lin<KIND, TS>(ck, S, let, rs, qs, stride, g, e, imax, jmax, tile, pb);
@@ -463,21 +378,16 @@ __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int
         trace16_tile_aff<KIND, TS>(ck, S, let, go, rs, qs, stride, g, e, imax, jmax, tile, pb);
 }
 
-// One step of the walk at tile cell (row, col) [row >= 1, col >= kfirst + 1]: which move the reference takes
-// from here, the layer it lands in and the score delta.
-//   Linear: the cell's code (diag, up, left; align/sw_letters.go:137-171).
-//   Affine: the seven candidates of align/sw_affine_letters.go:171-275 in their layer-independent order
-//   (1 U[up]+er, 2 L[left]+eq, 3 M[up]+go+er, 4 M[left]+go+eq, then the diagonal three: M,U,L for SW;
-//   U,L,M for NW/Fitted, nw_affine_letters.go:255-299), evaluated on the tile's stored values against
-//   `cur`, the value of the current cell in the current layer (tracked by the walk: every step subtracts
-//   the matched candidate's constant, which is exactly cur - pred).  Returns false when none matched.
-template <int KIND, bool LIN, int TS>
-__device__ __forceinline__ bool trace16_next(const TilePtr &t, int row, int col, int cur, int er, int eq, int sub,
-                                             int go, int &move, int &nl, int &delta)
+// One step of the walk: decode the cell's code for the current layer into (move, next layer,
+// score delta).  Affine: the seven candidates of align/sw_affine_letters.go:171-275 (diag
+// sub-order differs for NW/Fitted, nw_affine_letters.go:255-299).  Linear: diag, up, left
+// (align/sw_letters.go:137-171).  Returns false when no candidate matched.
+template <int KIND, bool LIN>
+__device__ __forceinline__ bool trace16_decode(unsigned code, int layer, int er, int eq, int sub, int go, int &move,
+                                               int &nl, int &delta)
 {
     nl = 0;
     if (LIN) {
-        const unsigned code = t.code[((row - 1) * BA_MAX_COLS + (col - 1)) * TS];
         switch (code & 3u) {
         case 3: move = MV_DIAG; delta = sub; return true;
         case 2: move = MV_UP;   delta = er;  return true;
@@ -485,28 +395,7 @@ __device__ __forceinline__ bool trace16_next(const TilePtr &t, int row, int col,
         default: move = MV_DIAG; delta = 0;  return false;
         }
     }
-    int uM, uU, uL, lM, lU, lL, dM, dU, dL;
-    tile_get<TS>(t, row - 1, col, uM, uU, uL);
-    tile_get<TS>(t, row, col - 1, lM, lU, lL);
-    tile_get<TS>(t, row - 1, col - 1, dM, dU, dL);
-    (void)uL;
-    (void)lU;
-    const int x = cur - sub;   // a diagonal candidate matches when its layer value equals cur - sub
-    // evaluated last to first, so the FIRST matching candidate of the reference's order wins
-    int f = 0;
-    if (KIND == KIND_SW) {
-        if (dL == x) f = 7;
-        if (dU == x) f = 6;
-        if (dM == x) f = 5;
-    } else {
-        if (dM == x) f = 7;
-        if (dL == x) f = 6;
-        if (dU == x) f = 5;
-    }
-    if (lM + go + eq == cur) f = 4;
-    if (uM + go + er == cur) f = 3;
-    if (lL + eq == cur) f = 2;
-    if (uU + er == cur) f = 1;
+    const unsigned f = (layer == 0) ? (code & 7u) : (layer == 1) ? ((code >> 3) & 3u) : (code >> 5);
     switch (f) {
     case 1: move = MV_UP;   nl = 1; delta = er;      return true;
     case 2: move = MV_LEFT; nl = 2; delta = eq;      return true;
@@ -526,20 +415,16 @@ __device__ __forceinline__ bool trace16_next(const TilePtr &t, int row, int col,
 template <int KIND, bool LIN, int TS = BA_TRACE_THREADS>
 __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THREADS / TS)) ba_trace16_kernel(Trace16Params P)
 {
-    // linear kinds: 8 KB of code bytes (static); affine kinds: the value tiles live in dynamic shared memory
-    // (up to 61 KB per CTA, beyond the 48 KB a kernel gets without opting in)
-    __shared__ __align__(16) uint8_t tiles_lin[LIN ? TileSmem<true, TS>::BYTES : 16];
-    uint8_t *tiles = LIN ? tiles_lin : ba_dyn_smem();
-    __shared__ int S[BA_MAX_LET * BA_MAX_LET];   // linear kinds: scaled by BA_SCALE (tagged cells); affine: unscaled
-    constexpr int SSH = LIN ? BA_SCALE_SHIFT : 0;
+    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * TS];
+    __shared__ int S[BA_MAX_LET * BA_MAX_LET];
     {
         const int ll = P.sc->let;
-        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] << SSH;
+        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] * BA_SCALE;
     }
     __syncthreads();
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= P.n_items) return;
-    const TilePtr tile = tile_ptr<LIN, TS>(tiles, threadIdx.x);
+    uint8_t *tile = tiles + threadIdx.x;
     const WorkItem item = P.items[it];
     const int p = item.pair;
     if (P.status[p] != 0) {
@@ -557,7 +442,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
     const DeviceScoring *sc = P.sc;
     const int let = sc->let;
     const int go = LIN ? 0 : sc->gap_open;
-    const int go8 = go << SSH;
+    const int go8 = go * BA_SCALE;
 
     CkView ck;
     ck.base = P.arena + item.code_off;
@@ -611,7 +496,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
                     if (rlast < 1 || clast < 1) continue;
                     if (rlast < i || (rlast == i && clast < j)) continue;  // cannot come later
                     TileProbe pb;
-                    pb.want = Smax << SSH;
+                    pb.want = Smax * BA_SCALE;
                     trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
                     if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
                         i = pb.fi;
@@ -638,11 +523,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
             best = pb.cU;
             layer = 1;
         }
-        if (pb.cL > best) {
-            best = pb.cL;
-            layer = 2;
-        }
-        cur = best;   // value of the start cell in its layer (the affine walk compares candidates with it)
+        if (pb.cL > best) layer = 2;
     }
     if (KIND == KIND_FIT) {
         // j = c-1; i = last row maximising M in the last column (fitted_affine_letters.go:170-181)
@@ -657,7 +538,6 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
             trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         i = pb.besti;
-        cur = pb.best;
     }
 
     int maxI = i, maxJ = j, score = 0, last = MV_DIAG;
@@ -675,10 +555,11 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
         while (i > rt && j > c0) {
             if (KIND == KIND_SW && cur == 0) break;
             const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
+            const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * TS];
             const bool corner = (i == n && j == m);
-            const int er = S[R * let] >> SSH, eq = S[Q] >> SSH;
+            const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
             int move, nl = 0, delta;
-            if (!trace16_next<KIND, LIN, TS>(tile, i - rt, j - cbase, cur, er, eq, S[R * let + Q] >> SSH, go, move, nl, delta))
+            if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl, delta))
                 bad = true;
             if (bad) break;
             // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
@@ -689,7 +570,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
                 score = 0;
             }
             score += delta;
-            if (KIND == KIND_SW || !LIN) cur -= delta;
+            if (KIND == KIND_SW) cur -= delta;
             if (move != MV_LEFT) i--;
             if (move != MV_UP) j--;
             layer = nl;
@@ -702,9 +583,9 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
         // nw_affine_letters.go:311-325: leading gap, its score is the border value
         int b = go;
         if (i == 0)
-            for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> SSH;
+            for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> BA_SCALE_SHIFT;
         else
-            for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> SSH;
+            for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> BA_SCALE_SHIFT;
         T16_EMIT(0, i, 0, j, b);
     }
 #undef T16_EMIT
@@ -728,23 +609,18 @@ enum { T16P_NEW = 0, T16P_SW_SEARCH, T16P_FIT_SEARCH, T16P_NW_PROBE, T16P_WALK, 
 template <int KIND, bool LIN>
 __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_kernel(Trace16Params P)
 {
-    constexpr int TS = BA_TRACE_THREADS;
-    // linear kinds: 8 KB of code bytes (static); affine kinds: the value tiles live in dynamic shared memory
-    // (up to 61 KB per CTA, beyond the 48 KB a kernel gets without opting in)
-    __shared__ __align__(16) uint8_t tiles_lin[LIN ? TileSmem<true, TS>::BYTES : 16];
-    uint8_t *tiles = LIN ? tiles_lin : ba_dyn_smem();
-    __shared__ int S[BA_MAX_LET * BA_MAX_LET];   // linear kinds: scaled by BA_SCALE (tagged cells); affine: unscaled
-    constexpr int SSH = LIN ? BA_SCALE_SHIFT : 0;
+    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    __shared__ int S[BA_MAX_LET * BA_MAX_LET];
     {
         const int ll = P.sc->let;
-        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] << SSH;
+        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] * BA_SCALE;
     }
     __syncthreads();
-    const TilePtr tile = tile_ptr<LIN, TS>(tiles, threadIdx.x);
+    uint8_t *tile = tiles + threadIdx.x;
     const int stride = P.stride;
     const int let = P.sc->let;
     const int go = LIN ? 0 : P.sc->gap_open;
-    const int go8 = go << SSH;
+    const int go8 = go * BA_SCALE;
 
     // ---- per-pair state
     int phase = T16P_NEW;
@@ -804,7 +680,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
                 }
                 sx = 0;
                 sh = 0;
-                pb.want = Smax << SSH;
+                pb.want = Smax * BA_SCALE;
                 phase = Smax > 0 ? T16P_SW_SEARCH : T16P_WALK;
             } else if (KIND == KIND_NW) {
                 i = n;
@@ -880,7 +756,6 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
             }
             if (!need) {
                 i = pb.besti;
-                cur = pb.best;
                 maxI = i;
                 maxJ = j;
                 pb.col = -1;
@@ -928,9 +803,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
                 // nw_affine_letters.go:311-325 / nw_letters.go:183-189: leading gap, its score is the border value
                 int b = go;
                 if (i == 0)
-                    for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> SSH;
+                    for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> BA_SCALE_SHIFT;
                 else
-                    for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> SSH;
+                    for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> BA_SCALE_SHIFT;
                 T16P_EMIT(0, i, 0, j, b);
             }
             if (bad) {
@@ -944,7 +819,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
         if (!need) continue;  // the phase changed: decide again
 
         // ---- the one tile computation all phases share
-        trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, tg, te, ti, tj, tile, pb);
+        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, tg, te, ti, tj, tile, pb);
 
         // ---- what the tile was for
         if (KIND == KIND_SW && phase == T16P_SW_SEARCH) {
@@ -959,11 +834,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
                 best = pb.cU;
                 layer = 1;
             }
-            if (pb.cL > best) {
-                best = pb.cL;
-                layer = 2;
-            }
-            cur = best;
+            if (pb.cL > best) layer = 2;
             pb.ci = pb.cj = -1;
             maxI = i;
             maxJ = j;
@@ -976,11 +847,12 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
             while (i > rt && j > c0) {
                 if (KIND == KIND_SW && cur == 0) break;
                 const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
+                const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
                 const bool corner = (i == n && j == m);
-                const int er = S[R * let] >> SSH, eq = S[Q] >> SSH;
+                const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
                 int move, nl = 0, delta;
-                if (!trace16_next<KIND, LIN, TS>(tile, i - rt, j - cbase, cur, er, eq, S[R * let + Q] >> SSH, go, move, nl,
-                                                 delta)) {
+                if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl,
+                                               delta)) {
                     bad = true;
                     break;
                 }
@@ -992,7 +864,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
                     score = 0;
                 }
                 score += delta;
-                if (KIND == KIND_SW || !LIN) cur -= delta;
+                if (KIND == KIND_SW) cur -= delta;
                 if (move != MV_LEFT) i--;
                 if (move != MV_UP) j--;
                 layer = nl;
@@ -1024,16 +896,11 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
 {
     static_assert(NT == 32 || NT == BA_TRACE_THREADS, "a team is a warp or the CTA");
     __shared__ int red[BA_TRACE_THREADS / 32][2];
-    constexpr int TS = BA_TRACE_THREADS;
-    // linear kinds: 8 KB of code bytes (static); affine kinds: the value tiles live in dynamic shared memory
-    // (up to 61 KB per CTA, beyond the 48 KB a kernel gets without opting in)
-    __shared__ __align__(16) uint8_t tiles_lin[LIN ? TileSmem<true, TS>::BYTES : 16];
-    uint8_t *tiles = LIN ? tiles_lin : ba_dyn_smem();
-    __shared__ int S[BA_MAX_LET * BA_MAX_LET];   // linear kinds: scaled by BA_SCALE (tagged cells); affine: unscaled
-    constexpr int SSH = LIN ? BA_SCALE_SHIFT : 0;
+    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    __shared__ int S[BA_MAX_LET * BA_MAX_LET];
     {
         const int ll = P.sc->let;
-        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] << SSH;
+        for (int x = threadIdx.x; x < ll * ll; x += blockDim.x) S[x] = P.sc->la[x] * BA_SCALE;
     }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
@@ -1074,7 +941,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             }                                                                                    \
         }                                                                                        \
     } while (0)
-    const TilePtr tile = tile_ptr<LIN, TS>(tiles, threadIdx.x);
+    uint8_t *tile = tiles + threadIdx.x;
     const WorkItem item = P.items[it];
     const int p = item.pair;
     if (P.status[p] != 0) {
@@ -1091,7 +958,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     const int stride = P.stride;
     const int let = P.sc->let;
     const int go = LIN ? 0 : P.sc->gap_open;
-    const int go8 = go << SSH;
+    const int go8 = go * BA_SCALE;
 
     CkView ck;
     ck.base = P.arena + item.code_off;
@@ -1147,8 +1014,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
                     if (rlast < 1 || clast < 1) continue;
                     if (rlast < i || (rlast == i && clast < j)) continue;
                     TileProbe pb;
-                    pb.want = Smax << SSH;
-                    trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    pb.want = Smax * BA_SCALE;
+                    trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
                     if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
                         i = pb.fi;
                         j = pb.fj;
@@ -1167,18 +1034,14 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         TileProbe pb;
         pb.ci = i;
         pb.cj = j;
-        trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
                            tile, pb);
         int best = pb.cM;
         if (pb.cU > best) {
             best = pb.cU;
             layer = 1;
         }
-        if (pb.cL > best) {
-            best = pb.cL;
-            layer = 2;
-        }
-        cur = best;   // value of the start cell in its layer (the affine walk compares candidates with it)
+        if (pb.cL > best) layer = 2;
     }
     if (KIND == KIND_FIT) {
         j = m;
@@ -1189,13 +1052,12 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         for (int e = lane; BA16_PERIOD * e - v < n; e += NT) {
             const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
             if (rlast < 1) continue;
-            trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+            trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         // last row attaining the maximum: larger value wins, ties go to the larger row
         int best = pb.best, besti = pb.besti;
         T16W_MAX2(best, besti);
         i = besti;
-        cur = best;
     }
     T16W_SYNC();
 
@@ -1219,7 +1081,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             const int rtop = max(BA16_PERIOD * e - v, 0);
             if (g >= 0 && e >= 0 && clast >= 1 && rlast > rtop) {
                 TileProbe pb0;
-                trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
+                trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
             }
         }
         T16W_SYNC();
@@ -1243,15 +1105,16 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             const int rt = max(BA16_PERIOD * ((i + v - 1) >> BA16_PSHIFT) - v, 0);
             const int cbase = ck.left_col(g);
             const int c0 = max(cbase, 0);
-            const TilePtr tcodes = tile_ptr<LIN, TS>(tiles, wbase + slot);
+            const uint8_t *tcodes = tiles + wbase + slot;
             while (i > rt && j > c0) {
                 if (KIND == KIND_SW && cur == 0) break;
                 const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
+                const unsigned code = tcodes[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
                 const bool corner = (i == n && j == m);
-                const int er = S[R * let] >> SSH, eq = S[Q] >> SSH;
+                const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
                 int move, nl = 0, delta;
-                if (!trace16_next<KIND, LIN, TS>(tcodes, i - rt, j - cbase, cur, er, eq, S[R * let + Q] >> SSH, go, move, nl,
-                                                 delta)) {
+                if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl,
+                                               delta)) {
                     bad = true;
                     break;
                 }
@@ -1263,7 +1126,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
                     score = 0;
                 }
                 score += delta;
-                if (KIND == KIND_SW || !LIN) cur -= delta;
+                if (KIND == KIND_SW) cur -= delta;
                 if (move != MV_LEFT) i--;
                 if (move != MV_UP) j--;
                 layer = nl;
@@ -1277,9 +1140,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     if (KIND == KIND_NW && i != j) {
         int b = go;
         if (i == 0)
-            for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> SSH;
+            for (int x = 0; x < j; x++) b += S[qs[x * stride]] >> BA_SCALE_SHIFT;
         else
-            for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> SSH;
+            for (int x = 0; x < i; x++) b += S[(int)rs[x * stride] * let] >> BA_SCALE_SHIFT;
         T16W_EMIT(0, i, 0, j, b);
     }
 #undef T16W_EMIT
