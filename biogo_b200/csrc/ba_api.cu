@@ -1162,6 +1162,8 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                         t.pair = -1;
                         t.cols = L.cols;
                         t.code_off = 0;
+                        t.n_ck = 0;
+                        t.ck = 0;
                         if (k < L.count) {
                             const WorkItem &it = plan.items[L.first + k];
                             if (ps < (B.h_qry_len[it.pair] + W16 - 1) / W16) t = it;
@@ -1268,6 +1270,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.slot_cap = (const int32_t *)ctx->slot_cap.p + w.first;
         tp.slots = slots_w;
         tp.counter = (int *)ctx->counters.p + 256 * wi + 255;
+        tp.row_bias = sym ? ctx->h_sc.gap_open + ctx->h_sc.la[1 * ctx->h_sc.let] : 0;
         // one thread per pair when the wave fills the GPU that way, else one warp per pair
         // (window of speculatively rebuilt tiles, see ba_trace16w_kernel), a whole CTA per pair when
         // even that leaves SMs idle; a mixed wave gives warps to its longest pairs (the head of

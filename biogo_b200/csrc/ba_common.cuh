@@ -42,6 +42,11 @@ struct WorkItem {
     int32_t pair;        // index into the batch
     int32_t cols;        // columns per lane used for this pair's code layout
     int64_t code_off;    // byte offset of this pair's codes in the arena
+    // packed 16-bit path (ba_fill16): the two pairs of a COUPLE -- items 2k and 2k+1 of a launch -- share one
+    // checkpoint region (their values sit in the low / high halves of the same words); the region's
+    // geometry comes from the larger of the two
+    int32_t n_ck;        // rows the region is laid out for: max(ref_len) over the couple
+    int32_t ck;          // bits 0..15: passes of the region (max over the couple); bit 16: this pair is the high half
 };
 
 struct DeviceScoring {

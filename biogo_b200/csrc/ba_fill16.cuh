@@ -86,65 +86,57 @@ __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffff
 __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
 
 // Checkpoint geometry shared with ba_trace16 ------------------------------------------------
-// Everything is organised in 32-byte SECTORS, one per (period e, strip g), so that the
-// traceback thread of a pair fetches a whole tile boundary with one or two DRAM sectors:
-//   colck[e][g] = 8 steps   x {M, L} int16 : last column of strip g at steps 8e .. 8e+7
-//   rowck[e][g] = 8 columns x {M, U} int16 : row of strip g processed at step 8e+7
-// A period is BA16_PERIOD = 8 steps; strip g belongs to lane g>>1, which handles row i at step
-// i-1+(g>>1).  One pass of one pair holds nper = ceil((n+15)/8) periods of 32 sectors for each
-// of the two arrays (about 1 byte per DP cell for 8-column strips).  The fill stages both
-// through shared memory and writes every period as fully coalesced 16-byte stores.
+// A COUPLE (pairs A and B of a 16-lane group: A in the low, B in the high 16-bit halves of every register)
+// shares one checkpoint region, and the fill stores its packed registers AS THEY ARE: no instruction is
+// spent on separating the two pairs (round 1 stored per pair and paid 64 PRMT + 16 VSUB per 8-step period
+// and lane for it -- 6.5 % of the kernel's ALU work).  Per pass and period e (BA16_PERIOD = 8 steps; strip
+// g = 2*lane + s belongs to lane g>>1, which handles row i at step i-1+lane):
+//   column block  [lane 0..15][strip s][step j] x element   last column of the strip at step 8e+j
+//                 affine element = {M word, L word} (8 bytes), linear element = {T word}; linear interleaves
+//                 the strips ([lane][step][strip]) so that a step is one 8-byte store
+//   row block     [lane 0..15][column kk = s*COLS + k] x element   the lane's row at step 8e+7
+//                 affine element = {M (or G = M + go + e for the SYM kernels) word, U word}, linear {T word};
+//                 a lane's row is RS = ba16_row_stride(COLS) double-elements long
+// so the traceback thread of one pair finds a tile's left column in one 64-byte piece (two sectors, which it
+// shares with its couple partner -- the neighbouring thread) and its top row in another.  Raw values: SW's
+// deferred clamp of U and L is re-applied by the reader, as is the SYM bias.
+// The fill stages a period in shared memory lane-major with an odd row stride (conflict-free stores) and
+// flushes it with fully coalesced 8/16-byte copies whose addresses are per-lane constants plus immediates.
 __host__ __device__ inline int64_t ba16_nper(int64_t n) { return (n + BA16_SKEW + BA16_PERIOD - 1) / BA16_PERIOD; }
-// Linear kinds (`lin`) have one table: their slots are int16 {T}, and a sector holds TWO
-// consecutive periods (low halves = even period, high halves = odd period), i.e. half the bytes.
-__host__ __device__ inline int64_t ba16_nsect(int64_t n, bool lin) { return lin ? (ba16_nper(n) + 1) / 2 : ba16_nper(n); }
-__host__ __device__ inline int64_t ba16_colck_bytes(int64_t n, bool lin) { return ba16_nsect(n, lin) * 32 * 32; }
-__host__ __device__ inline int64_t ba16_rowck_bytes(int64_t n, bool lin) { return ba16_nsect(n, lin) * 32 * 32; }
-__host__ __device__ inline int64_t ba16_pass_bytes(int64_t n, bool lin)
+// double-elements (two columns) per lane row in GLOBAL memory: COLS, except that an even COLS that is not a
+// power of two gets one pad (then the staged rows can be copied linearly)
+__host__ __device__ constexpr int ba16_row_stride(int cols)
 {
-    return ba16_colck_bytes(n, lin) + ba16_rowck_bytes(n, lin);
+    return ((cols & 1) || (cols & (cols - 1)) == 0) ? cols : cols + 1;
 }
-// After the passes: one candidate record per (pass, lane): {best score of the lane's two
-// strips, last period attaining it} -- the start-cell candidates of ba_trace16.
-__host__ __device__ inline int64_t ba16_npass(int cols, int64_t m) { return (m + 32LL * cols - 1) / (32LL * cols); }
-__host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t m, bool lin)
+__host__ __device__ inline int64_t ba16_colblk(bool lin) { return lin ? 1024 : 2048; }
+__host__ __device__ inline int64_t ba16_rowblk(int cols, bool lin) { return 16LL * ba16_row_stride(cols) * (lin ? 8 : 16); }
+__host__ __device__ inline int64_t ba16_colck_bytes(int64_t n, bool lin) { return ba16_nper(n) * ba16_colblk(lin); }
+__host__ __device__ inline int64_t ba16_rowck_bytes(int cols, int64_t n, bool lin) { return ba16_nper(n) * ba16_rowblk(cols, lin); }
+__host__ __device__ inline int64_t ba16_pass_bytes(int cols, int64_t n, bool lin)
 {
-    if (n <= 0 || m <= 0) return 0;
-    const int64_t np = ba16_npass(cols, m);
-    return np * ba16_pass_bytes(n, lin) + np * 16 * 8;
+    return ba16_colck_bytes(n, lin) + ba16_rowck_bytes(cols, n, lin);
+}
+// After the passes: per (pass, lane) one candidate record per pair {best score of the lane's two strips, last
+// period attaining it} -- the start-cell candidates of ba_trace16 (A at [2x], B at [2x+1]).
+__host__ __device__ inline int64_t ba16_npass(int cols, int64_t m) { return (m + 32LL * cols - 1) / (32LL * cols); }
+// bytes of a couple's region: n = rows (max over the couple), np = passes (max over the couple)
+__host__ __device__ inline int64_t ba16_ck_bytes(int cols, int64_t n, int64_t np, bool lin)
+{
+    if (n <= 0 || np <= 0) return 0;
+    return np * ba16_pass_bytes(cols, n, lin) + np * 16 * 16;
 }
 // Columns are RIGHT-aligned: strip g of pass p covers table columns
 //   jshift + p*W + g*COLS + 1 .. + COLS   with W = 32*COLS, jshift = m - npass*W  (<= 0),
 // so the last strip ends exactly at column m and the padding falls on columns <= 0, which
-// behave as the all-zero SW border (substitution 0 or -1 keeps M at 0 there).
+// behave as the all-zero SW border (substitution 0 or -1 keeps M at 0 there).  (Per PAIR: each pair of a
+// couple has its own m, npass and jshift; only the region's size is common.)
 
-// Staging buffers (shared memory): per pair one period = 32 sectors of 8 words = 64 chunks of
-// 16 bytes.  Lane t owns the four chunks of its two strips (2t: chunks 0,1; 2t+1: chunks 2,3),
-// i.e. the global chunks 4t .. 4t+3.  Layout: chunk plane c (padded to 72 words) x lane x 4 words,
-// so the 16-byte row stores, the per-step 4-byte column stores and the chunk-ordered 16-byte
-// flush loads are all bank-conflict free; the column stores additionally rotate the word inside
-// the chunk by one for lanes 8..15 (undone at flush time, where that is a compile-time fact).
-#define BA16_STAGE_PLANE 72
-#define BA16_STAGE_WORDS (4 * BA16_STAGE_PLANE)
-__device__ __forceinline__ int ba16_stage_word(int t, int chunk /*0..3*/)
-{
-    return chunk * BA16_STAGE_PLANE + 4 * t;
-}
-
-// Copy one staged period to global memory.  Lane t writes the 16-byte chunks t, 16+t, 32+t, 48+t
-// (sector-major order), so each store instruction covers 256 contiguous bytes.
-// ROTATED: the buffer was filled by the per-step column stores (word rotation for lanes >= 8).
-template <bool ROTATED>
-__device__ __forceinline__ void ba16_flush_period(const unsigned *buf, uint4 *gdst, int t)
-{
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int c = q * 16 + t;               // global chunk: owner lane c>>2 (= 4q + t/4), its chunk c&3
-        uint4 v = *(const uint4 *)(buf + ba16_stage_word(c >> 2, c & 3));
-        if (ROTATED && q >= 2) v = make_uint4(v.y, v.z, v.w, v.x);  // owner lane >= 8
-        gdst[c] = v;
-    }
-}
+// Staging (shared memory, per group): lane-major rows with an odd stride.
+//   column stage: 16 (affine) / 8 (linear) elements of 8 bytes per lane, row stride 17 / 9 elements
+//   row stage:    COLS double-elements of 16 (affine) / 8 (linear) bytes per lane, row stride COLS|1
+#define BA16_COLST_WORDS (16 * 17 * 2)
+__host__ __device__ constexpr int ba16_rowst_stride(int cols) { return cols | 1; }
 
 // MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
 // inter-pass boundary code is compiled out of the common single-pass instance).
@@ -235,8 +227,13 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     // confined to as many banks, so a lookup meets at most SHARE - 1 other lanes instead of 31;
     // row `let` is the virtual letter (-128 against everything).
     uint8_t *gtab = GSUB ? ba_dyn_smem() + (size_t)(threadIdx.x >> 5) * ba16_gsub_bytes_per_warp(P.sc->let) : nullptr;
-    __shared__ __align__(16) unsigned colbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged column checkpoints
-    __shared__ __align__(16) unsigned rowbuf[BA16_GROUPS][2][BA16_STAGE_WORDS];  // staged row checkpoint
+    // staged checkpoints of the current period, per group (couple): lane-major rows, odd row stride
+    constexpr int CST = LIN ? 9 : 17;                         // column stage: 8-byte elements per lane row
+    constexpr int RST = ba16_rowst_stride(COLS);              // row stage: double-elements per lane row
+    constexpr int RS = ba16_row_stride(COLS);                 // ... and in global memory
+    constexpr int REW = LIN ? 2 : 4;                          // words per row double-element
+    __shared__ __align__(16) unsigned colbuf[BA16_GROUPS][16 * CST * 2];
+    __shared__ __align__(16) unsigned rowbuf[BA16_GROUPS][16 * RST * REW];
     __shared__ uint4 bbuf[MULTI ? BA16_GROUPS : 1][BA16_PERIOD];  // boundary rows (M, L, H) of the current period
     const int let = P.sc->let;
     if (!GSUB) {
@@ -273,8 +270,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     const int grp = (threadIdx.x >> 4);            // group inside the CTA
     const int group_global = blockIdx.x * BA16_GROUPS + grp;
     unsigned *ringA = ring[grp][0], *ringB = ring[grp][1];
-    unsigned *colA = colbuf[grp][0], *colB = colbuf[grp][1];
-    unsigned *rowA = rowbuf[grp][0], *rowB = rowbuf[grp][1];
+    unsigned *colst = colbuf[grp] + t * CST * 2;   // my row of the column stage
+    unsigned *rowst = rowbuf[grp] + t * RST * REW;   // my row of the row stage
     ulonglong2 *bnd = (ulonglong2 *)(P.bnd + (int64_t)group_global * P.bnd_stride);  // LONG: re-pointed per task
     constexpr int W = 32 * COLS;
     const unsigned FULL = 0xffffffffu;
@@ -293,12 +290,15 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             bnd = (ulonglong2 *)(P.bnd + (int64_t)couple * P.bnd_stride);
         }
         int nA = 0, mA = 0, nB = 0, mB = 0, pA = 0, pB = 0;
-        int64_t offA = 0, offB = 0;
+        int64_t offC = 0;          // the couple's checkpoint region (both items carry the same offset and geometry)
+        int n_ck = 0, np_ck = 0;
         bool liveA = false, liveB = false;
         if (itA < P.n_items) {
             const WorkItem item = P.items[itA];
             pA = max(item.pair, 0);
-            offA = item.code_off;
+            offC = item.code_off;
+            n_ck = item.n_ck;
+            np_ck = item.ck & 0xffff;
             nA = P.ref_len[pA];
             mA = P.qry_len[pA];
             liveA = item.pair >= 0 && P.status[pA] == 0 && (P.acgt_only[pA] & P.flag_mask) == P.flag_mask && nA > 0 && mA > 0;
@@ -306,7 +306,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
         if (itB < P.n_items) {
             const WorkItem item = P.items[itB];
             pB = max(item.pair, 0);
-            offB = item.code_off;
+            if (itA >= P.n_items || P.items[itA].pair < 0) {   // (LONG task lists may hold B without A)
+                offC = item.code_off;
+                n_ck = item.n_ck;
+                np_ck = item.ck & 0xffff;
+            }
             nB = P.ref_len[pB];
             mB = P.qry_len[pB];
             liveB = item.pair >= 0 && P.status[pB] == 0 && (P.acgt_only[pB] & P.flag_mask) == P.flag_mask && nB > 0 && mB > 0;
@@ -322,7 +326,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
         int nsteps_w = max(nstepsA, nstepsB), npass_w = max(npassA, npassB);
         nsteps_w = max(nsteps_w, __shfl_xor_sync(FULL, nsteps_w, 16));
         npass_w = MULTI ? max(npass_w, __shfl_xor_sync(FULL, npass_w, 16)) : 1;
-        const int64_t passbA = ba16_pass_bytes(nA, LIN), passbB = ba16_pass_bytes(nB, LIN);
+        const int64_t passb = ba16_pass_bytes(COLS, n_ck, LIN);
+        const int nstepsC = max(nstepsA, nstepsB);   // the couple's region is written while either pair is live
         const int jshiftA = (KIND == KIND_SW) ? mA - npassA * W : 0, jshiftB = (KIND == KIND_SW) ? mB - npassB * W : 0;
         // rows staged between passes: only pairs that really have a next pass (bounds the scratch)
         const int nbnd = max(npassA > 1 ? nA : 0, npassB > 1 ? nB : 0);
@@ -417,20 +422,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             // per lane (both pairs packed): best value of this pass and the LAST period attaining it
             unsigned vbest = pack16(1, 1);
             int per_lo = -1, per_hi = -1;
-            uint4 *colckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA);
-            uint4 *rowckA = (uint4 *)(P.arena + offA + (int64_t)pass * passbA + ba16_colck_bytes(nA, LIN));
-            uint4 *colckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB);
-            uint4 *rowckB = (uint4 *)(P.arena + offB + (int64_t)pass * passbB + ba16_colck_bytes(nB, LIN));
+            const bool plC = plA || plB;
+            uint8_t *colck = P.arena + offC + (int64_t)pass * passb;
+            uint8_t *rowck = colck + ba16_colck_bytes(n_ck, LIN);
             unsigned ro = (unsigned)((1 - t) & (RING - 1)) * 4u;  // byte offset of my row in the rings
-            unsigned ck0a = 0, ck0b = 0; // affine: packed (M, L) checkpoint words of that column, pairs A and B
-
-            // staging addresses of my column-checkpoint words: [half of the period][word], pair A,
-            // strip 2t; strip 2t+1 is two chunk planes further, pair B one buffer further
-            unsigned *cst[2][4];
-#pragma unroll
-            for (int c = 0; c < 2; c++)
-#pragma unroll
-                for (int jj = 0; jj < 4; jj++) cst[c][jj] = colA + ba16_stage_word(t, c) + ((jj + (t >> 3)) & 3);
+            unsigned ckM0 = 0, ckL0 = 0; // affine: (M, L) of my first strip's last column, as they are (A | B packed)
             const int nper_w = (nsteps_w + BA16_PERIOD - 1) >> BA16_PSHIFT;
             // letters of the first ring chunk (prefetching variant, see the refill below)
             constexpr int PFN = (CHUNK <= 64) ? CHUNK / 16 : 0;
@@ -444,7 +440,6 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 }
             }
             for (int e = 0; e < nper_w; e++) {
-                const int parofs = (e & 1) * BA16_STAGE_PLANE;  // LIN: chunk of this period inside its sector
                 const int pre_row = 8 * (e + 1) + 1 + t;  // my boundary row of the NEXT period
                 const bool pre_on = rd_bnd && t < BA16_PERIOD && pre_row <= nbnd;
                 if (pre_on) pre = BA_LDCG(bnd + pre_row);  // lands at the end of this period
@@ -556,8 +551,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                                 Mprev = M;
                         }
                         if (k == COLS - 1) {
-                            ck0a = ba_prmt(M, Ll, 0x5410u);
-                            ck0b = ba_prmt(M, Ll, 0x7632u);
+                            ckM0 = M;
+                            ckL0 = Ll;
                         }
                         if (k == NC - 1) mlast = M;
                     }
@@ -594,8 +589,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     Hu[k] = __vimax3_s16x2(Ml, Uu[k], Ll);
                     if (k == COLS - 1) {
                         // checkpoint words of my first strip, taken where (M, L) are live
-                        ck0a = ba_prmt(Ml, Ll, 0x5410u);
-                        ck0b = ba_prmt(Ml, Ll, 0x7632u);
+                        ckM0 = Ml;
+                        ckL0 = Ll;
                     }
                 }
                 sdiagH = rH;
@@ -608,89 +603,70 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     bmax = LIN ? __vimax3_s16x2(bmax, Hu[k], Hu[k + 1]) : __vimax3_s16x2(bmax, Mu[k], Mu[k + 1]);
                 }
 
-                // column checkpoints (M, clamped L) of my two strips, staged per pair for this period
-                {
-                    // raw values: SW's deferred clamp of U and L is re-applied by the reader (ba_trace16 CkView)
-                    unsigned *w = cst[j >> 2][j & 3];
-                    if (LIN) {
-                        // int16 slots: the even period of a sector fills its first 16-byte chunk, the
-                        // odd period the second; step j is half-word j of the chunk
-                        unsigned short *h = (unsigned short *)(cst[0][j >> 1] + parofs) + (j & 1);
-                        h[0] = (unsigned short)Hu[COLS - 1];
-                        h[2 * BA16_STAGE_WORDS] = (unsigned short)(Hu[COLS - 1] >> 16);
-                        h[4 * BA16_STAGE_PLANE] = (unsigned short)Hu[NC - 1];
-                        h[4 * BA16_STAGE_PLANE + 2 * BA16_STAGE_WORDS] = (unsigned short)(Hu[NC - 1] >> 16);
-                    } else {
-                        w[0] = ck0a;
-                        w[BA16_STAGE_WORDS] = ck0b;
-                        const unsigned ml = SYM ? mlast : Mu[NC - 1];
-                        w[2 * BA16_STAGE_PLANE] = ba_prmt(ml, outL, 0x5410u);
-                        w[2 * BA16_STAGE_PLANE + BA16_STAGE_WORDS] = ba_prmt(ml, outL, 0x7632u);
-                    }
+                // column checkpoints of my two strips for this step, raw and packed as they are (SW's
+                // deferred clamp of U and L is re-applied by the reader, ba_trace16 CkView)
+                if (LIN) {
+                    // element j = {T of strip 2t, T of strip 2t+1}: one 8-byte store per step
+                    *(uint2 *)(colst + 2 * j) = make_uint2(Hu[COLS - 1], Hu[NC - 1]);
+                } else {
+                    // elements [strip][step] = {M, L}
+                    *(uint2 *)(colst + 2 * j) = make_uint2(ckM0, ckL0);
+                    *(uint2 *)(colst + 2 * (8 + j)) = make_uint2(SYM ? mlast : Mu[NC - 1], outL);
                 }
                 if (wr_bnd && t == 15 && i >= 1 && i <= nbnd) bnd[i] = ba16_bnd_pack(LIN ? 0u : Mu[NC - 1], outL, Hu[NC - 1], (unsigned)pass + 1u);
                 }
                 // ---- end of the period: row checkpoint, flush both arrays, best-cell bookkeeping
-                if (LIN) {
-                    // int16 {T}: eight columns of a strip make one 16-byte chunk (this period's half
-                    // of the sector); two columns per word
-                    unsigned wa[2 * 4], wb[2 * 4];
+                // my row as it is: double-element c = columns 2c, 2c+1 -> {M, U, M, U} (affine; M is G for SYM) / {T, T}
 #pragma unroll
-                    for (int x = 0; x < 8; x++) wa[x] = wb[x] = 0;
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; s2++)
-#pragma unroll
-                        for (int kk = 0; kk < COLS; kk += 2) {
-                            const unsigned lo = Hu[s2 * COLS + kk];  // LIN: the one table lives in Hu
-                            const unsigned hi = (kk + 1 < COLS) ? Hu[s2 * COLS + kk + 1] : 0u;
-                            wa[4 * s2 + (kk >> 1)] = ba_prmt(lo, hi, 0x5410u);
-                            wb[4 * s2 + (kk >> 1)] = ba_prmt(lo, hi, 0x7632u);
-                        }
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; s2++) {
-                        const int w = ba16_stage_word(t, 2 * s2) + parofs;
-                        *(uint4 *)(rowA + w) = make_uint4(wa[4 * s2], wa[4 * s2 + 1], wa[4 * s2 + 2], wa[4 * s2 + 3]);
-                        *(uint4 *)(rowB + w) = make_uint4(wb[4 * s2], wb[4 * s2 + 1], wb[4 * s2 + 2], wb[4 * s2 + 3]);
-                    }
-                } else {
-                    unsigned wa[4 * 4], wb[4 * 4];  // four chunks of four words per pair
-#pragma unroll
-                    for (int x = 0; x < 16; x++) wa[x] = wb[x] = 0;
-#pragma unroll
-                    for (int k = 0; k < NC; k++) {
-                        const unsigned u = LIN ? 0u : Uu[k];
-                        const int x = (k >= COLS ? 8 + (k - COLS) : k);  // word inside my 16-word region
-                        const unsigned mk = SYM ? __vsub2(Mu[k], goerp) : Mu[k];
-                        wa[x] = ba_prmt(mk, u, 0x5410u);
-                        wb[x] = ba_prmt(mk, u, 0x7632u);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int w = ba16_stage_word(t, c);
-                        *(uint4 *)(rowA + w) = make_uint4(wa[4 * c], wa[4 * c + 1], wa[4 * c + 2], wa[4 * c + 3]);
-                        *(uint4 *)(rowB + w) = make_uint4(wb[4 * c], wb[4 * c + 1], wb[4 * c + 2], wb[4 * c + 3]);
-                    }
+                for (int c = 0; c < COLS; c++) {
+                    if (LIN)
+                        *(uint2 *)(rowst + 2 * c) = make_uint2(Hu[2 * c], Hu[2 * c + 1]);
+                    else
+                        *(uint4 *)(rowst + 4 * c) = make_uint4(Mu[2 * c], Uu[2 * c], Mu[2 * c + 1], Uu[2 * c + 1]);
                 }
                 __syncwarp();
-                if (LIN) {
-                    // a sector holds two periods: flush after the odd one (or after the very last)
-                    if ((e & 1) || e == nper_w - 1) {
-                        const int e0 = e & ~1;
-                        const int64_t so = (int64_t)(e >> 1) * 64;
-                        if (plA && (e0 << BA16_PSHIFT) < nstepsA) {
-                            ba16_flush_period<true>(colA, colckA + so, t);
-                            ba16_flush_period<false>(rowA, rowckA + so, t);
+                if (plC && (e << BA16_PSHIFT) < nstepsC) {
+                    // column block: global [lane][element] (16 / 8 elements of 8 bytes per lane); lane t copies
+                    // element t of lane row x (+ 8 lanes further: row x + 1 for the 8-element linear rows)
+                    uint2 *g = (uint2 *)(colck + (int64_t)e * ba16_colblk(LIN));
+                    const unsigned *sb = colbuf[grp];
+                    if (LIN) {
+#pragma unroll
+                        for (int x = 0; x < 8; x++)
+                            g[x * 16 + t] = *(const uint2 *)(sb + ((2 * x + (t >> 3)) * CST + (t & 7)) * 2);
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 16; x++) g[x * 16 + t] = *(const uint2 *)(sb + (x * CST + t) * 2);
+                    }
+                }
+                if (plC && 8 * e + 7 < nstepsC) {
+                    // row block: global [lane][RS double-elements]
+                    uint8_t *gb = rowck + (int64_t)e * ba16_rowblk(COLS, LIN);
+                    const unsigned *sb = rowbuf[grp];
+                    constexpr bool POW2 = (COLS & (COLS - 1)) == 0;
+                    if (POW2 && COLS < 16) {
+                        // 16 lanes cover 16 / COLS lane rows per copy: stage element (lane row * RST + c) with
+                        // lane row = x * (16 / COLS) + t / COLS, c = t % COLS -- a per-lane constant plus an immediate
+                        constexpr int LPR = 16 / COLS;
+                        const int mine = ((t / COLS) * RST + (t % COLS)) * REW;
+#pragma unroll
+                        for (int x = 0; x < COLS; x++) {
+                            if (LIN)
+                                ((uint2 *)gb)[x * 16 + t] = *(const uint2 *)(sb + mine + x * LPR * RST * REW);
+                            else
+                                ((uint4 *)gb)[x * 16 + t] = *(const uint4 *)(sb + mine + x * LPR * RST * REW);
                         }
-                        if (plB && (e0 << BA16_PSHIFT) < nstepsB) {
-                            ba16_flush_period<true>(colB, colckB + so, t);
-                            ba16_flush_period<false>(rowB, rowckB + so, t);
+                    } else {
+                        // RS == RST: the staged rows are the global rows, copy them linearly
+                        static_assert(POW2 || RS == RST, "row stage and global row strides must agree");
+#pragma unroll
+                        for (int x = 0; x < RST; x++) {
+                            if (LIN)
+                                ((uint2 *)gb)[x * 16 + t] = *(const uint2 *)(sb + (x * 16 + t) * 2);
+                            else
+                                ((uint4 *)gb)[x * 16 + t] = *(const uint4 *)(sb + (x * 16 + t) * 4);
                         }
                     }
-                } else {
-                if (plA && (e << BA16_PSHIFT) < nstepsA) ba16_flush_period<true>(colA, colckA + (int64_t)e * 64, t);
-                if (plB && (e << BA16_PSHIFT) < nstepsB) ba16_flush_period<true>(colB, colckB + (int64_t)e * 64, t);
-                if (plA && 8 * e + 7 < nstepsA) ba16_flush_period<false>(rowA, rowckA + (int64_t)e * 64, t);
-                if (plB && 8 * e + 7 < nstepsB) ba16_flush_period<false>(rowB, rowckB + (int64_t)e * 64, t);
                 }
                 __syncwarp();
                 if (MULTI) {
@@ -708,13 +684,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 }
             }
 #undef BA16_BND_LAND
-            if (KIND == KIND_SW && plA) {
-                int2 *cand = (int2 *)(P.arena + offA + (int64_t)npassA * passbA) + pass * 16 + t;
-                *cand = make_int2(lo16(vbest), per_lo);
-            }
-            if (KIND == KIND_SW && plB) {
-                int2 *cand = (int2 *)(P.arena + offB + (int64_t)npassB * passbB) + pass * 16 + t;
-                *cand = make_int2(hi16(vbest), per_hi);
+            if (KIND == KIND_SW && plC) {
+                // start-cell candidates of this (pass, lane): pair A's record, then pair B's
+                int4 *cand = (int4 *)(P.arena + offC + (int64_t)np_ck * passb) + pass * 16 + t;
+                *cand = make_int4(lo16(vbest), plA ? per_lo : -1, hi16(vbest), plB ? per_hi : -1);
             }
             __syncwarp();
         }

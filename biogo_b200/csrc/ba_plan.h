@@ -72,24 +72,26 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         }
         if (same) {
             const int c = cols_for(m0);
-            int64_t cb = mode16 ? ba16_ck_bytes(c, n0, m0, !affine) : ba_code_bytes(affine, c, n0, m0);
+            // 16-bit path: cb is a COUPLE's region (two pairs); 32-bit path: one pair's codes
+            int64_t cb = mode16 ? ba16_ck_bytes(c, n0, ba16_npass(c, m0), !affine) : ba_code_bytes(affine, c, n0, m0);
             cb = (cb + 255) & ~(int64_t)255;
+            const int unit = mode16 ? 2 : 1;   // items per cb
             const int32_t cap = slot_cap_for(n0, m0, affine);
-            int64_t per_wave = cb > 0 ? arena_cap / cb : nids;
+            int64_t per_wave = cb > 0 ? (arena_cap / cb) * unit : nids;
             if (target_waves > 1) {
                 // equal waves, whole warp claims (4 items) each
                 int64_t even = (nids + target_waves - 1) / target_waves;
                 even = (even + 7) & ~(int64_t)7;
                 if (even < per_wave) per_wave = even;
             }
-            if (per_wave < 1) per_wave = 1;
+            if (per_wave < unit) per_wave = unit;
             if (per_wave > nids) per_wave = nids;
             for (int64_t first = 0; first < nids; first += per_wave) {
                 const int64_t count = std::min(per_wave, nids - first);
                 Plan::Wave w;
                 w.first = first;
                 w.count = count;
-                w.code_bytes = count * cb;
+                w.code_bytes = ((count + unit - 1) / unit) * cb;
                 w.aux_ints = need_aux ? count * ((int64_t)n0 + 1) : 0;
                 w.slots = mode16 ? count * (int64_t)cap : 0;
                 w.max_n_multipass = (m0 > 32 * c) ? n0 : 0;
@@ -103,7 +105,9 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
                     WorkItem it;
                     it.pair = ids ? ids[first + k] : (int32_t)(first + k);
                     it.cols = c;
-                    it.code_off = k * cb;
+                    it.code_off = (k / unit) * cb;
+                    it.n_ck = n0;
+                    it.ck = mode16 ? ((int32_t)ba16_npass(c, m0) | (int32_t)((k & 1) << 16)) : 0;
                     plan.items[first + k] = it;
                     if (it.pair > w.max_pair) w.max_pair = it.pair;
                 }
@@ -139,7 +143,8 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             if (ref_len[p] != tmemo_n || qry_len[p] != tmemo_m) {
                 tmemo_n = ref_len[p];
                 tmemo_m = qry_len[p];
-                tmemo_cb = mode16 ? ba16_ck_bytes(c, tmemo_n, tmemo_m, !affine) : ba_code_bytes(affine, c, tmemo_n, tmemo_m);
+                tmemo_cb = mode16 ? ba16_ck_bytes(c, tmemo_n, ba16_npass(c, tmemo_m), !affine) / 2
+                                  : ba_code_bytes(affine, c, tmemo_n, tmemo_m);
                 tmemo_cb = (tmemo_cb + 255) & ~(int64_t)255;
             }
             total_cb += tmemo_cb;
@@ -205,14 +210,19 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         int memo_n = -1, memo_m = -1;   // batches are often uniform: reuse the per-shape numbers
         int64_t memo_cb = 0;
         int32_t memo_cap = 0;
-        for (int64_t x = 0; x < cnt[c]; x++) {
+        // 16-bit path: items are placed a COUPLE at a time (items 2k, 2k+1 of a launch share one checkpoint
+        // region laid out for the larger of the two; the list is sorted by size, so partners are alike)
+        const int64_t step = mode16 ? 2 : 1;
+        for (int64_t x = 0; x < cnt[c]; x += step) {
             const int32_t p = v[x];
-            if (ref_len[p] != memo_n || qry_len[p] != memo_m) {
-                memo_n = ref_len[p];
-                memo_m = qry_len[p];
-                memo_cb = mode16 ? ba16_ck_bytes(c, memo_n, memo_m, !affine) : ba_code_bytes(affine, c, memo_n, memo_m);
+            const bool has2 = mode16 && x + 1 < cnt[c];
+            const int32_t p2 = has2 ? v[x + 1] : p;
+            const int cn = std::max(ref_len[p], ref_len[p2]), cm = std::max(qry_len[p], qry_len[p2]);
+            if (cn != memo_n || cm != memo_m) {
+                memo_n = cn;
+                memo_m = cm;
+                memo_cb = mode16 ? ba16_ck_bytes(c, cn, ba16_npass(c, cm), !affine) : ba_code_bytes(affine, c, cn, cm);
                 memo_cb = (memo_cb + 255) & ~(int64_t)255;
-                memo_cap = slot_cap_for(memo_n, memo_m, affine);
             }
             const int64_t cb = memo_cb;
             if (wave.count > 0 && (wave.code_bytes + cb > arena_cap ||
@@ -222,27 +232,32 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
                 L.first = wave.first;
                 L.count = 0;
             }
-            WorkItem it;
-            it.pair = p;
-            it.cols = c;
-            it.code_off = wave.code_bytes;
-            plan.items[w] = it;
-            if (p > wave.max_pair) wave.max_pair = p;
-            if (need_aux) {
-                plan.aux_off[w] = wave.aux_ints;
-                wave.aux_ints += (int64_t)ref_len[p] + 1;
+            for (int h = 0; h < (has2 ? 2 : 1); h++) {
+                const int32_t q = h ? p2 : p;
+                WorkItem it;
+                it.pair = q;
+                it.cols = c;
+                it.code_off = wave.code_bytes;
+                it.n_ck = cn;
+                it.ck = mode16 ? ((int32_t)ba16_npass(c, cm) | (h << 16)) : 0;
+                plan.items[w] = it;
+                if (q > wave.max_pair) wave.max_pair = q;
+                if (need_aux) {
+                    plan.aux_off[w] = wave.aux_ints;
+                    wave.aux_ints += (int64_t)ref_len[q] + 1;
+                }
+                if (mode16) {
+                    memo_cap = slot_cap_for(ref_len[q], qry_len[q], affine);
+                    plan.slot_off[w] = wave.slots;
+                    plan.slot_cap[w] = memo_cap;
+                    wave.slots += memo_cap;
+                }
+                w++;
+                wave.count++;
+                L.count++;
+                if (qry_len[q] > 32 * c && ref_len[q] > wave.max_n_multipass) wave.max_n_multipass = ref_len[q];
             }
-            if (mode16) {
-                const int32_t cap = memo_cap;
-                plan.slot_off[w] = wave.slots;
-                plan.slot_cap[w] = cap;
-                wave.slots += cap;
-            }
-            w++;
             wave.code_bytes += cb;
-            wave.count++;
-            L.count++;
-            if (qry_len[p] > 32 * c && ref_len[p] > wave.max_n_multipass) wave.max_n_multipass = ref_len[p];
         }
         if (L.count > 0) wave.launches.push_back(L);
     }

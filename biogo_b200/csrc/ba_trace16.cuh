@@ -41,51 +41,80 @@ struct Trace16Params {
     const int32_t *slot_cap;   // per item
     int32_t *slots;            // 5 ints per segment, in EMISSION order (reverse of final)
     int *counter;              // ba_trace16p_kernel: next work item
+    int row_bias;              // go + e when the fill ran the SYM kernels (their row checkpoints hold M + go + e), else 0
 };
 
+// One pair's view of its couple's checkpoint region (layout: ba_fill16.cuh "Checkpoint geometry").
 struct CkView {
     const uint8_t *base;
-    int n, m, cols, npass, jshift;
-    bool lin;  // linear kinds: int16 {T} slots, two periods per sector (ba_fill16.cuh)
+    int n, m, cols, npass, jshift;   // the PAIR's own shape: rows, columns, passes, column shift (SW right-aligns)
+    int n_ck, np_ck;                 // the region's: rows and passes it is laid out for (max over the couple)
+    int half;                        // 0: my values are the low 16-bit halves of the stored words, 1: the high halves
+    int rs;                          // double-elements per lane row of a row block
+    int bias;                        // SYM kernels store G = M + go + e in the row blocks: M = G - bias
+    bool lin;    // linear kinds: one table T (elements of one word)
     bool clamp;  // affine SW: the fill defers the clamp of U and L at zero and stores them raw
     int64_t pass_bytes, colck_bytes;
+    __device__ __forceinline__ void init(const uint8_t *arena, const WorkItem &item, int n_, int m_, bool lin_, bool clamp_,
+                                         int bias_)
+    {
+        base = arena + item.code_off;
+        n = n_;
+        m = m_;
+        cols = item.cols;
+        lin = lin_;
+        clamp = clamp_;
+        bias = bias_;
+        n_ck = item.n_ck;
+        np_ck = item.ck & 0xffff;
+        half = (item.ck >> 16) & 1;
+        rs = ba16_row_stride(cols);
+        pass_bytes = ba16_pass_bytes(cols, n_ck, lin);
+        colck_bytes = ba16_colck_bytes(n_ck, lin);
+    }
     // Strip g (global index: pass*32 + strip) belongs to lane (g & 31) >> 1 of the fill, which
     // handles row i at step i-1+lane.
     __device__ __forceinline__ static int lane_of(int g) { return (g & 31) >> 1; }
-    // (M, clamped L) of the last column of strip g at row r: sector (period, strip), step slot
+    __device__ __forceinline__ int pick(unsigned w) const { return (int)(short)(half ? (w >> 16) : (w & 0xffffu)); }
+    // (M, clamped L) of the last column of strip g at row r
     __device__ __forceinline__ void col_ml(int g, int r, int &M, int &L) const
     {
-        const int pass = g >> 5;
-        const int st = r - 1 + lane_of(g);
-        const int e = st >> BA16_PSHIFT;
+        const int pass = g >> 5, t = lane_of(g), s = g & 1;
+        const int st = r - 1 + t;
+        const int e = st >> BA16_PSHIFT, j = st & (BA16_PERIOD - 1);
+        const uint8_t *blk = base + (int64_t)pass * pass_bytes + (int64_t)e * ba16_colblk(lin);
         if (lin) {
-            const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
-                                             ((int64_t)((e >> 1) * 32 + (g & 31)) * 32 + (e & 1) * 16 +
-                                              (st & (BA16_PERIOD - 1)) * 2));
-            M = p[0];
+            // [lane][step][strip] words
+            M = pick(*(const unsigned *)(blk + t * 64 + j * 8 + s * 4));
             L = 0;
             return;
         }
-        const short *p = (const short *)(base + (int64_t)pass * pass_bytes +
-                                         ((int64_t)(e * 32 + (g & 31)) * 8 + (st & (BA16_PERIOD - 1))) * 4);
-        M = p[0];
-        L = clamp ? max((int)p[1], 0) : (int)p[1];
+        // [lane][strip][step] {M, L}
+        const uint2 w = *(const uint2 *)(blk + t * 128 + s * 64 + j * 8);
+        M = pick(w.x);
+        L = pick(w.y);
+        if (clamp) L = max(L, 0);
     }
     // (M, clamped U) of column k of strip g at its checkpoint row of period e
     __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const
     {
-        const int pass = g >> 5;
+        const int pass = g >> 5, t = lane_of(g), s = g & 1;
+        const int kk = s * cols + k;
+        const uint8_t *blk = base + (int64_t)pass * pass_bytes + colck_bytes + (int64_t)e * ba16_rowblk(cols, lin);
         if (lin) {
-            const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
-                                             ((int64_t)((e >> 1) * 32 + (g & 31)) * 32 + (e & 1) * 16 + k * 2));
-            M = p[0];
+            M = pick(*(const unsigned *)(blk + (t * rs * 2 + kk) * 4));
             U = 0;
             return;
         }
-        const short *p = (const short *)(base + (int64_t)pass * pass_bytes + colck_bytes +
-                                         ((int64_t)(e * 32 + (g & 31)) * 8 + k) * 4);
-        M = p[0];
-        U = clamp ? max((int)p[1], 0) : (int)p[1];
+        const uint2 w = *(const uint2 *)(blk + (t * rs * 2 + kk) * 8);
+        M = pick(w.x) - bias;
+        U = pick(w.y);
+        if (clamp) U = max(U, 0);
+    }
+    // start-cell candidate record x = pass*16 + lane of this pair: {best score, last period attaining it}
+    __device__ __forceinline__ int2 cand(int x) const
+    {
+        return ((const int2 *)(base + (int64_t)np_ck * pass_bytes))[2 * x + half];
     }
     __device__ __forceinline__ int strip_of(int j) const { return (j - jshift - 1) / cols; }
     __device__ __forceinline__ int left_col(int g) const { return jshift + g * cols; }
@@ -445,16 +474,9 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
     const int go8 = go * BA_SCALE;
 
     CkView ck;
-    ck.base = P.arena + item.code_off;
-    ck.n = n;
-    ck.m = m;
-    ck.cols = item.cols;
+    ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias);
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
-    ck.lin = LIN;
-    ck.clamp = (KIND == KIND_SW) && !LIN;
-    ck.pass_bytes = ba16_pass_bytes(n, LIN);
-    ck.colck_bytes = ba16_colck_bytes(n, LIN);
 
     int32_t *out = P.slots + 5 * P.slot_off[it];
     const int cap = P.slot_cap[it];
@@ -477,15 +499,14 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
     if (KIND == KIND_SW && n > 0 && m > 0) {
         // the last cell in row-major order holding the table maximum (sw_affine_letters.go:126-134
         // under condition C2 of ba_fill16.cuh)
-        const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
         int Smax = 0;
         for (int x = 0; x < ck.npass * 16; x++) {
-            const int2 c = cand[x];
+            const int2 c = ck.cand(x);
             if (c.y >= 0) Smax = max(Smax, c.x);
         }
         if (Smax > 0) {
             for (int x = 0; x < ck.npass * 16; x++) {
-                const int2 c = cand[x];
+                const int2 c = ck.cand(x);
                 if (c.y < 0 || c.x != Smax) continue;
                 const int e = c.y;
                 for (int h = 0; h < 2; h++) {  // the lane's two strips
@@ -652,16 +673,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
             m = P.qry_len[p];
             rs = P.enc + P.ref_off[p];
             qs = P.enc + P.qry_off[p];
-            ck.base = P.arena + item.code_off;
-            ck.n = n;
-            ck.m = m;
-            ck.cols = item.cols;
+            ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias);
             ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
             ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
-            ck.lin = LIN;
-            ck.clamp = (KIND == KIND_SW) && !LIN;
-            ck.pass_bytes = ba16_pass_bytes(n, LIN);
-            ck.colck_bytes = ba16_colck_bytes(n, LIN);
             out = P.slots + 5 * P.slot_off[it];
             cap = P.slot_cap[it];
             nseg = 0;
@@ -672,9 +686,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
             if (KIND == KIND_SW) {
                 Smax = 0;
                 if (n > 0 && m > 0) {
-                    const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
-                    for (int x = 0; x < ck.npass * 16; x++) {
-                        const int2 c = cand[x];
+                                for (int x = 0; x < ck.npass * 16; x++) {
+                        const int2 c = ck.cand(x);
                         if (c.y >= 0) Smax = max(Smax, c.x);
                     }
                 }
@@ -705,9 +718,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
         bool need = false;
         if (KIND == KIND_SW && phase == T16P_SW_SEARCH) {
             // candidates: per (pass, lane) {best score, last period attaining it}; a lane has two strips
-            const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
-            while (sx < ck.npass * 16) {
-                const int2 c = cand[sx];
+                while (sx < ck.npass * 16) {
+                const int2 c = ck.cand(sx);
                 if (c.y >= 0 && c.x == Smax) {
                     const int g = (sx >> 4) * 32 + 2 * (sx & 15) + sh;
                     const int v = CkView::lane_of(g);
@@ -961,16 +973,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     const int go8 = go * BA_SCALE;
 
     CkView ck;
-    ck.base = P.arena + item.code_off;
-    ck.n = n;
-    ck.m = m;
-    ck.cols = item.cols;
+    ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias);
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
-    ck.lin = LIN;
-    ck.clamp = (KIND == KIND_SW) && !LIN;
-    ck.pass_bytes = ba16_pass_bytes(n, LIN);
-    ck.colck_bytes = ba16_colck_bytes(n, LIN);
 
     int32_t *out = P.slots + 5 * P.slot_off[it];
     const int cap = P.slot_cap[it];
@@ -991,10 +996,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     // ---- start cell (rules as in ba_trace16_kernel), searched by all lanes
     int i = 0, j = 0, cur = 0, layer = 0;
     if (KIND == KIND_SW && n > 0 && m > 0) {
-        const int2 *cand = (const int2 *)(ck.base + (int64_t)ck.npass * ck.pass_bytes);
         int Smax = 0;
         for (int x = lane; x < ck.npass * 16; x += NT) {
-            const int2 c = cand[x];
+            const int2 c = ck.cand(x);
             if (c.y >= 0) Smax = max(Smax, c.x);
         }
         {
@@ -1003,7 +1007,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         }
         if (Smax > 0) {
             for (int x = lane; x < ck.npass * 16; x += NT) {
-                const int2 c = cand[x];
+                const int2 c = ck.cand(x);
                 if (c.y < 0 || c.x != Smax) continue;
                 const int e = c.y;
                 for (int h = 0; h < 2; h++) {

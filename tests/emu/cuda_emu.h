@@ -237,6 +237,10 @@ struct int2 {
     int x, y;
 };
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct alignas(16) int4 {
+    int x, y, z, w;
+};
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 struct ulonglong2 {
     unsigned long long x, y;
 };
