@@ -955,7 +955,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
 
     // ---- launch configurations
     const bool sym = !lin && ctx->opt_sym != 0 && g_sym_scoring(ctx->h_sc);
-
+    const size_t dyn = gsub ? (size_t)BA16_WARPS * ba16_gsub_bytes_per_warp(ctx->h_sc.let) : 0;
     std::vector<std::vector<FillCfg>> cfgs((size_t)nw);
     int64_t max_bnd_ints = 0, max_tasks = 0;
     for (int64_t wi = 0; wi < nw; wi++) {
@@ -964,8 +964,6 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         int64_t wave_bnd = 0, wave_tasks = 0;
         for (auto &L : w.launches) {
             FillCfg c;
-            // GSUB kernels keep their per-lane query profiles in dynamic shared memory
-            const size_t dyn = gsub ? (size_t)BA16_WARPS * ba16_gsub_bytes_per_warp(ctx->h_sc.let, L.cols) : 0;
             c.dyn = dyn;
             // ---- LONG: too few pairs to fill the GPU pair by pair, and many passes each: spread the
             // passes of every pair over warps (wavefront).  Items of a launch are sorted by cells.

@@ -140,18 +140,16 @@ __host__ __device__ constexpr int ba16_rowst_stride(int cols) { return cols | 1;
 
 // MULTI: the launch contains pairs whose query needs more than one 32*COLS-column pass (the
 // inter-pass boundary code is compiled out of the common single-pass instance).
-// Dynamic shared memory (GSUB query profiles); the emulator backs it with a static buffer.
-// GSUB (any alphabet up to 31 letters, e.g. Protein): every lane keeps a QUERY PROFILE of its own columns
-// for both pairs of its couple: word [pair][letter R][kk][lane] holds the four substitution scores of row
-// letter R against the lane's columns 4kk .. 4kk+3.  A row then needs one LDS.32 per four packed cells and
-// pair (address = per-row base + immediate; the lane index is the bank: never a conflict) and the same
-// single sign-extending PRMT per packed cell as the 4-letter path -- round 1 looked every cell up with two
-// byte loads from shared score tables (67 % of the shared-memory wavefront peak, 44 % of them conflicts).
-// The profiles are rebuilt per pass from a signed-byte copy of the matrix (27 x KK words per lane and pair).
-__host__ __device__ constexpr int ba16_gsub_kk(int cols) { return (2 * cols + 3) / 4; }
-__host__ __device__ inline size_t ba16_gsub_bytes_per_warp(int let, int cols)
+// Dynamic shared memory (GSUB score tables); the emulator backs it with a static buffer.
+// A replica serves BA16_GSUB_SHARE lanes and is confined to as many banks: byte (R, q) of replica r
+// lives at ((R*32 + q) / (4*SHARE)) * 128 + 4*SHARE*r + (R*32 + q) % (4*SHARE) of the warp's slab.
+#ifndef BA16_GSUB_SHARE
+#define BA16_GSUB_SHARE 2
+#endif
+#define BA16_GSUB_SPAN (4 * BA16_GSUB_SHARE)            // bytes of a replica per 128-byte bank row
+__host__ __device__ inline size_t ba16_gsub_bytes_per_warp(int let)
 {
-    return (size_t)2 * (let + 1) * ba16_gsub_kk(cols) * 32 * 4;
+    return (size_t)(let + 1) * 32 / BA16_GSUB_SPAN * 128;
 }
 #ifdef BA_EMULATE
 static inline uint8_t *ba_dyn_smem()
@@ -225,13 +223,10 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     constexpr int RING = GSUB ? 128 : LIN ? 256 : BA16_PROF_RING, CHUNK = GSUB ? 64 : LIN ? 128 : BA16_PROF_CHUNK;
     __shared__ unsigned ring[BA16_GROUPS][2][RING + 8];
     __shared__ unsigned proftab[BA_MAX_LET + 1];  // PRMT: letter -> 4 sub bytes; GSUB: letter -> row byte offset
-    // GSUB: per-lane query profiles in dynamic shared memory (see ba16_gsub_bytes_per_warp) and the matrix as
-    // signed bytes; row `let` is the virtual letter (-128 against everything).
-    constexpr int KK = ba16_gsub_kk(COLS);
-    unsigned *gtab = GSUB ? (unsigned *)(ba_dyn_smem() + (size_t)(threadIdx.x >> 5) * ba16_gsub_bytes_per_warp(P.sc->let, COLS)) +
-                                (threadIdx.x & 31)
-                          : nullptr;
-    __shared__ signed char smat[GSUB ? (BA_MAX_LET + 1) * 32 : 4];
+    // GSUB: signed-byte score tables in dynamic shared memory, replicated per BA16_GSUB_SHARE lanes and
+    // confined to as many banks, so a lookup meets at most SHARE - 1 other lanes instead of 31;
+    // row `let` is the virtual letter (-128 against everything).
+    uint8_t *gtab = GSUB ? ba_dyn_smem() + (size_t)(threadIdx.x >> 5) * ba16_gsub_bytes_per_warp(P.sc->let) : nullptr;
     // staged checkpoints of the current period, per group (couple): lane-major rows, odd row stride
     constexpr int CST = LIN ? 9 : 17;                         // column stage: 8-byte elements per lane row
     constexpr int RST = ba16_rowst_stride(COLS);              // row stage: double-elements per lane row
@@ -252,14 +247,16 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             proftab[threadIdx.x] = w;
         }
     } else {
-        for (int x = threadIdx.x; x < (let + 1) * 32; x += blockDim.x) {
-            const int R = x >> 5, q = x & 31;
-            smat[x] = (signed char)((R == let) ? -128 : (q < let ? P.sc->la[R * let + q] : 0));
+        constexpr int NREP = 32 / BA16_GSUB_SHARE;
+        for (int x = threadIdx.x & 31; x < (let + 1) * 32 * NREP; x += 32) {
+            const int r = x % NREP, bo = x / NREP, R = bo >> 5, q = bo & 31;
+            const int v = (R == let) ? -128 : (q < let ? P.sc->la[R * let + q] : 0);
+            gtab[(bo / BA16_GSUB_SPAN) * 128 + BA16_GSUB_SPAN * r + (bo % BA16_GSUB_SPAN)] = (uint8_t)v;
         }
         for (int x = threadIdx.x; x <= BA_MAX_LET; x += blockDim.x)
-            proftab[x] = (unsigned)(min(x, let) * (KK * 32 * 4));   // byte offset of the letter's profile row
+            proftab[x] = (unsigned)(min(x, let) * (32 / BA16_GSUB_SPAN * 128));
     }
-    const unsigned VROW = GSUB ? (unsigned)(let * (KK * 32 * 4)) : 0x80808080u;  // ring entry of a virtual row
+    const unsigned VROW = GSUB ? (unsigned)(let * (32 / BA16_GSUB_SPAN * 128)) : 0x80808080u;  // ring entry of a virtual row
     __syncthreads();
     const int er = P.sc->la[1 * let];  // C1: identical for letters 1..4
     const int eq = P.sc->la[1];
@@ -386,29 +383,12 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                     }
                     sel[k] = nl | nh;
                 } else {
-                    // the query letters of my columns (padding / virtual columns: the gap letter)
-                    sel[k] = oka ? (unsigned)qA[(int64_t)(ja - 1) * stride] : 0u;
-                    qb4[k] = okb ? (unsigned)qB[(int64_t)(jb - 1) * stride] : 0u;
-                }
-            }
-            if (GSUB) {
-                // my query profiles for this pass: word (R, kk) = scores of row letter R against columns 4kk..4kk+3
-                unsigned *tB = gtab + (let + 1) * KK * 32;
-                for (int R = 0; R <= let; R++) {
-                    const signed char *row = smat + R * 32;
-#pragma unroll
-                    for (int kk = 0; kk < KK; kk++) {
-                        unsigned wa = 0, wb = 0;
-#pragma unroll
-                        for (int x = 0; x < 4; x++) {
-                            if (4 * kk + x < NC) {
-                                wa |= ((unsigned)row[sel[4 * kk + x]] & 0xffu) << (8 * x);
-                                wb |= ((unsigned)row[qb4[4 * kk + x]] & 0xffu) << (8 * x);
-                            }
-                        }
-                        gtab[(R * KK + kk) * 32] = wa;
-                        tB[(R * KK + kk) * 32] = wb;
-                    }
+                    // byte offset of the query letter inside a table row of my replica (lane couple)
+                    const unsigned la_ = oka ? (unsigned)qA[(int64_t)(ja - 1) * stride] : 0u;
+                    const unsigned lb_ = okb ? (unsigned)qB[(int64_t)(jb - 1) * stride] : 0u;
+                    const unsigned rep_ = (unsigned)BA16_GSUB_SPAN * (unsigned)(lane / BA16_GSUB_SHARE);
+                    sel[k] = (la_ / BA16_GSUB_SPAN) * 128u + (la_ % BA16_GSUB_SPAN) + rep_;
+                    qb4[k] = (lb_ / BA16_GSUB_SPAN) * 128u + (lb_ % BA16_GSUB_SPAN) + rep_;
                 }
             }
             // ---- profile rings: rows -15..0 virtual, rows 1.. loaded in chunks inside the step loop
@@ -500,10 +480,6 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 const unsigned profA = *(const unsigned *)((const char *)ringA + ro);
                 const unsigned profB = *(const unsigned *)((const char *)ringB + ro);
                 ro = (ro + 4u) & (RING * 4u - 1u);
-                // GSUB: this row's profile rows of pairs A and B (mine: the lane index is folded into gtab)
-                const unsigned *gpA = GSUB ? (const unsigned *)((const char *)gtab + profA) : nullptr;
-                const unsigned *gpB = GSUB ? (const unsigned *)((const char *)gtab + profB) + (let + 1) * KK * 32 : nullptr;
-                unsigned gwA = 0, gwB = 0;
 
                 // boundary column of the left neighbour lane; lane 0: DP column 0 (all zero for SW)
                 // or the staged last column of the previous pass
@@ -537,16 +513,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 #pragma unroll
                     for (int k = 0; k < NC; k++) {
                         unsigned sub;
-                        if (!GSUB) {
+                        if (!GSUB)
                             sub = ba_prmt(profA, profB, sel[k]);
-                        } else {
-                            if ((k & 3) == 0) {
-                                gwA = gpA[(k >> 2) * 32];
-                                gwB = gpB[(k >> 2) * 32];
-                            }
-                            const unsigned X = (unsigned)(k & 3);
-                            sub = ba_prmt(gwA, gwB, X | ((X | 8u) << 4) | ((4u + X) << 8) | ((12u + X) << 12));
-                        }
+                        else
+                            sub = ba_prmt((unsigned)(int)*(const signed char *)(gtab + profA + sel[k]),
+                                          (unsigned)(int)*(const signed char *)(gtab + profB + qb4[k]), 0x5410u);
                         const unsigned old = Hu[k];
                         const unsigned X = __viaddmax_s16x2(Hd, sub, __vadd2(old, erp));
                         Tl = (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Tl, eqp, X) : __viaddmax_s16x2(Tl, eqp, X);
@@ -562,16 +533,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 #pragma unroll
                     for (int k = 0; k < NC; k++) {
                         unsigned sub;
-                        if (!GSUB) {
+                        if (!GSUB)
                             sub = ba_prmt(profA, profB, sel[k]);
-                        } else {
-                            if ((k & 3) == 0) {
-                                gwA = gpA[(k >> 2) * 32];
-                                gwB = gpB[(k >> 2) * 32];
-                            }
-                            const unsigned X = (unsigned)(k & 3);
-                            sub = ba_prmt(gwA, gwB, X | ((X | 8u) << 4) | ((4u + X) << 8) | ((12u + X) << 12));
-                        }
+                        else
+                            sub = ba_prmt((unsigned)(int)*(const signed char *)(gtab + profA + sel[k]),
+                                          (unsigned)(int)*(const signed char *)(gtab + profB + qb4[k]), 0x5410u);
                         const unsigned M = (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Hd, sub, erp) : __vadd2(Hd, sub);
                         Hd = Hu[k];
                         Ll = __viaddmax_s16x2(Ll, eqp, Gl);
@@ -603,16 +569,11 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 #pragma unroll
                     for (int k = 0; k < NC; k++) {
                         unsigned sub;
-                        if (!GSUB) {
+                        if (!GSUB)
                             sub = ba_prmt(profA, profB, sel[k]);
-                        } else {
-                            if ((k & 3) == 0) {
-                                gwA = gpA[(k >> 2) * 32];
-                                gwB = gpB[(k >> 2) * 32];
-                            }
-                            const unsigned X = (unsigned)(k & 3);
-                            sub = ba_prmt(gwA, gwB, X | ((X | 8u) << 4) | ((4u + X) << 8) | ((12u + X) << 12));
-                        }
+                        else
+                            sub = ba_prmt((unsigned)(int)*(const signed char *)(gtab + profA + sel[k]),
+                                          (unsigned)(int)*(const signed char *)(gtab + profB + qb4[k]), 0x5410u);
                         if (KIND == KIND_SW)
                             Mu[k] = __viaddmax_s16x2_relu(Hd, sub, erp);  // erp <= 0: same as max(.,0)
                         else
