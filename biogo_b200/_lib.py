@@ -30,6 +30,7 @@ ABI_SYMBOLS = (
     "ba_create_multi", "ba_destroy_multi", "ba_multi_devices", "ba_multi_last_error", "ba_multi_set_scoring",
     "ba_multi_set_option", "ba_align_batch_multi", "ba_multi_free_result",
     "ba_matrix_count", "ba_matrix_name", "ba_matrix_get", "ba_set_scoring_named",
+    "ba_pals_dp_batch", "ba_pals_free_result",
 )
 
 
@@ -91,6 +92,21 @@ class BaSeqFile(C.Structure):
     ]
 
 
+class BaPalsCosts(C.Structure):
+    _fields_ = [("max_igap", C.c_int32), ("diff_cost", C.c_int32), ("same_cost", C.c_int32), ("match_cost", C.c_int32),
+                ("block_cost", C.c_int32), ("rmatch_cost", C.c_double)]
+
+
+class BaPalsHit(C.Structure):
+    _fields_ = [("abpos", C.c_int64), ("bbpos", C.c_int64), ("aepos", C.c_int64), ("bepos", C.c_int64),
+                ("low_diagonal", C.c_int64), ("high_diagonal", C.c_int64), ("score", C.c_int64), ("error", C.c_double)]
+
+
+class BaPalsResult(C.Structure):
+    _fields_ = [("n", C.c_int64), ("hit_off", C.POINTER(C.c_int64)), ("hits", C.POINTER(BaPalsHit)),
+                ("n_hits", C.c_int64), ("status", C.POINTER(C.c_int32)), ("ms_kernels", C.c_float)]
+
+
 class AlignError(RuntimeError):
     """A ba_* call failed (CUDA error, range error ...)."""
 
@@ -146,6 +162,11 @@ def _bind(lib):
     lib.ba_matrix_get.restype = i32
     lib.ba_set_scoring_named.argtypes = [vp, i32, i32, C.c_char_p, i64, i32, i64, vp]
     lib.ba_set_scoring_named.restype = i32
+    lib.ba_pals_dp_batch.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, i32, C.c_double,
+                                     C.POINTER(BaPalsCosts), C.POINTER(BaPalsResult)]
+    lib.ba_pals_dp_batch.restype = i32
+    lib.ba_pals_free_result.argtypes = [vp, C.POINTER(BaPalsResult)]
+    lib.ba_pals_free_result.restype = None
     lib.ba_create_multi.argtypes = [vp, i32, C.POINTER(vp)]
     lib.ba_create_multi.restype = i32
     lib.ba_destroy_multi.argtypes = [vp]
@@ -256,6 +277,35 @@ class Context:
         self._scoring_key = None
         self._check(self.lib.ba_set_scoring_named(self._h, kind, int(bool(affine)), name.encode(), int(gap), alpha_len,
                                                   int(gap_open), index.ctypes.data))
+
+    def pals_dp_batch(self, letters, target_off, target_len, query_off, query_len, index, trap_off, traps, kmer: int,
+                      min_hit_length: int, min_id: float, costs):
+        """ba_pals_dp_batch.  costs = (MaxIGap, DiffCost, SameCost, MatchCost, BlockCost, RMatchCost).
+        Returns (hits per problem as lists of 8-tuples, kernel ms)."""
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        to, qo = np.ascontiguousarray(target_off, np.int64), np.ascontiguousarray(query_off, np.int64)
+        tl, ql = np.ascontiguousarray(target_len, np.int32), np.ascontiguousarray(query_len, np.int32)
+        idx = np.ascontiguousarray(index, np.int32)
+        troff = np.ascontiguousarray(trap_off, np.int64)
+        tr = np.ascontiguousarray(np.asarray(traps, np.int32).reshape(-1))
+        if len(tr) == 0:
+            tr = np.zeros(4, np.int32)
+        n = len(to)
+        c = BaPalsCosts(*[int(x) for x in costs[:5]], float(costs[5]))
+        res = BaPalsResult()
+        rc = self.lib.ba_pals_dp_batch(self._h, letters.ctypes.data if len(letters) else None, to.ctypes.data,
+                                       tl.ctypes.data, qo.ctypes.data, ql.ctypes.data, n, idx.ctypes.data,
+                                       troff.ctypes.data, tr.ctypes.data, int(kmer), int(min_hit_length), float(min_id),
+                                       C.byref(c), C.byref(res))
+        self._check(rc)
+        out = []
+        for p in range(n):
+            a, b = int(res.hit_off[p]), int(res.hit_off[p + 1])
+            out.append([(h.abpos, h.bbpos, h.aepos, h.bepos, h.low_diagonal, h.high_diagonal, h.score, h.error)
+                        for h in (res.hits[k] for k in range(a, b))])
+        ms = float(res.ms_kernels)
+        self.lib.ba_pals_free_result(self._h, C.byref(res))
+        return out, ms
 
     def _collect(self, res: BaResult) -> BatchResult:
         out = BatchResult()

@@ -26,6 +26,7 @@
 #include "ba_plan.h"
 #include "ba_format.cuh"
 #include "ba_matrices.inl"
+#include "ba_pals.cuh"
 
 // One spelling for kernel launches so the same scheduler source also drives the CPU
 // emulator of the no-GPU test tier (tests/emu).
@@ -134,6 +135,7 @@ struct ba_ctx {
     DevBuf items, aux_off, aux, bnd, seg_count, seg_base, segs, arena, scan_tmp, counters;
     DevBuf flags, slot_off, slot_cap, slots, seg_clip, tasks, prog;
     DevBuf pair_seg_start, pair_seg_count, meta, ovf;
+    DevBuf pals_meta, pals_traps, pals_vec, pals_stack, pals_hits;   // align/pals/dp batches (ba_pals.inl)
     DevBuf segs32;   // exact path's per-wave segments (ctx->segs keeps the 16-bit path's until they are fetched)
     // Plan cache: batches of the same shape (same length arrays, same scoring) reuse the split, the
     // work lists and their device copies.
@@ -1733,7 +1735,8 @@ void ba_destroy(ba_ctx *ctx)
                       &ctx->counters, &ctx->flags,  &ctx->slot_off,  &ctx->slot_cap, &ctx->slots, &ctx->seg_clip,
                       &ctx->tasks,   &ctx->prog,     &ctx->fmt_len, &ctx->fmt_off, &ctx->fmt_rows,
                       &ctx->fmt_segs, &ctx->fmt_seg_start, &ctx->fmt_seg_count, &ctx->pair_seg_start,
-                      &ctx->pair_seg_count, &ctx->meta, &ctx->ovf, &ctx->segs32};
+                      &ctx->pair_seg_count, &ctx->meta, &ctx->ovf, &ctx->segs32, &ctx->pals_meta,
+                      &ctx->pals_traps, &ctx->pals_vec, &ctx->pals_stack, &ctx->pals_hits};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &b : ctx->pinned) cudaFreeHost(b.p);
@@ -2366,3 +2369,4 @@ void ba_free_host(void *p)
 
 #include "ba_seqio.inl"
 #include "ba_multi.inl"
+#include "ba_pals.inl"

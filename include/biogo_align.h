@@ -243,6 +243,48 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride,
                          int64_t n, ba_result *out);
 void ba_multi_free_result(ba_multi *m, ba_result *res);
 
+/*
+ * align/pals/dp: PALS' banded x-drop dynamic programming over filter trapezoids,
+ * batched.  One problem = dp.NewAligner(target, query, k, minLength, minId) + Aligner.Costs +
+ * AlignTraps(trapezoids) (align/pals/dp/align.go:43-141; the DP itself: kernel.go:52-454).  A problem is
+ * processed by one warp -- AlignTraps is sequential between the trapezoids of a problem (covered marks,
+ * hit order) -- with the rows of every trace computed 32 columns at a time; many problems fill the GPU.
+ *   letters            one host buffer holding every target and query (raw letters, compared byte for byte)
+ *   target_off/len,    per problem
+ *   query_off/len
+ *   index              the TARGET alphabet's LetterIndex (256 entries, negative = not in the alphabet):
+ *                      a query letter outside it never matches (kernel.go:227)
+ *   trap_off           n + 1 offsets into traps (in trapezoids); traps: {Top, Bottom, Left, Right} each
+ *                      (align/pals/filter/trapezoid.go:8-11)
+ *   kmer               Aligner.k (trapezoids lower than k are skipped, align.go:79)
+ * Hits of problem p are hits[hit_off[p] .. hit_off[p+1]), de-duplicated like align.go:88-138 (the order of
+ * hits with EQUAL Abpos resp. Aepos inside that step follows a stable sort; Go's sort.Sort is not stable
+ * and the reference pins no such case).  Integer arithmetic is 32-bit on the device:
+ * (len(target) + len(query) + 8) * max(|MatchCost|, DiffCost) must stay below 2^29 (else BA_ERR_RANGE);
+ * DiffCost >= 1.
+ */
+typedef struct {
+    int32_t max_igap, diff_cost, same_cost, match_cost, block_cost;   /* dp.Costs, align/pals/dp/align.go:24-31 */
+    double rmatch_cost;
+} ba_pals_costs;
+typedef struct {
+    int64_t abpos, bbpos, aepos, bepos, low_diagonal, high_diagonal, score;   /* dp.Hit, align.go:143-150 */
+    double error;
+} ba_pals_hit;
+typedef struct {
+    int64_t n;
+    int64_t *hit_off;     /* n + 1 */
+    ba_pals_hit *hits;
+    int64_t n_hits;
+    int32_t *status;      /* per problem, 0 = ok */
+    float ms_kernels;
+} ba_pals_result;
+int ba_pals_dp_batch(ba_ctx *ctx, const uint8_t *letters, const int64_t *target_off, const int32_t *target_len,
+                     const int64_t *query_off, const int32_t *query_len, int64_t n, const int32_t *index,
+                     const int64_t *trap_off, const int32_t *traps, int kmer, int min_hit_length, double min_id,
+                     const ba_pals_costs *costs, ba_pals_result *out);
+void ba_pals_free_result(ba_ctx *ctx, ba_pals_result *res);
+
 /* Pinned host allocation so a caller (cgo, ctypes) can pack straight into DMA-able memory. */
 void *ba_alloc_host(size_t bytes);
 void ba_free_host(void *p);

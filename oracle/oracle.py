@@ -18,6 +18,18 @@ ORC_SW, ORC_NW, ORC_FITTED = 0, 1, 2
 ORC_OK, ORC_ILLEGAL_REF, ORC_ILLEGAL_QRY, ORC_PANIC, ORC_NO_PATH = 0, 1, 2, 3, 4
 
 
+class PalsCosts(C.Structure):
+    """dp.Costs (align/pals/dp/align.go:24-31)"""
+    _fields_ = [("max_igap", C.c_int64), ("diff_cost", C.c_int64), ("same_cost", C.c_int64), ("match_cost", C.c_int64),
+                ("block_cost", C.c_int64), ("rmatch_cost", C.c_double)]
+
+
+class PalsHit(C.Structure):
+    """dp.Hit (align/pals/dp/align.go:143-150)"""
+    _fields_ = [("abpos", C.c_int64), ("bbpos", C.c_int64), ("aepos", C.c_int64), ("bepos", C.c_int64),
+                ("low_diagonal", C.c_int64), ("high_diagonal", C.c_int64), ("score", C.c_int64), ("error", C.c_double)]
+
+
 class _Scoring(C.Structure):
     _fields_ = [("kind", C.c_int), ("affine", C.c_int), ("let", C.c_int), ("la", C.c_void_p),
                 ("gap_open", C.c_int64), ("index", C.c_void_p)]
@@ -25,10 +37,12 @@ class _Scoring(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (no GPU, no reference sources needed)."""
-    src = os.path.join(_HERE, "align_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "align_oracle.c"), os.path.join(_HERE, "pals_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-pthread", "-shared", "-o", _SO, src])
+        # -ffp-contract=off: the float64 expressions of align/pals/dp are evaluated operation by operation, as Go does on amd64
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-pthread", "-ffp-contract=off", "-shared", "-o", _SO,
+                               *srcs])
     return _SO
 
 
@@ -55,6 +69,14 @@ def lib():
         l.orc_format_alignment.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_uint8,
                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.orc_format_alignment.restype = C.c_int
+        l.pals_align_traps.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int64, C.c_int64, C.c_double, C.POINTER(PalsCosts), C.c_int,
+                                       C.POINTER(C.c_void_p)]
+        l.pals_align_traps.restype = C.c_int64
+        l.pals_free.argtypes = [C.c_void_p]
+        l.pals_free.restype = None
+        l.pals_debruijn.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        l.pals_debruijn.restype = C.c_int64
         _lib = l
     return _lib
 
@@ -139,3 +161,36 @@ def format_alignment(ref: bytes, qry: bytes, segs, gap: str = "-", stride: int =
     if rc != 0:
         raise ValueError("format_alignment failed")
     return oa[: lens[0]].tobytes().decode(), ob[: lens[1]].tobytes().decode()
+
+
+# ---- align/pals/dp (oracle/pals_oracle.c) ---------------------------------------------------------
+
+def pals_align_traps(target: bytes, query: bytes, index, traps, kmer: int, min_hit_length: int, min_id: float, costs,
+                     dedup: bool = True):
+    """dp.Aligner.AlignTraps restated.  traps: [(top, bottom, left, right)]; costs: (MaxIGap, DiffCost, SameCost,
+    MatchCost, BlockCost, RMatchCost).  Returns [(Abpos, Bbpos, Aepos, Bepos, LowDiagonal, HighDiagonal, Score, Error)]."""
+    l = lib()
+    t = np.frombuffer(target, dtype=np.uint8) if len(target) else np.zeros(1, np.uint8)
+    q = np.frombuffer(query, dtype=np.uint8) if len(query) else np.zeros(1, np.uint8)
+    idx = np.ascontiguousarray(index, dtype=np.int32)
+    tr = np.ascontiguousarray(np.array(traps, dtype=np.int64).reshape(-1, 4))
+    c = PalsCosts(*[int(x) for x in costs[:5]], float(costs[5]))
+    out = C.c_void_p()
+    n = l.pals_align_traps(t.ctypes.data, len(target), q.ctypes.data, len(query), idx.ctypes.data, tr.ctypes.data, len(tr),
+                           kmer, min_hit_length, float(min_id), C.byref(c), int(dedup), C.byref(out))
+    hits = []
+    if n > 0:
+        arr = C.cast(out, C.POINTER(PalsHit))
+        for k in range(n):
+            h = arr[k]
+            hits.append((h.abpos, h.bbpos, h.aepos, h.bepos, h.low_diagonal, h.high_diagonal, h.score, h.error))
+    if out:
+        l.pals_free(out)
+    return hits
+
+
+def debruijn(k: int, n: int) -> bytes:
+    """util.DeBruijn(k, n) (util/debruijn.go:8-40): letter values 0..k-1."""
+    buf = np.zeros(max(k ** n, n, 1), np.uint8)
+    m = lib().pals_debruijn(k, n, buf.ctypes.data)
+    return buf[:m].tobytes()
