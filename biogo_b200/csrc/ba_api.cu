@@ -113,6 +113,7 @@ struct ba_ctx {
     cudaStream_t s_trace = nullptr;  // traceback + compaction of wave w beside the fill of wave w+1 (high priority)
     cudaStream_t s_h2d = nullptr;    // input upload, in groups the first waves do not have to wait for
     cudaStream_t s_d2h = nullptr;    // result copies
+    cudaStream_t s_prep = nullptr;   // encode + validate of upload groups (host-buffer calls)
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // pooled events of one call (timing / no timing), handed out in order and reused by the next call
     std::vector<cudaEvent_t> ev_timed, ev_plain, ev_upload;
@@ -365,6 +366,9 @@ struct Batch {
     const int32_t *h_ref_len = nullptr, *h_qry_len = nullptr;
     int64_t n = 0;
     cudaStream_t st = nullptr;  // main stream (the caller's for ba_align_batch_device)
+    // encode + validate stream: the main stream, or -- while the input is still uploading in groups -- a
+    // stream of its own, so that the preparation of group g+1 is not queued behind the fill of chunk g
+    cudaStream_t prep_st = nullptr;
     int32_t *d_status = nullptr;
     int64_t *d_err_pos = nullptr;
     uint8_t *d_flags = nullptr;   // letter-class flags per pair (16-bit path eligibility), or nullptr
@@ -452,22 +456,23 @@ int cached_occupancy(ba_ctx *ctx, Fn fn, int threads, int &occ, size_t dyn_smem 
 int prep_pairs(ba_ctx *ctx, Batch &B, int64_t pmax)
 {
     const int kind = ctx->h_sc.kind, affine = ctx->h_sc.affine;
+    cudaStream_t PS = B.prep_st ? B.prep_st : B.st;
     while (B.next_group < B.groups.size() && B.groups[B.next_group].p_lo <= pmax) {
         UploadGroup &g = B.groups[B.next_group++];
-        if (g.ready) CK(cudaStreamWaitEvent(B.st, g.ready, 0));
+        if (g.ready) CK(cudaStreamWaitEvent(PS, g.ready, 0));
         const int64_t nb = g.b_hi - g.b_lo, np = g.p_hi - g.p_lo;
         if (nb > 0) {
             int64_t blocks = (nb / 16 + 255) / 256;
             if (blocks < 1) blocks = 1;
             if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-            BA_LAUNCH(ba_encode_kernel, (unsigned)blocks, 256, B.st, B.d_letters + g.b_lo, B.d_enc + g.b_lo, nb,
+            BA_LAUNCH(ba_encode_kernel, (unsigned)blocks, 256, PS, B.d_letters + g.b_lo, B.d_enc + g.b_lo, nb,
                       ctx->d_sc);
             B.launches++;
         }
         if (np > 0) {
             int64_t blocks = (np + 7) / 8;
             if (blocks > ctx->sm_count * 32) blocks = ctx->sm_count * 32;
-            BA_LAUNCH(ba_validate_kernel, (unsigned)blocks, 256, B.st, B.d_enc, B.stride, B.d_ref_off + g.p_lo,
+            BA_LAUNCH(ba_validate_kernel, (unsigned)blocks, 256, PS, B.d_enc, B.stride, B.d_ref_off + g.p_lo,
                       B.d_ref_len + g.p_lo, B.d_qry_off + g.p_lo, B.d_qry_len + g.p_lo, np, kind, affine,
                       B.d_status + g.p_lo, B.d_err_pos + g.p_lo, B.d_flags ? B.d_flags + g.p_lo : nullptr);
             B.launches++;
@@ -478,8 +483,16 @@ int prep_pairs(ba_ctx *ctx, Batch &B, int64_t pmax)
             ctx->err = "cudaEventCreate failed";
             return BA_ERR_CUDA;
         }
-        CK(cudaEventRecord(g.checked, B.st));
+        CK(cudaEventRecord(g.checked, PS));
     }
+    return BA_OK;
+}
+
+// Make `stream` see everything prepared so far (no-op when it IS the preparation stream).
+int sync_prep(ba_ctx *ctx, Batch &B, cudaStream_t stream)
+{
+    if (!B.prep_st || B.prep_st == stream || B.next_group == 0) return BA_OK;
+    CK(cudaStreamWaitEvent(stream, B.groups[B.next_group - 1].checked, 0));
     return BA_OK;
 }
 
@@ -560,6 +573,7 @@ int run_path32(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids)
     cudaStream_t st = B.st;
     int rc;
     if ((rc = prep_pairs(ctx, B, B.n - 1)) != BA_OK) return rc;
+    if ((rc = sync_prep(ctx, B, st)) != BA_OK) return rc;
     ctx->pc.dev_items = nullptr;  // this path reuses the work-list buffers
     int64_t arena_cap = 0;
     if (arena_budget(ctx, arena_cap) != 0) {
@@ -1114,6 +1128,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         bool used_alt = false;
         if (!chunked) {
             if ((rc = prep_pairs(ctx, B, w.max_pair)) != BA_OK) return rc;
+            if ((rc = sync_prep(ctx, B, F)) != BA_OK) return rc;
             if (F != st && B.next_group > 0) CK(cudaStreamWaitEvent(F, B.groups[B.next_group - 1].checked, 0));
         }
         if (wi >= R) CK(cudaStreamWaitEvent(F, ev_trace_end[(size_t)(wi - R)], 0));  // its region is free again
@@ -1151,6 +1166,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                     int32_t mp = 0;
                     for (int64_t k = 0; k < L.count; k++) mp = std::max(mp, plan.items[L.first + k].pair);
                     if ((rc = prep_pairs(ctx, B, mp)) != BA_OK) return rc;
+                    if ((rc = sync_prep(ctx, B, F)) != BA_OK) return rc;
                 }
                 WorkItem *h_tasks = (WorkItem *)lease.get(sizeof(WorkItem) * (size_t)c.ntasks);
                 if (!h_tasks) {
@@ -1213,8 +1229,9 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                     if (ctx->opt_fill_streams >= 2 && c.bnd_ints == 0 && ((c0 / per) & 1)) {
                         FS = ctx->s_fill2;
                         used_alt = true;
-                        if (B.next_group > 0) CK(cudaStreamWaitEvent(FS, B.groups[B.next_group - 1].checked, 0));
                     }
+                    if (B.next_group > 0 && FS != (B.prep_st ? B.prep_st : B.st))
+                        CK(cudaStreamWaitEvent(FS, B.groups[B.next_group - 1].checked, 0));
                 }
                 const int64_t need = (cnt + 2 * BA16_GROUPS - 1) / (2 * BA16_GROUPS);
                 const int64_t blocks = c.max_claims > 0 ? (need + c.max_claims - 1) / c.max_claims
@@ -1548,6 +1565,7 @@ int run_device_once(ba_ctx *ctx, Batch &B, int64_t letters_bytes)
     }
     (void)host_arrays_final;
     if ((rc = prep_pairs(ctx, B, n - 1)) != BA_OK) return rc;   // groups no wave asked for (nothing to align)
+    if ((rc = sync_prep(ctx, B, st)) != BA_OK) return rc;
 
     BA_TSEC("T paths done", t_call);
     // ---- per-pair status (the traceback may have changed it) and error positions
@@ -1590,7 +1608,7 @@ int run_device_once(ba_ctx *ctx, Batch &B, int64_t letters_bytes)
 // Drain every stream of the context (error paths: nothing may still be writing into pooled memory).
 void drain(ba_ctx *ctx, cudaStream_t extra)
 {
-    cudaStream_t all[] = {ctx->stream, ctx->s_fill2, ctx->s_trace, ctx->s_h2d, ctx->s_d2h, extra};
+    cudaStream_t all[] = {ctx->stream, ctx->s_fill2, ctx->s_trace, ctx->s_h2d, ctx->s_d2h, ctx->s_prep, extra};
     for (cudaStream_t s : all)
         if (s) cudaStreamSynchronize(s);
     (void)cudaGetLastError();
@@ -1710,6 +1728,8 @@ int ba_create(int device, ba_ctx **out)
     if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
     e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
     if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
+    e = cudaStreamCreateWithPriority(&ctx->s_prep, cudaStreamNonBlocking, prio_hi);   // short kernels between fill CTAs
+    if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
     for (int k = 0; k < 8; k++) {
         e = cudaEventCreate(&ctx->ev[k]);
         if (e != cudaSuccess) return fail(e, "cudaEventCreate");
@@ -1725,7 +1745,7 @@ void ba_destroy(ba_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStream_t streams[] = {ctx->stream, ctx->s_fill2, ctx->s_trace, ctx->s_h2d, ctx->s_d2h};
+    cudaStream_t streams[] = {ctx->stream, ctx->s_fill2, ctx->s_trace, ctx->s_h2d, ctx->s_d2h, ctx->s_prep};
     for (cudaStream_t s : streams)
         if (s) cudaStreamSynchronize(s);
     plan_cache_drop(ctx);
@@ -2163,6 +2183,7 @@ static int align_host(ba_ctx *ctx, const uint8_t *letters, int stride, const int
     B.h_qry_len = qry_len;
     B.n = n;
     B.st = st;
+    B.prep_st = B.groups.size() > 1 ? ctx->s_prep : nullptr;
     B.out = out;
     B.defer_segs = defer_segs;
     rc = run_device(ctx, B, letters_bytes);

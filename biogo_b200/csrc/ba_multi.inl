@@ -127,12 +127,15 @@ bool multi_deal(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int D
         acc += cnt[(size_t)b];
     }
     for (int d = 0; d < D; d++) shares[(size_t)d].reserve((size_t)(n / D + 2));
-    // pair p takes position start[bucket]++ of the order; position x goes to device snake(x)
-    for (int64_t p = 0; p < n; p++) {
-        const int64_t x = start[bk[(size_t)p]]++;
+    // pair p takes position start[bucket]++ of the largest-first order; position x goes to device snake(x).
+    // A share keeps that order: it is (nearly) the order the device's own planner works in, so the fill can
+    // start on the first uploaded pieces of the share while the rest is still being gathered and copied.
+    std::vector<int64_t> ord((size_t)n);
+    for (int64_t p = 0; p < n; p++) ord[(size_t)start[bk[(size_t)p]]++] = p;
+    for (int64_t x = 0; x < n; x++) {
         const int64_t r = x % (2 * D);
         const int d = (int)(r < D ? r : 2 * D - 1 - r);
-        shares[(size_t)d].push_back(p);
+        shares[(size_t)d].push_back(ord[(size_t)x]);
     }
     return false;
 }
