@@ -91,16 +91,14 @@ void multi_fail(ba_multi *m, int d, const std::string &msg)
     if (m->err.empty()) m->err = "device " + std::to_string(m->devices[(size_t)d]) + ": " + msg;
 }
 
-// Length-bucketed dealing.  shares[d] = pair ids of device d.  Returns true when the shares are
-// contiguous ranges of the caller's order (then share d is [cut[d], cut[d+1])).
+// Length-bucketed dealing.  shares[d] = pair ids of device d.  allow_ranges (all pairs of one shape): the
+// shares are contiguous ranges of the caller's order, share d is [cut[d], cut[d+1]); returns that flag.
 bool multi_deal(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int D, bool allow_ranges,
                 std::vector<std::vector<int64_t>> &shares, std::vector<int64_t> &cut)
 {
     shares.assign((size_t)D, std::vector<int64_t>());
     cut.assign((size_t)D + 1, 0);
-    bool same = allow_ranges;
-    for (int64_t p = 1; p < n && same; p++) same = ref_len[p] == ref_len[0] && qry_len[p] == qry_len[0];
-    if (same) {
+    if (allow_ranges) {   // the caller has checked that all pairs have one shape
         for (int d = 0; d <= D; d++) cut[(size_t)d] = n * d / D;
         return true;
     }
@@ -245,15 +243,30 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride, const 
     const int D = (int)m->ctx.size();
     if (D < 1) return BA_ERR_ARG;
     ba_ctx *c0 = m->ctx[0];
-    for (int64_t p = 0; p < n; p++)
-        if (ref_len[p] < 0 || qry_len[p] < 0 || ref_off[p] < 0 || qry_off[p] < 0) {
+    const double t0 = now_s();
+    // argument check and "are all pairs of one shape?" in one pass, every device thread over its slice
+    std::vector<int> bad((size_t)D, 0), differs((size_t)D, 0);
+    multi_parallel(m, [&](int d) {
+        const int64_t lo = n * d / D, hi = n * (d + 1) / D;
+        int b = 0, df = 0;
+        for (int64_t p = lo; p < hi; p++) {
+            b |= (ref_len[p] < 0) | (qry_len[p] < 0) | (ref_off[p] < 0) | (qry_off[p] < 0);
+            df |= (ref_len[p] != ref_len[0]) | (qry_len[p] != qry_len[0]);
+        }
+        bad[(size_t)d] = b;
+        differs[(size_t)d] = df;
+    });
+    bool uniform = m->opt_contiguous != 0;
+    for (int d = 0; d < D; d++) {
+        if (bad[(size_t)d]) {
             m->err = "negative sequence length or offset";
             return BA_ERR_ARG;
         }
-    const double t0 = now_s();
+        if (differs[(size_t)d]) uniform = false;
+    }
     std::vector<std::vector<int64_t>> shares;
     std::vector<int64_t> cut;
-    const bool ranges = multi_deal(ref_len, qry_len, n, D, m->opt_contiguous != 0, shares, cut);
+    const bool ranges = multi_deal(ref_len, qry_len, n, D, uniform, shares, cut);
     const double deal_s = now_s() - t0;
 
     // the one result block (pinned; owned by device 0's pool, freed by ba_multi_free_result)
