@@ -48,6 +48,10 @@ while time.time() < t_end:
     pk = helpers.pack(pairs, stride)
     opts = {"trace_mode": rng.choice([0, 1, 2, 3, 4, 5]), "long_mode": rng.choice([0, 1, 2]),
             "plan_cache": rng.choice([0, 1]), "sym_kernels": rng.choice([0, 1])}
+    # round-2 scheduler: waves with overlapped traceback, region reuse, grouped upload + chunked fill
+    opts.update({"waves": rng.choice([0, 0, 1, 2, 3, 5]), "upload_groups": rng.choice([0, 1, 3, 7]),
+                 "chunk_pairs": rng.choice([8, 64, 8192]), "fill_claims": rng.choice([0, 1, 2]),
+                 "fill_streams": rng.choice([1, 2]), "trace_cta": rng.choice([0, 64, 128])})
     if rng.random() < 0.1:
         opts["slot_cap"] = rng.choice([1, 3])
     if rng.random() < 0.15:
@@ -75,6 +79,9 @@ while time.time() < t_end:
         ctx.set_option("long_mode", 1)
         ctx.set_option("plan_cache", 1)
         ctx.set_option("sym_kernels", 1)
+        for k, v in (("waves", 0), ("upload_groups", 0), ("chunk_pairs", 8192), ("fill_claims", 1), ("fill_streams", 2),
+                     ("trace_cta", 0)):
+            ctx.set_option(k, v)
     rounds += 1
     fastpairs += fast.stats["pairs_fast16"]
     if not ok:
