@@ -159,7 +159,7 @@ struct ba_ctx {
     // fill warp takes before its CTA retires (0 = persistent grid), resident fill CTAs per SM (0 = all that
     // fit), threads per thread-per-pair traceback CTA (0 = automatic), upload groups (0 = automatic)
     int64_t opt_waves = 0, opt_fill_streams = 2, opt_fill_claims = 1, opt_fill_cap = 0, opt_trace_cta = 0;
-    int64_t opt_upload_groups = 0, opt_chunk_pairs = 8192;
+    int64_t opt_upload_groups = 0, opt_chunk_pairs = 8192, opt_test_long_timeout = 0;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
@@ -1432,6 +1432,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         B.dev_segs = B.seg_total;
     }
     BA_TSEC("P16 waves done", tp0);
+    const bool long_tasks_empty = long_tasks.empty();
     for (WorkItem *t : long_tasks) lease.drop(t);
     // spans on the device (the kernels of different waves overlap)
     {
@@ -1444,6 +1445,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             B.ms_trace += ms;
         }
     }
+    if (ctx->opt_test_long_timeout && !long_tasks_empty) h_long_err[0] = 1;   // test hook: exercise the retry path
     for (int64_t wi = 0; wi < nw; wi++)
         if (h_long_err[wi] != 0) {
             ctx->err = "fill16 wavefront: a pass waited too long for its left neighbour";
@@ -1839,6 +1841,10 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     }
     if (!strcmp(key, "chunk_pairs")) {     // fewest pairs a fill chunk of a still-uploading batch gets (0 = default)
         ctx->opt_chunk_pairs = value > 0 ? value : 8192;
+        return BA_OK;
+    }
+    if (!strcmp(key, "test_long_timeout")) {   // test hook: report the first wavefront launch as timed out
+        ctx->opt_test_long_timeout = value;
         return BA_OK;
     }
     if (!strcmp(key, "pinned_budget")) {   // bytes of idle pinned host memory a context keeps for reuse

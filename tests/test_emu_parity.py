@@ -452,3 +452,23 @@ def test_overlapped_waves_with_slot_overflow_and_mixed_alphabet(emu_ctx):
         emu_ctx.set_option("waves", 0)
         emu_ctx.set_option("slot_cap", 0)
     helpers.compare(res, helpers.run_oracle(0, True, M, -2, DNA_IDX, pk, 2), "overflow across waves")
+
+
+def test_wavefront_timeout_falls_back_to_the_pass_by_pass_kernels(emu_ctx):
+    """A wavefront pass that gives up waiting (never observed; injected here) must not fail the call: the
+    batch is re-run with the pass-by-pass kernels and the results are the oracle's."""
+    rng = random.Random(4242)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 5, [40, 130], [1025, 1300, 1700], related=0.85, dirty=0.0)
+    pk = helpers.pack(pairs)
+    emu_ctx.set_option("long_mode", 2)
+    emu_ctx.set_option("test_long_timeout", 1)
+    try:
+        res = helpers.run_lib(emu_ctx, 2, True, M, -4, DNA_IDX, 5, pk)
+    finally:
+        emu_ctx.set_option("long_mode", 1)
+        emu_ctx.set_option("test_long_timeout", 0)
+    assert res.stats["wavefront_launches"] >= 1          # the first attempt did use the wavefront
+    helpers.compare(res, helpers.run_oracle(2, True, M, -4, DNA_IDX, pk), "wavefront retry")
+    again = helpers.run_lib(emu_ctx, 2, True, M, -4, DNA_IDX, 5, pk)     # and the context is fine afterwards
+    helpers.compare(again, helpers.run_oracle(2, True, M, -4, DNA_IDX, pk), "after retry")
