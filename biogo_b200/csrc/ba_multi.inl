@@ -268,6 +268,7 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride, const 
     std::vector<int64_t> cut;
     const bool ranges = multi_deal(ref_len, qry_len, n, D, uniform, shares, cut);
     const double deal_s = now_s() - t0;
+    BA_TSEC("multi deal", t0);
 
     // the one result block (pinned; owned by device 0's pool, freed by ba_multi_free_result)
     out->n = n;
@@ -361,6 +362,7 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride, const 
         }
         if (s.rc != BA_OK) multi_fail(m, d, ba_last_error(c));
     });
+    BA_TSEC("multi phase 1 (align)", t0);
     int rc = BA_OK;
     int64_t total = 0;
     for (int d = 0; d < D; d++) {
@@ -418,6 +420,7 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride, const 
             multi_fail(m, d, cudaGetErrorString(e));
         }
     });
+    BA_TSEC("multi phase 2 (gather)", t0);
     // ---- bookkeeping: spans are the slowest device's, counters add up
     for (int d = 0; d < D; d++) {
         Share &s = S[(size_t)d];
@@ -444,6 +447,7 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride, const 
         release();
         return rc;
     }
+    BA_TSEC("multi total", t0);
     return BA_OK;
 }
 
