@@ -515,3 +515,39 @@ def test_waves_and_chunked_upload_equal_one_wave_on_a_large_batch(gpu_ctx):
     again = helpers.run_lib(gpu_ctx, w.kind, True, w.matrix, w.gap_open, w.alpha.LetterIndex(), 5, pk)
     for p in range(0, w.n, 11):
         assert np.array_equal(one.pairs(p), again.pairs(p)), p
+
+
+def test_wavefront_timeout_falls_back_to_the_pass_by_pass_kernels(gpu_ctx):
+    """A wavefront pass that gives up waiting (injected) re-runs the batch with the pass-by-pass kernels."""
+    rng = random.Random(4242)
+    M = gv.match(-1, 1, -1)
+    pairs = randcases.rand_pairs(rng, 9, [400, 1300], [1025, 1300, 2100], related=0.85, dirty=0.0)
+    pk = helpers.pack(pairs)
+    gpu_ctx.set_option("long_mode", 2)
+    gpu_ctx.set_option("test_long_timeout", 1)
+    try:
+        res = helpers.run_lib(gpu_ctx, 2, True, M, -4, DNA_IDX, 5, pk)
+    finally:
+        gpu_ctx.set_option("long_mode", 1)
+        gpu_ctx.set_option("test_long_timeout", 0)
+    assert res.stats["wavefront_launches"] >= 1
+    helpers.compare(res, helpers.run_oracle(2, True, M, -4, DNA_IDX, pk, 1, 8), "wavefront retry")
+
+
+def test_named_scoring_on_the_gpu(gpu_ctx):
+    """ba_set_scoring_named (align/matrix by name) against the explicit table and the oracle, and the resident
+    scoring cache when alternating between two aligners."""
+    rng = random.Random(8)
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    pairs = randcases.rand_pairs(rng, 200, [60, 150, 300], [60, 150, 300], related=0.8, dirty=0.0, alpha=aa)
+    pk = helpers.pack(pairs)
+    for name, gap, go in (("BLOSUM62", -1, -10), ("PAM250", -2, -8), ("BLOSUM80", -1, -12)):
+        M = matrix.with_gap(matrix.by_name(name), gap)
+        want = helpers.run_oracle(1, True, M, go, PROT_IDX, pk, 1, 16)
+        for _ in range(2):                                  # second round: both scorings come from the cache
+            gpu_ctx.set_scoring_named(1, True, name, gap, 26, go, PROT_IDX)
+            helpers.compare(gpu_ctx.align_packed(pk[0], 1, pk[1], pk[2], pk[3], pk[4]), want, f"named {name}")
+            helpers.compare(helpers.run_lib(gpu_ctx, 0, False, gv.match(-1, 2, -1), 0, DNA_IDX, 5,
+                                            helpers.pack([(b"ACGTACGTTT", b"ACGTCGTTT")])),
+                            helpers.run_oracle(0, False, gv.match(-1, 2, -1), 0, DNA_IDX,
+                                               helpers.pack([(b"ACGTACGTTT", b"ACGTCGTTT")])), "dna between")
