@@ -1067,7 +1067,6 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
 
     int maxI = i, maxJ = j, score = 0, last = MV_DIAG;
     bool bad = false;
-    const int er_c = S[let] >> BA_SCALE_SHIFT, eq_c = S[1] >> BA_SCALE_SHIFT;   // uniform over the letters of this path (C1)
     while (i > 0 && j > 0 && !bad) {
         if (KIND == KIND_SW && cur == 0) break;
         // ---- window anchored at (i, j).  Warp team: my tile is strip g_hi - lane / 8, period (period
@@ -1111,23 +1110,12 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             const int cbase = ck.left_col(g);
             const int c0 = max(cbase, 0);
             const uint8_t *tcodes = tiles + wbase + slot;
-            // The walk is one serial chain per pair here (every lane walks the same path), so its latency is
-            // what counts: the letters of the tile's rows and columns are fetched once, together, into two
-            // 64-bit registers instead of two dependent global loads per step, and the gap scores are the
-            // scoring's uniform ones (condition C1 of ba_fill16.cuh; no gap letter on this path).
-            unsigned long long rpack = 0, qpack = 0;
-#pragma unroll
-            for (int x = 0; x < BA_TILE_ROWS; x++)
-                if (rt + 1 + x <= i) rpack |= (unsigned long long)rs[(int64_t)(rt + x) * stride] << (8 * x);
-#pragma unroll
-            for (int x = 0; x < BA_MAX_COLS; x++)
-                if (cbase + 1 + x >= 1 && cbase + 1 + x <= j) qpack |= (unsigned long long)qs[(int64_t)(cbase + x) * stride] << (8 * x);
             while (i > rt && j > c0) {
                 if (KIND == KIND_SW && cur == 0) break;
-                const int R = (int)((rpack >> (8 * (i - rt - 1))) & 0xffu), Q = (int)((qpack >> (8 * (j - cbase - 1))) & 0xffu);
+                const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
                 const unsigned code = tcodes[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
                 const bool corner = (i == n && j == m);
-                const int er = er_c, eq = eq_c;
+                const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
                 int move, nl = 0, delta;
                 if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl,
                                                delta)) {
