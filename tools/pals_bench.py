@@ -34,6 +34,20 @@ pals.AlignTrapsBatch(aligners[:64], tzs[:64], ctx)
 t0 = time.perf_counter()
 got = pals.AlignTrapsBatch(aligners, tzs, ctx)
 gpu_s = time.perf_counter() - t0
+# the same batch through the ctypes call alone (packed once): library time without the Python packing
+chunks, to, tl, qo, ql, troff, trs, off = [], [], [], [], [], [0], [], 0
+for tgt, qry, traps in problems:
+    to.append(off); tl.append(len(tgt)); off += len(tgt)
+    qo.append(off); ql.append(len(qry)); off += len(qry)
+    chunks += [tgt, qry]
+    for z in traps:
+        trs += list(z)
+    troff.append(len(trs) // 4)
+letters = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+ctx.pals_dp_batch(letters, to, tl, qo, ql, tp.DNA_IDX, troff, trs, 6, 50, 0.8, tp.COSTS)
+t0 = time.perf_counter()
+_, kernel_ms = ctx.pals_dp_batch(letters, to, tl, qo, ql, tp.DNA_IDX, troff, trs, 6, 50, 0.8, tp.COSTS)
+lib_s = time.perf_counter() - t0
 threads = os.cpu_count() or 1
 sample = problems[:max(64, 8 * threads)]
 
@@ -49,6 +63,7 @@ cpu_s = time.perf_counter() - t0
 ok = all([(h.Abpos, h.Bbpos, h.Aepos, h.Bepos, h.LowDiagonal, h.HighDiagonal, h.Score, h.Error) for h in g] == w
          for g, w in zip(got, want))
 rec = {"problems": n, "hits": sum(len(g) for g in got), "gpu_s_end_to_end": gpu_s, "gpu_problems_per_s": n / gpu_s,
+       "library_call_s": lib_s, "kernel_ms": kernel_ms, "kernel_problems_per_s": n / (kernel_ms * 1e-3),
        "cpu_threads": threads, "cpu_sample": len(sample), "cpu_problems_per_s": len(sample) / cpu_s,
        "speedup": (n / gpu_s) / (len(sample) / cpu_s), "sample_equal_to_oracle": ok,
        "note": "GPU: host buffers in, de-duplicated hits out (python packing included); CPU: oracle/pals_oracle.c, one "
