@@ -159,7 +159,7 @@ struct ba_ctx {
     // fill warp takes before its CTA retires (0 = persistent grid), resident fill CTAs per SM (0 = all that
     // fit), threads per thread-per-pair traceback CTA (0 = automatic), upload groups (0 = automatic)
     int64_t opt_waves = 0, opt_fill_streams = 2, opt_fill_claims = 1, opt_fill_cap = 0, opt_trace_cta = 0;
-    int64_t opt_upload_groups = 0, opt_chunk_pairs = 8192, opt_test_long_timeout = 0;
+    int64_t opt_upload_groups = 0, opt_chunk_pairs = 8192, opt_test_long_timeout = 0, opt_wide10 = 1;
     int64_t cached_arena_cap = 0;                    // cudaMemGetInfo is slow: ask once per context
     std::vector<std::pair<const void *, int>> occ_cache;  // kernel -> resident CTAs per SM
     std::vector<PinnedBlock> pinned;
@@ -764,17 +764,23 @@ Fill16Fn pick_fill16(int kind, bool lin, int cols, bool multi, bool gsub, bool w
     return ba_pick_fill16_2_0(cols, multi, gsub, wavefront);
 }
 typedef void (*Trace16Fn)(Trace16Params);
-template <int NT>
-Trace16Fn pick_trace16t(int kind, bool lin)
+template <int NT, int MC>
+Trace16Fn pick_trace16t_mc(int kind, bool lin)
 {
     if (lin) {
-        if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, true, NT>;
-        if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, true, NT>;
-        return ba_trace16w_kernel<KIND_FIT, true, NT>;
+        if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, true, NT, MC>;
+        if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, true, NT, MC>;
+        return ba_trace16w_kernel<KIND_FIT, true, NT, MC>;
     }
-    if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, false, NT>;
-    if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, false, NT>;
-    return ba_trace16w_kernel<KIND_FIT, false, NT>;
+    if (kind == KIND_SW) return ba_trace16w_kernel<KIND_SW, false, NT, MC>;
+    if (kind == KIND_NW) return ba_trace16w_kernel<KIND_NW, false, NT, MC>;
+    return ba_trace16w_kernel<KIND_FIT, false, NT, MC>;
+}
+// mc: widest strip of the wave (8, or 10 when it contains the 257..320-column single-pass class)
+template <int NT>
+Trace16Fn pick_trace16t(int kind, bool lin, int mc = BA_MAX_COLS)
+{
+    return mc > BA_MAX_COLS ? pick_trace16t_mc<NT, BA16_MAX_COLS>(kind, lin) : pick_trace16t_mc<NT, BA_MAX_COLS>(kind, lin);
 }
 Trace16Fn pick_trace16p(int kind, bool lin)
 {
@@ -787,22 +793,23 @@ Trace16Fn pick_trace16p(int kind, bool lin)
     if (kind == KIND_NW) return ba_trace16p_kernel<KIND_NW, false>;
     return ba_trace16p_kernel<KIND_FIT, false>;
 }
-template <int TS>
+template <int TS, int MC>
 Trace16Fn pick_trace16ts(int kind, bool lin)
 {
     if (lin) {
-        if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, true, TS>;
-        if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, true, TS>;
-        return ba_trace16_kernel<KIND_FIT, true, TS>;
+        if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, true, TS, MC>;
+        if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, true, TS, MC>;
+        return ba_trace16_kernel<KIND_FIT, true, TS, MC>;
     }
-    if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, false, TS>;
-    if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, false, TS>;
-    return ba_trace16_kernel<KIND_FIT, false, TS>;
+    if (kind == KIND_SW) return ba_trace16_kernel<KIND_SW, false, TS, MC>;
+    if (kind == KIND_NW) return ba_trace16_kernel<KIND_NW, false, TS, MC>;
+    return ba_trace16_kernel<KIND_FIT, false, TS, MC>;
 }
 // thread-per-pair traceback with CTAs of `ts` threads (64: fits the SM slot a retiring fill CTA frees)
-Trace16Fn pick_trace16(int kind, bool lin, int ts)
+Trace16Fn pick_trace16(int kind, bool lin, int ts, int mc = BA_MAX_COLS)
 {
-    return ts == 64 ? pick_trace16ts<64>(kind, lin) : pick_trace16ts<BA_TRACE_THREADS>(kind, lin);
+    if (mc > BA_MAX_COLS) return pick_trace16ts<BA_TRACE_THREADS, BA16_MAX_COLS>(kind, lin);   // (128 threads only)
+    return ts == 64 ? pick_trace16ts<64, BA_MAX_COLS>(kind, lin) : pick_trace16ts<BA_TRACE_THREADS, BA_MAX_COLS>(kind, lin);
 }
 
 // Scoring-level eligibility of the packed 16-bit path (ba_fill16.cuh):
@@ -933,7 +940,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             return BA_ERR_NOMEM;
         }
         const double tp1 = now_s();
-        build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, lin ? 0 : 1, true, wave_cap, plan, (int)tw);
+        build_plan(ids, nids, B.h_ref_len, B.h_qry_len, kind, lin ? 0 : 1, true, wave_cap, plan, (int)tw, ctx->opt_wide10 != 0);
         BA_TSEC("plan16 pinned_get", tp0);
         BA_TSEC("plan16 build", tp1);
         if (ctx->opt_slot_cap > 0) {  // test hook: force the overflow -> exact-path fallback
@@ -1300,8 +1307,11 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                                 (ctx->opt_trace_mode == 1 &&
                                  w.count * 32 <= (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS * 2);
         // thread-per-pair CTAs: 64 threads beside a running fill (they fit the slot of one fill CTA)
-        const int tcta = ctx->opt_trace_cta == 64 || (ctx->opt_trace_cta == 0 && overlap && wi + 1 < nw) ? 64
-                                                                                                          : BA_TRACE_THREADS;
+        int wave_mc = BA_MAX_COLS;
+        for (auto &L : w.launches) wave_mc = std::max(wave_mc, L.cols);
+        const int tcta = wave_mc > BA_MAX_COLS ? BA_TRACE_THREADS
+                         : (ctx->opt_trace_cta == 64 || (ctx->opt_trace_cta == 0 && overlap && wi + 1 < nw)) ? 64
+                                                                                                             : BA_TRACE_THREADS;
         const size_t tsm128 = 0, tsm = 0;   // the traceback kernels use static shared memory only
         auto trace_launch = [&](Trace16Fn fn, unsigned grid, int threads, size_t smem, const Trace16Params &prm) -> int {
             int occ_unused = 0;
@@ -1311,12 +1321,12 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             return BA_OK;
         };
         if (cta_trace) {
-            if ((rc = trace_launch(pick_trace16t<BA_TRACE_THREADS>(kind, lin), (unsigned)w.count, BA_TRACE_THREADS, tsm128, tp)) != BA_OK)
+            if ((rc = trace_launch(pick_trace16t<BA_TRACE_THREADS>(kind, lin, wave_mc), (unsigned)w.count, BA_TRACE_THREADS, tsm128, tp)) != BA_OK)
                 return rc;
             B.out->warp_trace_launches++;
         } else if (warp_trace) {
             const unsigned tb = (unsigned)((w.count + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-            if ((rc = trace_launch(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, tsm128, tp)) != BA_OK) return rc;
+            if ((rc = trace_launch(pick_trace16t<32>(kind, lin, wave_mc), tb, BA_TRACE_THREADS, tsm128, tp)) != BA_OK) return rc;
             B.out->warp_trace_launches++;
         } else {
             const int64_t slots_free = (int64_t)ctx->sm_count * BA_TRACE_MINB * BA_TRACE_THREADS - w.count;
@@ -1340,7 +1350,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 Trace16Params th = tp;
                 th.n_items = (int)head;
                 const unsigned tb = (unsigned)((head + BA_TRACE_THREADS / 32 - 1) / (BA_TRACE_THREADS / 32));
-                if ((rc = trace_launch(pick_trace16t<32>(kind, lin), tb, BA_TRACE_THREADS, tsm128, th)) != BA_OK) return rc;
+                if ((rc = trace_launch(pick_trace16t<32>(kind, lin, wave_mc), tb, BA_TRACE_THREADS, tsm128, th)) != BA_OK) return rc;
                 B.out->warp_trace_launches++;
                 B.launches++;
             }
@@ -1351,10 +1361,10 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
                 tt.seg_count = tp.seg_count + head;
                 tt.slot_off = tp.slot_off + head;
                 tt.slot_cap = tp.slot_cap + head;
-                if (ctx->opt_trace_mode != 5) {
+                if (ctx->opt_trace_mode != 5 || wave_mc > BA_MAX_COLS) {   // (the persistent variant has 8-column tiles only)
                     // static assignment: thread k of the grid walks pair k
                     const int64_t tblocks = (w.count - head + tcta - 1) / tcta;
-                    if ((rc = trace_launch(pick_trace16(kind, lin, tcta), (unsigned)tblocks, tcta, tsm, tt)) != BA_OK) return rc;
+                    if ((rc = trace_launch(pick_trace16(kind, lin, tcta, wave_mc), (unsigned)tblocks, tcta, tsm, tt)) != BA_OK) return rc;
                 } else {
                     // persistent grid, pairs claimed from a counter (largest first).  Measured on B200:
                     // +5 % on configs 1 and 3, -9 % on config 2 against the static kernel, so it is
@@ -1841,6 +1851,11 @@ int ba_set_option(ba_ctx *ctx, const char *key, int64_t value)
     }
     if (!strcmp(key, "chunk_pairs")) {     // fewest pairs a fill chunk of a still-uploading batch gets (0 = default)
         ctx->opt_chunk_pairs = value > 0 ? value : 8192;
+        return BA_OK;
+    }
+    if (!strcmp(key, "wide10")) {          // 0: no 10-column single-pass class for queries of 257..320 letters
+        ctx->opt_wide10 = value;
+        plan_cache_drop(ctx);
         return BA_OK;
     }
     if (!strcmp(key, "test_long_timeout")) {   // test hook: report the first wavefront launch as timed out

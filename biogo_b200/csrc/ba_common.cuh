@@ -25,6 +25,7 @@
 #define BA_MAX_LET 32          // largest supported matrix dimension (Protein is 26)
 #define BA_WARP 32
 #define BA_MAX_COLS 8          // columns per lane in the 32-bit systolic kernels
+#define BA16_MAX_COLS 10       // columns per strip in the packed 16-bit kernels (10: the 257..320-column single-pass class)
 #define BA_FILL_WARPS 4        // warps per CTA in the fill kernels
 
 enum { KIND_SW = 0, KIND_NW = 1, KIND_FIT = 2 };

@@ -25,6 +25,7 @@ Fill16Fn pick_c(int cols)
     case 5: return ba_fill16_kernel<K, 5, MULTI, GSUB, false, LIN, SYM>;
     case 6: return ba_fill16_kernel<K, 6, MULTI, GSUB, false, LIN, SYM>;
     case 7: return ba_fill16_kernel<K, 7, MULTI, GSUB, false, LIN, SYM>;
+    case 10: return ba_fill16_kernel<K, 10, MULTI, GSUB, false, LIN, SYM>;   // 257..320 columns in one pass
     default: return ba_fill16_kernel<K, 8, MULTI, GSUB, false, LIN, SYM>;
     }
 }

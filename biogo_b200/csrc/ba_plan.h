@@ -40,6 +40,15 @@ inline int cols_for(int m)
     return c > BA_MAX_COLS ? BA_MAX_COLS : c;
 }
 
+// 16-bit path: queries of 257..320 letters get ONE pass of 10-column strips (two strips per lane, 20 columns)
+// instead of two passes of five -- half the steps, no inter-pass boundary rows, 0.95 instead of 1.48 bytes of
+// checkpoints per cell (BASELINE config 3: 300 aa x 300 aa).  wide10 = 0 keeps the 8-column ceiling.
+inline int cols16_for(int m, bool wide10)
+{
+    if (wide10 && m > 32 * BA_MAX_COLS && m <= 32 * BA16_MAX_COLS) return BA16_MAX_COLS;
+    return cols_for(m);
+}
+
 // capacity of the per-pair segment slot buffer of the 16-bit path; pairs that emit more are
 // re-run on the exact two-pass path
 inline int32_t slot_cap_for(int n, int m, int affine)
@@ -57,8 +66,9 @@ inline int32_t slot_cap_for(int n, int m, int affine)
 // target_waves > 1 (16-bit path): additionally cut the batch into about that many waves of equal
 // traceback bytes, so that the traceback of wave w overlaps the fill of wave w+1 (ba_api.cu).
 inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len, const int32_t *qry_len, int kind,
-                       int affine, bool mode16, int64_t arena_cap, Plan &plan, int target_waves = 1)
+                       int affine, bool mode16, int64_t arena_cap, Plan &plan, int target_waves = 1, bool wide10 = true)
 {
+    auto cols_of = [&](int m) { return mode16 ? cols16_for(m, wide10) : cols_for(m); };
     const bool need_aux = (kind == KIND_FIT) && !mode16;
     if (target_waves < 1) target_waves = 1;
     // fast path: every pair has the same shape (the common batch): closed-form plan
@@ -71,7 +81,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
             same = (ref_len[p] == n0) & (qry_len[p] == m0);
         }
         if (same) {
-            const int c = cols_for(m0);
+            const int c = cols_of(m0);
             // 16-bit path: cb is a COUPLE's region (two pairs); 32-bit path: one pair's codes
             int64_t cb = mode16 ? ba16_ck_bytes(c, n0, ba16_npass(c, m0), !affine) : ba_code_bytes(affine, c, n0, m0);
             cb = (cb + 255) & ~(int64_t)255;
@@ -124,10 +134,10 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         }
     }
     // pass 1: class sizes and whether a class is uniform (then no sort is needed)
-    int64_t cnt[BA_MAX_COLS + 1] = {0};
-    int64_t first_cells[BA_MAX_COLS + 1];
-    bool uniform[BA_MAX_COLS + 1];
-    for (int c = 0; c <= BA_MAX_COLS; c++) {
+    int64_t cnt[BA16_MAX_COLS + 1] = {0};
+    int64_t first_cells[BA16_MAX_COLS + 1];
+    bool uniform[BA16_MAX_COLS + 1];
+    for (int c = 0; c <= BA16_MAX_COLS; c++) {
         first_cells[c] = -1;
         uniform[c] = true;
     }
@@ -137,7 +147,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
     int64_t tmemo_cb = 0;
     for (int64_t x = 0; x < nids; x++) {
         const int32_t p = ids ? ids[x] : (int32_t)x;
-        const int c = cols_for(qry_len[p]);
+        const int c = cols_of(qry_len[p]);
         cls[(size_t)x] = (uint8_t)c;
         if (target_waves > 1) {
             if (ref_len[p] != tmemo_n || qry_len[p] != tmemo_m) {
@@ -158,15 +168,15 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
     }
     // pass 2: pair ids grouped by class (widest first), written into one array
     std::vector<int32_t> order((size_t)nids);
-    int64_t start[BA_MAX_COLS + 2];
+    int64_t start[BA16_MAX_COLS + 2];
     {
         int64_t acc = 0;
-        for (int c = BA_MAX_COLS; c >= 1; c--) {
+        for (int c = BA16_MAX_COLS; c >= 1; c--) {
             start[c] = acc;
             acc += cnt[c];
         }
-        int64_t fill[BA_MAX_COLS + 1];
-        for (int c = 1; c <= BA_MAX_COLS; c++) fill[c] = start[c];
+        int64_t fill[BA16_MAX_COLS + 1];
+        for (int c = 1; c <= BA16_MAX_COLS; c++) fill[c] = start[c];
         for (int64_t x = 0; x < nids; x++) {
             const int32_t p = ids ? ids[x] : (int32_t)x;
             order[(size_t)fill[cls[(size_t)x]]++] = p;
@@ -195,7 +205,7 @@ inline void build_plan(const int32_t *ids, int64_t nids, const int32_t *ref_len,
         wave.launches.clear();
     };
     int64_t w = 0;  // next item slot
-    for (int c = BA_MAX_COLS; c >= 1; c--) {
+    for (int c = BA16_MAX_COLS; c >= 1; c--) {
         if (cnt[c] == 0) continue;
         int32_t *v = order.data() + start[c];
         if (!uniform[c]) {

@@ -162,7 +162,7 @@ __device__ __forceinline__ Cell3 border_col0(int i, int go, int er)
 // Recompute the tile of strip g, period e, for rows rt+1 .. imax and columns up to jmax, and
 // store the cell codes in `tile` (byte (row*8 + k) * BA_TRACE_THREADS apart).
 // S is the scoring matrix scaled by BA_SCALE in shared memory (row stride `let`).
-template <int KIND, int TS>
+template <int KIND, int TS, int MC>
 __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                              uint8_t *tile, TileProbe &pb)
@@ -176,9 +176,9 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     const int er_u = S[let], eq_u = S[1];       // uniform gap entries (letters >= 1)
 
     // ---- per-column constants of this tile
-    int qo[BA_MAX_COLS], eqv[BA_MAX_COLS];
+    int qo[MC], eqv[MC];
 #pragma unroll
-    for (int k = 0; k < BA_MAX_COLS; k++) {
+    for (int k = 0; k < MC; k++) {
         qo[k] = 0;
         eqv[k] = 0;
         if (k >= kfirst && k <= klast) {
@@ -228,11 +228,11 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     }
 
     // ---- top boundary row rt for my columns
-    Cell3 Pv[BA_MAX_COLS];
+    Cell3 Pv[MC];
     {
         int lM = corner.M, lL = corner.L;
 #pragma unroll
-        for (int k = 0; k < BA_MAX_COLS; k++) {
+        for (int k = 0; k < MC; k++) {
             Pv[k].M = Pv[k].U = Pv[k].L = 0;
             if (k >= kfirst && k <= klast) {
                 if (rt >= 1) {
@@ -258,7 +258,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     // latency hides under the current row's cells
     int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0, nM = 0, nL = 0;
     if (cL > 0 && rt + 1 <= imax) ck.col_ml(gl, rt + 1, nM, nL);
-    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * TS) {
+    for (int r = rt + 1; r <= imax; r++, trow += MC * TS) {
         const int *Srow = S + nR * let;
         const int mm = nM, ll = nL;
         if (r + 1 <= imax) {
@@ -280,7 +280,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
         }
         Cell3 d = dprev, l = left;
 #pragma unroll
-        for (int k = 0; k < BA_MAX_COLS; k++) {
+        for (int k = 0; k < MC; k++) {
             if (k >= kfirst && k <= klast) {
                 unsigned code;
                 int dm;
@@ -312,7 +312,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
 
 // Linear-gap tile (ba_fill16 LIN): one table T; the checkpoints hold it in their M field.  Codes
 // are linear_cell<KIND>'s: 3 diag, 2 up, 1 left, 0 = SW cell clamped to zero (stop).
-template <int KIND, int TS>
+template <int KIND, int TS, int MC>
 __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S, int let, const uint8_t *rs,
                                                  const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                                  uint8_t *tile, TileProbe &pb)
@@ -326,9 +326,9 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
     const int er_u = S[let], eq_u = S[1];
     const int gl = g - 1;
 
-    int qo[BA_MAX_COLS], eqv[BA_MAX_COLS], Tv[BA_MAX_COLS];
+    int qo[MC], eqv[MC], Tv[MC];
 #pragma unroll
-    for (int k = 0; k < BA_MAX_COLS; k++) {
+    for (int k = 0; k < MC; k++) {
         qo[k] = 0;
         eqv[k] = 0;
         Tv[k] = 0;
@@ -360,7 +360,7 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
     // next row's letter and left boundary value, fetched one row ahead
     int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0;
     int nLeft = (rt + 1 <= imax) ? left_at(rt + 1) : 0;
-    for (int r = rt + 1; r <= imax; r++, trow += BA_MAX_COLS * TS) {
+    for (int r = rt + 1; r <= imax; r++, trow += MC * TS) {
         const int *Srow = S + nR * let;
         const int left = nLeft;
         if (r + 1 <= imax) {
@@ -370,7 +370,7 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
         const int er = Srow[0];
         int d = dprev, l = left;
 #pragma unroll
-        for (int k = 0; k < BA_MAX_COLS; k++) {
+        for (int k = 0; k < MC; k++) {
             if (k >= kfirst && k <= klast) {
                 unsigned code;
                 const int old = Tv[k];
@@ -396,15 +396,17 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
     }
 }
 
-template <int KIND, bool LIN, int TS = BA_TRACE_THREADS>
+// MC: widest strip (columns) the tile arrays are laid out for: BA_MAX_COLS, or BA16_MAX_COLS for waves that
+// contain the 10-column single-pass class (ba_plan.h cols16_for)
+template <int KIND, bool LIN, int TS = BA_TRACE_THREADS, int MC = BA_MAX_COLS>
 __device__ __forceinline__ void trace16_tile(const CkView &ck, const int *S, int let, int go, const uint8_t *rs,
                                              const uint8_t *qs, int stride, int g, int e, int imax, int jmax,
                                              uint8_t *tile, TileProbe &pb)
 {
     if (LIN)
-        trace16_tile_lin<KIND, TS>(ck, S, let, rs, qs, stride, g, e, imax, jmax, tile, pb);
+        trace16_tile_lin<KIND, TS, MC>(ck, S, let, rs, qs, stride, g, e, imax, jmax, tile, pb);
     else
-        trace16_tile_aff<KIND, TS>(ck, S, let, go, rs, qs, stride, g, e, imax, jmax, tile, pb);
+        trace16_tile_aff<KIND, TS, MC>(ck, S, let, go, rs, qs, stride, g, e, imax, jmax, tile, pb);
 }
 
 // One step of the walk: decode the cell's code for the current layer into (move, next layer,
@@ -441,10 +443,10 @@ __device__ __forceinline__ bool trace16_decode(unsigned code, int layer, int er,
 // TS = threads per CTA: 128, or 64 -- a CTA that fits into the SM slot one ba_fill16 CTA frees
 // (registers and shared memory), so a traceback running on a high-priority stream beside the next
 // wave's fill is scheduled as fill CTAs retire.
-template <int KIND, bool LIN, int TS = BA_TRACE_THREADS>
+template <int KIND, bool LIN, int TS = BA_TRACE_THREADS, int MC = BA_MAX_COLS>
 __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THREADS / TS)) ba_trace16_kernel(Trace16Params P)
 {
-    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * TS];
+    __shared__ uint8_t tiles[BA_TILE_ROWS * MC * TS];
     __shared__ int S[BA_MAX_LET * BA_MAX_LET];
     {
         const int ll = P.sc->let;
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
                     if (rlast < i || (rlast == i && clast < j)) continue;  // cannot come later
                     TileProbe pb;
                     pb.want = Smax * BA_SCALE;
-                    trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    trace16_tile<KIND, LIN, TS, MC>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
                     if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
                         i = pb.fi;
                         j = pb.fj;
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
         TileProbe pb;
         pb.ci = i;
         pb.cj = j;
-        trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+        trace16_tile<KIND, LIN, TS, MC>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
                            tile, pb);
         int best = pb.cM;
         if (pb.cU > best) {
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
         for (int e = 0; BA16_PERIOD * e - v < n; e++) {
             const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
             if (rlast < 1) continue;
-            trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+            trace16_tile<KIND, LIN, TS, MC>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         i = pb.besti;
     }
@@ -571,12 +573,12 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
         const int rt = max(BA16_PERIOD * e - v, 0);
         const int c0 = max(ck.left_col(g), 0);
         TileProbe pb0;
-        trace16_tile<KIND, LIN, TS>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
+        trace16_tile<KIND, LIN, TS, MC>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
         const int cbase = ck.left_col(g);
         while (i > rt && j > c0) {
             if (KIND == KIND_SW && cur == 0) break;
             const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
-            const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * TS];
+            const unsigned code = tile[((i - rt - 1) * MC + (j - cbase - 1)) * TS];
             const bool corner = (i == n && j == m);
             const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
             int move, nl = 0, delta;
@@ -903,12 +905,12 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
 #define BA_TW_PERIODS 8
 #define BA_TB_PERIODS 3
 #define BA_TB_STRIPS (BA_TRACE_THREADS / BA_TB_PERIODS)
-template <int KIND, bool LIN, int NT>
+template <int KIND, bool LIN, int NT, int MC = BA_MAX_COLS>
 __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_kernel(Trace16Params P)
 {
     static_assert(NT == 32 || NT == BA_TRACE_THREADS, "a team is a warp or the CTA");
     __shared__ int red[BA_TRACE_THREADS / 32][2];
-    __shared__ uint8_t tiles[BA_TILE_ROWS * BA_MAX_COLS * BA_TRACE_THREADS];
+    __shared__ uint8_t tiles[BA_TILE_ROWS * MC * BA_TRACE_THREADS];
     __shared__ int S[BA_MAX_LET * BA_MAX_LET];
     {
         const int ll = P.sc->let;
@@ -1019,7 +1021,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
                     if (rlast < i || (rlast == i && clast < j)) continue;
                     TileProbe pb;
                     pb.want = Smax * BA_SCALE;
-                    trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
+                    trace16_tile<KIND, LIN, BA_TRACE_THREADS, MC>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb);
                     if (pb.fi > i || (pb.fi == i && pb.fj > j)) {
                         i = pb.fi;
                         j = pb.fj;
@@ -1038,7 +1040,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         TileProbe pb;
         pb.ci = i;
         pb.cj = j;
-        trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
+        trace16_tile<KIND, LIN, BA_TRACE_THREADS, MC>(ck, S, let, go8, rs, qs, stride, g, (i + CkView::lane_of(g) - 1) >> BA16_PSHIFT, i, j,
                            tile, pb);
         int best = pb.cM;
         if (pb.cU > best) {
@@ -1056,7 +1058,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         for (int e = lane; BA16_PERIOD * e - v < n; e += NT) {
             const int rlast = min(n, BA16_PERIOD * e + BA16_PERIOD - v);
             if (rlast < 1) continue;
-            trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
+            trace16_tile<KIND, LIN, BA_TRACE_THREADS, MC>(ck, S, let, go8, rs, qs, stride, g, e, rlast, j, tile, pb);
         }
         // last row attaining the maximum: larger value wins, ties go to the larger row
         int best = pb.best, besti = pb.besti;
@@ -1085,7 +1087,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             const int rtop = max(BA16_PERIOD * e - v, 0);
             if (g >= 0 && e >= 0 && clast >= 1 && rlast > rtop) {
                 TileProbe pb0;
-                trace16_tile<KIND, LIN>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
+                trace16_tile<KIND, LIN, BA_TRACE_THREADS, MC>(ck, S, let, go8, rs, qs, stride, g, e, rlast, clast, tile, pb0);
             }
         }
         T16W_SYNC();
@@ -1113,7 +1115,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             while (i > rt && j > c0) {
                 if (KIND == KIND_SW && cur == 0) break;
                 const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
-                const unsigned code = tcodes[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
+                const unsigned code = tcodes[((i - rt - 1) * MC + (j - cbase - 1)) * BA_TRACE_THREADS];
                 const bool corner = (i == n && j == m);
                 const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
                 int move, nl = 0, delta;
