@@ -29,15 +29,14 @@ Fill16Fn pick_c(int cols)
     default: return ba_fill16_kernel<K, 8, MULTI, GSUB, false, LIN, SYM>;
     }
 }
-// LONG (inter-pass wavefront) instances exist for the widest column classes only (7, 8, 10): pairs with
-// four or more passes always land there (ba_plan.h cols_for / cols16_for)
+// LONG (inter-pass wavefront) instances exist for the two widest multi-pass column classes only: pairs with
+// four or more passes always land there (ba_plan.h cols_for; the 10-column class is single-pass)
 template <bool GSUB>
 Fill16Fn pick_long(int cols)
 {
     constexpr int K = BA_INST_KIND;
     constexpr bool LIN = BA_INST_LIN == 1, SYM = BA_INST_LIN == 2;
     if (cols == 7) return ba_fill16_kernel<K, 7, true, GSUB, true, LIN, SYM>;
-    if (cols == 10) return ba_fill16_kernel<K, 10, true, GSUB, true, LIN, SYM>;
     return ba_fill16_kernel<K, 8, true, GSUB, true, LIN, SYM>;
 }
 }  // namespace

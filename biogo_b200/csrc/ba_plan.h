@@ -40,20 +40,16 @@ inline int cols_for(int m)
     return c > BA_MAX_COLS ? BA_MAX_COLS : c;
 }
 
-// 16-bit path: strips may be 10 columns wide (two strips per lane: 20 columns, 320-column passes) wherever that
-// saves a pass over the 8-column plan: queries of 257..320 letters run in ONE pass instead of two (BASELINE
-// config 3, 300 aa x 300 aa: half the steps, no inter-pass boundary rows, 1.08 instead of 1.48 bytes of
-// checkpoints per cell), 513..640 in two instead of three, 10 000 in 32 instead of 40.  There is no 9-column
-// instance: such plans take 10.  wide10 = 0 keeps the 8-column ceiling.
+// 16-bit path: queries of 257..320 letters get ONE pass of 10-column strips (two strips per lane, 20 columns)
+// instead of two passes of five -- half the steps, no inter-pass boundary rows, 1.08 instead of 1.48 bytes of
+// checkpoints per cell (BASELINE config 3, 300 aa x 300 aa: 1.05 -> 1.28 TCUPS).  Using 10-column strips for
+// multi-pass plans as well (513..640 letters in two passes instead of three, 10 kb in 32 instead of 40) was
+// measured and dropped: the fill of config 4 gains 20 % but its traceback over 10-column tiles loses as much, and
+// config 5 loses 9 % overall.  wide10 = 0 keeps the 8-column ceiling.
 inline int cols16_for(int m, bool wide10)
 {
-    const int c8 = cols_for(m);
-    if (!wide10 || m <= 32 * BA_MAX_COLS) return c8;
-    const int np8 = (m + 32 * BA_MAX_COLS - 1) / (32 * BA_MAX_COLS);
-    const int np10 = (m + 32 * BA16_MAX_COLS - 1) / (32 * BA16_MAX_COLS);
-    if (np10 >= np8) return c8;
-    const int c = (m + 32 * np10 - 1) / (32 * np10);
-    return c >= 9 ? BA16_MAX_COLS : c;
+    if (wide10 && m > 32 * BA_MAX_COLS && m <= 32 * BA16_MAX_COLS) return BA16_MAX_COLS;
+    return cols_for(m);
 }
 
 // capacity of the per-pair segment slot buffer of the 16-bit path; pairs that emit more are
