@@ -237,6 +237,26 @@ def emit(line: dict) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+def bind_near_gpu(local_rank: int):
+    """Multi-rank runs: keep this rank's host threads (and therefore its pinned result / staging buffers, which
+    are placed by first touch) on the CPUs NVML reports as local to its GPU.  Eight ranks copying 16 MB of
+    segments per step otherwise cross sockets at random.  Returns the CPU list, or None when unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 ALG_BYTES_PER_CELL = {True: 1.0, False: 0.25}   # SURVEY 8(d): affine 1 byte/cell, linear 2 bits/cell
 AGG_KEYS = ("ms_fill", "ms_trace", "ms_host", "ms_kernels", "ms_d2h", "gpu_launches", "fill_launches", "code_bytes",
             "n_segs", "pairs_fast16", "waves")
@@ -323,6 +343,7 @@ def main():
         raise SystemExit("bench.py needs a B200: biogo_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_near_gpu(local_rank) if world > 1 else None
     cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -579,6 +600,8 @@ def main():
                 roof["dpx"]["ncu_thread_inst_per_cell"] = ent.get("inst_per_cell")
         cfg = workload_config(w.name, args.config, w.n, world)   # identical in the reference arm's line
         cfg_detail = {"cells_per_gpu_per_step": cells_step,
+                      "host_affinity": (f"each rank bound to the {len(affinity)} CPUs NVML reports as local to its GPU"
+                                        if affinity else "not bound"),
                       "host_plan": "work lists cached across same-shaped batches (lengths only, never results); "
                                    "the uncached cost is plan_cache_miss"}
         line = {

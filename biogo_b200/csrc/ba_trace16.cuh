@@ -1164,13 +1164,9 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
 }
 
 // ---- per-wave finish: clip + overflow list, scan (cub), compact + pair-order scatter, totals ----
-// Device-side bookkeeping of one batch: `total` = segments compacted so far (the next wave's base),
-// `n_overflow` = pairs handed to the exact path, then three int64 per wave {base, segments, overflow so far}
+// Device-side bookkeeping of one batch (an int64 array): [0] = segments compacted so far (the next wave's
+// base), [1] = pairs handed to the exact path, then three words per wave {base, segments, overflow so far}
 // that travel to the host after every wave.
-struct WaveMeta {
-    long long total;
-    long long n_overflow;
-};
 #define BA_META_HEAD 2   // int64 words before the per-wave records
 #define BA_META_WAVE 3   // int64 words per wave
 
