@@ -343,6 +343,7 @@ def main():
         raise SystemExit("bench.py needs a B200: biogo_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
     affinity = bind_near_gpu(local_rank) if world > 1 else None
     cpu_group = None
     if world > 1:
@@ -515,6 +516,8 @@ def main():
                          "copy and host work of a step are not hidden under the next step's kernels"}
         ctx.lib.ba_free_host(hp)
 
+    if affinity:
+        os.sched_setaffinity(0, all_cpus)   # the one-process multi-GPU batch and the CPU baseline use every core
     # ---- the other BASELINE configs, a few steps each on this rank's GPU (rank 0 reports them)
     other = {}
     hbm_peak, peak_src = load_peaks()
