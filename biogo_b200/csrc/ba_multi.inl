@@ -266,7 +266,8 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride, const 
     }
     std::vector<std::vector<int64_t>> shares;
     std::vector<int64_t> cut;
-    const bool ranges = multi_deal(ref_len, qry_len, n, D, uniform, shares, cut);
+    // (one device: its share is the whole batch as the caller laid it out -- nothing to deal or gather)
+    const bool ranges = multi_deal(ref_len, qry_len, n, D, uniform || D == 1, shares, cut);
     const double deal_s = now_s() - t0;
     BA_TSEC("multi deal", t0);
 
