@@ -963,7 +963,10 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     }
     B.host_s += now_s() - tp0;
     const int64_t nw = (int64_t)plan.waves.size();
-    const bool overlap = nw > 1;
+    // Overlap mode (non-persistent fill grids, 64-thread traceback CTAs, alternating fill streams) only when the
+    // caller asked for waves: a batch that is merely too large for the arena runs its waves with the
+    // single-wave kernels' settings (measured: 1 M pairs of config 2 on one GPU, 94.5 -> see DESIGN 4.4)
+    const bool overlap = nw > 1 && tw > 1;
     int64_t region_bytes = 0, region_slots = 0, total_slots = 0;
     for (auto &w : plan.waves) {
         region_bytes = std::max(region_bytes, w.code_bytes);
