@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ba_common.cuh"
@@ -377,6 +378,11 @@ struct Batch {
     Lease *lease = nullptr;
     std::vector<UploadGroup> groups;
     size_t next_group = 0;
+    // groups whose copy (and `ready` record) has been ENQUEUED; nullptr when all of them were before the
+    // call started.  A feeder thread gathers and enqueues the groups of a scattered share while the
+    // kernels of the first groups are already running; waiting on an event that has not been recorded
+    // yet would not wait at all, so the consumer first waits here on the host.
+    std::atomic<int64_t> *groups_enqueued = nullptr;
     // all segments of the batch in ONE pinned block (grown in the rare case the estimate was short)
     int32_t *h_segs = nullptr;
     int64_t h_segs_cap = 0;     // in segments
@@ -459,6 +465,8 @@ int prep_pairs(ba_ctx *ctx, Batch &B, int64_t pmax)
     cudaStream_t PS = B.prep_st ? B.prep_st : B.st;
     while (B.next_group < B.groups.size() && B.groups[B.next_group].p_lo <= pmax) {
         UploadGroup &g = B.groups[B.next_group++];
+        if (B.groups_enqueued)
+            while (B.groups_enqueued->load(std::memory_order_acquire) < (int64_t)B.next_group) std::this_thread::yield();
         if (g.ready) CK(cudaStreamWaitEvent(PS, g.ready, 0));
         const int64_t nb = g.b_hi - g.b_lo, np = g.p_hi - g.p_lo;
         if (nb > 0) {
@@ -2166,36 +2174,61 @@ static int align_host(ba_ctx *ctx, const uint8_t *letters, int stride, const int
     }
     // the letters, group by group, each in pieces of 4 MB (small copies of other contexts -- work lists,
     // per-wave records -- share the copy engines and must not queue behind one 100+ MB transfer)
-    std::vector<cudaEvent_t> ready(B.groups.size(), nullptr);
-    int64_t gathered = 0;   // pairs whose letters are in the staging buffer (gs)
-    for (size_t gi = 0; gi < B.groups.size(); gi++) {
-        const UploadGroup &g = B.groups[gi];
-        if (gs) {
-            // every pair that starts below the end of this piece
-            while (gathered < n && ref_off[gathered] < g.b_hi) {
-                const int64_t p = gs->ids[gathered];
-                const size_t rb = (size_t)ref_len[gathered] * stride, qb = (size_t)qry_len[gathered] * stride;
-                if (rb) memcpy(gs->stage + ref_off[gathered], gs->letters + gs->ref_off[p], rb);
-                if (qb) memcpy(gs->stage + qry_off[gathered], gs->letters + gs->qry_off[p], qb);
-                gathered++;
-            }
-        }
-        for (int64_t o = g.b_lo; o < g.b_hi; o += (4 << 20)) {
-            const size_t len = (size_t)std::min<int64_t>(4 << 20, g.b_hi - o);
-            CK(cudaMemcpyAsync((uint8_t *)ctx->letters.p + o, letters + o, len, cudaMemcpyHostToDevice, up));
-        }
-        // pooled events: run_device resets the pool cursor, so these come from a pool of their own
+    // pooled events: run_device resets the pool cursor, so these come from a pool of their own
+    while (ctx->ev_upload.size() < B.groups.size()) {
         cudaEvent_t e = nullptr;
-        if (gi < ctx->ev_upload.size())
-            e = ctx->ev_upload[gi];
-        else {
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ctx->ev_upload.push_back(e);
-        }
-        CK(cudaEventRecord(e, up));
-        ready[gi] = e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_upload.push_back(e);
     }
-    CK(cudaEventRecord(ctx->ev[7], up));
+    std::vector<cudaEvent_t> ready(ctx->ev_upload.begin(), ctx->ev_upload.begin() + B.groups.size());
+    std::atomic<int64_t> enqueued{0};
+    cudaError_t feed_err = cudaSuccess;
+    auto feed = [&, letters]() {
+        int64_t gathered = 0;   // pairs whose letters are in the staging buffer (gs)
+        cudaError_t e = cudaSuccess;
+        for (size_t gi = 0; gi < B.groups.size(); gi++) {
+            const UploadGroup &g = B.groups[gi];
+            if (gs) {
+                // every pair that starts below the end of this piece
+                while (gathered < n && ref_off[gathered] < g.b_hi) {
+                    const int64_t p = gs->ids[gathered];
+                    const size_t rb = (size_t)ref_len[gathered] * stride, qb = (size_t)qry_len[gathered] * stride;
+                    if (rb) memcpy(gs->stage + ref_off[gathered], gs->letters + gs->ref_off[p], rb);
+                    if (qb) memcpy(gs->stage + qry_off[gathered], gs->letters + gs->qry_off[p], qb);
+                    gathered++;
+                }
+            }
+            for (int64_t o = g.b_lo; o < g.b_hi && e == cudaSuccess; o += (4 << 20)) {
+                const size_t len = (size_t)std::min<int64_t>(4 << 20, g.b_hi - o);
+                e = cudaMemcpyAsync((uint8_t *)ctx->letters.p + o, letters + o, len, cudaMemcpyHostToDevice, up);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(ready[gi], up);
+            enqueued.store((int64_t)gi + 1, std::memory_order_release);   // (also on failure: nobody may wait forever)
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[7], up);
+        feed_err = e;
+    };
+    // A scattered share in several groups: the gather is host work (a few GB/s), so it runs on a thread of
+    // its own beside the launches and the kernels of the groups that are already on the device.
+    std::thread feeder;
+    struct Join {
+        std::thread &t;
+        ~Join() { if (t.joinable()) t.join(); }
+    } join_feeder{feeder};
+    if (gs && B.groups.size() > 1) {
+        B.groups_enqueued = &enqueued;
+        const int dev = ctx->device;
+        feeder = std::thread([&feed, dev]() {
+            cudaSetDevice(dev);
+            feed();
+        });
+    } else {
+        feed();
+        if (feed_err != cudaSuccess) {
+            ctx->err = std::string("upload: ") + cudaGetErrorString(feed_err);
+            return BA_ERR_CUDA;
+        }
+    }
     for (size_t gi = 0; gi < B.groups.size(); gi++) B.groups[gi].ready = ready[gi];
     B.d_letters = (const uint8_t *)ctx->letters.p;
     B.stride = stride;
@@ -2211,6 +2244,13 @@ static int align_host(ba_ctx *ctx, const uint8_t *letters, int stride, const int
     B.out = out;
     B.defer_segs = defer_segs;
     rc = run_device(ctx, B, letters_bytes);
+    if (feeder.joinable()) {
+        feeder.join();
+        if (rc == BA_OK && feed_err != cudaSuccess) {
+            ctx->err = std::string("upload: ") + cudaGetErrorString(feed_err);
+            rc = BA_ERR_CUDA;
+        }
+    }
     if (rc != BA_OK) {
         drain(ctx, nullptr);   // the staged copies may still be in flight
         memset(out, 0, sizeof *out);

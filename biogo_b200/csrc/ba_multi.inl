@@ -94,7 +94,7 @@ void multi_fail(ba_multi *m, int d, const std::string &msg)
 // Length-bucketed dealing.  shares[d] = pair ids of device d.  allow_ranges (all pairs of one shape): the
 // shares are contiguous ranges of the caller's order, share d is [cut[d], cut[d+1]); returns that flag.
 bool multi_deal(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int D, bool allow_ranges,
-                std::vector<std::vector<int64_t>> &shares, std::vector<int64_t> &cut)
+                std::vector<std::vector<int64_t>> &shares, std::vector<int64_t> &cut, bool wide10 = true)
 {
     shares.assign((size_t)D, std::vector<int64_t>());
     cut.assign((size_t)D + 1, 0);
@@ -103,17 +103,21 @@ bool multi_deal(const int32_t *ref_len, const int32_t *qry_len, int64_t n, int D
         return true;
     }
     // quarter-octave classes of cells: key = 4 * log2(cells) from the exponent and two mantissa bits
-    constexpr int NB = 4 * 64 + 4;
-    auto bucket = [](int64_t cells) -> int {
-        if (cells <= 0) return 0;
+    // in front of it the planner's own first key, the strip width of the pair's kernel instance (widest
+    // first, ba_plan.h), so that a share is in the order its device works through it
+    constexpr int NBC = 4 * 64 + 5;
+    constexpr int NB = (BA16_MAX_COLS + 1) * NBC - 1;
+    auto bucket = [wide10](int64_t cells, int m) -> int {
+        const int cls = cols16_for(m, wide10);
+        if (cells <= 0) return cls * NBC;
         const int e = 63 - __builtin_clzll((unsigned long long)cells);
         const int frac = e >= 2 ? (int)((cells >> (e - 2)) & 3) : 0;
-        return 4 * e + frac + 1;
+        return cls * NBC + 4 * e + frac + 1;
     };
     std::vector<int64_t> cnt(NB + 1, 0);
     std::vector<uint16_t> bk((size_t)n);
     for (int64_t p = 0; p < n; p++) {
-        const int b = bucket((int64_t)ref_len[p] * (int64_t)qry_len[p]);
+        const int b = bucket((int64_t)ref_len[p] * (int64_t)qry_len[p], qry_len[p]);
         bk[(size_t)p] = (uint16_t)b;
         cnt[(size_t)b]++;
     }
@@ -267,7 +271,7 @@ int ba_align_batch_multi(ba_multi *m, const uint8_t *letters, int stride, const 
     std::vector<std::vector<int64_t>> shares;
     std::vector<int64_t> cut;
     // (one device: its share is the whole batch as the caller laid it out -- nothing to deal or gather)
-    const bool ranges = multi_deal(ref_len, qry_len, n, D, uniform || D == 1, shares, cut);
+    const bool ranges = multi_deal(ref_len, qry_len, n, D, uniform || D == 1, shares, cut, m->ctx[0]->opt_wide10 != 0);
     const double deal_s = now_s() - t0;
     BA_TSEC("multi deal", t0);
 

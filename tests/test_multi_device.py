@@ -113,6 +113,17 @@ def test_c_abi_multi_device_on_two_emulated_devices(built):
         _check_multi(mc, 30, 14, kinds=((0, True, -2),))
     finally:
         mc.set_option("slot_cap", 0)
+    # a dealt share uploaded in several groups: a feeder thread gathers and enqueues them while the first
+    # chunks are already being filled
+    for ng, cp in ((3, 8), (7, 64)):
+        mc.set_option("upload_groups", ng)
+        mc.set_option("chunk_pairs", cp)
+        try:
+            _check_multi(mc, 90, 16 + ng, kinds=((0, True, -2), (2, False, 0)))
+            _check_multi(mc, 40, 17 + ng, stride=2, kinds=((1, True, -3),))
+        finally:
+            mc.set_option("upload_groups", 0)
+            mc.set_option("chunk_pairs", 8192)
     # one device, and an empty batch
     m1 = _lib.MultiContext((0,), helpers.EMU_LIB)
     _check_multi(m1, 9, 15)
