@@ -2452,6 +2452,17 @@ void ba_free_host(void *p)
 
 }  // extern "C"
 
+#ifdef BA_TRACE_STATS
+extern "C" int ba_debug_trace_stats(unsigned long long *out8, int reset)
+{
+    if (cudaMemcpyFromSymbol(out8, ba_trace_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return BA_ERR_CUDA;
+    if (reset) {
+        unsigned long long z[8] = {0};
+        if (cudaMemcpyToSymbol(ba_trace_stats, z, sizeof z) != cudaSuccess) return BA_ERR_CUDA;
+    }
+    return BA_OK;
+}
+#endif
 #include "ba_seqio.inl"
 #include "ba_multi.inl"
 #include "ba_pals.inl"

@@ -54,6 +54,7 @@ struct CkView {
     int bias;                        // SYM kernels store G = M + go + e in the row blocks: M = G - bias
     bool lin;    // linear kinds: one table T (elements of one word)
     bool clamp;  // affine SW: the fill defers the clamp of U and L at zero and stores them raw
+    unsigned inv_cols;         // ceil(2^32 / cols): strip_of without a division
     int64_t pass_bytes, colck_bytes;
     __device__ __forceinline__ void init(const uint8_t *arena, const WorkItem &item, int n_, int m_, bool lin_, bool clamp_,
                                          int bias_)
@@ -69,6 +70,7 @@ struct CkView {
         np_ck = item.ck & 0xffff;
         half = (item.ck >> 16) & 1;
         rs = ba16_row_stride(cols);
+        inv_cols = cols > 1 ? (unsigned)(0x100000000ull / (unsigned)cols) + 1u : 0u;
         pass_bytes = ba16_pass_bytes(cols, n_ck, lin);
         colck_bytes = ba16_colck_bytes(n_ck, lin);
     }
@@ -116,7 +118,12 @@ struct CkView {
     {
         return ((const int2 *)(base + (int64_t)np_ck * pass_bytes))[2 * x + half];
     }
-    __device__ __forceinline__ int strip_of(int j) const { return (j - jshift - 1) / cols; }
+    // (j - jshift - 1) / cols for j >= 1 (the numerator is non-negative and below 2^20: exact with a 32-bit reciprocal)
+    __device__ __forceinline__ int strip_of(int j) const
+    {
+        const unsigned x = (unsigned)max(j - jshift - 1, 0);
+        return cols > 1 ? (int)__umulhi(x, inv_cols) : (int)x;
+    }
     __device__ __forceinline__ int left_col(int g) const { return jshift + g * cols; }
 };
 
@@ -439,6 +446,161 @@ __device__ __forceinline__ bool trace16_decode(unsigned code, int layer, int er,
     }
 }
 
+// The walk inside one cached tile, shared by the three kernels.  State of a walk:
+struct Walk16 {
+    int i, j, layer, last, score, maxI, maxJ, cur, nseg;
+    int opens;   // NW / Fitted: gap-open steps of the current run (its score is summed when the run ends)
+    bool bad;
+};
+
+// Score of the run of `last` moves that led from (maxI, maxJ) to (i, j): the sum of the walk's per-step
+// deltas (trace16_decode), taken in one tight loop when the run ends instead of step by step inside the
+// latency-bound walk.  Only SW needs the running score (it stops when the score is used up).
+__device__ __forceinline__ int trace16_run_score(int last, int i, int maxI, int j, int maxJ, int opens, const uint8_t *rs,
+                                                 const uint8_t *qs, int stride, const int *S, int let, int go)
+{
+    int sc = opens * go;
+    if (last == MV_DIAG) {
+        const uint8_t *pr = rs + (ptrdiff_t)i * stride, *pq = qs + (ptrdiff_t)j * stride;
+        for (int x = i; x < maxI; x++, pr += stride, pq += stride) sc += S[(int)*pr * let + (int)*pq] >> BA_SCALE_SHIFT;
+    } else if (last == MV_UP) {
+        const uint8_t *pr = rs + (ptrdiff_t)i * stride;
+        for (int x = i; x < maxI; x++, pr += stride) sc += S[(int)*pr * let] >> BA_SCALE_SHIFT;
+    } else {
+        const uint8_t *pq = qs + (ptrdiff_t)j * stride;
+        for (int y = j; y < maxJ; y++, pq += stride) sc += S[(int)*pq] >> BA_SCALE_SHIFT;
+    }
+    return sc;
+}
+
+// Walks from (w.i, w.j) until the path leaves the tile (rows rt+1.., columns c0+1..), the SW score is
+// used up, or no candidate matches.  Same decisions as trace16_decode, arranged for a short instruction
+// chain (a team walks one path on one warp per scheduler, so every instruction of a step is exposed
+// latency -- measured with -DBA_TRACE_STATS: 230 cycles per row-or-column step before):
+//   * the move and the next layer come out of the code byte through constant tables (no branches);
+//   * positions are pointers that step by constants; rows and columns left in the tile are counters;
+//   * the code byte and the letters of the NEXT cell are requested as soon as the move is known, and
+//     only then is the score of the step looked up -- one table read, chosen by the move.
+// (Requesting the three possible next code bytes one step ahead and selecting by the move was measured
+// and dropped: the extra predicated loads cost more issue slots than the shorter chain saves, 120 -> 150.)
+// tcodes: the tile's code bytes, cell (r, k) at ((r * MCW) + k) * TSW.  emitter: this thread writes segments.
+// RUNS: sum a run's score when it ends (trace16_run_score) -- for teams, whose threads all walk the same path; a
+// thread per pair keeps the per-step score (the run loops of 32 different paths would serialise).  SW always does.
+template <int KIND, bool LIN, int MCW, int TSW, bool RUNS>
+__device__ __forceinline__ void trace16_walk_tile(Walk16 &w, const uint8_t *tcodes, int rt, int cbase, int c0,
+                                                  const uint8_t *rs, const uint8_t *qs, int stride, const int *S, int let,
+                                                  int go, int n, int m, int32_t *out, int cap, bool emitter)
+{
+    // tables indexed by the layer's field x = (code >> shift) & mask of the code byte (trace16_tile_aff packs
+    // f0 | f1 << 3 | f2 << 5: three bits for layers M and L, two for U), four bits per entry.
+    // MV: the move, 3 = no candidate.  SH / MK: shift and mask of the NEXT layer's field.  OP: the step opens a gap.
+    constexpr unsigned SH_D0 = (KIND == KIND_SW) ? 0u : 3u, SH_D1 = (KIND == KIND_SW) ? 3u : 5u,
+                       SH_D2 = (KIND == KIND_SW) ? 5u : 0u;   // next layer after the three diagonal candidates
+    constexpr unsigned MV_A = 3u | (unsigned)MV_UP << 4 | (unsigned)MV_LEFT << 8 | (unsigned)MV_UP << 12 |
+                              (unsigned)MV_LEFT << 16 | (unsigned)MV_DIAG << 20 | (unsigned)MV_DIAG << 24 |
+                              (unsigned)MV_DIAG << 28;
+    constexpr unsigned SH_A = 0u | 3u << 4 | 5u << 8 | 0u << 12 | 0u << 16 | SH_D0 << 20 | SH_D1 << 24 | SH_D2 << 28;
+#define BA_MK_OF(sh_) ((sh_) == 3u ? 3u : 7u)
+    constexpr unsigned MK_A = 7u | 3u << 4 | 7u << 8 | 7u << 12 | 7u << 16 | BA_MK_OF(SH_D0) << 20 | BA_MK_OF(SH_D1) << 24 |
+                              BA_MK_OF(SH_D2) << 28;
+#undef BA_MK_OF
+    constexpr unsigned MV_LIN = 3u | (unsigned)MV_LEFT << 4 | (unsigned)MV_UP << 8 | (unsigned)MV_DIAG << 12;
+    constexpr unsigned OP_A = 1u << 12 | 1u << 16;   // candidates 3 and 4 open a gap
+    constexpr bool STEPS = (KIND == KIND_SW) || !RUNS;   // per-step score
+    int ri = w.i - rt, cj = w.j - c0;   // rows / columns of the tile still ahead (including the current cell)
+    int cur = w.cur;
+    if (ri <= 0 || cj <= 0 || (KIND == KIND_SW && cur == 0)) return;
+    const uint8_t *pc = tcodes + ((ri - 1) * MCW + (w.j - cbase - 1)) * TSW;
+    const uint8_t *pr = rs + (ptrdiff_t)(w.i - 1) * stride, *pq = qs + (ptrdiff_t)(w.j - 1) * stride;
+    unsigned code = *pc;
+    int R = 0, Q = 0;
+    if (STEPS) {
+        R = *pr;
+        Q = *pq;
+    }
+    unsigned sh = LIN ? 0u : (w.layer == 0 ? 0u : w.layer == 1 ? 3u : 5u);
+    unsigned mk = LIN ? 3u : (w.layer == 1 ? 3u : 7u);
+    int last = w.last, score = w.score, opens = w.opens;
+    bool corner = (w.i == n && w.j == m);   // only the first cell of a walk can be the corner
+    for (;;) {
+        const unsigned t = ((code >> sh) & mk) << 2;
+        const int move = (int)(((LIN ? MV_LIN : MV_A) >> t) & 3u);
+        if (move == 3) {
+            w.bad = true;
+            break;
+        }
+        const bool open = !LIN && ((OP_A >> t) & 1u) != 0u;
+        // a new segment when the move changes
+        if (last != move) {
+            // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
+            if (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW)) {
+                const int i = rt + ri, j = c0 + cj;
+                const int sc = STEPS ? score
+                                     : trace16_run_score(last, i, w.maxI, j, w.maxJ, opens, rs, qs, stride, S, let, go);
+                if (emitter && w.nseg < cap) {
+                    int32_t *o_ = out + 5 * w.nseg;
+                    o_[0] = i;
+                    o_[1] = w.maxI;
+                    o_[2] = j;
+                    o_[3] = w.maxJ;
+                    o_[4] = sc;
+                }
+                w.nseg++;
+                w.maxI = i;
+                w.maxJ = j;
+                score = 0;
+                opens = 0;
+            }
+        }
+        corner = false;
+        if (move != MV_LEFT) {
+            ri--;
+            pc -= MCW * TSW;
+            if (STEPS) pr -= stride;
+        }
+        if (move != MV_UP) {
+            cj--;
+            pc -= TSW;
+            if (STEPS) pq -= stride;
+        }
+        const bool more = ri > 0 && cj > 0;
+        unsigned ncode = 0;
+        int nR = R, nQ = Q;
+        if (more) {
+            ncode = *pc;
+            if (STEPS) {
+                nR = *pr;
+                nQ = *pq;
+            }
+        }
+        if (STEPS) {
+            // the score of the step: one table read, chosen by the move
+            const int idx = (move == MV_DIAG) ? R * let + Q : (move == MV_UP) ? R * let : Q;
+            const int delta = (S[idx] >> BA_SCALE_SHIFT) + (open ? go : 0);
+            score += delta;
+            if (KIND == KIND_SW) cur -= delta;
+        } else {
+            opens += open ? 1 : 0;
+        }
+        if (!LIN) {
+            sh = (SH_A >> t) & 7u;
+            mk = (MK_A >> t) & 7u;
+        }
+        last = move;
+        if (!more || (KIND == KIND_SW && cur == 0)) break;
+        code = ncode;
+        R = nR;
+        Q = nQ;
+    }
+    w.i = rt + ri;
+    w.j = c0 + cj;
+    w.cur = cur;
+    w.last = last;
+    w.score = score;
+    w.opens = opens;
+    w.layer = LIN ? 0 : (sh == 0u ? 0 : sh == 3u ? 1 : 2);
+}
+
 // (linear tiles are cheap, the walk is bound by checkpoint-load latency: more resident CTAs)
 // TS = threads per CTA: 128, or 64 -- a CTA that fits into the SM slot one ba_fill16 CTA frees
 // (registers and shared memory), so a traceback running on a high-priority stream beside the next
@@ -563,44 +725,23 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
         i = pb.besti;
     }
 
-    int maxI = i, maxJ = j, score = 0, last = MV_DIAG;
-    bool bad = false;
-    while (i > 0 && j > 0 && !bad) {
-        if (KIND == KIND_SW && cur == 0) break;
-        const int g = ck.strip_of(j);
+    Walk16 w;
+    w.i = i, w.j = j, w.layer = layer, w.last = MV_DIAG, w.score = 0, w.maxI = i, w.maxJ = j, w.cur = cur, w.nseg = nseg;
+    w.opens = 0, w.bad = false;
+    while (w.i > 0 && w.j > 0 && !w.bad) {
+        if (KIND == KIND_SW && w.cur == 0) break;
+        const int g = ck.strip_of(w.j);
         const int v = CkView::lane_of(g);
-        const int e = (i + v - 1) >> BA16_PSHIFT;
+        const int e = (w.i + v - 1) >> BA16_PSHIFT;
         const int rt = max(BA16_PERIOD * e - v, 0);
         const int c0 = max(ck.left_col(g), 0);
         TileProbe pb0;
-        trace16_tile<KIND, LIN, TS, MC>(ck, S, let, go8, rs, qs, stride, g, e, i, j, tile, pb0);
-        const int cbase = ck.left_col(g);
-        while (i > rt && j > c0) {
-            if (KIND == KIND_SW && cur == 0) break;
-            const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
-            const unsigned code = tile[((i - rt - 1) * MC + (j - cbase - 1)) * TS];
-            const bool corner = (i == n && j == m);
-            const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
-            int move, nl = 0, delta;
-            if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl, delta))
-                bad = true;
-            if (bad) break;
-            // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
-            if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
-                T16_EMIT(i, maxI, j, maxJ, score);
-                maxI = i;
-                maxJ = j;
-                score = 0;
-            }
-            score += delta;
-            if (KIND == KIND_SW) cur -= delta;
-            if (move != MV_LEFT) i--;
-            if (move != MV_UP) j--;
-            layer = nl;
-            last = move;
-        }
-        if (KIND == KIND_SW && cur == 0) break;
+        trace16_tile<KIND, LIN, TS, MC>(ck, S, let, go8, rs, qs, stride, g, e, w.i, w.j, tile, pb0);
+        trace16_walk_tile<KIND, LIN, MC, TS, false>(w, tile, rt, ck.left_col(g), c0, rs, qs, stride, S, let, go, n, m, out, cap, true);
     }
+    i = w.i, j = w.j, nseg = w.nseg;
+    const int maxI = w.maxI, maxJ = w.maxJ, score = w.score;
+    const bool bad = w.bad;
     T16_EMIT(i, maxI, j, maxJ, score);
     if (KIND == KIND_NW && i != j) {
         // nw_affine_letters.go:311-325: leading gap, its score is the border value
@@ -651,7 +792,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
     const uint8_t *rs = nullptr, *qs = nullptr;
     int32_t *out = nullptr;
     CkView ck;
-    int i = 0, j = 0, cur = 0, layer = 0, maxI = 0, maxJ = 0, score = 0, last = MV_DIAG;
+    int i = 0, j = 0, cur = 0, layer = 0, maxI = 0, maxJ = 0, score = 0, last = MV_DIAG, opens = 0;
     bool bad = false;
     int sx = 0, sh = 0, Smax = 0;   // SW search: candidate index, strip half, table maximum
     int fe = 0;                     // Fitted search: period
@@ -681,7 +822,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
             out = P.slots + 5 * P.slot_off[it];
             cap = P.slot_cap[it];
             nseg = 0;
-            i = j = cur = layer = score = 0;
+            i = j = cur = layer = score = opens = 0;
             last = MV_DIAG;
             bad = false;
             pb = TileProbe();
@@ -858,32 +999,13 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
             const int rt = max(BA16_PERIOD * te - v, 0);
             const int c0 = max(ck.left_col(tg), 0);
             const int cbase = ck.left_col(tg);
-            while (i > rt && j > c0) {
-                if (KIND == KIND_SW && cur == 0) break;
-                const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
-                const unsigned code = tile[((i - rt - 1) * BA_MAX_COLS + (j - cbase - 1)) * BA_TRACE_THREADS];
-                const bool corner = (i == n && j == m);
-                const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
-                int move, nl = 0, delta;
-                if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl,
-                                               delta)) {
-                    bad = true;
-                    break;
-                }
-                // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
-                if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
-                    T16P_EMIT(i, maxI, j, maxJ, score);
-                    maxI = i;
-                    maxJ = j;
-                    score = 0;
-                }
-                score += delta;
-                if (KIND == KIND_SW) cur -= delta;
-                if (move != MV_LEFT) i--;
-                if (move != MV_UP) j--;
-                layer = nl;
-                last = move;
-            }
+            Walk16 w;
+            w.i = i, w.j = j, w.layer = layer, w.last = last, w.score = score, w.maxI = maxI, w.maxJ = maxJ, w.cur = cur;
+            w.nseg = nseg, w.bad = bad, w.opens = opens;
+            trace16_walk_tile<KIND, LIN, BA_MAX_COLS, BA_TRACE_THREADS, false>(w, tile, rt, cbase, c0, rs, qs, stride, S, let, go, n, m,
+                                                                        out, cap, true);
+            i = w.i, j = w.j, layer = w.layer, last = w.last, score = w.score, maxI = w.maxI, maxJ = w.maxJ, cur = w.cur;
+            nseg = w.nseg, bad = w.bad, opens = w.opens;
         }
 #undef T16P_EMIT
     }
@@ -901,6 +1023,14 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
 // window is centred on the period the main diagonal through the anchor reaches there -- so one
 // round covers ~330 columns of a near-diagonal path instead of 32.
 // Thread 0 emits.  A window always contains the tile under the walk, so every round advances.
+#ifdef BA_TRACE_STATS   // kernel experiments (tools/build_variant.sh): where the team traceback spends its time
+__device__ unsigned long long ba_trace_stats[8];   // rounds, steps, cycles: search, rebuild, walk
+#define BA_TSTAT_ADD(k, v) do { if (threadIdx.x == 0) atomicAdd(&ba_trace_stats[k], (unsigned long long)(v)); } while (0)
+#define BA_TSTAT_CLK() clock64()
+#else
+#define BA_TSTAT_ADD(k, v) do { } while (0)
+#define BA_TSTAT_CLK() 0ll
+#endif
 #define BA_TW_STRIPS 4
 #define BA_TW_PERIODS 8
 #define BA_TB_PERIODS 3
@@ -997,6 +1127,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
 
     // ---- start cell (rules as in ba_trace16_kernel), searched by all lanes
     int i = 0, j = 0, cur = 0, layer = 0;
+    long long tclk = BA_TSTAT_CLK();
+    (void)tclk;
     if (KIND == KIND_SW && n > 0 && m > 0) {
         int Smax = 0;
         for (int x = lane; x < ck.npass * 16; x += NT) {
@@ -1066,11 +1198,15 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
         i = besti;
     }
     T16W_SYNC();
+    BA_TSTAT_ADD(2, BA_TSTAT_CLK() - tclk);
 
-    int maxI = i, maxJ = j, score = 0, last = MV_DIAG;
+    int maxI = i, maxJ = j, score = 0, last = MV_DIAG, opens = 0;
     bool bad = false;
     while (i > 0 && j > 0 && !bad) {
         if (KIND == KIND_SW && cur == 0) break;
+        tclk = BA_TSTAT_CLK();
+        BA_TSTAT_ADD(0, 1);
+        BA_TSTAT_ADD(1, i + j);
         // ---- window anchored at (i, j).  Warp team: my tile is strip g_hi - lane / 8, period (period
         // of row i0 there) - lane % 8.  CTA team: strip g_hi - lane / 3, period (period of the
         // diagonal's row i0 - ws*cols there) + 1 - lane % 3.
@@ -1091,6 +1227,8 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             }
         }
         T16W_SYNC();
+        BA_TSTAT_ADD(3, BA_TSTAT_CLK() - tclk);
+        tclk = BA_TSTAT_CLK();
         for (;;) {
             if (i <= 0 || j <= 0) break;
             if (KIND == KIND_SW && cur == 0) break;
@@ -1112,36 +1250,20 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
             const int cbase = ck.left_col(g);
             const int c0 = max(cbase, 0);
             const uint8_t *tcodes = tiles + wbase + slot;
-            while (i > rt && j > c0) {
-                if (KIND == KIND_SW && cur == 0) break;
-                const int R = rs[(i - 1) * stride], Q = qs[(j - 1) * stride];
-                const unsigned code = tcodes[((i - rt - 1) * MC + (j - cbase - 1)) * BA_TRACE_THREADS];
-                const bool corner = (i == n && j == m);
-                const int er = S[R * let] >> BA_SCALE_SHIFT, eq = S[Q] >> BA_SCALE_SHIFT;
-                int move, nl = 0, delta;
-                if (!trace16_decode<KIND, LIN>(code, layer, er, eq, S[R * let + Q] >> BA_SCALE_SHIFT, go, move, nl,
-                                               delta)) {
-                    bad = true;
-                    break;
-                }
-                // linear SW has no corner guard (sw_letters.go:147-165); every other walk has
-                if (last != move && (move == MV_DIAG || !corner || (LIN && KIND == KIND_SW))) {
-                    T16W_EMIT(i, maxI, j, maxJ, score);
-                    maxI = i;
-                    maxJ = j;
-                    score = 0;
-                }
-                score += delta;
-                if (KIND == KIND_SW) cur -= delta;
-                if (move != MV_LEFT) i--;
-                if (move != MV_UP) j--;
-                layer = nl;
-                last = move;
-            }
+            Walk16 w;
+            w.i = i, w.j = j, w.layer = layer, w.last = last, w.score = score, w.maxI = maxI, w.maxJ = maxJ, w.cur = cur;
+            w.nseg = nseg, w.bad = bad, w.opens = opens;
+            trace16_walk_tile<KIND, LIN, MC, BA_TRACE_THREADS, true>(w, tcodes, rt, cbase, c0, rs, qs, stride, S, let, go, n, m, out, cap,
+                                                               lane == 0);
+            i = w.i, j = w.j, layer = w.layer, last = w.last, score = w.score, maxI = w.maxI, maxJ = w.maxJ, cur = w.cur;
+            nseg = w.nseg, bad = w.bad, opens = w.opens;
             if (bad) break;
         }
+        BA_TSTAT_ADD(4, BA_TSTAT_CLK() - tclk);
+        BA_TSTAT_ADD(1, -(long long)(i + j));
         T16W_SYNC();
     }
+    if (KIND != KIND_SW) score = trace16_run_score(last, i, maxI, j, maxJ, opens, rs, qs, stride, S, let, go);
     T16W_EMIT(i, maxI, j, maxJ, score);
     if (KIND == KIND_NW && i != j) {
         int b = go;

@@ -420,6 +420,7 @@ static inline unsigned __vmaxs2(unsigned a, unsigned b)
 {
     return emu_pk(std::max(emu_lo(a), emu_lo(b)), std::max(emu_hi(a), emu_hi(b)));
 }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vmaxs2(a, b), c); }
 static inline unsigned __vimax_s16x2_relu(unsigned a, unsigned b) { return __vmaxs2(__vmaxs2(a, b), 0u); }
 static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }

@@ -18,4 +18,4 @@ cp "$EMU" "$OUT/emu_backup.so"
 trap 'cp "$OUT/emu_backup.so" "$EMU"; touch "$EMU"' EXIT
 cp "$OUT/libemu_asan.so" "$EMU"; touch "$EMU"
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
-  python -m pytest "$ROOT/tests/test_emu_parity.py" "$ROOT/tests/test_format.py" -x -q -m "not gpu" -p no:cacheprovider
+  python -m pytest "$ROOT/tests/test_emu_parity.py" "$ROOT/tests/test_format.py" "$ROOT/tests/test_multi_device.py" -x -q -m "not gpu" -p no:cacheprovider
