@@ -78,41 +78,54 @@ struct CkView {
     // handles row i at step i-1+lane.
     __device__ __forceinline__ static int lane_of(int g) { return (g & 31) >> 1; }
     __device__ __forceinline__ int pick(unsigned w) const { return (int)(short)(half ? (w >> 16) : (w & 0xffffu)); }
-    // (M, clamped L) of the last column of strip g at row r
-    __device__ __forceinline__ void col_ml(int g, int r, int &M, int &L) const
+    // Raw checkpoint words and their decoding are separate steps: a tile requests everything its boundary needs
+    // in one batch and decodes afterwards, so the loads' latencies overlap instead of adding up (ncu r02: 45 % of
+    // the traceback's stall samples sat on the first use of a checkpoint word).
+    // {M, L} words of the last column of strip g at row r
+    __device__ __forceinline__ uint2 col_raw(int g, int r) const
     {
         const int pass = g >> 5, t = lane_of(g), s = g & 1;
         const int st = r - 1 + t;
         const int e = st >> BA16_PSHIFT, j = st & (BA16_PERIOD - 1);
         const uint8_t *blk = base + (int64_t)pass * pass_bytes + (int64_t)e * ba16_colblk(lin);
+        // linear: [lane][step][strip] words; affine: [lane][strip][step] {M, L}
+        if (lin) return make_uint2(*(const unsigned *)(blk + t * 64 + j * 8 + s * 4), 0u);
+        return *(const uint2 *)(blk + t * 128 + s * 64 + j * 8);
+    }
+    __device__ __forceinline__ void col_pick(const uint2 &w, int &M, int &L) const
+    {
+        M = pick(w.x);
         if (lin) {
-            // [lane][step][strip] words
-            M = pick(*(const unsigned *)(blk + t * 64 + j * 8 + s * 4));
             L = 0;
             return;
         }
-        // [lane][strip][step] {M, L}
-        const uint2 w = *(const uint2 *)(blk + t * 128 + s * 64 + j * 8);
-        M = pick(w.x);
         L = pick(w.y);
         if (clamp) L = max(L, 0);
     }
-    // (M, clamped U) of column k of strip g at its checkpoint row of period e
-    __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const
+    // (M, clamped L) of the last column of strip g at row r
+    __device__ __forceinline__ void col_ml(int g, int r, int &M, int &L) const { col_pick(col_raw(g, r), M, L); }
+    // {M or G, U} words of column k of strip g at its checkpoint row of period e
+    __device__ __forceinline__ uint2 row_raw(int g, int e, int k) const
     {
         const int pass = g >> 5, t = lane_of(g), s = g & 1;
         const int kk = s * cols + k;
         const uint8_t *blk = base + (int64_t)pass * pass_bytes + colck_bytes + (int64_t)e * ba16_rowblk(cols, lin);
+        if (lin) return make_uint2(*(const unsigned *)(blk + (t * rs * 2 + kk) * 4), 0u);
+        return *(const uint2 *)(blk + (t * rs * 2 + kk) * 8);
+    }
+    __device__ __forceinline__ void row_pick(const uint2 &w, int &M, int &U) const
+    {
         if (lin) {
-            M = pick(*(const unsigned *)(blk + (t * rs * 2 + kk) * 4));
+            M = pick(w.x);
             U = 0;
             return;
         }
-        const uint2 w = *(const uint2 *)(blk + (t * rs * 2 + kk) * 8);
         M = pick(w.x) - bias;
         U = pick(w.y);
         if (clamp) U = max(U, 0);
     }
+    // (M, clamped U) of column k of strip g at its checkpoint row of period e
+    __device__ __forceinline__ void row_mu(int g, int e, int k, int &M, int &U) const { row_pick(row_raw(g, e, k), M, U); }
     // start-cell candidate record x = pass*16 + lane of this pair: {best score, last period attaining it}
     __device__ __forceinline__ int2 cand(int x) const
     {
@@ -182,6 +195,44 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     const int klast = jmax - c0 - 1;            // last needed column (inclusive)
     const int er_u = S[let], eq_u = S[1];       // uniform gap entries (letters >= 1)
 
+    const int gl = g - 1;                       // strip whose last column is cL
+    const bool hasL = cL > 0;                   // the left boundary is a checkpointed column (else the DP border)
+
+    // ---- request everything the boundary needs in ONE batch (decoded below): query letters, the top row's
+    // checkpoints, the left column at the corner and at the first row, and the rows U's recurrence starts from
+    unsigned qraw[MC];
+    uint2 rowraw[MC];
+#pragma unroll
+    for (int k = 0; k < MC; k++) {
+        const bool on = k >= kfirst && k <= klast;
+        qraw[k] = on ? (unsigned)qs[(c0 + k) * stride] : 0u;
+        rowraw[k] = (on && rt >= 1) ? ck.row_raw(g, e - 1, k) : make_uint2(0u, 0u);
+    }
+    const uint2 cornraw = (hasL && rt >= 1) ? ck.col_raw(gl, rt) : make_uint2(0u, 0u);
+    uint2 nraw = (hasL && rt + 1 <= imax) ? ck.col_raw(gl, rt + 1) : make_uint2(0u, 0u);   // row loop: one row ahead
+    int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0;
+    // U of column cL is checkpointed (with M) only at strip gl's own rows; start from the closest one at or
+    // above rt (r0) and run U's recurrence down the column on the stored M of rows r0 .. rt-1 (at most
+    // BA16_PERIOD - 1 of them).
+    constexpr int NCH = BA16_PERIOD - 1;
+    int r0 = 0;
+    uint2 u0raw = make_uint2(0u, 0u), chraw[NCH];
+#pragma unroll
+    for (int x = 0; x < NCH; x++) chraw[x] = make_uint2(0u, 0u);
+    if (hasL) {
+        const int vl = CkView::lane_of(gl);
+        r0 = rt - ((rt + vl) & (BA16_PERIOD - 1));  // largest row <= rt with (r0 + vl) % PERIOD == 0
+        if (r0 >= 1)
+            u0raw = ck.row_raw(gl, (r0 + vl) / BA16_PERIOD - 1, ck.cols - 1);
+        else
+            r0 = 0;                             // DP border row
+#pragma unroll
+        for (int x = 0; x < NCH; x++) {
+            const int rr = r0 + x;
+            if (rr < rt && rr >= 1) chraw[x] = ck.col_raw(gl, rr);
+        }
+    }
+
     // ---- per-column constants of this tile
     int qo[MC], eqv[MC];
 #pragma unroll
@@ -189,7 +240,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
         qo[k] = 0;
         eqv[k] = 0;
         if (k >= kfirst && k <= klast) {
-            qo[k] = qs[(c0 + k) * stride];
+            qo[k] = (int)qraw[k];
             eqv[k] = S[qo[k]];
         }
     }
@@ -197,37 +248,36 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     // ---- corner (rt, cL) and the U layer of the left boundary column
     Cell3 corner = (rt == 0) ? border_row0<KIND>(cL, go, eq_u) : border_col0<KIND>(rt, go, er_u);
     int leftU = corner.U;                       // U at (row, cL), advanced row by row
-    const int gl = g - 1;                       // strip whose last column is cL
-    if (cL > 0) {
-        const int vl = CkView::lane_of(gl);
-        // U of column cL is checkpointed (with M) only at strip gl's own rows; start from the
-        // closest one at or above rt and run U's recurrence down the column on the stored M.
-        int r0 = rt - ((rt + vl) & (BA16_PERIOD - 1));  // largest row <= rt with (r0 + vl) % PERIOD == 0
+    if (hasL) {
         int u;
         if (r0 >= 1) {
             int mm;
-            ck.row_mu(gl, (r0 + vl) / BA16_PERIOD - 1, ck.cols - 1, mm, u);
+            ck.row_pick(u0raw, mm, u);
             u *= BA_SCALE;
         } else {
-            r0 = 0;                             // DP border row
             u = border_row0<KIND>(cL, go, eq_u).U;
         }
-        for (int r = r0 + 1; r <= rt; r++) {
-            int mp, lp;
-            if (r - 1 >= 1) {
-                ck.col_ml(gl, r - 1, mp, lp);
-                mp *= BA_SCALE;
-            } else {
-                mp = border_row0<KIND>(cL, go, eq_u).M;
+        // rows r0+1 .. rt: U[r] = max(M[r-1] + go + er, U[r-1] + er [, 0]); the gap entry is the same for every
+        // letter this path admits (condition C1 of ba_fill16.cuh), so no letter is looked up here
+#pragma unroll
+        for (int x = 0; x < NCH; x++) {
+            const int rr = r0 + x;              // the row whose M feeds row rr + 1
+            if (rr < rt) {
+                int mp, lp;
+                if (rr >= 1) {
+                    ck.col_pick(chraw[x], mp, lp);
+                    mp *= BA_SCALE;
+                } else {
+                    mp = border_row0<KIND>(cL, go, eq_u).M;
+                }
+                u = max(mp + go + er_u, u + er_u);
+                if (KIND == KIND_SW) u = max(u, 0);
             }
-            const int er = S[(int)rs[(r - 1) * stride] * let];
-            u = max(mp + go + er, u + er);
-            if (KIND == KIND_SW) u = max(u, 0);
         }
         leftU = u;
         if (rt >= 1) {
             int mm, ll;
-            ck.col_ml(gl, rt, mm, ll);
+            ck.col_pick(cornraw, mm, ll);
             corner.M = mm * BA_SCALE;
             corner.L = ll * BA_SCALE;
             corner.U = u;
@@ -244,7 +294,7 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
             if (k >= kfirst && k <= klast) {
                 if (rt >= 1) {
                     int mm, uu;
-                    ck.row_mu(g, e - 1, k, mm, uu);
+                    ck.row_pick(rowraw[k], mm, uu);
                     Pv[k].M = mm * BA_SCALE;
                     Pv[k].U = uu * BA_SCALE;
                     Pv[k].L = max(lM + go + eqv[k], lL + eqv[k]);
@@ -261,16 +311,15 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     // ---- rows rt+1 .. imax
     Cell3 dprev = corner;  // (row-1, cL)
     uint8_t *trow = tile;
-    // the next row's letter and left-boundary checkpoint are fetched one row ahead, so their
-    // latency hides under the current row's cells
-    int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0, nM = 0, nL = 0;
-    if (cL > 0 && rt + 1 <= imax) ck.col_ml(gl, rt + 1, nM, nL);
+    // the next row's letter and left-boundary checkpoint are requested one row ahead and decoded when their
+    // row comes, so their latency hides under the current row's cells
     for (int r = rt + 1; r <= imax; r++, trow += MC * TS) {
         const int *Srow = S + nR * let;
-        const int mm = nM, ll = nL;
+        int mm = 0, ll = 0;
+        if (hasL) ck.col_pick(nraw, mm, ll);
         if (r + 1 <= imax) {
             nR = (int)rs[(int64_t)r * stride];
-            if (cL > 0) ck.col_ml(gl, r + 1, nM, nL);
+            if (hasL) nraw = ck.col_raw(gl, r + 1);
         }
         const int er = Srow[0];
         const int goer = go + er;
@@ -333,6 +382,20 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
     const int er_u = S[let], eq_u = S[1];
     const int gl = g - 1;
 
+    const bool hasL = cL > 0;
+    // request the boundary in one batch, decode afterwards (see trace16_tile_aff)
+    unsigned qraw[MC];
+    uint2 rowraw[MC];
+#pragma unroll
+    for (int k = 0; k < MC; k++) {
+        const bool on = k >= kfirst && k <= klast;
+        qraw[k] = on ? (unsigned)qs[(c0 + k) * stride] : 0u;
+        rowraw[k] = (on && rt >= 1) ? ck.row_raw(g, e - 1, k) : make_uint2(0u, 0u);
+    }
+    const uint2 cornraw = (hasL && rt >= 1) ? ck.col_raw(gl, rt) : make_uint2(0u, 0u);
+    uint2 nraw = (hasL && rt + 1 <= imax) ? ck.col_raw(gl, rt + 1) : make_uint2(0u, 0u);
+    int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0;
+
     int qo[MC], eqv[MC], Tv[MC];
 #pragma unroll
     for (int k = 0; k < MC; k++) {
@@ -340,11 +403,11 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
         eqv[k] = 0;
         Tv[k] = 0;
         if (k >= kfirst && k <= klast) {
-            qo[k] = qs[(c0 + k) * stride];
+            qo[k] = (int)qraw[k];
             eqv[k] = S[qo[k]];
             if (rt >= 1) {
                 int mm, uu;
-                ck.row_mu(g, e - 1, k, mm, uu);
+                ck.row_pick(rowraw[k], mm, uu);
                 Tv[k] = mm * BA_SCALE;
             } else if (KIND != KIND_SW) {
                 Tv[k] = (c0 + k + 1) * eq_u;    // row 0: nw_letters.go:91-93, fitted_letters.go:83-85
@@ -352,27 +415,25 @@ __device__ __forceinline__ void trace16_tile_lin(const CkView &ck, const int *S,
         }
     }
     // T at (row, cL): DP border column (nw_letters.go:94-96; zero for SW and Fitted) or strip gl's
-    // checkpointed last column
-    auto left_at = [&](int r) -> int {
-        if (cL > 0) {
+    // checkpointed last column (its raw word w was requested earlier)
+    auto left_of = [&](int r, const uint2 &w) -> int {
+        if (hasL) {
             if (r == 0) return (KIND == KIND_SW) ? 0 : cL * eq_u;
             int mm, ll;
-            ck.col_ml(gl, r, mm, ll);
+            ck.col_pick(w, mm, ll);
             return mm * BA_SCALE;
         }
         return (KIND == KIND_NW) ? r * er_u : 0;
     };
-    int dprev = left_at(rt);
+    int dprev = left_of(rt, cornraw);
     uint8_t *trow = tile;
-    // next row's letter and left boundary value, fetched one row ahead
-    int nR = (rt + 1 <= imax) ? (int)rs[(int64_t)rt * stride] : 0;
-    int nLeft = (rt + 1 <= imax) ? left_at(rt + 1) : 0;
+    // the next row's letter and left boundary word are requested one row ahead
     for (int r = rt + 1; r <= imax; r++, trow += MC * TS) {
         const int *Srow = S + nR * let;
-        const int left = nLeft;
+        const int left = left_of(r, nraw);
         if (r + 1 <= imax) {
             nR = (int)rs[(int64_t)r * stride];
-            nLeft = left_at(r + 1);
+            if (hasL) nraw = ck.col_raw(gl, r + 1);
         }
         const int er = Srow[0];
         int d = dprev, l = left;
@@ -664,6 +725,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
         // the last cell in row-major order holding the table maximum (sw_affine_letters.go:126-134
         // under condition C2 of ba_fill16.cuh)
         int Smax = 0;
+#pragma unroll 8
         for (int x = 0; x < ck.npass * 16; x++) {
             const int2 c = ck.cand(x);
             if (c.y >= 0) Smax = max(Smax, c.x);
