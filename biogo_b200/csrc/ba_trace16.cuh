@@ -22,6 +22,9 @@
 #endif
 #define BA_TILE_ROWS BA16_PERIOD
 
+struct ba_true_c { static constexpr bool value = true; };
+struct ba_false_c { static constexpr bool value = false; };
+
 struct Trace16Params {
     const uint8_t *enc;
     int stride;
@@ -309,61 +312,73 @@ __device__ __forceinline__ void trace16_tile_aff(const CkView &ck, const int *S,
     }
 
     // ---- rows rt+1 .. imax
-    Cell3 dprev = corner;  // (row-1, cL)
-    uint8_t *trow = tile;
-    // the next row's letter and left-boundary checkpoint are requested one row ahead and decoded when their
-    // row comes, so their latency hides under the current row's cells
-    for (int r = rt + 1; r <= imax; r++, trow += MC * TS) {
-        const int *Srow = S + nR * let;
-        int mm = 0, ll = 0;
-        if (hasL) ck.col_pick(nraw, mm, ll);
-        if (r + 1 <= imax) {
-            nR = (int)rs[(int64_t)r * stride];
-            if (hasL) nraw = ck.col_raw(gl, r + 1);
-        }
-        const int er = Srow[0];
-        const int goer = go + er;
-        Cell3 left;
-        if (cL > 0) {
-            // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er [, 0])
-            leftU = max(dprev.M + goer, leftU + er);
-            if (KIND == KIND_SW) leftU = max(leftU, 0);
-            left.M = mm * BA_SCALE;
-            left.L = ll * BA_SCALE;
-            left.U = leftU;
-        } else {
-            left = border_col0<KIND>(r, go, er_u);
-        }
-        Cell3 d = dprev, l = left;
-#pragma unroll
-        for (int k = 0; k < MC; k++) {
-            if (k >= kfirst && k <= klast) {
-                unsigned code;
-                int dm;
-                const Cell3 old = Pv[k];
-                const Cell3 nw = affine_cell<KIND>(d, old, l, Srow[qo[k]], er, goer, eqv[k], go + eqv[k], code, dm);
-                trow[k * TS] = (uint8_t)code;
-                const int col = c0 + k + 1;
-                if (KIND == KIND_SW && pb.want >= 0 && nw.M == pb.want) {
-                    pb.fi = r;
-                    pb.fj = col;
-                }
-                if (KIND == KIND_FIT && col == pb.col && nw.M >= pb.best) {
-                    pb.best = nw.M;
-                    pb.besti = r;
-                }
-                if (KIND == KIND_NW && r == pb.ci && col == pb.cj) {
-                    pb.cM = nw.M;
-                    pb.cU = nw.U;
-                    pb.cL = nw.L;
-                }
-                Pv[k] = nw;
-                d = old;
-                l = nw;
+    // Two forms of the row loop.  ALL: the strip is as wide as the tile arrays and starts at a real column, so
+    // every cell of a row is computed without a test -- cells right of jmax are never read (values flow left to
+    // right, the walk stays up-left of (imax, jmax)), and leaving out the per-cell branch region saves a fifth of
+    // a cell's instructions.  Otherwise (narrower strips, SW's padding columns) each cell is tested.
+    auto rows = [&](auto all_c) {
+        constexpr bool ALL = decltype(all_c)::value;
+        Cell3 dprev = corner;  // (row-1, cL)
+        uint8_t *trow = tile;
+        // the next row's letter and left-boundary checkpoint are requested one row ahead and decoded when their
+        // row comes, so their latency hides under the current row's cells
+        for (int r = rt + 1; r <= imax; r++, trow += MC * TS) {
+            const int *Srow = S + nR * let;
+            int mm = 0, ll = 0;
+            if (hasL) ck.col_pick(nraw, mm, ll);
+            if (r + 1 <= imax) {
+                nR = (int)rs[(int64_t)r * stride];
+                if (hasL) nraw = ck.col_raw(gl, r + 1);
             }
+            const int er = Srow[0];
+            const int goer = go + er;
+            Cell3 left;
+            if (hasL) {
+                // U[r][cL] = max(M[r-1][cL] + go + er, U[r-1][cL] + er [, 0])
+                leftU = max(dprev.M + goer, leftU + er);
+                if (KIND == KIND_SW) leftU = max(leftU, 0);
+                left.M = mm * BA_SCALE;
+                left.L = ll * BA_SCALE;
+                left.U = leftU;
+            } else {
+                left = border_col0<KIND>(r, go, er_u);
+            }
+            Cell3 d = dprev, l = left;
+#pragma unroll
+            for (int k = 0; k < MC; k++) {
+                if (ALL || (k >= kfirst && k <= klast)) {
+                    unsigned code;
+                    int dm;
+                    const Cell3 old = Pv[k];
+                    const Cell3 nw = affine_cell<KIND>(d, old, l, Srow[qo[k]], er, goer, eqv[k], go + eqv[k], code, dm);
+                    trow[k * TS] = (uint8_t)code;
+                    const int col = c0 + k + 1;
+                    const bool in = !ALL || k <= klast;   // the probes look at real cells only
+                    if (KIND == KIND_SW && pb.want >= 0 && nw.M == pb.want && in) {
+                        pb.fi = r;
+                        pb.fj = col;
+                    }
+                    if (KIND == KIND_FIT && col == pb.col && nw.M >= pb.best && in) {
+                        pb.best = nw.M;
+                        pb.besti = r;
+                    }
+                    if (KIND == KIND_NW && r == pb.ci && col == pb.cj && in) {
+                        pb.cM = nw.M;
+                        pb.cU = nw.U;
+                        pb.cL = nw.L;
+                    }
+                    Pv[k] = nw;
+                    d = old;
+                    l = nw;
+                }
+            }
+            dprev = left;
         }
-        dprev = left;
-    }
+    };
+    if (kfirst == 0 && ck.cols == MC)
+        rows(ba_true_c{});
+    else
+        rows(ba_false_c{});
 }
 
 // Linear-gap tile (ba_fill16 LIN): one table T; the checkpoints hold it in their M field.  Codes
