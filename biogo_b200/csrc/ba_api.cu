@@ -753,7 +753,8 @@ bool g_sym_scoring(const DeviceScoring &s)
 {
     // affine with one gap-extension value for both sequences and go + e <= 0: the SYM kernels apply
     const int er = s.la[1 * s.let], eq = s.la[1];
-    return s.affine && er == eq && s.gap_open + er <= 0;
+    // (SW: the biased kernels add -(go + e) to every value; the head room of condition C4 covers up to 2000)
+    return s.affine && er == eq && s.gap_open + er <= 0 && (s.kind != KIND_SW || s.gap_open + er >= -2000);
 }
 Fill16Fn pick_fill16(int kind, bool lin, int cols, bool multi, bool gsub, bool wavefront, bool sym = false)
 {
@@ -1308,6 +1309,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         tp.slots = slots_w;
         tp.counter = (int *)ctx->counters.p + 256 * wi + 255;
         tp.row_bias = sym ? ctx->h_sc.gap_open + ctx->h_sc.la[1 * ctx->h_sc.let] : 0;
+        tp.val_bias = (sym && kind == KIND_SW) ? -tp.row_bias : 0;
         // one thread per pair when the wave fills the GPU that way, else one warp per pair
         // (window of speculatively rebuilt tiles, see ba_trace16w_kernel), a whole CTA per pair when
         // even that leaves SMs idle; a mixed wave gives warps to its longest pairs (the head of

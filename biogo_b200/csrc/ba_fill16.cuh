@@ -264,6 +264,15 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
     const unsigned erp = pack16(er, er), eqp = pack16(eq, eq);
     const unsigned goerp = pack16(go + er, go + er), goeqp = pack16(go + eq, go + eq);
     const unsigned NEGP = pack16(BA16_NEG, BA16_NEG);
+    // BIAS (the SYM SW kernels): every value of the tables carries +vb, vb = -(go + e) >= 0.  Then M >= vb in both
+    // halves of a packed word, G = M + go + e = M - vb >= 0, and the packed add is ONE 32-bit subtraction that never
+    // borrows between the halves -- an integer add ptxas may issue on the FMA pipe (IMAD.IADD) instead of the
+    // saturated ALU pipe that every DPX instruction needs.  Zero borders become vb, the clamp of M is the third
+    // operand of the add-max, checkpoints hold biased values (ba_trace16 CkView subtracts vb), the start-cell
+    // candidates are stored unbiased.  The host bounds vb (g_sym_scoring) so that C4's head room covers it.
+    constexpr bool BIAS = SYM && KIND == KIND_SW && !LIN;
+    const int vb = BIAS ? -(go + er) : 0;
+    const unsigned vbp = pack16(vb, vb);
 
     const int lane = threadIdx.x & 31;
     const int t = lane & 15;                       // lane inside the group
@@ -403,8 +412,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
 #pragma unroll
             for (int k = 0; k < NC; k++) {
                 if (KIND == KIND_SW) {
-                    Mu[k] = SYM ? goerp : 0u;   // SYM: Mu holds M + go + e
-                    Uu[k] = Hu[k] = 0;
+                    Mu[k] = BIAS ? 0u : SYM ? goerp : 0u;   // SYM: Mu holds M + go + e (BIAS: + vb, i.e. zero)
+                    Uu[k] = Hu[k] = vbp;
                 } else {
                     // row 0: M = U = -inf, L = go + j*eq (nw_affine_letters.go:119-131); H = L
                     const int j = pass * W + t * NC + k + 1;
@@ -417,10 +426,12 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 const int j0 = pass * W + t * NC;  // the column left of my first one: H[0][j0]
                 sdiagH = (j0 == 0) ? 0u : pack16(go + j0 * eq, go + j0 * eq);
                 outL = NEGP;
+            } else if (BIAS) {
+                outL = sdiagH = mlast = vbp;
             }
             unsigned bmax = 0;  // running max of the current period
             // per lane (both pairs packed): best value of this pass and the LAST period attaining it
-            unsigned vbest = pack16(1, 1);
+            unsigned vbest = pack16(vb + 1, vb + 1);
             int per_lo = -1, per_hi = -1;
             const bool plC = plA || plB;
             uint8_t *colck = P.arena + offC + (int64_t)pass * passb;
@@ -488,8 +499,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                 unsigned rH = __shfl_up_sync(FULL, Hu[NC - 1], 1, 16);
                 if (t == 0) {
                     if (KIND == KIND_SW) {
-                        rM = SYM ? goerp : 0u;
-                        rL = rH = 0;
+                        rM = BIAS ? 0u : SYM ? goerp : 0u;
+                        rL = rH = vbp;
                     } else {
                         // DP column 0: M = L = -inf; U = go + i*er (NW, nw_affine_letters.go:132-142)
                         // or 0 (Fitted, fitted_affine_letters.go:123-132); H = U
@@ -538,11 +549,13 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         else
                             sub = ba_prmt((unsigned)(int)*(const signed char *)(gtab + profA + sel[k]),
                                           (unsigned)(int)*(const signed char *)(gtab + profB + qb4[k]), 0x5410u);
-                        const unsigned M = (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Hd, sub, erp) : __vadd2(Hd, sub);
+                        const unsigned M = BIAS                ? __viaddmax_s16x2(Hd, sub, vbp)   // clamp at the biased zero
+                                           : (KIND == KIND_SW) ? __viaddmax_s16x2_relu(Hd, sub, erp)
+                                                               : __vadd2(Hd, sub);
                         Hd = Hu[k];
                         Ll = __viaddmax_s16x2(Ll, eqp, Gl);
                         Hu[k] = __vimax3_s16x2(M, Uu[k], Ll);
-                        Gl = __vadd2(M, goerp);
+                        Gl = BIAS ? M - vbp : __vadd2(M, goerp);   // BIAS: both halves >= vb, no borrow
                         Mu[k] = Gl;
                         if (KIND == KIND_SW) {
                             if (k & 1)
@@ -687,7 +700,7 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
             if (KIND == KIND_SW && plC) {
                 // start-cell candidates of this (pass, lane): pair A's record, then pair B's
                 int4 *cand = (int4 *)(P.arena + offC + (int64_t)np_ck * passb) + pass * 16 + t;
-                *cand = make_int4(lo16(vbest), plA ? per_lo : -1, hi16(vbest), plB ? per_hi : -1);
+                *cand = make_int4(lo16(vbest) - vb, plA ? per_lo : -1, hi16(vbest) - vb, plB ? per_hi : -1);
             }
             __syncwarp();
         }

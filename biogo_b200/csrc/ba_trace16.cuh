@@ -45,6 +45,7 @@ struct Trace16Params {
     int32_t *slots;            // 5 ints per segment, in EMISSION order (reverse of final)
     int *counter;              // ba_trace16p_kernel: next work item
     int row_bias;              // go + e when the fill ran the SYM kernels (their row checkpoints hold M + go + e), else 0
+    int val_bias;              // vb of the biased SYM SW kernels (every checkpointed value carries + vb), else 0
 };
 
 // One pair's view of its couple's checkpoint region (layout: ba_fill16.cuh "Checkpoint geometry").
@@ -55,13 +56,15 @@ struct CkView {
     int half;                        // 0: my values are the low 16-bit halves of the stored words, 1: the high halves
     int rs;                          // double-elements per lane row of a row block
     int bias;                        // SYM kernels store G = M + go + e in the row blocks: M = G - bias
+    int vb;                          // biased SYM SW kernels: every stored value carries + vb
     bool lin;    // linear kinds: one table T (elements of one word)
     bool clamp;  // affine SW: the fill defers the clamp of U and L at zero and stores them raw
     unsigned inv_cols;         // ceil(2^32 / cols): strip_of without a division
     int64_t pass_bytes, colck_bytes;
     __device__ __forceinline__ void init(const uint8_t *arena, const WorkItem &item, int n_, int m_, bool lin_, bool clamp_,
-                                         int bias_)
+                                         int bias_, int vb_)
     {
+        vb = vb_;
         base = arena + item.code_off;
         n = n_;
         m = m_;
@@ -97,12 +100,13 @@ struct CkView {
     }
     __device__ __forceinline__ void col_pick(const uint2 &w, int &M, int &L) const
     {
-        M = pick(w.x);
         if (lin) {
+            M = pick(w.x);
             L = 0;
             return;
         }
-        L = pick(w.y);
+        M = pick(w.x) - vb;
+        L = pick(w.y) - vb;
         if (clamp) L = max(L, 0);
     }
     // (M, clamped L) of the last column of strip g at row r
@@ -123,8 +127,8 @@ struct CkView {
             U = 0;
             return;
         }
-        M = pick(w.x) - bias;
-        U = pick(w.y);
+        M = pick(w.x) - bias - vb;
+        U = pick(w.y) - vb;
         if (clamp) U = max(U, 0);
     }
     // (M, clamped U) of column k of strip g at its checkpoint row of period e
@@ -714,7 +718,7 @@ __global__ void __launch_bounds__(TS, (LIN ? 6 : BA_TRACE_MINB) * (BA_TRACE_THRE
     const int go8 = go * BA_SCALE;
 
     CkView ck;
-    ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias);
+    ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias, P.val_bias);
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
 
@@ -893,7 +897,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16p_k
             m = P.qry_len[p];
             rs = P.enc + P.ref_off[p];
             qs = P.enc + P.qry_off[p];
-            ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias);
+            ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias, P.val_bias);
             ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
             ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
             out = P.slots + 5 * P.slot_off[it];
@@ -1182,7 +1186,7 @@ __global__ void __launch_bounds__(BA_TRACE_THREADS, BA_TRACE_MINB) ba_trace16w_k
     const int go8 = go * BA_SCALE;
 
     CkView ck;
-    ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias);
+    ck.init(P.arena, item, n, m, LIN, (KIND == KIND_SW) && !LIN, P.row_bias, P.val_bias);
     ck.npass = (n > 0 && m > 0) ? (int)ba16_npass(item.cols, m) : 0;
     ck.jshift = (KIND == KIND_SW) ? m - ck.npass * 32 * item.cols : 0;
 

@@ -76,18 +76,37 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
         // per pair at the end (no warp collective inside the scan, so the byte loads pipeline).
         int bad_r = 0x7fffffff, bad_q = 0x7fffffff;  // first illegal position
         unsigned flags = 0;                          // 1: index beyond the matrix, 2: outside 1..4, 4: gap letter
+        // A sequence is scanned in aligned 32-bit words (four or two letters per load; the encoded buffer has
+        // slack behind its last byte): bytes outside [0, len*stride) or on a quality position are masked out.
+        auto scan = [&](const uint8_t *sq, int len, int &bad) {
+            if (stride <= 2) {
+                const int head = (int)((uintptr_t)sq & 3u);
+                const uint32_t *wp = (const uint32_t *)(sq - head);
+                const int total = len * stride, nwords = (head + total + 3) >> 2;
 #pragma unroll 4
-        for (int x = lane; x < n; x += 32) {
-            const unsigned v = r[(int64_t)x * stride];
-            if (v == 0xFFu) bad_r = min(bad_r, x);
-            flags |= (v == 0xFEu ? 1u : 0u) | ((v < 1u || v > 4u) ? 2u : 0u) | (v == 0u ? 4u : 0u);
-        }
+                for (int w = lane; w < nwords; w += 32) {
+                    const uint32_t word = wp[w];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int o = 4 * w + b - head;   // byte offset inside the sequence
+                        if (o >= 0 && o < total && (stride == 1 || (o & 1) == 0)) {
+                            const unsigned v = (word >> (8 * b)) & 0xFFu;
+                            if (v == 0xFFu) bad = min(bad, stride == 1 ? o : o >> 1);
+                            flags |= (v == 0xFEu ? 1u : 0u) | ((v < 1u || v > 4u) ? 2u : 0u) | (v == 0u ? 4u : 0u);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 4
-        for (int x = lane; x < m; x += 32) {
-            const unsigned v = q[(int64_t)x * stride];
-            if (v == 0xFFu) bad_q = min(bad_q, x);
-            flags |= (v == 0xFEu ? 1u : 0u) | ((v < 1u || v > 4u) ? 2u : 0u) | (v == 0u ? 4u : 0u);
-        }
+                for (int x = lane; x < len; x += 32) {
+                    const unsigned v = sq[(int64_t)x * stride];
+                    if (v == 0xFFu) bad = min(bad, x);
+                    flags |= (v == 0xFEu ? 1u : 0u) | ((v < 1u || v > 4u) ? 2u : 0u) | (v == 0u ? 4u : 0u);
+                }
+            }
+        };
+        scan(r, n, bad_r);
+        scan(q, m, bad_q);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             bad_r = min(bad_r, __shfl_xor_sync(0xffffffffu, bad_r, o));

@@ -52,6 +52,9 @@ SETS = [
     ("w8-no-plan-cache", dict(waves=8, plan_cache=0), True),
     ("one-wave-no-plan-cache", dict(waves=1, plan_cache=0), False),
 ]
+if os.environ.get("SWEEP_SETS"):   # custom sets: JSON {"name": {option: value, ...}, ...}
+    SETS = [(k, v, False) for k, v in json.loads(os.environ["SWEEP_SETS"]).items()]
+    DEFAULTS = {}
 if os.environ.get("SWEEP_ONLY"):
     keep = set(os.environ["SWEEP_ONLY"].split(","))
     SETS = [s for s in SETS if s[0] in keep]
