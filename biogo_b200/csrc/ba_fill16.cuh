@@ -30,8 +30,10 @@
 
 #include "ba_common.cuh"
 
+#ifndef BA16_PROF_RING
 #define BA16_PROF_RING 512           // ring of row profiles per group (entries)
-#define BA16_PROF_CHUNK 256          // rows loaded per refill
+#endif
+#define BA16_PROF_CHUNK (BA16_PROF_RING / 2)   // rows loaded per refill
 #define BA16_WARPS 2                 // warps per CTA
 #define BA16_PERIOD 8                // steps between two row checkpoints (= tile rows of ba_trace16)
 #define BA16_PSHIFT 3
@@ -214,7 +216,8 @@ __device__ __forceinline__ uint4 ba16_bnd_unpack(const ulonglong2 &w)
 // instructions (+ half a max3 of best tracking) instead of 7.5.  M itself is transient inside
 // the step; checkpoints recover it as G - (go + e).
 template <int KIND, int COLS, bool MULTI, bool GSUB, bool LONG, bool LIN, bool SYM = false>
-__global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params P)
+__global__ void __launch_bounds__(BA16_WARPS * 32)
+    ba_fill16_kernel(Fill16Params P)
 {
     constexpr int NC = 2 * COLS;  // columns per lane
     // row profiles: ring[group][pair][i & (RING-1)] = 4 substitution bytes of the letter of row i
@@ -464,8 +467,8 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                         for (int y = 0; y < (PFN > 0 ? PFN : 1); y++) {
                             const int i = 8 * e + 1 + t + 16 * y;
                             unsigned wa = VROW, wb = VROW;
-                            if (plA && i <= nA) wa = proftab[pfA[y] & 31];
-                            if (plB && i <= nB) wb = proftab[pfB[y] & 31];
+                            if (plA && i <= nA) wa = proftab[pfA[y] & (GSUB ? 31 : 7)];
+                            if (plB && i <= nB) wb = proftab[pfB[y] & (GSUB ? 31 : 7)];
                             ringA[i & (RING - 1)] = wa;
                             ringB[i & (RING - 1)] = wb;
                             const int i2 = i + CHUNK;
@@ -473,13 +476,27 @@ __global__ void __launch_bounds__(BA16_WARPS * 32) ba_fill16_kernel(Fill16Params
                             pfB[y] = (plB && i2 <= nB) ? rB[(int64_t)(i2 - 1) * stride] : 0;
                         }
                     } else {
-                        for (int x = t; x < CHUNK; x += 16) {
-                            const int i = 8 * e + 1 + x;
-                            unsigned wa = VROW, wb = VROW;
-                            if (plA && i <= nA) wa = proftab[rA[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
-                            if (plB && i <= nB) wb = proftab[rB[(int64_t)(i - 1) * stride] & (GSUB ? 31 : 7)];
-                            ringA[i & (RING - 1)] = wa;
-                            ringB[i & (RING - 1)] = wb;
+                        // four rows per lane and pair at a time: the eight letter loads of a batch are in flight
+                        // together (one load, one lookup, one store at a time cost 16 exposed latencies per
+                        // refill -- 11 % of the stall samples of config 5's wavefront kernel, ncu r02)
+                        static_assert(CHUNK % 64 == 0, "a refill is a whole number of 4-row batches");
+                        for (int x0 = t; x0 < CHUNK; x0 += 64) {
+                            unsigned la[4], lb[4];
+#pragma unroll
+                            for (int y = 0; y < 4; y++) {
+                                const int i = 8 * e + 1 + x0 + 16 * y;
+                                la[y] = (plA && i <= nA) ? (unsigned)rA[(int64_t)(i - 1) * stride] : 0u;
+                                lb[y] = (plB && i <= nB) ? (unsigned)rB[(int64_t)(i - 1) * stride] : 0u;
+                            }
+#pragma unroll
+                            for (int y = 0; y < 4; y++) {
+                                const int i = 8 * e + 1 + x0 + 16 * y;
+                                unsigned wa = VROW, wb = VROW;
+                                if (plA && i <= nA) wa = proftab[la[y] & (GSUB ? 31 : 7)];
+                                if (plB && i <= nB) wb = proftab[lb[y] & (GSUB ? 31 : 7)];
+                                ringA[i & (RING - 1)] = wa;
+                                ringB[i & (RING - 1)] = wb;
+                            }
                         }
                     }
                     __syncwarp();
