@@ -76,24 +76,36 @@ __global__ void ba_validate_kernel(const uint8_t *__restrict__ enc, int stride,
         // per pair at the end (no warp collective inside the scan, so the byte loads pipeline).
         int bad_r = 0x7fffffff, bad_q = 0x7fffffff;  // first illegal position
         unsigned flags = 0;                          // 1: index beyond the matrix, 2: outside 1..4, 4: gap letter
-        // A sequence is scanned in aligned 32-bit words (four or two letters per load; the encoded buffer has
-        // slack behind its last byte): bytes outside [0, len*stride) or on a quality position are masked out.
+        // A sequence is scanned in aligned 32-bit words (the encoded buffer has slack behind its last byte), four
+        // (Letters) or two (QLetters) letters per load, and every test is made on the whole word: bytes outside
+        // [0, len*stride) and quality bytes are first replaced by the harmless index 1, then "some byte is 0 / 0xFF /
+        // 0xFE / above 4" are the classic carry tricks (exact as ANY-byte tests; a per-byte loop cost ten
+        // instructions per letter and made this kernel instruction-bound).  Only a word that holds an illegal
+        // letter (0xFF) is looked at byte by byte, for the position.
         auto scan = [&](const uint8_t *sq, int len, int &bad) {
             if (stride <= 2) {
                 const int head = (int)((uintptr_t)sq & 3u);
                 const uint32_t *wp = (const uint32_t *)(sq - head);
                 const int total = len * stride, nwords = (head + total + 3) >> 2;
+                // letter positions inside a word: all four bytes, or every second one starting at the head's parity
+                const uint32_t lmask = stride == 1 ? 0xFFFFFFFFu : ((head & 1) ? 0xFF00FF00u : 0x00FF00FFu);
 #pragma unroll 4
                 for (int w = lane; w < nwords; w += 32) {
                     const uint32_t word = wp[w];
+                    const int o0 = 4 * w - head;            // sequence offset of the word's byte 0
+                    uint32_t vm = lmask;
+                    if (o0 < 0) vm &= 0xFFFFFFFFu << (8 * (-o0));                       // bytes before the sequence
+                    if (o0 + 4 > total) vm &= 0xFFFFFFFFu >> (8 * (o0 + 4 - total));    // bytes behind it
+                    const uint32_t x = (word & vm) | (0x01010101u & ~vm);
+                    const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;            // some byte == 0
+                    const uint32_t nx = ~x, ff = (nx - 0x01010101u) & ~nx & 0x80808080u;   // some byte == 0xFF
+                    const uint32_t y = x ^ 0xFEFEFEFEu, fe = (y - 0x01010101u) & ~y & 0x80808080u;   // some byte == 0xFE
+                    const uint32_t gt4 = ((x & 0x7F7F7F7Fu) + 0x7B7B7B7Bu | x) & 0x80808080u;   // some byte > 4
+                    flags |= (fe ? 1u : 0u) | ((z | gt4) ? 2u : 0u) | (z ? 4u : 0u);
+                    if (ff) {
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int o = 4 * w + b - head;   // byte offset inside the sequence
-                        if (o >= 0 && o < total && (stride == 1 || (o & 1) == 0)) {
-                            const unsigned v = (word >> (8 * b)) & 0xFFu;
-                            if (v == 0xFFu) bad = min(bad, stride == 1 ? o : o >> 1);
-                            flags |= (v == 0xFEu ? 1u : 0u) | ((v < 1u || v > 4u) ? 2u : 0u) | (v == 0u ? 4u : 0u);
-                        }
+                        for (int b = 3; b >= 0; b--)
+                            if (((x >> (8 * b)) & 0xFFu) == 0xFFu) bad = min(bad, (o0 + b) / stride);
                     }
                 }
             } else {

@@ -37,3 +37,25 @@ def rand_pairs(rng, count, lens_r, lens_q, related=0.5, dirty=0.2, alpha=DNA_LET
             q = bytes(rng.choice(al) for _ in range(m))
         pairs.append((r, q))
     return pairs
+
+
+def sparse_dirty_pairs(rng, count, max_len=45):
+    """Pairs with at most a few stray letters -- one illegal letter ('N'), a gap letter ('-') or none -- at random
+    positions of reference and/or query, lengths 0..max_len: packed back to back they give every word alignment
+    of a sequence start, of its end and of the stray letter (the validation kernel scans aligned words)."""
+    pairs = []
+    for _ in range(count):
+        seqs = []
+        for _s in range(2):
+            n = rng.randrange(0, max_len + 1)
+            s = bytearray(rng.choice(b"ACGT") for _ in range(n))
+            u = rng.random()
+            if n and u < 0.35:
+                s[rng.randrange(n)] = ord("N")
+            elif n and u < 0.5:
+                s[rng.randrange(n)] = ord("-")
+            if n and rng.random() < 0.1:
+                s[rng.randrange(n)] = ord("N")
+            seqs.append(bytes(s))
+        pairs.append((seqs[0], seqs[1]))
+    return pairs

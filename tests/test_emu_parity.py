@@ -472,3 +472,17 @@ def test_wavefront_timeout_falls_back_to_the_pass_by_pass_kernels(emu_ctx):
     helpers.compare(res, helpers.run_oracle(2, True, M, -4, DNA_IDX, pk), "wavefront retry")
     again = helpers.run_lib(emu_ctx, 2, True, M, -4, DNA_IDX, 5, pk)     # and the context is fine afterwards
     helpers.compare(again, helpers.run_oracle(2, True, M, -4, DNA_IDX, pk), "after retry")
+
+
+@pytest.mark.parametrize("stride", [1, 2], ids=["Letters", "QLetters"])
+def test_validation_word_scan_every_alignment(emu_ctx, stride):
+    """Which error the reference raises first (and where) for stray illegal / gap letters at every alignment of the
+    sequences inside the packed buffer -- ba_validate_kernel scans aligned 32-bit words."""
+    rng = random.Random(4242 + stride)
+    pairs = randcases.sparse_dirty_pairs(rng, 160)
+    pk = helpers.pack(pairs, stride)
+    M = gv.match(-1, 1, -1)
+    for kind, affine in helpers.KINDS:
+        res = helpers.run_lib(emu_ctx, kind, affine, M, -5 if affine else 0, DNA_IDX, 5, pk, stride)
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, -5 if affine else 0, DNA_IDX, pk, stride),
+                        f"validation scan kind {kind} affine {affine} stride {stride}")

@@ -553,3 +553,17 @@ def test_named_scoring_on_the_gpu(gpu_ctx):
                                             helpers.pack([(b"ACGTACGTTT", b"ACGTCGTTT")])),
                             helpers.run_oracle(0, False, gv.match(-1, 2, -1), 0, DNA_IDX,
                                                helpers.pack([(b"ACGTACGTTT", b"ACGTCGTTT")])), "dna between")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stride", [1, 2], ids=["Letters", "QLetters"])
+def test_validation_word_scan_every_alignment(gpu_ctx, stride):
+    """Twin of the emulator-tier test: stray illegal / gap letters at every word alignment, all six aligners."""
+    rng = random.Random(4242 + stride)
+    pairs = randcases.sparse_dirty_pairs(rng, 600)
+    pk = helpers.pack(pairs, stride)
+    M = gv.match(-1, 1, -1)
+    for kind, affine in helpers.KINDS:
+        res = helpers.run_lib(gpu_ctx, kind, affine, M, -5 if affine else 0, DNA_IDX, 5, pk, stride)
+        helpers.compare(res, helpers.run_oracle(kind, affine, M, -5 if affine else 0, DNA_IDX, pk, stride),
+                        f"validation scan kind {kind} affine {affine} stride {stride}")
