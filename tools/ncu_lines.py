@@ -19,6 +19,9 @@ for r in rows:
     if r[0] == "Function Name" or hdr is None:
         continue
     if r[0] != "" and r[0].isdigit():
+        if len(r) > len(hdr):   # a source line with unescaped quotes and commas (inline asm): re-join its pieces
+            extra = len(r) - len(hdr)
+            r = r[:1] + [",".join(r[1:2 + extra])] + r[2 + extra:]
         lines.append((cur_file, int(r[0]), r[1], r))
 ix = {n: i for i, n in enumerate(hdr)}
 si = ix["# Samples"]; ii = ix["Instructions Executed"]; ti = ix["Thread Instructions Executed"]
