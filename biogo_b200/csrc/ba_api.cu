@@ -1120,9 +1120,19 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
     // the fills of this batch follow the fills of the previous batch on this device
     DeviceGate &gate = g_gate[ctx->device & 63];
     std::unique_lock<std::mutex> gate_lock(gate.mu, std::defer_lock);
+    // gate_busy: the previous batch on this device is still filling, so this batch's fill cannot start before its
+    // own upload has (very likely) landed -- then one fill launch per class beats the chunked fill, whose only
+    // purpose is to start early on a partly uploaded batch (two pipelined callers: every batch but the first)
+    bool gate_busy = false;
     if (ctx->opt_exclusive) {
         gate_lock.lock();
-        if (gate.armed) CK(cudaStreamWaitEvent(st, gate.last_fill, 0));
+        if (gate.armed) {
+            if (cudaEventQuery(gate.last_fill) == cudaErrorNotReady) {
+                gate_busy = true;
+                (void)cudaGetLastError();
+            }
+            CK(cudaStreamWaitEvent(st, gate.last_fill, 0));
+        }
     }
     cudaEvent_t ev_setup = ev_new(ctx, true);   // also the start of the fill span
     if (!ev_setup) {
@@ -1143,7 +1153,7 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
         // groups), the fill starts on the pairs that are already here -- one launch per chunk of the
         // work list, alternating between the two fill streams so the tail of one overlaps the head of
         // the next; the traceback follows once, after the last chunk.
-        const bool chunked = !overlap && B.groups.size() > 1 && B.next_group < B.groups.size();
+        const bool chunked = !overlap && !gate_busy && B.groups.size() > 1 && B.next_group < B.groups.size();
         bool used_alt = false;
         if (!chunked) {
             if ((rc = prep_pairs(ctx, B, w.max_pair)) != BA_OK) return rc;

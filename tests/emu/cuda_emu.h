@@ -308,7 +308,7 @@ static inline unsigned __vimin3_u32(unsigned a, unsigned b, unsigned c) { return
 // ---- a minimal CUDA *runtime* so biogo_b200/csrc/ba_api.cu (the host scheduler) builds
 // and runs unchanged on the CPU: device memory is host memory, streams are synchronous.
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
@@ -363,6 +363,7 @@ static inline cudaError_t cudaGetDeviceCount(int *n)
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }   // everything runs synchronously here
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t)
 {
     *ms = 0.f;
