@@ -53,7 +53,8 @@ SETS = [
     ("one-wave-no-plan-cache", dict(waves=1, plan_cache=0), False),
 ]
 if os.environ.get("SWEEP_SETS"):   # custom sets: JSON {"name": {option: value, ...}, ...}
-    SETS = [(k, v, False) for k, v in json.loads(os.environ["SWEEP_SETS"]).items()]
+    SETS = [(k, {a: b for a, b in v.items() if a != "_e2e"}, bool(v.get("_e2e"))) for k, v in
+            json.loads(os.environ["SWEEP_SETS"]).items()]   # "_e2e": 1 adds the host-buffer measurements
     DEFAULTS = {}
 if os.environ.get("SWEEP_ONLY"):
     keep = set(os.environ["SWEEP_ONLY"].split(","))
