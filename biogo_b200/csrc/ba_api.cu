@@ -1160,7 +1160,15 @@ int run_path16(ba_ctx *ctx, Batch &B, const int32_t *ids, int64_t nids, bool gsu
             if ((rc = sync_prep(ctx, B, F)) != BA_OK) return rc;
             if (F != st && B.next_group > 0) CK(cudaStreamWaitEvent(F, B.groups[B.next_group - 1].checked, 0));
         }
-        if (wi >= R) CK(cudaStreamWaitEvent(F, ev_trace_end[(size_t)(wi - R)], 0));  // its region is free again
+        if (wi >= R) {
+            CK(cudaStreamWaitEvent(F, ev_trace_end[(size_t)(wi - R)], 0));  // its region is free again
+            // a chunked fill alternates its chunks between F and the second fill stream: that one must not write
+            // into the region either before the traceback of wave wi - R has read it (found by tools/fuzz_oracle.py:
+            // arena-limited waves + grouped upload + two fill streams gave wrong segments or an illegal access, one
+            // round in ~1500)
+            if (chunked && ctx->opt_fill_streams >= 2 && F != ctx->s_fill2)
+                CK(cudaStreamWaitEvent(ctx->s_fill2, ev_trace_end[(size_t)(wi - R)], 0));
+        }
         const int64_t reg = wi % R;
         uint8_t *arena_w = (uint8_t *)ctx->arena.p + reg * region_bytes;
         int32_t *slots_w = (int32_t *)ctx->slots.p + 5 * reg * region_slots;

@@ -1,4 +1,11 @@
-"""GPU fuzz against the CPU oracle: random scorings, kinds, lengths and strides, both device paths."""
+"""GPU fuzz against the CPU oracle: random scorings, kinds, lengths and strides, both device paths.
+
+    python tools/fuzz_oracle.py [seed] [seconds]
+
+FUZZ_LIB=<path> runs another build of the library (e.g. the CPU emulation, plain or AddressSanitizer);
+FUZZ_SHAPES=short,edge restricts the length classes (the emulator is slow on long pairs); FUZZ_LOG=1 prints every
+round's parameters before it runs (the last line names the round that crashed).
+"""
 import os
 import random
 import sys
@@ -19,7 +26,8 @@ PROT_IDX = O.build_index("-abcdefghijklmnpqrstvwxyz*")
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
 rng = random.Random(seed)
-ctx = _lib.Context(0)
+ctx = _lib.Context(0, os.environ.get("FUZZ_LIB") or None)
+SHAPES = (os.environ.get("FUZZ_SHAPES") or "short,mid,long,mixed,edge,edge").split(",")
 t_end = time.time() + budget
 rounds = mism = fastpairs = 0
 while time.time() < t_end:
@@ -35,7 +43,7 @@ while time.time() < t_end:
         M = [[0] + [gap2] * 4] + [[gap] + [ma if a == b else mi for b in range(4)] for a in range(4)]
         idx, al, alpha = DNA_IDX, 5, b"ACGT"
     go = rng.choice([-2, -5, -8, -12]) if affine else 0
-    shape = rng.choice(["short", "mid", "long", "mixed", "edge", "edge"])
+    shape = rng.choice(SHAPES)
     lens_r = {"short": [1, 7, 33, 90], "mid": [150, 300, 700], "long": [900, 2200, 4000], "mixed": [5, 120, 900, 3000],
               "edge": [1, 2, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 513]}[shape]
     lens_q = {"short": [1, 9, 40, 100], "mid": [100, 257, 520], "long": [1030, 1800, 3100], "mixed": [3, 250, 1100, 2600],
@@ -56,12 +64,23 @@ while time.time() < t_end:
         opts["slot_cap"] = rng.choice([1, 3])
     if rng.random() < 0.15:
         opts["arena_bytes"] = rng.choice([200_000, 5_000_000])
+    if os.environ.get("FUZZ_ONLY") and rounds + 1 != int(os.environ["FUZZ_ONLY"]):   # replay one round of a seed
+        rounds += 1
+        if rounds > int(os.environ["FUZZ_ONLY"]):
+            break
+        continue
+    for kv in (os.environ.get("FUZZ_SET") or "").split(","):   # e.g. FUZZ_SET=trace_mode=1: override drawn options
+        if "=" in kv:
+            opts[kv.split("=")[0]] = int(kv.split("=")[1])
+    if os.environ.get("FUZZ_LOG"):
+        print("ROUND", dict(round=rounds + 1, kind=kind, affine=affine, protein=protein, go=go, M0=M[1][:3], shape=shape,
+                            stride=stride, npairs=len(pairs), opts=opts), flush=True)
     for k, v in opts.items():
         ctx.set_option(k, v)
     orc = helpers.run_oracle(kind, affine, M, go, idx, pk, stride, 16)
     ok = True
     try:
-        for force in (0, 1):
+        for force in (0, 1) * int(os.environ.get("FUZZ_REPEAT") or 1):   # (races: the same round many times)
             ctx.set_option("force_path", force)
             res = helpers.run_lib(ctx, kind, affine, M, go, idx, al, pk, stride)
             if force == 0:
