@@ -59,3 +59,28 @@ def sparse_dirty_pairs(rng, count, max_len=45):
             seqs.append(bytes(s))
         pairs.append((seqs[0], seqs[1]))
     return pairs
+
+
+def region_reuse_chunked_case(ctx, helpers, match_matrix, dna_idx, repeats):
+    """Arena-limited waves (tiny arena: every wave re-uses a checkpoint region) of a batch whose letters arrive in
+    several upload groups, so that the fill is chunked and alternates between the two fill streams -- the
+    combination in which tools/fuzz_oracle.py found a stream race (the second fill stream did not wait for the
+    traceback of the wave that last used the region).  Timing-dependent, hence repeated."""
+    import random
+
+    rng = random.Random(1474)
+    pairs = rand_pairs(rng, 200, [1, 7, 33, 90], [1, 9, 40, 100], related=0.7, dirty=0.0)
+    pk = helpers.pack(pairs)
+    M = match_matrix(-3, 2, -1)
+    orc = helpers.run_oracle(0, True, M, -8, dna_idx, pk)
+    opts = {"arena_bytes": 200000, "upload_groups": 7, "chunk_pairs": 8, "fill_streams": 2, "waves": 1}
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        for it in range(repeats):
+            res = helpers.run_lib(ctx, 0, True, M, -8, dna_idx, 5, pk)
+            assert res.stats["waves"] > 2
+            helpers.compare(res, orc, f"region reuse under a chunked fill, run {it}")
+    finally:
+        for k, v in (("arena_bytes", 0), ("upload_groups", 0), ("chunk_pairs", 8192), ("fill_streams", 2), ("waves", 0)):
+            ctx.set_option(k, v)

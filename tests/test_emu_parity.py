@@ -486,3 +486,8 @@ def test_validation_word_scan_every_alignment(emu_ctx, stride):
         res = helpers.run_lib(emu_ctx, kind, affine, M, -5 if affine else 0, DNA_IDX, 5, pk, stride)
         helpers.compare(res, helpers.run_oracle(kind, affine, M, -5 if affine else 0, DNA_IDX, pk, stride),
                         f"validation scan kind {kind} affine {affine} stride {stride}")
+
+
+def test_region_reuse_under_a_chunked_fill(emu_ctx):
+    """Arena-limited waves + grouped upload + two fill streams (the stream race the GPU fuzzer found)."""
+    randcases.region_reuse_chunked_case(emu_ctx, helpers, gv.match, DNA_IDX, 2)

@@ -567,3 +567,9 @@ def test_validation_word_scan_every_alignment(gpu_ctx, stride):
         res = helpers.run_lib(gpu_ctx, kind, affine, M, -5 if affine else 0, DNA_IDX, 5, pk, stride)
         helpers.compare(res, helpers.run_oracle(kind, affine, M, -5 if affine else 0, DNA_IDX, pk, stride),
                         f"validation scan kind {kind} affine {affine} stride {stride}")
+
+
+@pytest.mark.gpu
+def test_region_reuse_under_a_chunked_fill(gpu_ctx):
+    """Arena-limited waves + grouped upload + two fill streams (the stream race the GPU fuzzer found)."""
+    randcases.region_reuse_chunked_case(gpu_ctx, helpers, gv.match, DNA_IDX, 40)
