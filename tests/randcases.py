@@ -84,3 +84,20 @@ def region_reuse_chunked_case(ctx, helpers, match_matrix, dna_idx, repeats):
     finally:
         for k, v in (("arena_bytes", 0), ("upload_groups", 0), ("chunk_pairs", 8192), ("fill_streams", 2), ("waves", 0)):
             ctx.set_option(k, v)
+
+
+def biased_sym_sw_case(ctx, helpers, match_matrix, dna_idx, go, gap):
+    """SWAffine with match 10 / mismatch -9 on long identical stretches (scores near the top of the 16-bit range)
+    plus random related pairs, against the oracle; see test_biased_sym_sw_kernel_at_its_bounds."""
+    import random
+
+    rng = random.Random(20261020 + go)
+    M = match_matrix(gap, 10, -9)
+    base = bytes(rng.choice(b"ACGT") for _ in range(2900))
+    pairs = [(base, base), (base[:700], base[100:600]), (base[:300] + base[400:1500], base[:1400])]
+    pairs += rand_pairs(rng, 24, [1, 9, 60, 130, 300], [1, 16, 64, 257, 300], related=0.9, dirty=0.0)
+    pk = helpers.pack(pairs)
+    res = helpers.run_lib(ctx, 0, True, M, go, dna_idx, 5, pk)
+    helpers.compare(res, helpers.run_oracle(0, True, M, go, dna_idx, pk), f"biased SYM SW go {go} gap {gap}")
+    if gap < 0:
+        assert res.stats["pairs_fast16"] == len(pairs)

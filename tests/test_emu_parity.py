@@ -491,3 +491,13 @@ def test_validation_word_scan_every_alignment(emu_ctx, stride):
 def test_region_reuse_under_a_chunked_fill(emu_ctx):
     """Arena-limited waves + grouped upload + two fill streams (the stream race the GPU fuzzer found)."""
     randcases.region_reuse_chunked_case(emu_ctx, helpers, gv.match, DNA_IDX, 2)
+
+
+@pytest.mark.parametrize("go,gap", [(-1900, -100), (-1990, -11), (-40, -1), (0, 0)],
+                         ids=["bias2000", "bias2001-general", "bias41", "bias0"])
+def test_biased_sym_sw_kernel_at_its_bounds(emu_ctx, go, gap):
+    """The SYM SW fill keeps every value biased by vb = -(go + e) (one 32-bit subtraction gives M + go + e for both
+    packed pairs): the largest admitted bias (2000), one beyond it (general kernels), a small one, and zero gap
+    scores (vb = 0, where SW's exactness condition sends affine pairs to the exact path) -- each with scores near
+    the top of the 16-bit range (long identical stretches, match 10)."""
+    randcases.biased_sym_sw_case(emu_ctx, helpers, gv.match, DNA_IDX, go, gap)

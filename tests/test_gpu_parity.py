@@ -573,3 +573,11 @@ def test_validation_word_scan_every_alignment(gpu_ctx, stride):
 def test_region_reuse_under_a_chunked_fill(gpu_ctx):
     """Arena-limited waves + grouped upload + two fill streams (the stream race the GPU fuzzer found)."""
     randcases.region_reuse_chunked_case(gpu_ctx, helpers, gv.match, DNA_IDX, 40)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("go,gap", [(-1900, -100), (-1990, -11), (-40, -1), (0, 0)],
+                         ids=["bias2000", "bias2001-general", "bias41", "bias0"])
+def test_biased_sym_sw_kernel_at_its_bounds(gpu_ctx, go, gap):
+    """Twin of the emulator-tier test: the biased SYM SW fill at the bounds of its bias, scores near the 16-bit top."""
+    randcases.biased_sym_sw_case(gpu_ctx, helpers, gv.match, DNA_IDX, go, gap)
